@@ -1,0 +1,114 @@
+/* klsh.h — C ABI of the B200-native kmerLSH mode-C clustering hot path.
+ *
+ * The reference (wthanone/kmerLSH) has no plugin/FFI interface: the seam of its hot path is the
+ * C++ free function
+ *     void Cluster(vector<Abundance*>*, float min_similarity, int cluster_iteration,
+ *                  unsigned threads_to_use, int dim, int bucket_size_threshold, bool verbose)
+ * (reference function/cluster.h:42; call sites app/kmerLSH.cc:323, :377, :490) plus the files
+ * either side of it.  This header is what a binding for that seam binds: plain C types, caller-
+ * owned host buffers, library-owned device memory, `int` status (0 = ok) instead of exit().
+ * INTEGRATION.md shows the reference-side shim that routes Cluster() through it.
+ *
+ * One context = one GPU = one driving host thread (not re-entrant).  The library never prints.
+ * There is no CPU fallback: every entry point fails with KLSH_ERR_CUDA when no sm_100 device is
+ * usable.
+ */
+#ifndef KLSH_H
+#define KLSH_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KLSH_OK 0
+#define KLSH_ERR_ARG 1   /* bad argument / wrong state */
+#define KLSH_ERR_CUDA 2  /* CUDA runtime failure (see klsh_last_error) */
+#define KLSH_ERR_IO 3    /* file could not be opened / short read */
+#define KLSH_ERR_NOMEM 4 /* device or host allocation failed */
+
+typedef struct klsh_ctx klsh_ctx;
+
+/* Fills out[H][D] with the hyperplanes of one hash table.  Replaces
+ * LSH::generateHashTable(H, D) (reference hash/lshash.cc:36-42); a reference-side binding passes a
+ * trampoline to that very function so both sides draw from the reference's own generator. */
+typedef void (*klsh_plane_fn)(void* user, int H, int D, float* out);
+
+/* Per-iteration record; mirrors the reference's --verbose lines (function/cluster.cc:209-211,
+ * :263, :307, :325-326) plus device timings. */
+typedef struct {
+  uint64_t rows_in, rows_out;
+  int32_t H;
+  float threshold;
+  uint64_t buckets, bucket_max, nested_calls;
+  uint64_t eps_margin_rows; /* rows whose key needed the exact re-evaluation path (0 = exact everywhere) */
+  float ms_sign, ms_group, ms_merge, ms_compact, ms_total; /* CUDA-event times on the context's stream */
+} klsh_iter_stats;
+
+/* ---- lifetime -------------------------------------------------------------------------------- */
+int klsh_create(int device, klsh_ctx** out);
+void klsh_destroy(klsh_ctx* ctx);
+/* Message of the last failure on ctx (ctx == NULL: last klsh_create failure).  Never NULL. */
+const char* klsh_last_error(const klsh_ctx* ctx);
+/* Number of kernels this context has launched so far (bench.py's gpu_launches). */
+uint64_t klsh_launch_count(const klsh_ctx* ctx);
+
+/* ---- hyperplane source (reference hash/lshash.cc:3-17, :36-42) -------------------------------- */
+/* Built-in source: one process-wide-style master std::mt19937_64(seed); every hash function is
+ * std::mt19937(uint32(master())) + std::normal_distribution<double>(0,1) narrowed to float —
+ * the reference's generator with its std::random_device replaced by a seeded one. */
+int klsh_set_seed(klsh_ctx* ctx, uint64_t seed);
+int klsh_set_plane_source(klsh_ctx* ctx, klsh_plane_fn fn, void* user);
+/* Draw one table from the current source (advances it), e.g. to replay what a run used. */
+int klsh_draw_table(klsh_ctx* ctx, int H, int D, float* out);
+
+/* ---- rows in --------------------------------------------------------------------------------- */
+/* = ReadHT (reference io/ioHT.cc:59-81) output handed to IOMat::convertHTMat
+ * (io/ioMatrix.cc:353-408): counts is the sample-major uint16 block [D][batch_size] of
+ * kmer_count.bin, v_kmers[j] = float(coverage_j)/kmap_size (app/kmerLSH.cc:480).  Row i becomes
+ * value_j = float(log(cnt+1.0)) - v_kmers[j], kept iff sum_j cnt > 0.1*D, with id batch_offset+i.
+ * Replaces the context's row set. */
+int klsh_load_counts(klsh_ctx* ctx, const uint16_t* counts, const float* v_kmers, int D, uint64_t batch_size,
+                     uint64_t batch_offset);
+/* = a vector<Abundance*> handed to Cluster: values[n][D], ids of row r = ids[id_offsets[r] ..
+ * id_offsets[r+1]).  Replaces the context's row set. */
+int klsh_set_rows(klsh_ctx* ctx, const float* values, const uint64_t* id_offsets, const uint64_t* ids,
+                  uint64_t n, int D);
+/* = IOMat::ReadCluster / ReadClusterAll (io/ioMatrix.cc:121-196, :48-119): rows
+ * [start_line, start_line+num_lines) of <bin_path> and <bin_path>.clust; num_lines == 0 reads all. */
+int klsh_load_cluster_file(klsh_ctx* ctx, const char* bin_path, int D, uint64_t start_line, uint64_t num_lines);
+
+/* ---- the hot path ---------------------------------------------------------------------------- */
+/* = Cluster(rows, min_similarity, cluster_iteration, T, dim, bucket_size_threshold, verbose)
+ * (function/cluster.cc:181-340) on the context's row set, in place.  threads_to_use has no
+ * meaning here; results equal the reference's T=1 run (its only deterministic schedule).
+ * stats may be NULL, else has room for `iterations` records. */
+int klsh_cluster(klsh_ctx* ctx, float min_similarity, int iterations, int64_t bucket_size_threshold,
+                 klsh_iter_stats* stats);
+
+/* Function-level entry points (parity tests call these; they are the pieces of Cluster): */
+/* LSH::random_projection(row, table) for n host rows (hash/lshash.cc:44-59); key bit order as the
+ * reference: plane 0 is the most significant of the H bits. */
+int klsh_sign(klsh_ctx* ctx, const float* rows, uint64_t n, int D, const float* table, int H, uint64_t* keys_out);
+/* p_cluster (function/cluster.cc:56-87) on the context's whole row set as ONE bucket. */
+int klsh_p_cluster(klsh_ctx* ctx, float threshold);
+/* nestedCluster (function/cluster.cc:89-178) on the context's whole row set. */
+int klsh_nested_cluster(klsh_ctx* ctx, float threshold);
+
+/* ---- rows out -------------------------------------------------------------------------------- */
+int klsh_row_count(klsh_ctx* ctx, uint64_t* n_rows, uint64_t* n_ids);
+int klsh_get_rows(klsh_ctx* ctx, float* values, uint64_t* id_offsets, uint64_t* ids);
+/* = IOMat::SaveResult(rows, path+".clust", delfile, ignore_small) + IOMat::SaveBinary(rows, path,
+ * delfile, ignore_small) (io/ioMatrix.cc:265-294, :322-351). */
+int klsh_save(klsh_ctx* ctx, const char* bin_path, int delfile, int64_t ignore_small);
+
+/* ---- device-resident state control (benchmarks; multi-batch phase 1) --------------------------- */
+/* Remember / restore the current row set on the device (no host traffic). */
+int klsh_snapshot(klsh_ctx* ctx);
+int klsh_restore(klsh_ctx* ctx);
+/* Block until all work queued on the context's stream is done. */
+int klsh_sync(klsh_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

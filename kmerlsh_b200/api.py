@@ -1,0 +1,257 @@
+"""ctypes binding of include/klsh.h.
+
+`Cluster(rows, min_similarity, cluster_iteration, threads_to_use, dim, bucket_size_threshold,
+verbose)` mirrors the reference seam (reference function/cluster.h:42): same argument names and
+meaning; `rows` is the (values, id_offsets, ids) triple that stands for `vector<Abundance*>`.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+u64 = C.c_uint64
+i64 = C.c_int64
+f32p = C.POINTER(C.c_float)
+u64p = C.POINTER(C.c_uint64)
+u16p = C.POINTER(C.c_uint16)
+
+PLANE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, f32p)
+
+
+class KlshError(RuntimeError):
+    pass
+
+
+class IterStats(C.Structure):
+    _fields_ = [
+        ("rows_in", u64),
+        ("rows_out", u64),
+        ("H", C.c_int32),
+        ("threshold", C.c_float),
+        ("buckets", u64),
+        ("bucket_max", u64),
+        ("nested_calls", u64),
+        ("eps_margin_rows", u64),
+        ("ms_sign", C.c_float),
+        ("ms_group", C.c_float),
+        ("ms_merge", C.c_float),
+        ("ms_compact", C.c_float),
+        ("ms_total", C.c_float),
+    ]
+
+
+def lib_path() -> str:
+    return os.path.join(_HERE, "libklsh.so")
+
+
+_LIB = None
+
+# every symbol include/klsh.h declares: (name, restype, argtypes)
+SYMBOLS = [
+    ("klsh_create", C.c_int, [C.c_int, C.POINTER(C.c_void_p)]),
+    ("klsh_destroy", None, [C.c_void_p]),
+    ("klsh_last_error", C.c_char_p, [C.c_void_p]),
+    ("klsh_launch_count", u64, [C.c_void_p]),
+    ("klsh_set_seed", C.c_int, [C.c_void_p, u64]),
+    ("klsh_set_plane_source", C.c_int, [C.c_void_p, PLANE_FN, C.c_void_p]),
+    ("klsh_draw_table", C.c_int, [C.c_void_p, C.c_int, C.c_int, f32p]),
+    ("klsh_load_counts", C.c_int, [C.c_void_p, u16p, f32p, C.c_int, u64, u64]),
+    ("klsh_set_rows", C.c_int, [C.c_void_p, f32p, u64p, u64p, u64, C.c_int]),
+    ("klsh_load_cluster_file", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, u64, u64]),
+    ("klsh_cluster", C.c_int, [C.c_void_p, C.c_float, C.c_int, i64, C.POINTER(IterStats)]),
+    ("klsh_sign", C.c_int, [C.c_void_p, f32p, u64, C.c_int, f32p, C.c_int, u64p]),
+    ("klsh_p_cluster", C.c_int, [C.c_void_p, C.c_float]),
+    ("klsh_nested_cluster", C.c_int, [C.c_void_p, C.c_float]),
+    ("klsh_row_count", C.c_int, [C.c_void_p, u64p, u64p]),
+    ("klsh_get_rows", C.c_int, [C.c_void_p, f32p, u64p, u64p]),
+    ("klsh_save", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, i64]),
+    ("klsh_snapshot", C.c_int, [C.c_void_p]),
+    ("klsh_restore", C.c_int, [C.c_void_p]),
+    ("klsh_sync", C.c_int, [C.c_void_p]),
+]
+
+
+def load_library():
+    """Load libklsh.so.  Raises KlshError if it has not been built — there is no fallback."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = lib_path()
+    if not os.path.exists(path):
+        raise KlshError("%s is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'`" % path)
+    lib = C.CDLL(path)
+    for name, res, args in SYMBOLS:
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _LIB = lib
+    return lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(t)
+
+
+class Context:
+    """One GPU context (klsh_ctx)."""
+
+    def __init__(self, device: int = 0, seed: int | None = None):
+        self.lib = load_library()
+        h = C.c_void_p()
+        rc = self.lib.klsh_create(device, C.byref(h))
+        if rc != 0:
+            raise KlshError("klsh_create: " + self.lib.klsh_last_error(None).decode())
+        self.h = h
+        self._cb = None
+        self.D = 0
+        if seed is not None:
+            self.set_seed(seed)
+
+    def _ck(self, rc, what):
+        if rc != 0:
+            raise KlshError("%s failed (%d): %s" % (what, rc, self.lib.klsh_last_error(self.h).decode()))
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.klsh_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    # ---- planes
+    def set_seed(self, seed: int):
+        self._ck(self.lib.klsh_set_seed(self.h, seed), "klsh_set_seed")
+
+    def set_plane_source(self, fn):
+        """fn(H, D) -> float32 array [H][D]."""
+
+        def tramp(_user, H, D, out):
+            t = np.ascontiguousarray(fn(H, D), dtype=np.float32).reshape(H, D)
+            C.memmove(out, t.ctypes.data, 4 * H * D)
+
+        self._cb = PLANE_FN(tramp)
+        self._ck(self.lib.klsh_set_plane_source(self.h, self._cb, None), "klsh_set_plane_source")
+
+    def draw_table(self, H: int, D: int):
+        out = np.empty((H, D), dtype=np.float32)
+        self._ck(self.lib.klsh_draw_table(self.h, H, D, _p(out, f32p)), "klsh_draw_table")
+        return out
+
+    # ---- rows in
+    def load_counts(self, counts, v_kmers, batch_offset: int = 0):
+        counts = np.ascontiguousarray(counts, dtype=np.uint16)
+        d, batch = counts.shape
+        vk = np.ascontiguousarray(v_kmers, dtype=np.float32)
+        assert vk.shape[0] == d
+        self.D = d
+        self._ck(self.lib.klsh_load_counts(self.h, _p(counts, u16p), _p(vk, f32p), d, batch, batch_offset),
+                 "klsh_load_counts")
+
+    def set_rows(self, values, id_offsets=None, ids=None):
+        values = np.ascontiguousarray(values, dtype=np.float32)
+        n, d = values.shape
+        if id_offsets is None:
+            id_offsets = np.arange(n + 1, dtype=np.uint64)
+            ids = np.arange(n, dtype=np.uint64)
+        id_offsets = np.ascontiguousarray(id_offsets, dtype=np.uint64)
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        self.D = d
+        self._ck(self.lib.klsh_set_rows(self.h, _p(values, f32p), _p(id_offsets, u64p), _p(ids, u64p), n, d),
+                 "klsh_set_rows")
+
+    def load_cluster_file(self, path: str, d: int, start_line: int = 0, num_lines: int = 0):
+        self.D = d
+        self._ck(self.lib.klsh_load_cluster_file(self.h, path.encode(), d, start_line, num_lines),
+                 "klsh_load_cluster_file")
+
+    # ---- hot path
+    def cluster(self, min_similarity: float, iterations: int, bucket_size_threshold: int):
+        stats = (IterStats * max(1, iterations))()
+        self._ck(self.lib.klsh_cluster(self.h, min_similarity, iterations, bucket_size_threshold, stats), "klsh_cluster")
+        return list(stats)
+
+    def sign(self, rows, table):
+        rows = np.ascontiguousarray(rows, dtype=np.float32)
+        table = np.ascontiguousarray(table, dtype=np.float32)
+        n, d = rows.shape
+        h = table.shape[0]
+        keys = np.empty(n, dtype=np.uint64)
+        self._ck(self.lib.klsh_sign(self.h, _p(rows, f32p), n, d, _p(table, f32p), h, _p(keys, u64p)), "klsh_sign")
+        return keys
+
+    def p_cluster(self, threshold: float):
+        self._ck(self.lib.klsh_p_cluster(self.h, threshold), "klsh_p_cluster")
+
+    def nested_cluster(self, threshold: float):
+        self._ck(self.lib.klsh_nested_cluster(self.h, threshold), "klsh_nested_cluster")
+
+    # ---- rows out
+    def row_count(self, with_ids: bool = True):
+        n, m = u64(), u64()
+        self._ck(self.lib.klsh_row_count(self.h, C.byref(n), C.byref(m) if with_ids else None), "klsh_row_count")
+        return n.value, m.value
+
+    def get_rows(self):
+        n, m = self.row_count()
+        values = np.empty((n, self.D), dtype=np.float32)
+        offs = np.empty(n + 1, dtype=np.uint64)
+        ids = np.empty(max(m, 1), dtype=np.uint64)
+        self._ck(self.lib.klsh_get_rows(self.h, _p(values, f32p), _p(offs, u64p), _p(ids, u64p)), "klsh_get_rows")
+        return values, offs, ids[:m]
+
+    def save(self, path: str, delfile: bool = True, ignore_small: int = 0):
+        self._ck(self.lib.klsh_save(self.h, path.encode(), int(delfile), ignore_small), "klsh_save")
+
+    # ---- state
+    def snapshot(self):
+        self._ck(self.lib.klsh_snapshot(self.h), "klsh_snapshot")
+
+    def restore(self):
+        self._ck(self.lib.klsh_restore(self.h), "klsh_restore")
+
+    def sync(self):
+        self._ck(self.lib.klsh_sync(self.h), "klsh_sync")
+
+    def launch_count(self) -> int:
+        return self.lib.klsh_launch_count(self.h)
+
+
+def Cluster(rows, min_similarity, cluster_iteration, threads_to_use, dim, bucket_size_threshold, verbose=False,
+            seed=None, plane_source=None, device=0):
+    """Drop-in for the reference's Cluster() (function/cluster.cc:181-340).
+
+    rows = (values[n][dim], id_offsets[n+1], ids) in, the clustered triple out (the reference
+    mutates its vector in place).  threads_to_use is accepted for signature compatibility; results
+    equal the reference's single-thread schedule.  Hyperplanes come from `seed` (the reference
+    generator behind a seeded random_device) or from `plane_source(H, D)`.
+    """
+    values, id_offsets, ids = rows
+    values = np.asarray(values, dtype=np.float32)
+    assert values.shape[1] == dim
+    with Context(device) as ctx:
+        if plane_source is not None:
+            ctx.set_plane_source(plane_source)
+        elif seed is not None:
+            ctx.set_seed(seed)
+        ctx.set_rows(values, id_offsets, ids)
+        stats = ctx.cluster(min_similarity, cluster_iteration, bucket_size_threshold)
+        if verbose:
+            for k, s in enumerate(stats):
+                print("Iteration:\t%d, cos sim threshold:\t%g dimension : %d" % (k + 1, s.threshold, dim))
+                print("Size of profilings : %d" % s.rows_in)
+                print("#k-mers after clustering:\t%d" % s.rows_out)
+        return ctx.get_rows()

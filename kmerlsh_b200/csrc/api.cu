@@ -1,0 +1,615 @@
+// C ABI (include/klsh.h) and the host-side iteration driver of the clustering loop.
+//
+// Device layout (DESIGN.md "Layout"): rows live in an arena vals[n_born][ld] and never move.
+// The working set of an iteration is the list `alive` of row indices in the reference's canonical
+// order (ascending bucket key, in-bucket order as left by p_cluster).  A merge overwrites the
+// surviving representative's row in place and splices the member chains (head/tail per row, next
+// per member slot).  Per iteration:
+//   sign (gather rows by alive[]) -> stable radix sort of (key,row) -> bucket bounds + size classes
+//   -> greedy merge per bucket (in place in the sorted row list) -> nested passes for oversized
+//   buckets -> order-preserving compaction of the sorted row list = next alive[].
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <algorithm>
+
+#include "klsh_internal.cuh"
+
+static std::string g_create_error;
+
+int klsh_fail(klsh_ctx* ctx, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  if (ctx) ctx->err = buf;
+  else g_create_error = buf;
+  return code;
+}
+
+int dev_reserve(klsh_ctx* ctx, DevBuf& b, size_t bytes) {
+  if (bytes <= b.bytes) return KLSH_OK;
+  size_t want = std::max(bytes, b.bytes + b.bytes / 2);
+  want = (want + 255) & ~(size_t)255;
+  void* p = nullptr;
+  cudaError_t e = cudaMalloc(&p, want);
+  if (e != cudaSuccess) {
+    (void)cudaGetLastError();
+    want = (bytes + 255) & ~(size_t)255;
+    e = cudaMalloc(&p, want);
+    if (e != cudaSuccess) {
+      (void)cudaGetLastError();
+      return klsh_fail(ctx, KLSH_ERR_NOMEM, "cudaMalloc(%zu bytes) failed: %s", want, cudaGetErrorString(e));
+    }
+  }
+  if (b.p) {
+    // contents are preserved (grow)
+    cudaMemcpyAsync(p, b.p, b.bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(b.p);
+  }
+  b.p = p;
+  b.bytes = want;
+  return KLSH_OK;
+}
+
+static void dev_free(DevBuf& b) {
+  if (b.p) cudaFree(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+}
+
+static void free_scratch(PassScratch& s) {
+  dev_free(s.keys_a); dev_free(s.keys_b); dev_free(s.rows_a); dev_free(s.rows_b);
+  dev_free(s.hist); dev_free(s.blkcnt); dev_free(s.bstart);
+  dev_free(s.list_small); dev_free(s.list_large); dev_free(s.list_nested);
+  dev_free(s.planes); dev_free(s.counters);
+}
+
+static void free_state(RowState& r) {
+  dev_free(r.vals); dev_free(r.cnt); dev_free(r.head); dev_free(r.tail); dev_free(r.next); dev_free(r.alive);
+  r.n_alive = 0;
+}
+
+static int floor_log2_u64(uint64_t n) {  // floor(log2(n)), reference function/cluster.cc:194, :203
+  int h = 0;
+  while ((n >> (h + 1)) != 0) ++h;
+  return h;
+}
+
+extern "C" {
+
+int klsh_create(int device, klsh_ctx** out) {
+  if (!out) return klsh_fail(nullptr, KLSH_ERR_ARG, "klsh_create: out is NULL");
+  *out = nullptr;
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    (void)cudaGetLastError();
+    return klsh_fail(nullptr, KLSH_ERR_CUDA, "no CUDA device available (%s); this library has no CPU fallback",
+                     e != cudaSuccess ? cudaGetErrorString(e) : "device count 0");
+  }
+  if (device < 0 || device >= count) return klsh_fail(nullptr, KLSH_ERR_ARG, "device %d out of range [0,%d)", device, count);
+  cudaDeviceProp prop;
+  if ((e = cudaGetDeviceProperties(&prop, device)) != cudaSuccess)
+    return klsh_fail(nullptr, KLSH_ERR_CUDA, "cudaGetDeviceProperties: %s", cudaGetErrorString(e));
+  if (prop.major != 10)
+    return klsh_fail(nullptr, KLSH_ERR_CUDA, "device %d is sm_%d%d; this library is built for sm_100a only", device,
+                     prop.major, prop.minor);
+  if ((e = cudaSetDevice(device)) != cudaSuccess)
+    return klsh_fail(nullptr, KLSH_ERR_CUDA, "cudaSetDevice: %s", cudaGetErrorString(e));
+  klsh_ctx* ctx = new klsh_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking)) != cudaSuccess) {
+    delete ctx;
+    return klsh_fail(nullptr, KLSH_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
+  for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  if ((e = cudaMallocHost(&ctx->h_counters, sizeof(PassCounters) * 2)) != cudaSuccess) {
+    delete ctx;
+    return klsh_fail(nullptr, KLSH_ERR_NOMEM, "cudaMallocHost: %s", cudaGetErrorString(e));
+  }
+  ctx->planes = planes_new();
+  *out = ctx;
+  return KLSH_OK;
+}
+
+void klsh_destroy(klsh_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  free_state(ctx->cur);
+  free_state(ctx->snap);
+  free_scratch(ctx->top);
+  free_scratch(ctx->nested);
+  dev_free(ctx->lut);
+  dev_free(ctx->io_a);
+  dev_free(ctx->io_b);
+  dev_free(ctx->alive_alt);
+  dev_free(ctx->nested_out);
+  if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
+  for (auto& ev : ctx->ev)
+    if (ev) cudaEventDestroy(ev);
+  cudaStreamDestroy(ctx->stream);
+  planes_free(ctx->planes);
+  delete ctx;
+}
+
+const char* klsh_last_error(const klsh_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+uint64_t klsh_launch_count(const klsh_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+int klsh_set_seed(klsh_ctx* ctx, uint64_t seed) {
+  if (!ctx) return KLSH_ERR_ARG;
+  planes_seed(ctx->planes, seed);
+  return KLSH_OK;
+}
+
+int klsh_set_plane_source(klsh_ctx* ctx, klsh_plane_fn fn, void* user) {
+  if (!ctx || !fn) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_set_plane_source: NULL argument");
+  planes_callback(ctx->planes, fn, user);
+  return KLSH_OK;
+}
+
+int klsh_draw_table(klsh_ctx* ctx, int H, int D, float* out) {
+  if (!ctx || H < 0 || D <= 0 || (!out && H > 0)) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_draw_table: bad argument");
+  planes_draw(ctx->planes, H, D, out);
+  return KLSH_OK;
+}
+
+int klsh_sync(klsh_ctx* ctx) {
+  if (!ctx) return KLSH_ERR_ARG;
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return KLSH_OK;
+}
+
+}  // extern "C"
+
+// ------------------------------------------------------------------------------------------------
+// Row-set setup
+// ------------------------------------------------------------------------------------------------
+static int reserve_rows(klsh_ctx* ctx, uint64_t n_rows, uint64_t n_slots, int D) {
+  if (n_rows >= 0xFFFFFFF0ull || n_slots >= 0x7FFFFFF0ull)
+    return klsh_fail(ctx, KLSH_ERR_ARG, "row set too large for one GPU context (%llu rows, %llu ids)",
+                     (unsigned long long)n_rows, (unsigned long long)n_slots);
+  ctx->D = D;
+  ctx->ld = (D + 3) & ~3;
+  KTRY(dev_reserve(ctx, ctx->cur.vals, sizeof(float) * (n_rows * (uint64_t)ctx->ld + 4)));
+  KTRY(dev_reserve(ctx, ctx->cur.cnt, sizeof(int32_t) * (n_rows + 1)));
+  KTRY(dev_reserve(ctx, ctx->cur.head, sizeof(int32_t) * (n_rows + 1)));
+  KTRY(dev_reserve(ctx, ctx->cur.tail, sizeof(int32_t) * (n_rows + 1)));
+  KTRY(dev_reserve(ctx, ctx->cur.next, sizeof(int32_t) * (n_slots + 1)));
+  KTRY(dev_reserve(ctx, ctx->cur.alive, sizeof(uint32_t) * (n_rows + 1)));
+  return KLSH_OK;
+}
+
+static int ensure_lut(klsh_ctx* ctx) {
+  if (ctx->lut_ready) return KLSH_OK;
+  // float(log(cnt+1.0)) for every uint16 count, by the host libm the reference itself would call
+  // (io/ioMatrix.cc:378)
+  std::vector<float> lut(65536);
+  for (uint32_t c = 0; c < 65536; ++c) lut[c] = (float)std::log((double)c + 1.0);
+  KTRY(dev_reserve(ctx, ctx->lut, sizeof(float) * 65536));
+  KCUDA(ctx, cudaMemcpyAsync(ctx->lut.p, lut.data(), sizeof(float) * 65536, cudaMemcpyHostToDevice, ctx->stream));
+  KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->lut_ready = true;
+  return KLSH_OK;
+}
+
+extern "C" int klsh_load_counts(klsh_ctx* ctx, const uint16_t* counts, const float* v_kmers, int D, uint64_t batch_size,
+                                uint64_t batch_offset) {
+  if (!ctx || !counts || !v_kmers || D <= 0) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_load_counts: bad argument");
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->has_snap = false;
+  KTRY(ensure_lut(ctx));
+  KTRY(reserve_rows(ctx, batch_size, batch_size, D));
+  KTRY(dev_reserve(ctx, ctx->io_a, sizeof(uint16_t) * ((uint64_t)D * batch_size + 8)));
+  KTRY(dev_reserve(ctx, ctx->io_b, sizeof(float) * (D + 1)));
+  KCUDA(ctx, cudaMemcpyAsync(ctx->io_a.p, counts, sizeof(uint16_t) * (uint64_t)D * batch_size, cudaMemcpyHostToDevice,
+                             ctx->stream));
+  KCUDA(ctx, cudaMemcpyAsync(ctx->io_b.p, v_kmers, sizeof(float) * D, cudaMemcpyHostToDevice, ctx->stream));
+  uint64_t kept = 0;
+  if (batch_size) KTRY(launch_transform(ctx, ctx->io_a.as<uint16_t>(), ctx->io_b.as<float>(), batch_size, &kept));
+  ctx->n_born = kept;
+  ctx->n_slots = batch_size;
+  ctx->ids.clear();
+  ctx->ids_implicit = true;
+  ctx->id_base = batch_offset;
+  KTRY(launch_init_meta(ctx, ctx->n_slots));
+  KTRY(launch_iota(ctx, ctx->cur.alive.as<uint32_t>(), kept, 0));
+  ctx->cur.n_alive = kept;
+  KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return KLSH_OK;
+}
+
+extern "C" int klsh_set_rows(klsh_ctx* ctx, const float* values, const uint64_t* id_offsets, const uint64_t* ids,
+                             uint64_t n, int D) {
+  if (!ctx || D <= 0 || (n && (!values || !id_offsets || !ids)))
+    return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_set_rows: bad argument");
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  ctx->has_snap = false;
+  const uint64_t m = n ? id_offsets[n] : 0;
+  KTRY(reserve_rows(ctx, n, m, D));
+  const int ld = ctx->ld;
+  // values: pad rows to ld
+  if (n) {
+    if (ld == D) {
+      KCUDA(ctx, cudaMemcpyAsync(ctx->cur.vals.p, values, sizeof(float) * n * (uint64_t)D, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+      KCUDA(ctx, cudaMemsetAsync(ctx->cur.vals.p, 0, sizeof(float) * n * (uint64_t)ld, ctx->stream));
+      KCUDA(ctx, cudaMemcpy2DAsync(ctx->cur.vals.p, sizeof(float) * ld, values, sizeof(float) * D, sizeof(float) * D, n,
+                                   cudaMemcpyHostToDevice, ctx->stream));
+    }
+  }
+  std::vector<int32_t> cnt(n), head(n), tail(n), next(m);
+  for (uint64_t r = 0; r < n; ++r) {
+    uint64_t b = id_offsets[r], e = id_offsets[r + 1];
+    cnt[r] = (int32_t)(e - b);
+    head[r] = e > b ? (int32_t)b : -1;
+    tail[r] = e > b ? (int32_t)(e - 1) : -1;
+    for (uint64_t s = b; s < e; ++s) next[s] = (s + 1 < e) ? (int32_t)(s + 1) : -1;
+  }
+  if (n) {
+    KCUDA(ctx, cudaMemcpyAsync(ctx->cur.cnt.p, cnt.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    KCUDA(ctx, cudaMemcpyAsync(ctx->cur.head.p, head.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+    KCUDA(ctx, cudaMemcpyAsync(ctx->cur.tail.p, tail.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
+  }
+  if (m) KCUDA(ctx, cudaMemcpyAsync(ctx->cur.next.p, next.data(), sizeof(int32_t) * m, cudaMemcpyHostToDevice, ctx->stream));
+  ctx->ids.assign(ids, ids + m);
+  ctx->ids_implicit = false;
+  ctx->id_base = 0;
+  ctx->n_born = n;
+  ctx->n_slots = m;
+  KTRY(launch_iota(ctx, ctx->cur.alive.as<uint32_t>(), n, 0));
+  ctx->cur.n_alive = n;
+  KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return KLSH_OK;
+}
+
+extern "C" int klsh_load_cluster_file(klsh_ctx* ctx, const char* bin_path, int D, uint64_t start_line, uint64_t num_lines) {
+  if (!ctx || !bin_path || D <= 0) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_load_cluster_file: bad argument");
+  std::vector<float> values;
+  std::vector<uint64_t> offs, ids;
+  int rc = io_read_cluster(bin_path, D, start_line, num_lines, values, offs, ids);
+  if (rc != KLSH_OK) return klsh_fail(ctx, rc, "cannot read %s(.clust)", bin_path);
+  return klsh_set_rows(ctx, values.data(), offs.data(), ids.data(), offs.size() - 1, D);
+}
+
+// ------------------------------------------------------------------------------------------------
+// One signing + grouping + merge pass over rows_in[0..n).  Survivors are written, in canonical
+// order, to out[0..*n_out).  nest_threshold < 0 disables nesting (the pass nestedCluster itself
+// runs, reference function/cluster.cc:153-159).
+// ------------------------------------------------------------------------------------------------
+struct PassInfo {
+  uint64_t buckets = 0, bucket_max = 0, nested_calls = 0;
+  float ms_sign = 0, ms_group = 0, ms_merge = 0, ms_compact = 0;
+};
+
+static int reserve_scratch(klsh_ctx* ctx, PassScratch& s, uint64_t n, int H) {
+  KTRY(dev_reserve(ctx, s.keys_a, sizeof(uint32_t) * (n + 1)));
+  KTRY(dev_reserve(ctx, s.keys_b, sizeof(uint32_t) * (n + 1)));
+  KTRY(dev_reserve(ctx, s.rows_a, sizeof(uint32_t) * (n + 1)));
+  KTRY(dev_reserve(ctx, s.rows_b, sizeof(uint32_t) * (n + 1)));
+  KTRY(dev_reserve(ctx, s.planes, sizeof(float) * ((size_t)H * ctx->ld + 4)));
+  KTRY(dev_reserve(ctx, s.counters, sizeof(PassCounters)));
+  return KLSH_OK;
+}
+
+static int upload_planes(klsh_ctx* ctx, PassScratch& s, int H) {
+  const int D = ctx->D, ld = ctx->ld;
+  std::vector<float> t((size_t)H * D + 1), padded((size_t)H * ld + 1, 0.f);
+  planes_draw(ctx->planes, H, D, t.data());
+  for (int h = 0; h < H; ++h) std::memcpy(&padded[(size_t)h * ld], &t[(size_t)h * D], sizeof(float) * D);
+  if (H) {
+    KCUDA(ctx, cudaMemcpyAsync(s.planes.p, padded.data(), sizeof(float) * (size_t)H * ld, cudaMemcpyHostToDevice, ctx->stream));
+    KCUDA(ctx, cudaStreamSynchronize(ctx->stream));  // `padded` is pageable and goes out of scope
+  }
+  return KLSH_OK;
+}
+
+static int run_pass(klsh_ctx* ctx, PassScratch& s, const uint32_t* rows_in, uint64_t n, int H, float threshold,
+                    int64_t nest_threshold, uint32_t* out, uint64_t* n_out, PassInfo* info, bool timed) {
+  cudaStream_t st = ctx->stream;
+  KTRY(reserve_scratch(ctx, s, n, H));
+  KTRY(upload_planes(ctx, s, H));
+  if (timed) cudaEventRecord(ctx->ev[0], st);
+  KTRY(launch_sign(ctx, ctx->cur.vals.as<float>(), ctx->D, ctx->ld, rows_in, n, s.planes.as<float>(), H,
+                   s.keys_a.as<uint32_t>(), s.rows_a.as<uint32_t>()));
+  if (timed) cudaEventRecord(ctx->ev[1], st);
+  uint32_t *keys_sorted, *rows_sorted;
+  KTRY(launch_sort_pairs(ctx, s, n, H, &keys_sorted, &rows_sorted));
+  KTRY(launch_bounds(ctx, s, keys_sorted, n, nest_threshold));
+  PassCounters* hc = ctx->h_counters + (&s == &ctx->nested ? 1 : 0);
+  KCUDA(ctx, cudaMemcpyAsync(hc, s.counters.p, sizeof(PassCounters), cudaMemcpyDeviceToHost, st));
+  if (timed) cudaEventRecord(ctx->ev[2], st);
+  KCUDA(ctx, cudaStreamSynchronize(st));
+  const PassCounters c = *hc;
+  ctx->h_counters->bucket_max = c.bucket_max;  // launch_merge sizes its spill slab from slot 0
+  KTRY(launch_merge(ctx, s, rows_sorted, threshold, c.n_small, c.n_large));
+  uint64_t nested_calls = 0;
+  if (c.n_nested) {
+    // oversized buckets in ascending key order (= ascending bucket index), like the reference's
+    // serial bucket loop; each consumes one fresh table from the plane source
+    std::vector<uint32_t> nb(c.n_nested);
+    KCUDA(ctx, cudaMemcpyAsync(nb.data(), s.list_nested.p, sizeof(uint32_t) * c.n_nested, cudaMemcpyDeviceToHost, st));
+    KCUDA(ctx, cudaStreamSynchronize(st));
+    std::sort(nb.begin(), nb.end());
+    std::vector<uint32_t> bs(2);
+    for (uint32_t b : nb) {
+      KCUDA(ctx, cudaMemcpyAsync(bs.data(), s.bstart.as<uint32_t>() + b, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, st));
+      KCUDA(ctx, cudaStreamSynchronize(st));
+      const uint64_t seg_n = bs[1] - bs[0];
+      uint32_t* seg = rows_sorted + bs[0];
+      const int H2 = floor_log2_u64(seg_n);
+      if (&s == &ctx->nested) return klsh_fail(ctx, KLSH_ERR_ARG, "internal: nested pass may not nest");
+      // survivors of the sub-pass go to a side buffer ...
+      uint64_t kept = 0;
+      KTRY(reserve_scratch(ctx, ctx->nested, seg_n, H2));
+      KTRY(dev_reserve(ctx, ctx->nested_out, sizeof(uint32_t) * (seg_n + 2)));
+      uint32_t* tmp_out = ctx->nested_out.as<uint32_t>();
+      KTRY(run_pass(ctx, ctx->nested, seg, seg_n, H2, threshold, -1, tmp_out, &kept, nullptr, false));
+      // ... and back to the front of the segment, sentinels behind
+      KCUDA(ctx, cudaMemcpyAsync(seg, tmp_out, sizeof(uint32_t) * kept, cudaMemcpyDeviceToDevice, st));
+      KTRY(launch_fill_tail(ctx, seg, kept, seg_n));
+      ++nested_calls;
+    }
+  }
+  if (timed) cudaEventRecord(ctx->ev[3], st);
+  KTRY(launch_compact(ctx, s, rows_sorted, n, out));
+  KCUDA(ctx, cudaMemcpyAsync(&hc->n_out, &s.counters.as<PassCounters>()->n_out, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  if (timed) cudaEventRecord(ctx->ev[4], st);
+  KCUDA(ctx, cudaStreamSynchronize(st));
+  *n_out = hc->n_out;
+  if (info) {
+    info->buckets = c.n_buckets;
+    info->bucket_max = c.bucket_max;
+    info->nested_calls = nested_calls;
+    if (timed) {
+      cudaEventElapsedTime(&info->ms_sign, ctx->ev[0], ctx->ev[1]);
+      cudaEventElapsedTime(&info->ms_group, ctx->ev[1], ctx->ev[2]);
+      cudaEventElapsedTime(&info->ms_merge, ctx->ev[2], ctx->ev[3]);
+      cudaEventElapsedTime(&info->ms_compact, ctx->ev[3], ctx->ev[4]);
+    }
+  }
+  return KLSH_OK;
+}
+
+extern "C" int klsh_cluster(klsh_ctx* ctx, float min_similarity, int iterations, int64_t bucket_size_threshold,
+                            klsh_iter_stats* stats) {
+  if (!ctx || iterations <= 0) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_cluster: bad argument");
+  if (ctx->D <= 0) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_cluster: no rows loaded");
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  if (stats) std::memset(stats, 0, sizeof(klsh_iter_stats) * (size_t)iterations);
+  // reference function/cluster.cc:190-192
+  float max_similarity = 0.95f;
+  float sim_step = (max_similarity - min_similarity) / iterations;
+  float threshold = max_similarity;
+  for (int iter = 1; iter <= iterations; ++iter) {
+    const uint64_t n = ctx->cur.n_alive;
+    if (n == 0) break;  // the reference takes log2(0) here (undefined); an empty set stays empty
+    const int H = floor_log2_u64(n);
+    PassInfo info;
+    uint64_t kept = 0;
+    // survivors are compacted into a second list, then the lists swap roles
+    KTRY(dev_reserve(ctx, ctx->alive_alt, sizeof(uint32_t) * (n + 1)));
+    KTRY(run_pass(ctx, ctx->top, ctx->cur.alive.as<uint32_t>(), n, H, threshold,
+                  bucket_size_threshold < 0 ? -1 : bucket_size_threshold, ctx->alive_alt.as<uint32_t>(), &kept, &info, true));
+    std::swap(ctx->cur.alive, ctx->alive_alt);
+    ctx->cur.n_alive = kept;
+    if (stats) {
+      klsh_iter_stats& s = stats[iter - 1];
+      s.rows_in = n;
+      s.rows_out = kept;
+      s.H = H;
+      s.threshold = threshold;
+      s.buckets = info.buckets;
+      s.bucket_max = info.bucket_max;
+      s.nested_calls = info.nested_calls;
+      s.eps_margin_rows = 0;
+      s.ms_sign = info.ms_sign;
+      s.ms_group = info.ms_group;
+      s.ms_merge = info.ms_merge;
+      s.ms_compact = info.ms_compact;
+      s.ms_total = info.ms_sign + info.ms_group + info.ms_merge + info.ms_compact;
+    }
+    threshold -= sim_step;  // fp32 recurrence, reference function/cluster.cc:330
+  }
+  return KLSH_OK;
+}
+
+extern "C" int klsh_sign(klsh_ctx* ctx, const float* rows, uint64_t n, int D, const float* table, int H, uint64_t* keys_out) {
+  if (!ctx || D <= 0 || H < 0 || H > 32 || (n && (!rows || !keys_out)) || (H && !table))
+    return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_sign: bad argument (H must be in [0,32])");
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  if (!n) return KLSH_OK;
+  const int ld = (D + 3) & ~3;
+  DevBuf dv, dp, dk, dr;
+  int rc = KLSH_OK;
+  std::vector<float> padded((size_t)H * ld + 1, 0.f);
+  for (int h = 0; h < H; ++h) std::memcpy(&padded[(size_t)h * ld], table + (size_t)h * D, sizeof(float) * D);
+  std::vector<uint32_t> k32(n);
+  do {
+    if ((rc = dev_reserve(ctx, dv, sizeof(float) * (n * (uint64_t)ld + 4)))) break;
+    if ((rc = dev_reserve(ctx, dp, sizeof(float) * ((size_t)H * ld + 4)))) break;
+    if ((rc = dev_reserve(ctx, dk, sizeof(uint32_t) * n))) break;
+    if ((rc = dev_reserve(ctx, dr, sizeof(uint32_t) * n))) break;
+    cudaMemsetAsync(dv.p, 0, sizeof(float) * n * (uint64_t)ld, ctx->stream);
+    cudaMemcpy2DAsync(dv.p, sizeof(float) * ld, rows, sizeof(float) * D, sizeof(float) * D, n, cudaMemcpyHostToDevice,
+                      ctx->stream);
+    if (H) cudaMemcpyAsync(dp.p, padded.data(), sizeof(float) * (size_t)H * ld, cudaMemcpyHostToDevice, ctx->stream);
+    if ((rc = launch_sign(ctx, dv.as<float>(), D, ld, nullptr, n, dp.as<float>(), H, dk.as<uint32_t>(), dr.as<uint32_t>())))
+      break;
+    cudaMemcpyAsync(k32.data(), dk.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = klsh_fail(ctx, KLSH_ERR_CUDA, "klsh_sign: %s", cudaGetErrorString(e));
+  } while (0);
+  dev_free(dv); dev_free(dp); dev_free(dk); dev_free(dr);
+  if (rc == KLSH_OK)
+    for (uint64_t i = 0; i < n; ++i) keys_out[i] = k32[i];
+  return rc;
+}
+
+extern "C" int klsh_p_cluster(klsh_ctx* ctx, float threshold) {
+  if (!ctx || ctx->D <= 0) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_p_cluster: no rows loaded");
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  const uint64_t n = ctx->cur.n_alive;
+  if (n < 2) return KLSH_OK;
+  KTRY(dev_reserve(ctx, ctx->top.counters, sizeof(PassCounters)));
+  KTRY(dev_reserve(ctx, ctx->top.rows_a, sizeof(uint32_t) * (n + 1)));
+  uint32_t* seg = ctx->top.rows_a.as<uint32_t>();
+  KCUDA(ctx, cudaMemcpyAsync(seg, ctx->cur.alive.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  KTRY(launch_merge_one(ctx, ctx->top, seg, n, threshold));
+  KTRY(launch_compact(ctx, ctx->top, seg, n, ctx->cur.alive.as<uint32_t>()));
+  KCUDA(ctx, cudaMemcpyAsync(&ctx->h_counters->n_out, &ctx->top.counters.as<PassCounters>()->n_out, sizeof(uint32_t),
+                             cudaMemcpyDeviceToHost, ctx->stream));
+  KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->cur.n_alive = ctx->h_counters->n_out;
+  return KLSH_OK;
+}
+
+extern "C" int klsh_nested_cluster(klsh_ctx* ctx, float threshold) {
+  if (!ctx || ctx->D <= 0) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_nested_cluster: no rows loaded");
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  const uint64_t n = ctx->cur.n_alive;
+  if (n == 0) return KLSH_OK;
+  const int H = floor_log2_u64(n);
+  uint64_t kept = 0;
+  KTRY(dev_reserve(ctx, ctx->alive_alt, sizeof(uint32_t) * (n + 1)));
+  KTRY(run_pass(ctx, ctx->top, ctx->cur.alive.as<uint32_t>(), n, H, threshold, -1, ctx->alive_alt.as<uint32_t>(), &kept,
+                nullptr, false));
+  std::swap(ctx->cur.alive, ctx->alive_alt);
+  ctx->cur.n_alive = kept;
+  return KLSH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Rows out
+// ------------------------------------------------------------------------------------------------
+static int export_rows(klsh_ctx* ctx, std::vector<float>* values, std::vector<uint64_t>& offs, std::vector<uint64_t>* ids) {
+  const uint64_t n = ctx->cur.n_alive;
+  const int D = ctx->D;
+  offs.assign(n + 1, 0);
+  if (values) values->resize(n * (uint64_t)D);
+  if (!n) {
+    if (ids) ids->clear();
+    return KLSH_OK;
+  }
+  DevBuf dv, dc, dh;
+  int rc = KLSH_OK;
+  std::vector<int32_t> cnt(n), head(n), next(ctx->n_slots);
+  do {
+    if ((rc = dev_reserve(ctx, dv, sizeof(float) * n * (uint64_t)D))) break;
+    if ((rc = dev_reserve(ctx, dc, sizeof(int32_t) * n))) break;
+    if ((rc = dev_reserve(ctx, dh, sizeof(int32_t) * n))) break;
+    if ((rc = launch_gather_rows(ctx, ctx->cur.alive.as<uint32_t>(), n, dv.as<float>(), dc.as<int32_t>(), dh.as<int32_t>())))
+      break;
+    if (values) cudaMemcpyAsync(values->data(), dv.p, sizeof(float) * n * (uint64_t)D, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(cnt.data(), dc.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaMemcpyAsync(head.data(), dh.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (ids && ctx->n_slots)
+      cudaMemcpyAsync(next.data(), ctx->cur.next.p, sizeof(int32_t) * ctx->n_slots, cudaMemcpyDeviceToHost, ctx->stream);
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = klsh_fail(ctx, KLSH_ERR_CUDA, "export: %s", cudaGetErrorString(e));
+  } while (0);
+  dev_free(dv); dev_free(dc); dev_free(dh);
+  if (rc != KLSH_OK) return rc;
+  for (uint64_t r = 0; r < n; ++r) offs[r + 1] = offs[r] + (uint64_t)cnt[r];
+  if (ids) {
+    ids->resize(offs[n]);
+    for (uint64_t r = 0; r < n; ++r) {
+      uint64_t o = offs[r];
+      const uint64_t end = offs[r + 1];
+      for (int32_t s = head[r]; s >= 0 && o < end; s = next[s])
+        (*ids)[o++] = ctx->ids_implicit ? ctx->id_base + (uint64_t)s : ctx->ids[s];
+      if (o != end) return klsh_fail(ctx, KLSH_ERR_ARG, "internal: member chain of row %llu is inconsistent", (unsigned long long)r);
+    }
+  }
+  return KLSH_OK;
+}
+
+extern "C" int klsh_row_count(klsh_ctx* ctx, uint64_t* n_rows, uint64_t* n_ids) {
+  if (!ctx) return KLSH_ERR_ARG;
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  if (n_rows) *n_rows = ctx->cur.n_alive;
+  if (n_ids) {
+    std::vector<uint64_t> offs;
+    KTRY(export_rows(ctx, nullptr, offs, nullptr));
+    *n_ids = offs.back();
+  }
+  return KLSH_OK;
+}
+
+extern "C" int klsh_get_rows(klsh_ctx* ctx, float* values, uint64_t* id_offsets, uint64_t* ids) {
+  if (!ctx || !id_offsets) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_get_rows: bad argument");
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<float> v;
+  std::vector<uint64_t> offs, idv;
+  KTRY(export_rows(ctx, values ? &v : nullptr, offs, ids ? &idv : nullptr));
+  if (values && !v.empty()) std::memcpy(values, v.data(), sizeof(float) * v.size());
+  std::memcpy(id_offsets, offs.data(), sizeof(uint64_t) * offs.size());
+  if (ids && !idv.empty()) std::memcpy(ids, idv.data(), sizeof(uint64_t) * idv.size());
+  return KLSH_OK;
+}
+
+extern "C" int klsh_save(klsh_ctx* ctx, const char* bin_path, int delfile, int64_t ignore_small) {
+  if (!ctx || !bin_path) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_save: bad argument");
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  std::vector<float> v;
+  std::vector<uint64_t> offs, idv;
+  KTRY(export_rows(ctx, &v, offs, &idv));
+  int rc = io_save(bin_path, delfile, ignore_small, v.data(), ctx->D, offs.data(), idv.data(), ctx->cur.n_alive);
+  if (rc != KLSH_OK) return klsh_fail(ctx, rc, "cannot write %s(.clust)", bin_path);
+  return KLSH_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// Snapshot / restore (device to device)
+// ------------------------------------------------------------------------------------------------
+static int copy_state(klsh_ctx* ctx, RowState& dst, const RowState& src, uint64_t n_born, uint64_t n_slots) {
+  const size_t vb = sizeof(float) * (n_born * (uint64_t)ctx->ld + 4);
+  KTRY(dev_reserve(ctx, dst.vals, vb));
+  KTRY(dev_reserve(ctx, dst.cnt, sizeof(int32_t) * (n_born + 1)));
+  KTRY(dev_reserve(ctx, dst.head, sizeof(int32_t) * (n_born + 1)));
+  KTRY(dev_reserve(ctx, dst.tail, sizeof(int32_t) * (n_born + 1)));
+  KTRY(dev_reserve(ctx, dst.next, sizeof(int32_t) * (n_slots + 1)));
+  KTRY(dev_reserve(ctx, dst.alive, sizeof(uint32_t) * (n_born + 1)));
+  cudaStream_t st = ctx->stream;
+  KCUDA(ctx, cudaMemcpyAsync(dst.vals.p, src.vals.p, sizeof(float) * n_born * (uint64_t)ctx->ld, cudaMemcpyDeviceToDevice, st));
+  KCUDA(ctx, cudaMemcpyAsync(dst.cnt.p, src.cnt.p, sizeof(int32_t) * n_born, cudaMemcpyDeviceToDevice, st));
+  KCUDA(ctx, cudaMemcpyAsync(dst.head.p, src.head.p, sizeof(int32_t) * n_born, cudaMemcpyDeviceToDevice, st));
+  KCUDA(ctx, cudaMemcpyAsync(dst.tail.p, src.tail.p, sizeof(int32_t) * n_born, cudaMemcpyDeviceToDevice, st));
+  KCUDA(ctx, cudaMemcpyAsync(dst.next.p, src.next.p, sizeof(int32_t) * n_slots, cudaMemcpyDeviceToDevice, st));
+  KCUDA(ctx, cudaMemcpyAsync(dst.alive.p, src.alive.p, sizeof(uint32_t) * src.n_alive, cudaMemcpyDeviceToDevice, st));
+  dst.n_alive = src.n_alive;
+  KCUDA(ctx, cudaStreamSynchronize(st));
+  return KLSH_OK;
+}
+
+extern "C" int klsh_snapshot(klsh_ctx* ctx) {
+  if (!ctx || ctx->D <= 0) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_snapshot: no rows loaded");
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  KTRY(copy_state(ctx, ctx->snap, ctx->cur, ctx->n_born, ctx->n_slots));
+  ctx->snap_born = ctx->n_born;
+  ctx->snap_slots = ctx->n_slots;
+  ctx->snap_ids = ctx->ids;
+  ctx->snap_id_base = ctx->id_base;
+  ctx->snap_ids_implicit = ctx->ids_implicit;
+  ctx->has_snap = true;
+  return KLSH_OK;
+}
+
+extern "C" int klsh_restore(klsh_ctx* ctx) {
+  if (!ctx || !ctx->has_snap) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_restore: no snapshot");
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  KTRY(copy_state(ctx, ctx->cur, ctx->snap, ctx->snap_born, ctx->snap_slots));
+  ctx->n_born = ctx->snap_born;
+  ctx->n_slots = ctx->snap_slots;
+  ctx->ids = ctx->snap_ids;
+  ctx->id_base = ctx->snap_id_base;
+  ctx->ids_implicit = ctx->snap_ids_implicit;
+  return KLSH_OK;
+}

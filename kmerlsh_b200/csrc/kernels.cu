@@ -1,0 +1,934 @@
+// Hand-written sm_100a kernels of the kmerLSH mode-C clustering hot path.
+//
+// Arithmetic contract (DESIGN.md "Exactness"): every floating-point operation that decides a
+// key bit, a merge, or a centroid value is an IEEE binary32 operation with one rounding, in the
+// reference's source order, and NEVER a fused multiply-add — the reference's x86-64 build has no
+// FMA (SURVEY.md section 7 hard part 2).  This file is compiled with -fmad=false and uses the
+// explicit-rounding intrinsics (__fmul_rn, __fadd_rn, __fdiv_rn, __fsqrt_rn), which ptxas never
+// contracts.
+#include <cooperative_groups.h>
+
+#include "klsh_internal.cuh"
+
+namespace {
+
+constexpr int kScanTile = 4096;  // elements per block in the count/scatter style kernels
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+__device__ __forceinline__ uint32_t lanemask_lt() {
+  uint32_t m;
+  asm("mov.u32 %0, %%lanemask_lt;" : "=r"(m));
+  return m;
+}
+
+// ================================================================================================
+// Generic helpers: block-level exclusive scan of one value per thread (blockDim.x <= 1024).
+// ================================================================================================
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* warp_sums /*[33]*/, uint32_t* total) {
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, nwarp = (blockDim.x + 31) >> 5;
+  uint32_t inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    uint32_t t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= (uint32_t)o) inc += t;
+  }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    uint32_t w = (lane < nwarp) ? warp_sums[lane] : 0u;
+    uint32_t winc = w;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      uint32_t t = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= (uint32_t)o) winc += t;
+    }
+    warp_sums[lane] = winc - w;  // exclusive
+    if (lane == 31) warp_sums[32] = winc;
+  }
+  __syncthreads();
+  uint32_t res = warp_sums[warp] + inc - v;
+  if (total) *total = warp_sums[32];
+  __syncthreads();
+  return res;
+}
+
+// Exclusive scan of a small array (block counts) by ONE block; writes the grand total to *total.
+__global__ void k_scan_single(uint32_t* data, uint32_t n, uint32_t* total) {
+  __shared__ uint32_t ws[33];
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < n; base += blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = (i < n) ? data[i] : 0u;
+    uint32_t tot;
+    uint32_t ex = block_exclusive_scan(v, ws, &tot);
+    if (i < n) data[i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0 && total) *total = carry;
+}
+
+__global__ void k_iota(uint32_t* out, uint64_t n, uint32_t base) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = base + (uint32_t)i;
+}
+
+__global__ void k_fill(uint32_t* out, uint64_t from, uint64_t to, uint32_t v) {
+  uint64_t i = from + (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < to) out[i] = v;
+}
+
+// ================================================================================================
+// Row transform (reference IOMat::convertHTMat, io/ioMatrix.cc:353-408).
+//   counts: sample-major uint16 [D][batch]; lut[c] = float(log(c+1.0)) from the host libm.
+//   pass 1: keep flag per row (sum_j cnt > 0.1*D, uint64 vs double) -> per-block counts
+//   pass 2: kept rows written densely, value_j = lut[cnt] - v_kmers[j]; slot = original index i
+// ================================================================================================
+__device__ __forceinline__ bool row_kept(const uint16_t* counts, uint64_t batch, int D, uint64_t i) {
+  unsigned long long total = 0;
+  for (int j = 0; j < D; ++j) total += counts[(uint64_t)j * batch + i];
+  return (double)total > 0.1 * (double)D;
+}
+
+__global__ void k_transform_count(const uint16_t* __restrict__ counts, uint64_t batch, int D, uint32_t* blkcnt) {
+  __shared__ uint32_t ws[33];
+  uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+  uint32_t c = 0;
+  for (int k = 0; k < kScanTile / 256; ++k) {
+    uint64_t i = base + (uint64_t)k * 256 + threadIdx.x;
+    if (i < batch && row_kept(counts, batch, D, i)) ++c;
+  }
+  uint32_t tot;
+  block_exclusive_scan(c, ws, &tot);
+  if (threadIdx.x == 0) blkcnt[blockIdx.x] = tot;
+}
+
+__global__ void k_transform_write(const uint16_t* __restrict__ counts, const float* __restrict__ lut,
+                                  const float* __restrict__ vk, uint64_t batch, int D, int ld,
+                                  const uint32_t* __restrict__ blkoff, float* vals, int32_t* cnt, int32_t* head,
+                                  int32_t* tail, uint64_t row_base) {
+  __shared__ uint32_t ws[33];
+  uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+  uint32_t run = blkoff[blockIdx.x];
+  for (int k = 0; k < kScanTile / 256; ++k) {
+    uint64_t i = base + (uint64_t)k * 256 + threadIdx.x;
+    bool keep = (i < batch) && row_kept(counts, batch, D, i);
+    uint32_t tot;
+    uint32_t ex = block_exclusive_scan(keep ? 1u : 0u, ws, &tot);
+    if (keep) {
+      uint64_t r = row_base + run + ex;
+      float* dst = vals + r * (uint64_t)ld;
+      for (int j = 0; j < D; ++j) {
+        uint16_t cc = counts[(uint64_t)j * batch + i];
+        dst[j] = __fsub_rn(lut[cc], vk[j]);
+      }
+      for (int j = D; j < ld; ++j) dst[j] = 0.f;
+      cnt[r] = 1;
+      head[r] = (int32_t)i;  // member slot = original index within the batch
+      tail[r] = (int32_t)i;
+    }
+    run += tot;
+  }
+}
+
+__global__ void k_fill_i32(int32_t* p, uint64_t n, int32_t v) {
+  uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) p[i] = v;
+}
+
+// ================================================================================================
+// Signing (reference LSH::random_projection, hash/lshash.cc:44-59):
+//   bit_h = (sum_h >= 0), sum_h = fl(fl(... fl(0 + fl(w_h0*x_0)) ...) + fl(w_h,D-1 * x_D-1))
+//   key = ((bit_0*2 + bit_1)*2 + ...) — plane 0 is the most significant bit.
+// One thread per row.  A warp stages its 32 rows through shared memory with coalesced 16-byte
+// loads (rows are gathered by index: the row arena never moves, DESIGN.md "Layout"), then every
+// lane walks its own row (odd stride -> conflict-free) against the planes held in shared memory
+// (broadcast reads).
+// ================================================================================================
+constexpr int kSignWarps = 4;
+
+__global__ void __launch_bounds__(kSignWarps * 32)
+k_sign(const float* __restrict__ vals, int D, int ld, const uint32_t* __restrict__ rows, uint64_t n,
+       const float* __restrict__ planes, int H, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ rows_out) {
+  extern __shared__ float smem[];
+  float* sp = smem;                      // planes [H][ld]
+  const int stride = ld + 1;             // odd
+  float* tiles = smem + (size_t)H * ld;  // [kSignWarps][32][stride]
+  for (int i = threadIdx.x; i < H * ld; i += blockDim.x) sp[i] = planes[i];
+  __syncthreads();
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  float* tile = tiles + (size_t)warp * 32 * stride;
+  const uint64_t nwarps_total = (uint64_t)gridDim.x * kSignWarps;
+  const int vec_per_row = ld >> 2;
+  for (uint64_t t0 = ((uint64_t)blockIdx.x * kSignWarps + warp) * 32; t0 < n; t0 += nwarps_total * 32) {
+    uint64_t t = t0 + lane;
+    uint32_t r = (t < n) ? (rows ? rows[t] : (uint32_t)t) : 0u;
+    int nrow = (int)min((uint64_t)32, n - t0);
+    // coalesced staging: consecutive lanes fetch consecutive float4 of the same row
+    const int total = nrow * vec_per_row;
+    for (int v0 = 0; v0 < total; v0 += 32) {
+      const int v = v0 + (int)lane;
+      const int rr = min(v, total - 1) / vec_per_row, cc = v - rr * vec_per_row;
+      const uint32_t ri = __shfl_sync(0xffffffffu, r, rr);
+      if (v < total) {
+        float4 q = __ldg(reinterpret_cast<const float4*>(vals + (uint64_t)ri * ld) + cc);
+        float* d = tile + rr * stride + cc * 4;
+        d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+      }
+    }
+    __syncwarp();
+    if (t < n) {
+      const float* x = tile + lane * stride;
+      uint32_t key = 0;
+      for (int h = 0; h < H; ++h) {
+        const float* w = sp + h * ld;
+        float sum = 0.f;
+        for (int i = 0; i < D; ++i) sum = __fadd_rn(sum, __fmul_rn(w[i], x[i]));
+        key = key * 2u + (sum >= 0.f ? 1u : 0u);
+      }
+      keys_out[t] = key;
+      rows_out[t] = r;
+    }
+    __syncwarp();
+  }
+}
+
+// ================================================================================================
+// Stable LSD radix sort of (key, row) pairs, 8 bits per pass.
+// Equivalent to the reference's merge_hashtable (function/cluster.cc:15-30): push rows in input
+// order into a dense table indexed by key, then visit keys ascending.
+//   k_radix_hist    : per-block digit histogram          -> hist[digit][block]
+//   k_radix_scan    : per digit, exclusive scan over blocks; digit totals -> dtot[digit]
+//   k_radix_scatter : block re-ranks its tile stably and scatters
+// A block's tile is 8 warps x 16 rounds x 32 lanes, warp-major, so that (warp, round, lane) order
+// is input order.
+// ================================================================================================
+constexpr int kRadixWarps = 8;
+constexpr int kRadixRounds = 16;
+constexpr int kRadixTile = kRadixWarps * kRadixRounds * 32;  // 4096
+
+__global__ void __launch_bounds__(kRadixWarps * 32)
+k_radix_hist(const uint32_t* __restrict__ keys, uint64_t n, int shift, uint32_t* __restrict__ hist, uint32_t nblk) {
+  __shared__ uint32_t h[256];
+  h[threadIdx.x] = 0;
+  __syncthreads();
+  uint64_t base = (uint64_t)blockIdx.x * kRadixTile;
+  for (int k = 0; k < kRadixTile / 256; ++k) {
+    uint64_t i = base + (uint64_t)k * 256 + threadIdx.x;
+    if (i < n) atomicAdd(&h[(keys[i] >> shift) & 255u], 1u);
+  }
+  __syncthreads();
+  hist[(uint64_t)threadIdx.x * nblk + blockIdx.x] = h[threadIdx.x];
+}
+
+// one block per digit
+__global__ void k_radix_scan(uint32_t* hist, uint32_t nblk, uint32_t* dtot) {
+  __shared__ uint32_t ws[33];
+  uint32_t* row = hist + (uint64_t)blockIdx.x * nblk;
+  uint32_t carry = 0;
+  for (uint32_t base = 0; base < nblk; base += blockDim.x) {
+    uint32_t i = base + threadIdx.x;
+    uint32_t v = (i < nblk) ? row[i] : 0u;
+    uint32_t tot;
+    uint32_t ex = block_exclusive_scan(v, ws, &tot);
+    if (i < nblk) row[i] = carry + ex;
+    carry += tot;
+  }
+  if (threadIdx.x == 0) dtot[blockIdx.x] = carry;
+}
+
+__global__ void __launch_bounds__(kRadixWarps * 32)
+k_radix_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rows, uint64_t n, int shift,
+                const uint32_t* __restrict__ hist, const uint32_t* __restrict__ dtot, uint32_t nblk,
+                uint32_t* __restrict__ keys_out, uint32_t* __restrict__ rows_out) {
+  __shared__ uint32_t wc[kRadixWarps][256];
+  __shared__ uint32_t dbase[256];
+  __shared__ uint32_t ws[33];
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  for (int w = 0; w < kRadixWarps; ++w) wc[w][threadIdx.x] = 0;
+  // exclusive scan of the 256 digit totals (256 threads)
+  {
+    uint32_t tot;
+    uint32_t ex = block_exclusive_scan(dtot[threadIdx.x], ws, &tot);
+    dbase[threadIdx.x] = ex + hist[(uint64_t)threadIdx.x * nblk + blockIdx.x];
+  }
+  __syncthreads();
+  uint32_t k[kRadixRounds], r[kRadixRounds];
+  uint16_t rank[kRadixRounds];
+  const uint64_t base = (uint64_t)blockIdx.x * kRadixTile + (uint64_t)warp * (kRadixRounds * 32);
+#pragma unroll
+  for (int rd = 0; rd < kRadixRounds; ++rd) {
+    uint64_t i = base + (uint64_t)rd * 32 + lane;
+    bool valid = i < n;
+    k[rd] = valid ? keys[i] : 0u;
+    r[rd] = valid ? rows[i] : 0u;
+    uint32_t d = valid ? ((k[rd] >> shift) & 255u) : 0xFFFFFFFFu;
+    uint32_t peers = __match_any_sync(0xffffffffu, d);
+    uint32_t before = __popc(peers & lanemask_lt());
+    uint32_t old = 0;
+    if (valid) {
+      int leader = __ffs(peers) - 1;
+      if ((int)lane == leader) {
+        old = wc[warp][d];
+        wc[warp][d] = old + __popc(peers);
+      }
+      old = __shfl_sync(peers, old, leader);
+    }
+    rank[rd] = (uint16_t)(old + before);
+    __syncwarp();
+  }
+  __syncthreads();
+  // per digit: exclusive prefix over warps, plus the block's global base
+  {
+    uint32_t run = dbase[threadIdx.x];
+    for (int w = 0; w < kRadixWarps; ++w) {
+      uint32_t c = wc[w][threadIdx.x];
+      wc[w][threadIdx.x] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+#pragma unroll
+  for (int rd = 0; rd < kRadixRounds; ++rd) {
+    uint64_t i = base + (uint64_t)rd * 32 + lane;
+    if (i < n) {
+      uint32_t d = (k[rd] >> shift) & 255u;
+      uint32_t dst = wc[warp][d] + rank[rd];
+      keys_out[dst] = k[rd];
+      rows_out[dst] = r[rd];
+    }
+  }
+}
+
+// ================================================================================================
+// Bucket boundaries (run-length encode of sorted keys) and size classes.
+// ================================================================================================
+__device__ __forceinline__ bool is_head(const uint32_t* keys, uint64_t i) { return i == 0 || keys[i] != keys[i - 1]; }
+
+__global__ void k_heads_count(const uint32_t* __restrict__ keys, uint64_t n, uint32_t* blkcnt) {
+  __shared__ uint32_t ws[33];
+  uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+  uint32_t c = 0;
+  for (int k = 0; k < kScanTile / 256; ++k) {
+    uint64_t i = base + (uint64_t)k * 256 + threadIdx.x;
+    if (i < n && is_head(keys, i)) ++c;
+  }
+  uint32_t tot;
+  block_exclusive_scan(c, ws, &tot);
+  if (threadIdx.x == 0) blkcnt[blockIdx.x] = tot;
+}
+
+__global__ void k_heads_write(const uint32_t* __restrict__ keys, uint64_t n, const uint32_t* __restrict__ blkoff,
+                              uint32_t* bstart) {
+  __shared__ uint32_t ws[33];
+  uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+  uint32_t run = blkoff[blockIdx.x];
+  for (int k = 0; k < kScanTile / 256; ++k) {
+    uint64_t i = base + (uint64_t)k * 256 + threadIdx.x;
+    bool hd = (i < n) && is_head(keys, i);
+    uint32_t tot;
+    uint32_t ex = block_exclusive_scan(hd ? 1u : 0u, ws, &tot);
+    if (hd) bstart[run + ex] = (uint32_t)i;
+    run += tot;
+  }
+}
+
+// nest_threshold < 0: nesting disabled.  Reads the bucket count from counters->n_buckets.
+// Appends are warp-aggregated: one atomic per warp and class.
+__device__ __forceinline__ void warp_append(bool pred, uint32_t* counter, uint32_t* list, uint32_t value) {
+  const uint32_t m = __ballot_sync(0xffffffffu, pred);
+  if (m == 0u) return;
+  uint32_t base = 0;
+  const int leader = __ffs(m) - 1;
+  if ((int)lane_id() == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (pred) list[base + __popc(m & lanemask_lt())] = value;
+}
+
+__global__ void k_classify(uint32_t* bstart, uint64_t n, long long nest_threshold, PassCounters* counters,
+                           uint32_t* list_small, uint32_t* list_large, uint32_t* list_nested) {
+  const uint32_t nb = counters->n_buckets;
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) bstart[nb] = (uint32_t)n;
+  uint32_t size = 0;
+  if (b < nb) {
+    const uint32_t s = bstart[b];
+    const uint32_t e = (b + 1 < nb) ? bstart[b + 1] : (uint32_t)n;
+    size = e - s;
+  }
+  const uint32_t wmax = __reduce_max_sync(0xffffffffu, size);
+  if (lane_id() == 0 && wmax > 0) atomicMax(&counters->bucket_max, wmax);
+  const bool nested = nest_threshold >= 0 && (long long)size > nest_threshold && size >= 2;
+  const bool small = !nested && size >= 2 && size <= KLSH_SMALL_MAX;
+  const bool large = !nested && size > KLSH_SMALL_MAX;
+  warp_append(nested, &counters->n_nested, list_nested, b);
+  warp_append(small, &counters->n_small, list_small, b);
+  warp_append(large, &counters->n_large, list_large, b);
+}
+
+// ================================================================================================
+// Greedy in-bucket merge (reference p_cluster, function/cluster.cc:56-87) with
+//   Distance::cosine   (function/distance.cc:27-38)
+//   AB::SetConsensus   (function/funcAB.cc:49-71)
+// Bucket = positions [s, e) of rows_sorted (row indices in bucket order).  On return
+// rows_sorted[s .. s+size) are the survivors in the reference's order and rows_sorted[s+size .. e)
+// hold KLSH_SENTINEL.  A merge of current (position i) into candidate (position j<i) overwrites
+// candidate's row in the arena with the consensus, prepends current's member chain to
+// candidate's, and moves the tail position into i (swap-remove).
+// ================================================================================================
+
+// sqrt(sum v_i^2), accumulated in index order (the magnitude_* sums of Distance::cosine)
+__device__ __forceinline__ float row_norm(const float* v, int D) {
+  float m = 0.f;
+  for (int i = 0; i < D; ++i) m = __fadd_rn(m, __fmul_rn(v[i], v[i]));
+  return __fsqrt_rn(m);
+}
+
+// similarity test of Distance::cosine + p_cluster's `1 - distance >= threshold`
+__device__ __forceinline__ bool cos_match(float dot, float nl, float nr, float threshold) {
+  float sim = __fdiv_rn(dot, __fmul_rn(nl, nr));
+  float dist = __fsub_rn(1.f, sim);
+  return __fsub_rn(1.f, dist) >= threshold;
+}
+
+// one dimension of AB::SetConsensus: cur*c1/all + cand*c2/all, counts converted like cvtsi2ss
+__device__ __forceinline__ float consensus1(float cur, int c1, float cand, int c2) {
+  const float fa = __int2float_rn(c1 + c2);
+  float a = __fdiv_rn(__fmul_rn(cur, __int2float_rn(c1)), fa);
+  float b = __fdiv_rn(__fmul_rn(cand, __int2float_rn(c2)), fa);
+  return __fadd_rn(a, b);
+}
+
+// ---- small buckets: one warp per bucket, rows resident in shared memory -------------------------
+__global__ void __launch_bounds__(128)
+k_merge_small(float* __restrict__ vals, int D, int ld, int32_t* __restrict__ cnt, int32_t* __restrict__ head,
+              int32_t* __restrict__ tail, int32_t* __restrict__ next, uint32_t* __restrict__ rows_sorted,
+              const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ list, const PassCounters* counters,
+              float threshold) {
+  extern __shared__ float smem[];
+  const int stride = ld + 1;
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
+  float* tile = smem + (size_t)warp * KLSH_SMALL_MAX * stride;
+  const uint32_t nlist = counters->n_small;
+  for (uint32_t w = blockIdx.x * wpb + warp; w < nlist; w += gridDim.x * wpb) {
+    const uint32_t b = list[w];
+    const uint32_t s = bstart[b];
+    const int n = (int)(bstart[b + 1] - s);
+    // slot = lane: row index and metadata of the row originally at position `lane`
+    uint32_t ridx = (lane < (uint32_t)n) ? rows_sorted[s + lane] : 0u;
+    for (int k = 0; k < n; ++k) {
+      uint32_t rk = __shfl_sync(0xffffffffu, ridx, k);
+      const float* src = vals + (uint64_t)rk * ld;
+      for (int d = lane; d < D; d += 32) tile[k * stride + d] = src[d];
+    }
+    __syncwarp();
+    int my_cnt = 0, my_head = -1, my_tail = -1;
+    float my_nrm = 0.f;
+    bool my_dirty = false;
+    if (lane < (uint32_t)n) {
+      my_cnt = cnt[ridx];
+      my_head = head[ridx];
+      my_tail = tail[ridx];
+      my_nrm = row_norm(tile + lane * stride, D);
+    }
+    int pos_slot = (int)lane;  // slot held by position `lane`
+    int size = n, i = 1;
+    while (i < size) {
+      const int cs = __shfl_sync(0xffffffffu, pos_slot, i);
+      const float cn = __shfl_sync(0xffffffffu, my_nrm, cs);
+      const float rn = __shfl_sync(0xffffffffu, my_nrm, pos_slot & 31);
+      bool match = false;
+      if ((int)lane < i) {
+        const float* c = tile + cs * stride;
+        const float* r = tile + pos_slot * stride;
+        float dot = 0.f;
+        for (int d = 0; d < D; ++d) dot = __fadd_rn(dot, __fmul_rn(c[d], r[d]));
+        match = cos_match(dot, cn, rn, threshold);
+      }
+      const uint32_t m = __ballot_sync(0xffffffffu, match);
+      if (m == 0u) {
+        ++i;
+        continue;
+      }
+      const int j = __ffs(m) - 1;
+      const int rs = __shfl_sync(0xffffffffu, pos_slot, j);
+      const int c1 = __shfl_sync(0xffffffffu, my_cnt, cs);
+      const int c2 = __shfl_sync(0xffffffffu, my_cnt, rs);
+      const int h1 = __shfl_sync(0xffffffffu, my_head, cs);
+      const int t1 = __shfl_sync(0xffffffffu, my_tail, cs);
+      const int h2 = __shfl_sync(0xffffffffu, my_head, rs);
+      {
+        float* c = tile + cs * stride;
+        float* r = tile + rs * stride;
+        for (int d = lane; d < D; d += 32) r[d] = consensus1(c[d], c1, r[d], c2);
+      }
+      __syncwarp();
+      if ((int)lane == rs) {
+        // ids(current) ++ ids(candidate): current's chain goes first
+        if (t1 >= 0) {
+          next[t1] = h2;
+          my_head = h1;
+          if (my_tail < 0) my_tail = t1;
+        }
+        my_cnt = c1 + c2;
+        my_nrm = row_norm(tile + rs * stride, D);
+        my_dirty = true;
+      }
+      // position i takes the tail position's slot
+      const int last = __shfl_sync(0xffffffffu, pos_slot, size - 1);
+      if ((int)lane == i) pos_slot = last;
+      --size;
+      __syncwarp();
+    }
+    // write back: survivors' order, dirty rows and metadata
+    {
+      const uint32_t my_ridx_for_pos = __shfl_sync(0xffffffffu, ridx, pos_slot & 31);
+      if (lane < (uint32_t)n) rows_sorted[s + lane] = ((int)lane < size) ? my_ridx_for_pos : KLSH_SENTINEL;
+    }
+    const uint32_t dirty = __ballot_sync(0xffffffffu, my_dirty);
+    if (my_dirty) {
+      cnt[ridx] = my_cnt;
+      head[ridx] = my_head;
+      tail[ridx] = my_tail;
+    }
+    uint32_t dm = dirty;
+    while (dm) {
+      const int sl = __ffs(dm) - 1;
+      dm &= dm - 1;
+      const uint32_t rk = __shfl_sync(0xffffffffu, ridx, sl);
+      float* dst = vals + (uint64_t)rk * ld;
+      for (int d = lane; d < D; d += 32) dst[d] = tile[sl * stride + d];
+    }
+    __syncwarp();
+  }
+}
+
+// ---- large buckets: one block per bucket, representatives cached in shared memory ---------------
+constexpr int kLargeThreads = 256;
+
+struct LargeShared {
+  int match_j;
+  int c1, c2, h1, t1, h2;
+  float cand_nrm;
+  uint32_t cand_ridx;
+  uint32_t work;
+};
+
+// merges ONE bucket [s, e) with the whole block; rep_cap = representatives that fit in smem
+__device__ void merge_large_bucket(float* vals, int D, int ld, int32_t* cnt, int32_t* head, int32_t* tail,
+                                   int32_t* next, uint32_t* seg, uint32_t n, float threshold, float* cand,
+                                   float* rep_nrm, float* rep_rows, int rep_cap, float* nrm_spill, LargeShared* sh) {
+  const int stride = ld + 1;
+  const int tid = threadIdx.x;
+  // representative 0
+  {
+    const uint32_t r0 = seg[0];
+    const float* src = vals + (uint64_t)r0 * ld;
+    for (int d = tid; d < D; d += blockDim.x) rep_rows[d] = src[d];
+    __syncthreads();
+    if (tid == 0) rep_nrm[0] = row_norm(rep_rows, D);
+  }
+  uint32_t size = n, i = 1;
+  __syncthreads();
+  while (i < size) {
+    // stage the candidate
+    const uint32_t cr = seg[i];
+    {
+      const float* src = vals + (uint64_t)cr * ld;
+      for (int d = tid; d < D; d += blockDim.x) cand[d] = src[d];
+      if (tid == 0) sh->match_j = 0x7fffffff;
+    }
+    __syncthreads();
+    if (tid == 0) sh->cand_nrm = row_norm(cand, D);
+    __syncthreads();
+    const float cn = sh->cand_nrm;
+    int best = 0x7fffffff;
+    for (uint32_t j = tid; j < i; j += blockDim.x) {
+      float dot = 0.f, rn;
+      if ((int)j < rep_cap) {
+        const float* r = rep_rows + (size_t)j * stride;
+        for (int d = 0; d < D; ++d) dot = __fadd_rn(dot, __fmul_rn(cand[d], r[d]));
+        rn = rep_nrm[j];
+      } else {
+        const float* r = vals + (uint64_t)seg[j] * ld;
+        for (int d = 0; d < D; ++d) dot = __fadd_rn(dot, __fmul_rn(cand[d], r[d]));
+        rn = nrm_spill[j - rep_cap];
+      }
+      if (cos_match(dot, cn, rn, threshold)) {
+        best = (int)j;
+        break;  // this thread's later j are larger
+      }
+    }
+    // block-wide minimum
+    for (int o = 16; o > 0; o >>= 1) best = min(best, __shfl_xor_sync(0xffffffffu, best, o));
+    if (lane_id() == 0 && best != 0x7fffffff) atomicMin(&sh->match_j, best);
+    __syncthreads();
+    const int j = sh->match_j;
+    if (j == 0x7fffffff) {
+      // no merge: the candidate becomes representative i
+      if ((int)i < rep_cap) {
+        float* dst = rep_rows + (size_t)i * stride;
+        for (int d = tid; d < D; d += blockDim.x) dst[d] = cand[d];
+        if (tid == 0) rep_nrm[i] = cn;
+      } else if (tid == 0) {
+        nrm_spill[i - rep_cap] = cn;
+      }
+      ++i;
+      __syncthreads();
+      continue;
+    }
+    const uint32_t rr = seg[j];
+    if (tid == 0) {
+      sh->c1 = cnt[cr];
+      sh->c2 = cnt[rr];
+      sh->h1 = head[cr];
+      sh->t1 = tail[cr];
+      sh->h2 = head[rr];
+    }
+    __syncthreads();
+    {
+      const int c1 = sh->c1, c2 = sh->c2;
+      float* g = vals + (uint64_t)rr * ld;
+      if (j < rep_cap) {
+        float* r = rep_rows + (size_t)j * stride;
+        for (int d = tid; d < D; d += blockDim.x) {
+          float v = consensus1(cand[d], c1, r[d], c2);
+          r[d] = v;
+          g[d] = v;
+        }
+      } else {
+        for (int d = tid; d < D; d += blockDim.x) g[d] = consensus1(cand[d], c1, g[d], c2);
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      if (sh->t1 >= 0) {
+        next[sh->t1] = sh->h2;
+        head[rr] = sh->h1;
+        if (tail[rr] < 0) tail[rr] = sh->t1;
+      }
+      cnt[rr] = sh->c1 + sh->c2;
+      if (j < rep_cap) rep_nrm[j] = row_norm(rep_rows + (size_t)j * stride, D);
+      else nrm_spill[j - rep_cap] = row_norm(vals + (uint64_t)rr * ld, D);
+      seg[i] = seg[size - 1];
+      seg[size - 1] = KLSH_SENTINEL;
+    }
+    --size;
+    __syncthreads();
+  }
+}
+
+__global__ void __launch_bounds__(kLargeThreads)
+k_merge_large(float* vals, int D, int ld, int32_t* cnt, int32_t* head, int32_t* tail, int32_t* next,
+              uint32_t* rows_sorted, const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ list,
+              PassCounters* counters, float threshold, int rep_cap, float* nrm_spill_all, uint64_t spill_stride,
+              int single_bucket_n) {
+  extern __shared__ float smem[];
+  __shared__ LargeShared sh;
+  float* cand = smem;                 // [ld]
+  float* rep_nrm = cand + ld;         // [rep_cap]
+  float* rep_rows = rep_nrm + rep_cap;  // [rep_cap][ld+1]
+  float* nrm_spill = nrm_spill_all + (uint64_t)blockIdx.x * spill_stride;
+  if (single_bucket_n >= 0) {  // klsh_p_cluster: the whole list is one bucket
+    if (blockIdx.x == 0 && single_bucket_n >= 2)
+      merge_large_bucket(vals, D, ld, cnt, head, tail, next, rows_sorted, (uint32_t)single_bucket_n, threshold, cand,
+                         rep_nrm, rep_rows, rep_cap, nrm_spill, &sh);
+    return;
+  }
+  const uint32_t nlist = counters->n_large;
+  for (;;) {
+    if (threadIdx.x == 0) sh.work = atomicAdd(&counters->large_cursor, 1u);
+    __syncthreads();
+    const uint32_t w = sh.work;
+    __syncthreads();
+    if (w >= nlist) break;
+    const uint32_t b = list[w];
+    const uint32_t s = bstart[b];
+    merge_large_bucket(vals, D, ld, cnt, head, tail, next, rows_sorted + s, bstart[b + 1] - s, threshold, cand, rep_nrm,
+                       rep_rows, rep_cap, nrm_spill, &sh);
+    __syncthreads();
+  }
+}
+
+// ================================================================================================
+// Survivor compaction: keep entries != sentinel, order preserved.
+// ================================================================================================
+__global__ void k_alive_count(const uint32_t* __restrict__ rows, uint64_t n, uint32_t* blkcnt) {
+  __shared__ uint32_t ws[33];
+  uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+  uint32_t c = 0;
+  for (int k = 0; k < kScanTile / 256; ++k) {
+    uint64_t i = base + (uint64_t)k * 256 + threadIdx.x;
+    if (i < n && rows[i] != KLSH_SENTINEL) ++c;
+  }
+  uint32_t tot;
+  block_exclusive_scan(c, ws, &tot);
+  if (threadIdx.x == 0) blkcnt[blockIdx.x] = tot;
+}
+
+__global__ void k_alive_write(const uint32_t* __restrict__ rows, uint64_t n, const uint32_t* __restrict__ blkoff,
+                              uint32_t* out) {
+  __shared__ uint32_t ws[33];
+  uint64_t base = (uint64_t)blockIdx.x * kScanTile;
+  uint32_t run = blkoff[blockIdx.x];
+  for (int k = 0; k < kScanTile / 256; ++k) {
+    uint64_t i = base + (uint64_t)k * 256 + threadIdx.x;
+    uint32_t r = (i < n) ? rows[i] : KLSH_SENTINEL;
+    bool keep = r != KLSH_SENTINEL;
+    uint32_t tot;
+    uint32_t ex = block_exclusive_scan(keep ? 1u : 0u, ws, &tot);
+    if (keep) out[run + ex] = r;
+    run += tot;
+  }
+}
+
+// ================================================================================================
+// Export: gather surviving rows densely.
+// ================================================================================================
+__global__ void k_gather_rows(const float* __restrict__ vals, int D, int ld, const int32_t* __restrict__ cnt,
+                              const int32_t* __restrict__ head, const uint32_t* __restrict__ rows, uint64_t n,
+                              float* out_vals, int32_t* out_cnt, int32_t* out_head) {
+  const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t lane = lane_id();
+  if (w >= n) return;
+  const uint32_t r = rows[w];
+  const float* src = vals + (uint64_t)r * ld;
+  float* dst = out_vals + w * (uint64_t)D;
+  for (int d = lane; d < D; d += 32) dst[d] = src[d];
+  if (lane == 0) {
+    out_cnt[w] = cnt[r];
+    out_head[w] = head[r];
+  }
+}
+
+}  // namespace
+
+// ================================================================================================
+// Launch wrappers
+// ================================================================================================
+#define KLAUNCH(ctx)                                                                                   \
+  do {                                                                                                 \
+    (ctx)->launches++;                                                                                 \
+    cudaError_t e__ = cudaGetLastError();                                                              \
+    if (e__ != cudaSuccess)                                                                            \
+      return klsh_fail((ctx), KLSH_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e__), \
+                       __FILE__, __LINE__);                                                            \
+  } while (0)
+
+static inline uint32_t cdiv64(uint64_t a, uint64_t b) { return (uint32_t)((a + b - 1) / b); }
+
+static int scan_blkcnt(klsh_ctx* ctx, uint32_t* blkcnt, uint32_t nblk, uint32_t* total_dev) {
+  k_scan_single<<<1, 1024, 0, ctx->stream>>>(blkcnt, nblk, total_dev);
+  KLAUNCH(ctx);
+  return KLSH_OK;
+}
+
+int launch_iota(klsh_ctx* ctx, uint32_t* out, uint64_t n, uint32_t base) {
+  if (!n) return KLSH_OK;
+  k_iota<<<cdiv64(n, 256), 256, 0, ctx->stream>>>(out, n, base);
+  KLAUNCH(ctx);
+  return KLSH_OK;
+}
+
+int launch_fill_tail(klsh_ctx* ctx, uint32_t* seg, uint64_t from, uint64_t to) {
+  if (to <= from) return KLSH_OK;
+  k_fill<<<cdiv64(to - from, 256), 256, 0, ctx->stream>>>(seg, from, to, KLSH_SENTINEL);
+  KLAUNCH(ctx);
+  return KLSH_OK;
+}
+
+int launch_init_meta(klsh_ctx* ctx, uint64_t n) {
+  // next[] = -1 for n member slots
+  if (!n) return KLSH_OK;
+  k_fill_i32<<<cdiv64(n, 256), 256, 0, ctx->stream>>>(ctx->cur.next.as<int32_t>(), n, -1);
+  KLAUNCH(ctx);
+  return KLSH_OK;
+}
+
+int launch_transform(klsh_ctx* ctx, const uint16_t* d_counts, const float* d_vk, uint64_t batch, uint64_t* kept_out) {
+  PassScratch& s = ctx->top;
+  uint32_t nblk = cdiv64(batch, kScanTile);
+  KTRY(dev_reserve(ctx, s.blkcnt, sizeof(uint32_t) * (nblk + 1)));
+  KTRY(dev_reserve(ctx, s.counters, sizeof(PassCounters)));
+  uint32_t* blk = s.blkcnt.as<uint32_t>();
+  PassCounters* dc = s.counters.as<PassCounters>();
+  k_transform_count<<<nblk, 256, 0, ctx->stream>>>(d_counts, batch, ctx->D, blk);
+  KLAUNCH(ctx);
+  KTRY(scan_blkcnt(ctx, blk, nblk, &dc->n_out));
+  k_transform_write<<<nblk, 256, 0, ctx->stream>>>(d_counts, ctx->lut.as<float>(), d_vk, batch, ctx->D, ctx->ld, blk,
+                                                   ctx->cur.vals.as<float>(), ctx->cur.cnt.as<int32_t>(),
+                                                   ctx->cur.head.as<int32_t>(), ctx->cur.tail.as<int32_t>(), 0);
+  KLAUNCH(ctx);
+  KCUDA(ctx, cudaMemcpyAsync(&ctx->h_counters->n_out, &dc->n_out, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+  KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *kept_out = ctx->h_counters->n_out;
+  return KLSH_OK;
+}
+
+int launch_sign(klsh_ctx* ctx, const float* vals, int D, int ld, const uint32_t* rows, uint64_t n,
+                const float* d_planes, int H, uint32_t* keys_out, uint32_t* rows_out) {
+  if (!n) return KLSH_OK;
+  size_t smem = sizeof(float) * ((size_t)H * ld + (size_t)kSignWarps * 32 * (ld + 1));
+  static size_t configured = 0;
+  if (smem > 48 * 1024 && smem > configured) {
+    KCUDA(ctx, cudaFuncSetAttribute(k_sign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = smem;
+  }
+  uint64_t want = (n + kSignWarps * 32 - 1) / (kSignWarps * 32);
+  uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * 16);
+  k_sign<<<grid, kSignWarps * 32, smem, ctx->stream>>>(vals, D, ld, rows, n, d_planes, H, keys_out, rows_out);
+  KLAUNCH(ctx);
+  return KLSH_OK;
+}
+
+int launch_sort_pairs(klsh_ctx* ctx, PassScratch& s, uint64_t n, int bits, uint32_t** keys_sorted,
+                      uint32_t** rows_sorted) {
+  uint32_t* ka = s.keys_a.as<uint32_t>();
+  uint32_t* kb = s.keys_b.as<uint32_t>();
+  uint32_t* ra = s.rows_a.as<uint32_t>();
+  uint32_t* rb = s.rows_b.as<uint32_t>();
+  if (n >= 2 && bits > 0) {
+    uint32_t nblk = cdiv64(n, kRadixTile);
+    KTRY(dev_reserve(ctx, s.hist, sizeof(uint32_t) * ((size_t)256 * nblk + 256)));
+    uint32_t* hist = s.hist.as<uint32_t>();
+    uint32_t* dtot = hist + (size_t)256 * nblk;
+    for (int shift = 0; shift < bits; shift += 8) {
+      k_radix_hist<<<nblk, kRadixWarps * 32, 0, ctx->stream>>>(ka, n, shift, hist, nblk);
+      KLAUNCH(ctx);
+      k_radix_scan<<<256, 256, 0, ctx->stream>>>(hist, nblk, dtot);
+      KLAUNCH(ctx);
+      k_radix_scatter<<<nblk, kRadixWarps * 32, 0, ctx->stream>>>(ka, ra, n, shift, hist, dtot, nblk, kb, rb);
+      KLAUNCH(ctx);
+      std::swap(ka, kb);
+      std::swap(ra, rb);
+    }
+  }
+  *keys_sorted = ka;
+  *rows_sorted = ra;
+  return KLSH_OK;
+}
+
+int launch_bounds(klsh_ctx* ctx, PassScratch& s, const uint32_t* keys_sorted, uint64_t n, int64_t nest_threshold) {
+  uint32_t nblk = cdiv64(n, kScanTile);
+  KTRY(dev_reserve(ctx, s.blkcnt, sizeof(uint32_t) * (nblk + 1)));
+  KTRY(dev_reserve(ctx, s.bstart, sizeof(uint32_t) * (n + 2)));
+  KTRY(dev_reserve(ctx, s.list_small, sizeof(uint32_t) * (n / 2 + 2)));
+  KTRY(dev_reserve(ctx, s.list_large, sizeof(uint32_t) * (n / (KLSH_SMALL_MAX + 1) + 2)));
+  KTRY(dev_reserve(ctx, s.list_nested, sizeof(uint32_t) * (n / 2 + 2)));
+  KTRY(dev_reserve(ctx, s.counters, sizeof(PassCounters)));
+  PassCounters* dc = s.counters.as<PassCounters>();
+  KCUDA(ctx, cudaMemsetAsync(dc, 0, sizeof(PassCounters), ctx->stream));
+  uint32_t* blk = s.blkcnt.as<uint32_t>();
+  k_heads_count<<<nblk, 256, 0, ctx->stream>>>(keys_sorted, n, blk);
+  KLAUNCH(ctx);
+  KTRY(scan_blkcnt(ctx, blk, nblk, &dc->n_buckets));
+  k_heads_write<<<nblk, 256, 0, ctx->stream>>>(keys_sorted, n, blk, s.bstart.as<uint32_t>());
+  KLAUNCH(ctx);
+  // bucket count is on the device; launch enough threads for the worst case (n buckets)
+  k_classify<<<cdiv64(n, 256), 256, 0, ctx->stream>>>(s.bstart.as<uint32_t>(), n, (long long)nest_threshold, dc,
+                                                      s.list_small.as<uint32_t>(), s.list_large.as<uint32_t>(),
+                                                      s.list_nested.as<uint32_t>());
+  KLAUNCH(ctx);
+  return KLSH_OK;
+}
+
+static int large_smem_config(klsh_ctx* ctx, int ld, int* rep_cap, size_t* smem) {
+  size_t budget = (size_t)ctx->max_smem_optin - 1024;
+  size_t per_rep = sizeof(float) * (size_t)(ld + 1 + 1);
+  size_t fixed = sizeof(float) * (size_t)ld;
+  int cap = (int)((budget - fixed) / per_rep);
+  if (cap < 1) return klsh_fail(ctx, KLSH_ERR_ARG, "dimension %d too large for the merge kernel", ld);
+  *rep_cap = cap;
+  *smem = fixed + per_rep * (size_t)cap;
+  static size_t configured = 0;
+  if (*smem > configured) {
+    KCUDA(ctx, cudaFuncSetAttribute(k_merge_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
+    configured = *smem;
+  }
+  return KLSH_OK;
+}
+
+int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, uint32_t n_small,
+                 uint32_t n_large) {
+  const int D = ctx->D, ld = ctx->ld;
+  float* vals = ctx->cur.vals.as<float>();
+  int32_t* cnt = ctx->cur.cnt.as<int32_t>();
+  int32_t* head = ctx->cur.head.as<int32_t>();
+  int32_t* tail = ctx->cur.tail.as<int32_t>();
+  int32_t* next = ctx->cur.next.as<int32_t>();
+  PassCounters* dc = s.counters.as<PassCounters>();
+  if (n_small) {
+    size_t per_warp = sizeof(float) * (size_t)KLSH_SMALL_MAX * (ld + 1);
+    int wpb = 4;
+    while (wpb > 1 && per_warp * wpb > (size_t)ctx->max_smem_optin - 1024) wpb >>= 1;
+    size_t smem = per_warp * wpb;
+    if (smem > (size_t)ctx->max_smem_optin) return klsh_fail(ctx, KLSH_ERR_ARG, "dimension %d too large", D);
+    static size_t configured = 0;
+    if (smem > 48 * 1024 && smem > configured) {
+      KCUDA(ctx, cudaFuncSetAttribute(k_merge_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      configured = smem;
+    }
+    uint32_t grid = std::min<uint32_t>((n_small + wpb - 1) / wpb, (uint32_t)ctx->sm_count * 32);
+    k_merge_small<<<grid, wpb * 32, smem, ctx->stream>>>(vals, D, ld, cnt, head, tail, next, rows_sorted,
+                                                         s.bstart.as<uint32_t>(), s.list_small.as<uint32_t>(), dc,
+                                                         threshold);
+    KLAUNCH(ctx);
+  }
+  if (n_large) {
+    int rep_cap;
+    size_t smem;
+    KTRY(large_smem_config(ctx, ld, &rep_cap, &smem));
+    uint32_t grid = std::min<uint32_t>(n_large, (uint32_t)ctx->sm_count);
+    // norms of representatives that do not fit in shared memory: one slab per block
+    uint64_t spill_stride = 0;
+    {
+      uint32_t bmax = ctx->h_counters->bucket_max;
+      if ((int64_t)bmax > rep_cap) spill_stride = bmax - rep_cap;
+      KTRY(dev_reserve(ctx, ctx->io_b, sizeof(float) * (spill_stride * grid + 1)));
+    }
+    k_merge_large<<<grid, kLargeThreads, smem, ctx->stream>>>(vals, D, ld, cnt, head, tail, next, rows_sorted,
+                                                              s.bstart.as<uint32_t>(), s.list_large.as<uint32_t>(), dc,
+                                                              threshold, rep_cap, ctx->io_b.as<float>(), spill_stride, -1);
+    KLAUNCH(ctx);
+  }
+  return KLSH_OK;
+}
+
+int launch_merge_one(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, uint64_t n, float threshold) {
+  if (n < 2) return KLSH_OK;
+  int rep_cap;
+  size_t smem;
+  KTRY(large_smem_config(ctx, ctx->ld, &rep_cap, &smem));
+  uint64_t spill = (n > (uint64_t)rep_cap) ? n - rep_cap : 0;
+  KTRY(dev_reserve(ctx, ctx->io_b, sizeof(float) * (spill + 1)));
+  KTRY(dev_reserve(ctx, s.counters, sizeof(PassCounters)));
+  k_merge_large<<<1, kLargeThreads, smem, ctx->stream>>>(
+      ctx->cur.vals.as<float>(), ctx->D, ctx->ld, ctx->cur.cnt.as<int32_t>(), ctx->cur.head.as<int32_t>(),
+      ctx->cur.tail.as<int32_t>(), ctx->cur.next.as<int32_t>(), rows_sorted, nullptr, nullptr,
+      s.counters.as<PassCounters>(), threshold, rep_cap, ctx->io_b.as<float>(), spill, (int)n);
+  KLAUNCH(ctx);
+  return KLSH_OK;
+}
+
+int launch_compact(klsh_ctx* ctx, PassScratch& s, const uint32_t* rows_sorted, uint64_t n, uint32_t* out) {
+  if (!n) return KLSH_OK;
+  uint32_t nblk = cdiv64(n, kScanTile);
+  KTRY(dev_reserve(ctx, s.blkcnt, sizeof(uint32_t) * (nblk + 1)));
+  PassCounters* dc = s.counters.as<PassCounters>();
+  uint32_t* blk = s.blkcnt.as<uint32_t>();
+  k_alive_count<<<nblk, 256, 0, ctx->stream>>>(rows_sorted, n, blk);
+  KLAUNCH(ctx);
+  KTRY(scan_blkcnt(ctx, blk, nblk, &dc->n_out));
+  k_alive_write<<<nblk, 256, 0, ctx->stream>>>(rows_sorted, n, blk, out);
+  KLAUNCH(ctx);
+  return KLSH_OK;
+}
+
+int launch_gather_rows(klsh_ctx* ctx, const uint32_t* rows, uint64_t n, float* out_vals, int32_t* out_cnt,
+                       int32_t* out_head) {
+  if (!n) return KLSH_OK;
+  k_gather_rows<<<cdiv64(n * 32, 256), 256, 0, ctx->stream>>>(ctx->cur.vals.as<float>(), ctx->D, ctx->ld,
+                                                             ctx->cur.cnt.as<int32_t>(), ctx->cur.head.as<int32_t>(),
+                                                             rows, n, out_vals, out_cnt, out_head);
+  KLAUNCH(ctx);
+  return KLSH_OK;
+}

@@ -1,0 +1,133 @@
+// Internal declarations shared by the CUDA translation units of libklsh.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/klsh.h"
+
+#define KLSH_SENTINEL 0xFFFFFFFFu
+#define KLSH_SMALL_MAX 32  // buckets of 2..32 rows: one warp each
+
+struct PlaneSource;  // planes.cc
+
+// Grow-only device buffer.
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  template <typename T>
+  T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// Scratch for one signing+grouping+merge pass over a list of rows.  The top-level pass and the
+// nested pass (reference nestedCluster) each own one.
+struct PassScratch {
+  DevBuf keys_a, keys_b, rows_a, rows_b;  // sort ping-pong (uint32 each)
+  DevBuf hist;                            // radix histograms
+  DevBuf blkcnt;                          // per-block counts for compaction-style kernels
+  DevBuf bstart;                          // bucket start offsets (uint32, nb+1)
+  DevBuf list_small, list_large, list_nested;
+  DevBuf planes;    // H*ld floats
+  DevBuf counters;  // device counters (see PassCounters)
+};
+
+struct PassCounters {  // lives in device memory, mirrored to pinned host memory
+  uint32_t n_buckets;
+  uint32_t n_small;
+  uint32_t n_large;
+  uint32_t n_nested;
+  uint32_t n_out;
+  uint32_t bucket_max;
+  uint32_t large_cursor;
+  uint32_t pad;
+};
+
+struct RowState {  // everything klsh_snapshot copies
+  DevBuf vals, cnt, head, tail, next, alive;
+  uint64_t n_alive = 0;
+};
+
+struct klsh_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int sm_count = 148;
+  int max_smem_optin = 0;
+
+  // row arena: rows are born once and never move; a merge overwrites the surviving row in place.
+  int D = 0, ld = 0;       // ld = D rounded up to a multiple of 4 floats
+  uint64_t n_born = 0;     // rows in the arena
+  uint64_t n_slots = 0;    // member slots (id list nodes)
+  RowState cur, snap;
+  bool has_snap = false;
+  uint64_t snap_born = 0, snap_slots = 0;
+  // id payload of member slots: explicit (ids.size()==n_slots) or implicit id = id_base + slot
+  std::vector<uint64_t> ids;
+  uint64_t id_base = 0;
+  bool ids_implicit = true;
+  std::vector<uint64_t> snap_ids;
+  uint64_t snap_id_base = 0;
+  bool snap_ids_implicit = true;
+
+  PassScratch top, nested;
+  DevBuf lut;       // 65536 floats: float(log(c+1.0)) computed by the host libm
+  bool lut_ready = false;
+  DevBuf io_a, io_b;  // staging for loads/exports
+  DevBuf alive_alt;   // the other half of the alive-list ping-pong
+  DevBuf nested_out;  // survivors of one nested pass
+  PassCounters* h_counters = nullptr;  // pinned
+
+  PlaneSource* planes = nullptr;
+  cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+};
+
+// ---- error handling -------------------------------------------------------------------------
+int klsh_fail(klsh_ctx* ctx, int code, const char* fmt, ...);
+#define KCUDA(ctx, call)                                                                         \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess)                                                                      \
+      return klsh_fail((ctx), KLSH_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e__), \
+                       __FILE__, __LINE__);                                                      \
+  } while (0)
+#define KTRY(expr)            \
+  do {                        \
+    int rc__ = (expr);        \
+    if (rc__ != KLSH_OK) return rc__; \
+  } while (0)
+
+int dev_reserve(klsh_ctx* ctx, DevBuf& b, size_t bytes);
+
+// ---- planes.cc ---------------------------------------------------------------------------------
+PlaneSource* planes_new();
+void planes_free(PlaneSource* p);
+void planes_seed(PlaneSource* p, uint64_t seed);
+void planes_callback(PlaneSource* p, klsh_plane_fn fn, void* user);
+void planes_draw(PlaneSource* p, int H, int D, float* out);
+
+// ---- io.cc -------------------------------------------------------------------------------------
+int io_save(const char* bin_path, int delfile, int64_t ignore_small, const float* values, int D,
+            const uint64_t* id_offsets, const uint64_t* ids, uint64_t n);
+int io_read_cluster(const char* bin_path, int D, uint64_t start_line, uint64_t num_lines,
+                    std::vector<float>& values, std::vector<uint64_t>& id_offsets, std::vector<uint64_t>& ids);
+
+// ---- kernels.cu (launch wrappers; all enqueue on ctx->stream) ---------------------------------
+int launch_transform(klsh_ctx* ctx, const uint16_t* d_counts, const float* d_vk, uint64_t batch,
+                     uint64_t* kept_out);
+int launch_sign(klsh_ctx* ctx, const float* vals, int D, int ld, const uint32_t* rows, uint64_t n,
+                const float* d_planes, int H, uint32_t* keys_out, uint32_t* rows_out);
+int launch_sort_pairs(klsh_ctx* ctx, PassScratch& s, uint64_t n, int bits, uint32_t** keys_sorted,
+                      uint32_t** rows_sorted);
+int launch_bounds(klsh_ctx* ctx, PassScratch& s, const uint32_t* keys_sorted, uint64_t n, int64_t nest_threshold);
+int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, uint32_t n_small,
+                 uint32_t n_large);
+int launch_merge_one(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, uint64_t n, float threshold);
+int launch_compact(klsh_ctx* ctx, PassScratch& s, const uint32_t* rows_sorted, uint64_t n, uint32_t* out);
+int launch_iota(klsh_ctx* ctx, uint32_t* out, uint64_t n, uint32_t base);
+int launch_fill_tail(klsh_ctx* ctx, uint32_t* seg, uint64_t from, uint64_t to);
+int launch_init_meta(klsh_ctx* ctx, uint64_t n);
+int launch_gather_rows(klsh_ctx* ctx, const uint32_t* rows, uint64_t n, float* out_vals, int32_t* out_cnt,
+                       int32_t* out_head);

@@ -1,0 +1,202 @@
+"""GPU parity: the CUDA path (through the C ABI) against the oracle on the same seeded inputs.
+Bit-exact for keys, assignments, id order AND centroid floats (stricter than the 1e-5 the
+north star allows)."""
+import numpy as np
+import pytest
+
+from helpers import assert_rows_equal, synth_rows
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("D,H", [(1, 0), (1, 3), (7, 5), (20, 19), (32, 25), (64, 29), (256, 27), (12, 32)])
+def test_sign_keys(gpu, oracle, D, H):
+    rng = np.random.default_rng(100 + D + H)
+    n = 5000 if D < 256 else 1500
+    rows = rng.standard_normal((n, D)).astype(np.float32)
+    rows[::17] = 0.0                      # zero rows: every sum is +0 -> bit 1
+    rows[1::29] *= np.float32(1e-30)      # denormal products
+    table = oracle.planes(5).table(H, D) if H else np.zeros((0, D), np.float32)
+    want = oracle.sign(rows, table).astype(np.uint64)
+    got = gpu.sign(rows, table)
+    assert np.array_equal(got, want)
+
+
+def test_sign_nan_rows(gpu, oracle):
+    rows = np.zeros((64, 8), np.float32)
+    rows[3, 2] = np.nan                   # NaN sum -> bit 0 (sum >= 0 is false)
+    rows[5, 0] = np.inf
+    table = oracle.planes(9).table(6, 8)
+    assert np.array_equal(gpu.sign(rows, table), oracle.sign(rows, table).astype(np.uint64))
+
+
+@pytest.mark.parametrize("n,sa,sb", [(4096, 2, 2), (50000, 4, 4), (30011, 10, 10)])
+def test_convert_counts(gpu, oracle, n, sa, sb):
+    counts, vk, values, ids = synth_rows(oracle, n, sa, sb, 11)
+    counts = counts.copy()
+    counts[:, 5] = 0                      # dropped: total 0
+    counts[:, 6] = 0
+    counts[0, 6] = 65535                  # kept; LUT's last entry
+    d = sa + sb
+    counts[:, 7] = 0
+    counts[0, 7] = int(0.1 * d)           # total == floor(0.1*D): dropped unless > 0.1*D
+    counts[:, 8] = 0
+    counts[0, 8] = int(0.1 * d) + 1       # kept
+    values, ids = oracle.convert_counts(counts, vk, 1000)
+    gpu.load_counts(counts, vk, 1000)
+    gv, go, gi = gpu.get_rows()
+    assert np.array_equal(gi, ids)
+    assert gv.tobytes() == values.tobytes()
+    assert np.array_equal(go, np.arange(len(ids) + 1, dtype=np.uint64))
+
+
+def _bucket_cases():
+    rng = np.random.default_rng(3)
+    base = rng.standard_normal((1, 16)).astype(np.float32)
+    cases = {}
+    cases["all_identical"] = np.repeat(base, 40, axis=0)
+    cases["two"] = np.concatenate([base, base * np.float32(1.0000001)])
+    cases["none_merge"] = rng.standard_normal((37, 16)).astype(np.float32)
+    x = base + np.float32(0.25) * rng.standard_normal((300, 16)).astype(np.float32)
+    cases["noisy_cluster_300"] = x
+    y = np.concatenate([base + np.float32(0.2) * rng.standard_normal((20, 16)).astype(np.float32),
+                        -base + np.float32(0.2) * rng.standard_normal((20, 16)).astype(np.float32)])
+    cases["two_groups_interleaved"] = y[rng.permutation(40)]
+    z = rng.standard_normal((9, 16)).astype(np.float32)
+    z[4] = 0.0                            # zero vector: cosine is NaN, never merges
+    z[7] = z[1]
+    cases["zero_row"] = z
+    cases["chain_2000"] = (base + np.float32(0.3) * rng.standard_normal((2000, 16)).astype(np.float32))
+    return cases
+
+
+@pytest.mark.parametrize("name", sorted(_bucket_cases()))
+@pytest.mark.parametrize("thr", [0.95, 0.8, 0.5])
+def test_p_cluster(gpu, oracle, name, thr):
+    values = _bucket_cases()[name]
+    rows = oracle.rows(values)
+    rows.p_cluster(thr)
+    gpu.set_rows(values)
+    gpu.p_cluster(thr)
+    assert_rows_equal(gpu.get_rows(), rows.export(), name)
+
+
+def test_p_cluster_prior_members(gpu, oracle):
+    """Rows that already carry id lists (phase-2 input): count-weighted consensus and id order."""
+    rng = np.random.default_rng(8)
+    values = (rng.standard_normal((1, 20)) + 0.2 * rng.standard_normal((60, 20))).astype(np.float32)
+    sizes = rng.integers(1, 9, size=60)
+    offs = np.concatenate([[0], np.cumsum(sizes)]).astype(np.uint64)
+    ids = rng.permutation(int(offs[-1])).astype(np.uint64) + 1000
+    rows = oracle.rows(values, offs, ids)
+    rows.p_cluster(0.9)
+    gpu.set_rows(values, offs, ids)
+    gpu.p_cluster(0.9)
+    assert_rows_equal(gpu.get_rows(), rows.export())
+
+
+@pytest.mark.parametrize("n,sa,sb,iters,minsim,thr,seed", [
+    (1, 2, 2, 3, 0.8, 1000, 1),            # N=1 -> H=0, one bucket
+    (2, 2, 2, 2, 0.8, 1000, 1),
+    (3000, 3, 3, 4, 0.85, 100000, 2),
+    (40000, 4, 4, 8, 0.85, 100000, 7),
+    (40000, 4, 4, 3, 0.85, 50, 7),         # nested buckets (fresh tables consumed in bucket order)
+    (30000, 6, 6, 8, 0.80, 100000, 3),
+    (120000, 10, 10, 5, 0.80, 1000, 4),    # nested + large buckets
+    (60000, 16, 16, 6, 0.90, 100000, 5),
+    (20000, 32, 32, 4, 0.80, 100000, 6),
+])
+def test_cluster(gpu, oracle, n, sa, sb, iters, minsim, thr, seed):
+    _, _, values, ids = synth_rows(oracle, n, sa, sb, 40 + seed)
+    offs = np.arange(len(ids) + 1, dtype=np.uint64)
+    rows = oracle.rows(values, offs, ids)
+    planes = oracle.planes(seed)
+    ost = rows.cluster(minsim, iters, thr, planes)
+    gpu.set_seed(seed)
+    gpu.set_rows(values, offs, ids)
+    gst = gpu.cluster(minsim, iters, thr)
+    for k in range(iters):
+        if ost[k].rows_in == 0:
+            break
+        assert (gst[k].rows_in, gst[k].rows_out, gst[k].H) == (ost[k].rows_in, ost[k].rows_out, ost[k].H), k
+        assert gst[k].nested_calls == ost[k].nested_calls
+        assert np.float32(gst[k].threshold) == np.float32(ost[k].threshold)
+    assert_rows_equal(gpu.get_rows(), rows.export())
+
+
+def test_cluster_wide_rows(gpu, oracle):
+    """D=256 (config 5's shape): multi-chunk rows in every kernel."""
+    _, _, values, ids = synth_rows(oracle, 6000, 128, 128, 77)
+    rows = oracle.rows(values)
+    rows.cluster(0.8, 3, 100000, oracle.planes(5))
+    gpu.set_seed(5)
+    gpu.set_rows(values)
+    gpu.cluster(0.8, 3, 100000)
+    assert_rows_equal(gpu.get_rows(), rows.export())
+
+
+def test_nested_cluster(gpu, oracle):
+    _, _, values, ids = synth_rows(oracle, 20000, 4, 4, 21)
+    rows = oracle.rows(values)
+    rows.nested_cluster(0.9, oracle.planes(13))
+    gpu.set_seed(13)
+    gpu.set_rows(values)
+    gpu.nested_cluster(0.9)
+    assert_rows_equal(gpu.get_rows(), rows.export())
+
+
+def test_two_phase_from_counts(gpu, oracle):
+    """load_counts -> Cluster(I=1) -> Cluster(I=6) on resident rows == oracle's two calls."""
+    counts, vk, values, ids = synth_rows(oracle, 50000, 5, 5, 31)
+    planes = oracle.planes(99)
+    rows = oracle.rows(values, np.arange(len(ids) + 1, dtype=np.uint64), ids)
+    rows.cluster(0.8, 1, 100, planes)
+    rows.cluster(0.8, 6, 1000, planes)
+    gpu.set_seed(99)
+    gpu.load_counts(counts, vk, 0)
+    gpu.cluster(0.8, 1, 100)
+    gpu.cluster(0.8, 6, 1000)
+    assert_rows_equal(gpu.get_rows(), rows.export())
+
+
+def test_snapshot_restore(gpu, oracle):
+    _, _, values, ids = synth_rows(oracle, 20000, 4, 4, 5)
+    gpu.set_rows(values)
+    gpu.snapshot()
+    gpu.set_seed(1)
+    gpu.cluster(0.8, 3, 100000)
+    a = gpu.get_rows()
+    gpu.restore()
+    gpu.set_seed(1)
+    gpu.cluster(0.8, 3, 100000)
+    assert_rows_equal(gpu.get_rows(), a)
+
+
+def test_plane_callback(gpu, oracle):
+    """Caller-supplied tables (what a reference-side binding does with its own generator)."""
+    _, _, values, ids = synth_rows(oracle, 15000, 4, 4, 6)
+    src = oracle.planes(321)
+    rows = oracle.rows(values)
+    rows.cluster(0.85, 4, 100000, oracle.planes(321))
+    gpu.set_plane_source(lambda H, D: src.table(H, D))
+    gpu.set_rows(values)
+    gpu.cluster(0.85, 4, 100000)
+    gpu.set_seed(0)
+    assert_rows_equal(gpu.get_rows(), rows.export())
+
+
+def test_save_files(gpu, oracle, tmp_path):
+    _, _, values, ids = synth_rows(oracle, 30000, 4, 4, 9)
+    rows = oracle.rows(values)
+    rows.cluster(0.8, 6, 100000, oracle.planes(2))
+    rows.save(str(tmp_path / "o.bin"), True, 5)
+    gpu.set_seed(2)
+    gpu.set_rows(values)
+    gpu.cluster(0.8, 6, 100000)
+    gpu.save(str(tmp_path / "g.bin"), True, 5)
+    assert (tmp_path / "o.bin").read_bytes() == (tmp_path / "g.bin").read_bytes()
+    assert (tmp_path / "o.bin.clust").read_bytes() == (tmp_path / "g.bin.clust").read_bytes()
+    # reload through the reference's reader restatement and through ours
+    gpu.load_cluster_file(str(tmp_path / "g.bin"), 8)
+    back = oracle.read_cluster(str(tmp_path / "o.bin"), 8)
+    assert_rows_equal(gpu.get_rows(), back.export())
