@@ -1,0 +1,359 @@
+#!/usr/bin/env python
+"""bench.py — k-mer vectors clustered per second per LSH iteration (BASELINE.json's metric).
+
+A *step* is one pass of the mode-C clustering hot path over one synthetic abundance matrix of the
+named shape: Cluster(I=1) (phase 1, threshold 0.95, nested above batch/1000) followed by
+Cluster(I=<iters>) (phase 2), i.e. every LSH iteration the reference's mode C would run on it.
+
+  value : sum over all iterations of rows entering the iteration / device time, rows already in HBM
+          (state reset between steps by an untimed device-to-device restore)
+  e2e   : same metric through the C ABI with HOST buffers: per step the uint16 count matrix is
+          copied from pinned host memory, transformed, clustered, and the clusters (centroids +
+          member lists) are read back
+  roofline     : the dominant kernel family (the in-bucket merge) against the measured HBM peak
+  cpu_baseline : the reference's own OpenMP build (oracle/_ref/kmerLSH_ref) on a bounded sample
+
+`--impl reference` times the reference's CPU implementation instead (rank 0 only).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import shutil
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+from kmerlsh_b200 import synth  # noqa: E402
+
+METRIC = "kmer_vectors_clustered_per_sec_per_lsh_iteration"
+UNIT = "rows/s"
+REF_BIN = os.path.join(ROOT, "oracle", "_ref", "kmerLSH_ref")
+
+
+def b_alg(d, s):
+    """Algorithmic bytes per input row per iteration."""
+    return 8 * d + 32 + s * (4 * d + 12)
+
+
+def b_alg_merge(d, s):
+    """The merge kernel's share: gather row, write surviving centroid + count/head/tail."""
+    return 4 * d + 4 + s * (4 * d + 12)
+
+
+def measured_peaks():
+    try:
+        p = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        return float(p["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self.stop_flag = False
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, timeout=5).stdout.strip()
+                f = [x.strip() for x in out.split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for n, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+        top = sorted(self.samples)[len(self.samples) // 2:]  # under-load half
+        return {"sm_mhz": float(np.median(top)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
+
+
+def make_inputs(workload, rows_override, device):
+    n, sa, sb, seed = synth.CONFIGS[workload]
+    if rows_override:
+        n = rows_override
+    if n <= 2_000_000:
+        counts, cov = synth.synth_counts(n, sa, sb, seed)
+        import torch
+
+        pinned = torch.empty(counts.shape, dtype=torch.int16, pin_memory=True)
+        pinned.numpy().view(np.uint16)[:] = counts
+        counts = pinned.numpy().view(np.uint16)
+        keep = pinned
+    else:
+        from kmerlsh_b200.synth_gpu import synth_counts_gpu
+
+        counts, cov = synth_counts_gpu(n, sa, sb, seed, device=device)
+        keep = None
+    kmap, cov32 = synth.parse_log_line(synth.format_log_line(n, cov), sa + sb)
+    vk = synth.v_kmers_from_cov(cov32, kmap)
+    return n, sa, sb, counts, cov, vk, keep
+
+
+def run_cpu_reference(counts, cov, sa, sb, sample_rows, iters, min_sim, threads, seed=42):
+    """Run the reference binary on the first `sample_rows` rows; parse its own --verbose phase
+    lines (function/cluster.cc:263, :307, :325).  Returns (rows_iter_per_s, detail)."""
+    d = sa + sb
+    work = tempfile.mkdtemp(prefix="klsh_cpu_")
+    try:
+        os.makedirs(os.path.join(work, "tmp"))
+        sub = np.ascontiguousarray(counts[:, :sample_rows])
+        sub.tofile(os.path.join(work, "kmer_count.bin"))
+        subcov = np.log(np.maximum(sub, 1).astype(np.float64)).sum(axis=1)
+        open(os.path.join(work, "kmer_count.log"), "w").write(synth.format_log_line(sample_rows, subcov))
+        for name, k in (("A.txt", sa), ("B.txt", sb)):
+            open(os.path.join(work, name), "w").write("".join("s%d.fq s%d\n" % (i, i) for i in range(k)))
+        env = dict(os.environ, KLSH_SEED=str(seed))
+        env.pop("OMP_THREAD_LIMIT", None)
+        t0 = time.time()
+        out = subprocess.run([REF_BIN, "-a", "A.txt", "-b", "B.txt", "-o", "oa", "-p", "ob", "-M", "C", "--only", "-I", str(iters),
+                              "-N", str(min_sim), "-K", "23", "-T", str(threads), "--verbose"], cwd=work, env=env, check=True,
+                             stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True).stdout
+        wall = time.time() - t0
+    finally:
+        shutil.rmtree(work, ignore_errors=True)
+    rows = sum(int(x) for x in re.findall(r"^Size of profilings : (\d+)", out, flags=re.M))
+    secs = sum(float(x) for x in re.findall(r"^(?:hashing|clustering|merging) takes secs:\t([0-9.eE+-]+)", out, flags=re.M))
+    return rows / secs, {"rows_iterations": rows, "phase_seconds": secs, "wall_seconds": wall, "dim": d}
+
+
+def reference_arm(args, rank, world):
+    if rank != 0:
+        return
+    if not os.path.exists(REF_BIN):
+        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/kmerLSH_ref not built (needs /root/reference at build time)"}))
+        return
+    n, sa, sb, counts, cov, vk, _ = make_inputs(args.workload, args.rows, "cuda:0")
+    cores = os.cpu_count() or 1
+    sample_rows = min(n, args.cpu_sample_rows)
+    iters = args.cpu_sample_iters
+    vals = []
+    for k in range(args.warmup + args.steps):
+        v, detail = run_cpu_reference(counts, cov, sa, sb, sample_rows, iters, args.min_similarity, cores)
+        if k >= args.warmup:
+            vals.append((v, detail))
+    value = float(np.mean([v for v, _ in vals]))
+    ms = float(np.mean([d["phase_seconds"] for _, d in vals]) * 1e3)
+    sample = "first %d rows of the %s generator x %d samples, phase 1 + I=%d, -T %d (hash+cluster+merge phase seconds)" % (
+        sample_rows, args.workload, sa + sb, iters, cores)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args, n, sa, sb, world),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def workload_config(args, n, sa, sb, world):
+    return {
+        "workload": "%s: mode C on synthetic %d k-mers x %d samples (%d A + %d B), phase 1 I=1 + phase 2 I=%d, N=%.2f" % (
+            args.workload, n, sa + sb, sa, sb, args.iters, args.min_similarity),
+        "rows_per_gpu": n, "dim": sa + sb, "iterations": 1 + args.iters, "min_similarity": args.min_similarity,
+        "parallelism": "1 GPU" if world == 1 else "%d independent row shards (one mode-C job per GPU, no data-path collective)" % world,
+        "l2_policy": "inputs larger than L2 (row arena %.1f GB per GPU); no flush" % (n * (sa + sb) * 4 / 1e9),
+        "state_reset": "untimed device-to-device restore between steps",
+    }
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default=os.environ.get("KLSH_BENCH_WORKLOAD", "C2"), choices=sorted(synth.CONFIGS))
+    ap.add_argument("--rows", type=int, default=0, help="override rows per GPU (debug only; invalidates the number)")
+    ap.add_argument("--iters", type=int, default=100)
+    ap.add_argument("--min-similarity", dest="min_similarity", type=float, default=0.80)
+    ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
+    ap.add_argument("--cpu-sample-iters", type=int, default=10)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from kmerlsh_b200 import Context
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a B200; there is no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- inputs (each rank its own shard: generator seed offset by rank) --------------------------
+    n, sa, sb, gseed = synth.CONFIGS[args.workload]
+    if world > 1:
+        synth.CONFIGS[args.workload] = (n, sa, sb, gseed + 1000 * rank)
+    n, sa, sb, counts, cov, vk, _keep = make_inputs(args.workload, args.rows, "cuda:%d" % local_rank)
+    d = sa + sb
+    torch.cuda.empty_cache()
+
+    ctx = Context(local_rank, seed=42)
+    p1_thr, p2_thr = 100000, 1000000
+
+    def one_pass():
+        st = ctx.cluster(args.min_similarity, 1, p1_thr)
+        st += ctx.cluster(args.min_similarity, args.iters, p2_thr)
+        return st
+
+    # ---- device-resident arm ------------------------------------------------------------------------
+    ctx.load_counts(counts, vk, 0)
+    ctx.snapshot()
+    for _ in range(args.warmup):
+        ctx.restore()
+        ctx.set_seed(42)
+        one_pass()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    launches0 = ctx.launch_count()
+    t_steps, rows_steps, all_stats = [], [], []
+    for _ in range(args.steps):
+        ctx.restore()
+        ctx.set_seed(42)
+        ctx.sync()
+        barrier()
+        t0 = time.perf_counter()
+        st = one_pass()
+        ctx.sync()
+        t_steps.append(time.perf_counter() - t0)
+        rows_steps.append(sum(s.rows_in for s in st))
+        all_stats.append(st)
+    barrier()
+    launches = ctx.launch_count() - launches0
+    dev_ms = [sum(s.ms_total for s in st) for st in all_stats]
+
+    # ---- end-to-end arm (host buffers in, clusters out) ---------------------------------------------
+    e2e_t, e2e_rows, d2h_bytes = [], [], 0
+    for k in range(1 + args.steps):  # one warm-up
+        ctx.set_seed(42)
+        barrier()
+        t0 = time.perf_counter()
+        ctx.load_counts(counts, vk, 0)               # H2D of the uint16 matrix + transform
+        st = one_pass()
+        values, offs, ids = ctx.get_rows()           # D2H: centroids, counts, heads, member chains
+        dt = time.perf_counter() - t0
+        if k:
+            e2e_t.append(dt)
+            e2e_rows.append(sum(s.rows_in for s in st))
+            d2h_bytes = values.nbytes + 8 * (len(offs) - 1) + 4 * n
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    h2d_bytes = counts.nbytes + vk.nbytes
+
+    # ---- aggregate over ranks (max time, sum rows) -----------------------------------------------------
+    t_total, rows_total = float(sum(t_steps)), float(sum(rows_steps))
+    e_total, erows_total = float(sum(e2e_t)), float(sum(e2e_rows))
+    if world > 1:
+        tt = torch.tensor([t_total, e_total], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        rr = torch.tensor([rows_total, erows_total, float(launches)], device="cuda", dtype=torch.float64)
+        dist.all_reduce(rr, op=dist.ReduceOp.SUM)
+        t_total, e_total = tt.tolist()
+        rows_total, erows_total, launches = rr.tolist()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel family (rank 0's steps) -----------------------------------
+    peak, peak_src = measured_peaks()
+    fam = {"sign": 0.0, "group": 0.0, "merge": 0.0, "compact": 0.0}
+    merge_bytes = job_bytes = 0.0
+    n_iter = 0
+    for st in all_stats:
+        for s in st:
+            if not s.rows_in:
+                continue
+            n_iter += 1
+            surv = s.rows_out / s.rows_in
+            fam["sign"] += s.ms_sign
+            fam["group"] += s.ms_group
+            fam["merge"] += s.ms_merge
+            fam["compact"] += s.ms_compact
+            merge_bytes += s.rows_in * b_alg_merge(d, surv)
+            job_bytes += s.rows_in * b_alg(d, surv)
+    dom = max(fam, key=fam.get)
+    dev_total_ms = sum(fam.values())
+    achieved = merge_bytes / (fam["merge"] * 1e-3) / 1e9 if fam["merge"] > 0 else 0.0
+    job_achieved = job_bytes / (dev_total_ms * 1e-3) / 1e9 if dev_total_ms > 0 else 0.0
+    roofline = {
+        "bound": "hbm", "kernel": "k_merge_* (in-bucket greedy merge, per iteration)", "achieved": achieved, "peak": peak,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "share_of_step": fam["merge"] / dev_total_ms if dev_total_ms else None, "dominant_family": dom,
+        "family_ms_per_step": {k: v / args.steps for k, v in fam.items()},
+        "job": {"achieved": job_achieved, "frac": job_achieved / peak, "bytes_per_row_iter": "8D+32+s(4D+12)"},
+    }
+
+    cpu = None
+    if not args.no_cpu_baseline and os.path.exists(REF_BIN):
+        cores = os.cpu_count() or 1
+        sample_rows = min(n, args.cpu_sample_rows)
+        v, detail = run_cpu_reference(counts, cov, sa, sb, sample_rows, args.cpu_sample_iters, args.min_similarity, cores)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "reference",
+               "sample": "first %d rows of the same generator x %d samples, phase 1 + I=%d, -T %d, %.1f s of hash+cluster+merge" % (
+                   sample_rows, d, args.cpu_sample_iters, cores, detail["phase_seconds"])}
+    elif not args.no_cpu_baseline:
+        cpu = {"value": None, "unit": UNIT, "cores": 0, "kind": "reference", "sample": "oracle/_ref/kmerLSH_ref not present"}
+
+    out = {
+        "metric": METRIC, "value": rows_total / t_total, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic", "config": workload_config(args, n, sa, sb, world),
+        "clocks": sampler.summary(),
+        "e2e": {"value": erows_total / e_total, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
+                "ms_per_step": e_total / args.steps * 1e3},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "cpu_baseline": cpu,
+        "device_ms_per_step": float(np.mean(dev_ms)),
+        "rows_iterations_per_step": rows_total / args.steps / world,
+        "final_clusters": int(all_stats[-1][-1].rows_out),
+    }
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
