@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <algorithm>
 
@@ -64,7 +65,8 @@ static void dev_free(DevBuf& b) {
 static void free_scratch(PassScratch& s) {
   dev_free(s.keys_a); dev_free(s.keys_b); dev_free(s.rows_a); dev_free(s.rows_b);
   dev_free(s.hist); dev_free(s.blkcnt); dev_free(s.bstart);
-  dev_free(s.list_small); dev_free(s.list_large); dev_free(s.list_nested);
+  dev_free(s.list_small); dev_free(s.list_large); dev_free(s.list_big); dev_free(s.esc1); dev_free(s.esc2); dev_free(s.esc3); dev_free(s.list_nested);
+  dev_free(s.pos_nrm);
   dev_free(s.planes); dev_free(s.counters);
 }
 
@@ -114,6 +116,17 @@ int klsh_create(int device, klsh_ctx** out) {
     return klsh_fail(nullptr, KLSH_ERR_NOMEM, "cudaMallocHost: %s", cudaGetErrorString(e));
   }
   ctx->planes = planes_new();
+  // development knobs (bucket size classes of the windowed merge)
+  if (const char* e = std::getenv("KLSH_DEBUG")) ctx->debug = std::atoi(e) != 0;
+  if (const char* e = std::getenv("KLSH_MERGE_V1")) ctx->merge_v1 = std::atoi(e) != 0;
+  if (const char* e = std::getenv("KLSH_CTA_MAX")) ctx->cta_max = (uint32_t)std::strtoul(e, nullptr, 10);
+  if (const char* e = std::getenv("KLSH_CLUSTER_MAX")) ctx->cluster_max = (uint32_t)std::strtoul(e, nullptr, 10);
+  if (const char* e = std::getenv("KLSH_CLUSTER_SIZE")) ctx->cluster_size = std::atoi(e);
+  if (const char* e = std::getenv("KLSH_CLUSTER2_MAX")) ctx->cluster2_max = (uint32_t)std::strtoul(e, nullptr, 10);
+  if (const char* e = std::getenv("KLSH_CLUSTER2_SIZE")) ctx->cluster2_size = std::atoi(e);
+  if (ctx->cta_max < 1) ctx->cta_max = 1;
+  if (ctx->cluster_max < ctx->cta_max) ctx->cluster_max = ctx->cta_max;
+  if (ctx->cluster2_max < ctx->cluster_max) ctx->cluster2_max = ctx->cluster_max;
   *out = ctx;
   return KLSH_OK;
 }
@@ -131,6 +144,8 @@ void klsh_destroy(klsh_ctx* ctx) {
   dev_free(ctx->io_b);
   dev_free(ctx->alive_alt);
   dev_free(ctx->nested_out);
+  dev_free(ctx->team_ctl);
+  dev_free(ctx->dbg);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
@@ -329,7 +344,7 @@ static int run_pass(klsh_ctx* ctx, PassScratch& s, const uint32_t* rows_in, uint
   KCUDA(ctx, cudaStreamSynchronize(st));
   const PassCounters c = *hc;
   ctx->h_counters->bucket_max = c.bucket_max;  // launch_merge sizes its spill slab from slot 0
-  KTRY(launch_merge(ctx, s, rows_sorted, threshold, c.n_small, c.n_large));
+  KTRY(launch_merge(ctx, s, rows_sorted, threshold, c));
   uint64_t nested_calls = 0;
   if (c.n_nested) {
     // oversized buckets in ascending key order (= ascending bucket index), like the reference's

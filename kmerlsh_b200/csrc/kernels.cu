@@ -6,7 +6,7 @@
 // FMA (SURVEY.md section 7 hard part 2).  This file is compiled with -fmad=false and uses the
 // explicit-rounding intrinsics (__fmul_rn, __fadd_rn, __fdiv_rn, __fsqrt_rn), which ptxas never
 // contracts.
-#include <cooperative_groups.h>
+#include <cstring>
 
 #include "klsh_internal.cuh"
 
@@ -344,8 +344,23 @@ __device__ __forceinline__ void warp_append(bool pred, uint32_t* counter, uint32
   if (pred) list[base + __popc(m & lanemask_lt())] = value;
 }
 
+__device__ __forceinline__ void warp_append_item(bool pred, uint32_t* counter, uint32_t* list, uint32_t bucket) {
+  const uint32_t m = __ballot_sync(0xffffffffu, pred);
+  if (m == 0u) return;
+  uint32_t base = 0;
+  const int leader = __ffs(m) - 1;
+  if ((int)lane_id() == leader) base = atomicAdd(counter, (uint32_t)__popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (pred) {
+    uint32_t* it = list + 3 * (size_t)(base + __popc(m & lanemask_lt()));
+    it[0] = bucket;
+    it[1] = 0u;  // not started
+    it[2] = 0u;
+  }
+}
+
 __global__ void k_classify(uint32_t* bstart, uint64_t n, long long nest_threshold, PassCounters* counters,
-                           uint32_t* list_small, uint32_t* list_large, uint32_t* list_nested) {
+                           uint32_t* list_small, uint32_t* list_large, uint32_t* list_big, uint32_t* list_nested) {
   const uint32_t nb = counters->n_buckets;
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b == 0) bstart[nb] = (uint32_t)n;
@@ -359,10 +374,12 @@ __global__ void k_classify(uint32_t* bstart, uint64_t n, long long nest_threshol
   if (lane_id() == 0 && wmax > 0) atomicMax(&counters->bucket_max, wmax);
   const bool nested = nest_threshold >= 0 && (long long)size > nest_threshold && size >= 2;
   const bool small = !nested && size >= 2 && size <= KLSH_SMALL_MAX;
-  const bool large = !nested && size > KLSH_SMALL_MAX;
+  const bool large = !nested && size > KLSH_SMALL_MAX && size < KLSH_BIG;
+  const bool big = !nested && size >= KLSH_BIG;
   warp_append(nested, &counters->n_nested, list_nested, b);
   warp_append(small, &counters->n_small, list_small, b);
-  warp_append(large, &counters->n_large, list_large, b);
+  warp_append_item(large, &counters->n_large, list_large, b);
+  warp_append_item(big, &counters->n_big, list_big, b);
 }
 
 // ================================================================================================
@@ -620,8 +637,8 @@ __device__ void merge_large_bucket(float* vals, int D, int ld, int32_t* cnt, int
 __global__ void __launch_bounds__(kLargeThreads)
 k_merge_large(float* vals, int D, int ld, int32_t* cnt, int32_t* head, int32_t* tail, int32_t* next,
               uint32_t* rows_sorted, const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ list,
-              PassCounters* counters, float threshold, int rep_cap, float* nrm_spill_all, uint64_t spill_stride,
-              int single_bucket_n) {
+              const uint32_t* __restrict__ list_big, PassCounters* counters, float threshold, int rep_cap,
+              float* nrm_spill_all, uint64_t spill_stride, int single_bucket_n) {
   extern __shared__ float smem[];
   __shared__ LargeShared sh;
   float* cand = smem;                 // [ld]
@@ -634,14 +651,14 @@ k_merge_large(float* vals, int D, int ld, int32_t* cnt, int32_t* head, int32_t* 
                          rep_nrm, rep_rows, rep_cap, nrm_spill, &sh);
     return;
   }
-  const uint32_t nlist = counters->n_large;
+  const uint32_t nbig = counters->n_big, nlist = nbig + counters->n_large;
   for (;;) {
     if (threadIdx.x == 0) sh.work = atomicAdd(&counters->large_cursor, 1u);
     __syncthreads();
     const uint32_t w = sh.work;
     __syncthreads();
     if (w >= nlist) break;
-    const uint32_t b = list[w];
+    const uint32_t b = (w < nbig) ? list_big[3 * (size_t)w] : list[3 * (size_t)(w - nbig)];
     const uint32_t s = bstart[b];
     merge_large_bucket(vals, D, ld, cnt, head, tail, next, rows_sorted + s, bstart[b + 1] - s, threshold, cand, rep_nrm,
                        rep_rows, rep_cap, nrm_spill, &sh);
@@ -812,8 +829,10 @@ int launch_bounds(klsh_ctx* ctx, PassScratch& s, const uint32_t* keys_sorted, ui
   KTRY(dev_reserve(ctx, s.blkcnt, sizeof(uint32_t) * (nblk + 1)));
   KTRY(dev_reserve(ctx, s.bstart, sizeof(uint32_t) * (n + 2)));
   KTRY(dev_reserve(ctx, s.list_small, sizeof(uint32_t) * (n / 2 + 2)));
-  KTRY(dev_reserve(ctx, s.list_large, sizeof(uint32_t) * (n / (KLSH_SMALL_MAX + 1) + 2)));
+  KTRY(dev_reserve(ctx, s.list_large, sizeof(uint32_t) * 3 * (n / (KLSH_SMALL_MAX + 1) + 2)));
+  KTRY(dev_reserve(ctx, s.list_big, sizeof(uint32_t) * 3 * (n / KLSH_BIG + 2)));
   KTRY(dev_reserve(ctx, s.list_nested, sizeof(uint32_t) * (n / 2 + 2)));
+  KTRY(dev_reserve(ctx, s.pos_nrm, sizeof(float) * (n + 2)));
   KTRY(dev_reserve(ctx, s.counters, sizeof(PassCounters)));
   PassCounters* dc = s.counters.as<PassCounters>();
   KCUDA(ctx, cudaMemsetAsync(dc, 0, sizeof(PassCounters), ctx->stream));
@@ -826,7 +845,7 @@ int launch_bounds(klsh_ctx* ctx, PassScratch& s, const uint32_t* keys_sorted, ui
   // bucket count is on the device; launch enough threads for the worst case (n buckets)
   k_classify<<<cdiv64(n, 256), 256, 0, ctx->stream>>>(s.bstart.as<uint32_t>(), n, (long long)nest_threshold, dc,
                                                       s.list_small.as<uint32_t>(), s.list_large.as<uint32_t>(),
-                                                      s.list_nested.as<uint32_t>());
+                                                      s.list_big.as<uint32_t>(), s.list_nested.as<uint32_t>());
   KLAUNCH(ctx);
   return KLSH_OK;
 }
@@ -847,8 +866,7 @@ static int large_smem_config(klsh_ctx* ctx, int ld, int* rep_cap, size_t* smem) 
   return KLSH_OK;
 }
 
-int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, uint32_t n_small,
-                 uint32_t n_large) {
+int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, const PassCounters& c) {
   const int D = ctx->D, ld = ctx->ld;
   float* vals = ctx->cur.vals.as<float>();
   int32_t* cnt = ctx->cur.cnt.as<int32_t>();
@@ -856,6 +874,7 @@ int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float thr
   int32_t* tail = ctx->cur.tail.as<int32_t>();
   int32_t* next = ctx->cur.next.as<int32_t>();
   PassCounters* dc = s.counters.as<PassCounters>();
+  const uint32_t n_small = c.n_small, n_large = c.n_large + c.n_big;
   if (n_small) {
     size_t per_warp = sizeof(float) * (size_t)KLSH_SMALL_MAX * (ld + 1);
     int wpb = 4;
@@ -873,37 +892,54 @@ int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float thr
                                                          threshold);
     KLAUNCH(ctx);
   }
-  if (n_large) {
-    int rep_cap;
-    size_t smem;
-    KTRY(large_smem_config(ctx, ld, &rep_cap, &smem));
-    uint32_t grid = std::min<uint32_t>(n_large, (uint32_t)ctx->sm_count);
-    // norms of representatives that do not fit in shared memory: one slab per block
-    uint64_t spill_stride = 0;
-    {
-      uint32_t bmax = ctx->h_counters->bucket_max;
-      if ((int64_t)bmax > rep_cap) spill_stride = bmax - rep_cap;
-      KTRY(dev_reserve(ctx, ctx->io_b, sizeof(float) * (spill_stride * grid + 1)));
-    }
-    k_merge_large<<<grid, kLargeThreads, smem, ctx->stream>>>(vals, D, ld, cnt, head, tail, next, rows_sorted,
-                                                              s.bstart.as<uint32_t>(), s.list_large.as<uint32_t>(), dc,
-                                                              threshold, rep_cap, ctx->io_b.as<float>(), spill_stride, -1);
-    KLAUNCH(ctx);
-  }
+  if (!n_large) return KLSH_OK;
+  if (!ctx->merge_v1) return launch_merge_window(ctx, s, rows_sorted, threshold, n_large, c.bucket_max);
+  // first-generation kernel (KLSH_MERGE_V1=1): one block per bucket, kept for A/B checks
+  int rep_cap;
+  size_t smem;
+  KTRY(large_smem_config(ctx, ld, &rep_cap, &smem));
+  uint32_t grid = std::min<uint32_t>(n_large, (uint32_t)ctx->sm_count);
+  uint64_t spill_stride = 0;
+  if ((int64_t)c.bucket_max > rep_cap) spill_stride = c.bucket_max - rep_cap;
+  KTRY(dev_reserve(ctx, ctx->io_b, sizeof(float) * (spill_stride * grid + 1)));
+  k_merge_large<<<grid, kLargeThreads, smem, ctx->stream>>>(vals, D, ld, cnt, head, tail, next, rows_sorted,
+                                                            s.bstart.as<uint32_t>(), s.list_large.as<uint32_t>(),
+                                                            s.list_big.as<uint32_t>(), dc, threshold, rep_cap,
+                                                            ctx->io_b.as<float>(), spill_stride, -1);
+  KLAUNCH(ctx);
   return KLSH_OK;
 }
 
+// klsh_p_cluster: rows_sorted[0..n) is ONE bucket
 int launch_merge_one(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, uint64_t n, float threshold) {
   if (n < 2) return KLSH_OK;
+  KTRY(dev_reserve(ctx, s.counters, sizeof(PassCounters)));
+  if (!ctx->merge_v1) {
+    KTRY(dev_reserve(ctx, s.pos_nrm, sizeof(float) * (n + 2)));
+    KTRY(dev_reserve(ctx, s.bstart, sizeof(uint32_t) * 4));
+    KTRY(dev_reserve(ctx, s.list_big, sizeof(uint32_t) * 4));
+    KTRY(dev_reserve(ctx, s.list_large, sizeof(uint32_t) * 4));
+    PassCounters hc;
+    std::memset(&hc, 0, sizeof hc);
+    hc.n_buckets = 1;
+    hc.n_big = 1;
+    hc.bucket_max = (uint32_t)n;
+    const uint32_t bs[2] = {0u, (uint32_t)n};
+    const uint32_t item[3] = {0u, 0u, 0u};
+    KCUDA(ctx, cudaMemcpyAsync(s.counters.p, &hc, sizeof hc, cudaMemcpyHostToDevice, ctx->stream));
+    KCUDA(ctx, cudaMemcpyAsync(s.bstart.p, bs, sizeof bs, cudaMemcpyHostToDevice, ctx->stream));
+    KCUDA(ctx, cudaMemcpyAsync(s.list_big.p, item, sizeof item, cudaMemcpyHostToDevice, ctx->stream));
+    KCUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the sources above are on the stack
+    return launch_merge_window(ctx, s, rows_sorted, threshold, 1, (uint32_t)n);
+  }
   int rep_cap;
   size_t smem;
   KTRY(large_smem_config(ctx, ctx->ld, &rep_cap, &smem));
   uint64_t spill = (n > (uint64_t)rep_cap) ? n - rep_cap : 0;
   KTRY(dev_reserve(ctx, ctx->io_b, sizeof(float) * (spill + 1)));
-  KTRY(dev_reserve(ctx, s.counters, sizeof(PassCounters)));
   k_merge_large<<<1, kLargeThreads, smem, ctx->stream>>>(
       ctx->cur.vals.as<float>(), ctx->D, ctx->ld, ctx->cur.cnt.as<int32_t>(), ctx->cur.head.as<int32_t>(),
-      ctx->cur.tail.as<int32_t>(), ctx->cur.next.as<int32_t>(), rows_sorted, nullptr, nullptr,
+      ctx->cur.tail.as<int32_t>(), ctx->cur.next.as<int32_t>(), rows_sorted, nullptr, nullptr, nullptr,
       s.counters.as<PassCounters>(), threshold, rep_cap, ctx->io_b.as<float>(), spill, (int)n);
   KLAUNCH(ctx);
   return KLSH_OK;

@@ -10,6 +10,7 @@
 
 #define KLSH_SENTINEL 0xFFFFFFFFu
 #define KLSH_SMALL_MAX 32  // buckets of 2..32 rows: one warp each
+#define KLSH_BIG 4096      // buckets at least this large are scheduled first
 
 struct PlaneSource;  // planes.cc
 
@@ -28,20 +29,29 @@ struct PassScratch {
   DevBuf hist;                            // radix histograms
   DevBuf blkcnt;                          // per-block counts for compaction-style kernels
   DevBuf bstart;                          // bucket start offsets (uint32, nb+1)
-  DevBuf list_small, list_large, list_nested;
+  DevBuf list_small, list_nested;   // bucket ids
+  DevBuf list_big, list_large;      // windowed-merge work items {bucket, i, size}: >= KLSH_BIG rows / the rest
+  DevBuf esc1, esc2, esc3;          // buckets handed on: CTA -> cluster -> large cluster -> grid
+  DevBuf pos_nrm;   // norm of the representative at each sorted position (merge scratch)
   DevBuf planes;    // H*ld floats
   DevBuf counters;  // device counters (see PassCounters)
 };
 
 struct PassCounters {  // lives in device memory, mirrored to pinned host memory
   uint32_t n_buckets;
-  uint32_t n_small;
-  uint32_t n_large;
-  uint32_t n_nested;
+  uint32_t n_small;    // 2..KLSH_SMALL_MAX rows: one warp each
+  uint32_t n_large;    // > KLSH_SMALL_MAX rows: windowed merge, starts on one CTA
+  uint32_t n_big;      // ... the ones with >= KLSH_BIG rows (scheduled first)
+  uint32_t n_esc1;     // handed on to a thread-block cluster
+  uint32_t n_esc2;     // handed on to a large (non-portable size) cluster
+  uint32_t n_esc3;     // handed on to the whole cooperative grid
+  uint32_t n_nested;   // above bucket_size_threshold: reference nestedCluster
   uint32_t n_out;
   uint32_t bucket_max;
   uint32_t large_cursor;
-  uint32_t pad;
+  uint32_t cluster_cursor;
+  uint32_t cluster2_cursor;
+  uint32_t pad[3];
 };
 
 struct RowState {  // everything klsh_snapshot copies
@@ -78,6 +88,14 @@ struct klsh_ctx {
   DevBuf io_a, io_b;  // staging for loads/exports
   DevBuf alive_alt;   // the other half of the alive-list ping-pong
   DevBuf nested_out;  // survivors of one nested pass
+  DevBuf team_ctl;    // per-team control blocks of the windowed merge
+  // escalation of the windowed merge: a bucket leaves its CTA for a cluster once it has more than
+  // cta_max representatives, and the cluster for the whole grid above cluster_max
+  uint32_t cta_max = 512, cluster_max = 8192, cluster2_max = 65536;
+  int cluster_size = 8, cluster2_size = 16;
+  bool debug = false;     // KLSH_DEBUG=1
+  DevBuf dbg;
+  bool merge_v1 = false;  // KLSH_MERGE_V1=1: first-generation block-per-bucket kernel (A/B checks)
   PassCounters* h_counters = nullptr;  // pinned
 
   PlaneSource* planes = nullptr;
@@ -122,8 +140,9 @@ int launch_sign(klsh_ctx* ctx, const float* vals, int D, int ld, const uint32_t*
 int launch_sort_pairs(klsh_ctx* ctx, PassScratch& s, uint64_t n, int bits, uint32_t** keys_sorted,
                       uint32_t** rows_sorted);
 int launch_bounds(klsh_ctx* ctx, PassScratch& s, const uint32_t* keys_sorted, uint64_t n, int64_t nest_threshold);
-int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, uint32_t n_small,
-                 uint32_t n_large);
+int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, const PassCounters& c);
+int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, uint32_t n_items_host,
+                        uint32_t bucket_max_host);
 int launch_merge_one(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, uint64_t n, float threshold);
 int launch_compact(klsh_ctx* ctx, PassScratch& s, const uint32_t* rows_sorted, uint64_t n, uint32_t* out);
 int launch_iota(klsh_ctx* ctx, uint32_t* out, uint64_t n, uint32_t base);

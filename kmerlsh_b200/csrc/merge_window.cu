@@ -1,0 +1,918 @@
+// Windowed greedy merge for buckets of more than KLSH_SMALL_MAX rows.
+//
+// Reference semantics (p_cluster, function/cluster.cc:56-87): candidates are examined one at a
+// time; the candidate at position i is compared with the representatives at positions 0..i-1 in
+// order and merged into the FIRST one whose cosine similarity reaches the threshold (the merged
+// representative becomes the count-weighted consensus, AB::SetConsensus funcAB.cc:49-71; the tail
+// position is swapped into i and examined next); otherwise it becomes representative i.
+//
+// The work is candidates x representatives x D, strictly sequential in the reference.  Here a
+// TEAM processes a WINDOW of up to 64 upcoming candidates at once:
+//   parallel phase : every thread owns representatives (row held in registers) and compares them
+//                    with all window candidates (shared-memory tile, broadcast reads), recording
+//                    per candidate the first matching representative as of the window start
+//                    (atomicMin), plus the candidate x candidate match bits;
+//   resolver       : one warp replays the reference's sequential order over the window using
+//                    those results; representatives modified inside the window live in a small
+//                    "dirty" cache and are re-compared exactly with their current values; when a
+//                    decision cannot be proven from what was precomputed the window is truncated
+//                    and the candidate is re-examined in the next window.
+// Teams escalate with the amount of compare work: every bucket starts on ONE CTA; when its
+// representative count passes max_reps the bucket's state (it lives entirely in global memory) is
+// handed to a thread-block CLUSTER, and from there to the whole cooperative GRID.  Merge-heavy
+// buckets (few representatives, long dependent chains) therefore stay on one SM each and run side
+// by side, while compare-heavy buckets get more SMs as their representative set grows.
+// Every decision and every centroid is bit-identical to the sequential algorithm (DESIGN.md
+// "Windowed merge: why it is exact").
+#include <cooperative_groups.h>
+
+#include <chrono>
+#include <cstdio>
+
+#include "klsh_internal.cuh"
+
+namespace cg = cooperative_groups;
+
+namespace {
+
+constexpr int kW = 64;    // window capacity
+constexpr int kKD = 32;   // dirty-cache entries
+constexpr int kMT = 256;  // threads per CTA
+constexpr int kWbMax = 62;
+constexpr uint32_t kInf = 0x7fffffffu;
+
+__device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
+
+// ---- exact arithmetic ---------------------------------------------------------------------------------
+// Rows are padded with zeros to a multiple of 4 floats; the padded products are +0 and x + (+0) == x
+// (a running sum that starts at +0 is never -0), so walking quads gives the reference's D-term sums.
+__device__ __forceinline__ float dot_seq(const float4* a, const float4* b, int nq) {
+  float s = 0.f;
+#pragma unroll 4
+  for (int q = 0; q < nq; ++q) {
+    const float4 x = a[q], y = b[q];
+    s = __fadd_rn(s, __fmul_rn(x.x, y.x));
+    s = __fadd_rn(s, __fmul_rn(x.y, y.y));
+    s = __fadd_rn(s, __fmul_rn(x.z, y.z));
+    s = __fadd_rn(s, __fmul_rn(x.w, y.w));
+  }
+  return s;
+}
+__device__ __forceinline__ float norm_seq(const float4* a, int nq) {  // sqrt(sum v_i^2), Distance::cosine's magnitudes
+  float s = 0.f;
+#pragma unroll 4
+  for (int q = 0; q < nq; ++q) {
+    const float4 x = a[q];
+    s = __fadd_rn(s, __fmul_rn(x.x, x.x));
+    s = __fadd_rn(s, __fmul_rn(x.y, x.y));
+    s = __fadd_rn(s, __fmul_rn(x.z, x.z));
+    s = __fadd_rn(s, __fmul_rn(x.w, x.w));
+  }
+  return __fsqrt_rn(s);
+}
+__device__ __forceinline__ bool cos_match(float dot, float nl, float nr, float threshold) {
+  float sim = __fdiv_rn(dot, __fmul_rn(nl, nr));
+  float dist = __fsub_rn(1.f, sim);
+  return __fsub_rn(1.f, dist) >= threshold;
+}
+// cheap conservative reject: a match implies dot >= den*(thr - 2^-21) when den > 0;
+// thr_lo = thr - 2e-6 leaves room for the rounding of den*thr_lo.  NaN/0/inf fall through to the
+// exact test or are rejected correctly.
+__device__ __forceinline__ bool pair_match(float dot, float nl, float nr, float threshold, float thr_lo) {
+  if (dot < __fmul_rn(__fmul_rn(nl, nr), thr_lo)) return false;
+  return cos_match(dot, nl, nr, threshold);
+}
+__device__ __forceinline__ float consensus1(float cur, int c1, float cand, int c2) {
+  const float fa = __int2float_rn(c1 + c2);
+  float a = __fdiv_rn(__fmul_rn(cur, __int2float_rn(c1)), fa);
+  float b = __fdiv_rn(__fmul_rn(cand, __int2float_rn(c2)), fa);
+  return __fadd_rn(a, b);
+}
+
+// ---- teams -----------------------------------------------------------------------------------------
+template <int TEAM>
+struct Team;
+template <>
+struct Team<0> {  // one CTA
+  static __device__ __forceinline__ void sync() { __syncthreads(); }
+  static __device__ __forceinline__ uint32_t rank() { return 0; }
+  static __device__ __forceinline__ uint32_t ncta() { return 1; }
+  static __device__ __forceinline__ uint32_t id() { return blockIdx.x; }
+};
+template <>
+struct Team<1> {  // one thread-block cluster
+  static __device__ __forceinline__ void sync() { cg::this_cluster().sync(); }
+  static __device__ __forceinline__ uint32_t rank() { return cg::this_cluster().block_rank(); }
+  static __device__ __forceinline__ uint32_t ncta() { return cg::this_cluster().num_blocks(); }
+  static __device__ __forceinline__ uint32_t id() { return blockIdx.x / cg::this_cluster().num_blocks(); }
+};
+template <>
+struct Team<2> {  // the whole cooperative grid
+  static __device__ __forceinline__ void sync() { cg::this_grid().sync(); }
+  static __device__ __forceinline__ uint32_t rank() { return blockIdx.x; }
+  static __device__ __forceinline__ uint32_t ncta() { return gridDim.x; }
+  static __device__ __forceinline__ uint32_t id() { return 0; }
+};
+
+struct TeamCtl {  // global memory, one per team
+  uint32_t f[kW];  // per window candidate: first matching old representative (position), kInf if none
+  uint32_t i, size, wb, work;
+  uint32_t pad[4];
+};
+
+struct MergeArgs {
+  float* vals;
+  int D, ld;
+  int32_t *cnt, *head, *tail, *next;
+  uint32_t* rows_sorted;
+  const uint32_t* bstart;
+  // work items are triples {bucket, i, size}; i == 0 means "not started".  Two lists, walked in order.
+  const uint32_t* list_a;
+  const uint32_t* n_a;
+  const uint32_t* list_b;
+  const uint32_t* n_b;
+  uint32_t* cursor;
+  // buckets whose representative count passes max_reps are appended here for the next, larger team
+  uint32_t* esc_list;
+  uint32_t* esc_count;
+  uint32_t max_reps;
+  float* pos_nrm;  // norm of the representative at each sorted position (scratch, N floats)
+  TeamCtl* ctl;
+  unsigned long long* dbg;  // [16] (8..13: leader cycles in stage/parallel/sync1/prefetch/resolve/sync2) windows, candidates, merges, undecidable, cache_full, back_exhausted, accepted, escalated
+  float threshold, thr_lo;
+};
+
+struct Smem {
+  float* tile;   // [kW][ts]
+  float* dvals;  // [kKD][ts]
+  float* pre;    // [kW][ts]  row of each candidate's first-match representative, prefetched for the resolver
+  float* cnorm;  // [kW]
+  float* dnorm;  // [kKD]
+  uint32_t* ridx;   // [kW]
+  int32_t* ccnt;    // [kW]
+  int32_t* chead;   // [kW]
+  int32_t* ctail;   // [kW]
+  uint32_t* s_f;    // [kW]
+  uint32_t* pair;   // [kW][2]
+  uint32_t* acc;    // [kW]
+  uint32_t* dpos;   // [kKD]
+  int32_t* dcnt;    // [kKD]
+  int32_t* dhead;   // [kKD]
+  int32_t* dtail;   // [kKD]
+  uint32_t* dridx;  // [kKD]
+  uint32_t* pridx;  // [kW]
+  int32_t* pcnt;    // [kW]
+  int32_t* phead;   // [kW]
+  int32_t* ptail;   // [kW]
+  int32_t* mprev;   // [kW] merge log: previous candidate merged into the same entry (-1: none)
+  int32_t* ment;    // [kW] merge log: dirty entry the candidate was merged into (-1: not merged)
+  int ts;
+};
+
+__host__ __device__ inline size_t smem_bytes_for(int ld) {
+  return sizeof(float) * ((size_t)(2 * kW + kKD) * (ld + 4) + kW + kKD) + sizeof(uint32_t) * (kW * 14 + kKD * 5) + 64;
+}
+
+__device__ __forceinline__ void carve(Smem& s, float* base, int ld) {
+  s.ts = ld + 4;
+  s.tile = base;
+  s.dvals = s.tile + (size_t)kW * s.ts;
+  s.pre = s.dvals + (size_t)kKD * s.ts;
+  s.cnorm = s.pre + (size_t)kW * s.ts;
+  s.dnorm = s.cnorm + kW;
+  uint32_t* u = reinterpret_cast<uint32_t*>(s.dnorm + kKD);
+  s.ridx = u; u += kW;
+  s.ccnt = reinterpret_cast<int32_t*>(u); u += kW;
+  s.chead = reinterpret_cast<int32_t*>(u); u += kW;
+  s.ctail = reinterpret_cast<int32_t*>(u); u += kW;
+  s.s_f = u; u += kW;
+  s.pair = u; u += 2 * kW;
+  s.acc = u; u += kW;
+  s.dpos = u; u += kKD;
+  s.dcnt = reinterpret_cast<int32_t*>(u); u += kKD;
+  s.dhead = reinterpret_cast<int32_t*>(u); u += kKD;
+  s.dtail = reinterpret_cast<int32_t*>(u); u += kKD;
+  s.dridx = u; u += kKD;
+  s.pridx = u; u += kW;
+  s.pcnt = reinterpret_cast<int32_t*>(u); u += kW;
+  s.phead = reinterpret_cast<int32_t*>(u); u += kW;
+  s.ptail = reinterpret_cast<int32_t*>(u); u += kW;
+  s.mprev = reinterpret_cast<int32_t*>(u); u += kW;
+  s.ment = reinterpret_cast<int32_t*>(u);
+}
+
+// Compare one representative (row at rowp, norm rn) with window candidates [tb, te); call hit(t) on
+// a match.  DR > 0: the row is held in registers (ld <= DR); DR == 0: read through the pointer.
+// SM: rowp points to shared memory, else to global memory (read through L2: another CTA may have
+// rewritten the row in the previous window).
+// Candidates whose recorded first match (this CTA's view, s_f) already lies before position j cannot
+// be improved by representative j and are skipped in groups of four.
+template <int DR, bool SM, typename Hit>
+__device__ __forceinline__ void compare_rep(const float* rowp, float rn, const Smem& s, int tb, int te, int nq,
+                                            float threshold, float thr_lo, int skip_t, uint32_t j, Hit hit) {
+  float r[DR > 0 ? DR : 4];
+  if (DR > 0) {
+#pragma unroll
+    for (int q = 0; q < DR / 4; ++q)
+      if (q < nq) {
+        const float4 v = SM ? reinterpret_cast<const float4*>(rowp)[q] : __ldcg(reinterpret_cast<const float4*>(rowp) + q);
+        r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
+      }
+  }
+  const float4* t4 = reinterpret_cast<const float4*>(s.tile);
+  const int ts4 = s.ts >> 2;
+  for (int t0 = tb; t0 < te; t0 += 4) {  // rows t0..t0+3 always lie inside the kW-row tile
+    if (!SM) {
+      const uint4 f4 = *reinterpret_cast<const uint4*>(s.s_f + t0);
+      if (f4.x < j && f4.y < j && f4.z < j && f4.w < j) continue;
+    }
+    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+    const float4* a0 = t4 + (size_t)(t0 + 0) * ts4;
+    const float4* a1 = t4 + (size_t)(t0 + 1) * ts4;
+    const float4* a2 = t4 + (size_t)(t0 + 2) * ts4;
+    const float4* a3 = t4 + (size_t)(t0 + 3) * ts4;
+    if (DR > 0) {
+#pragma unroll
+      for (int q = 0; q < DR / 4; ++q)
+        if (q < nq) {
+          const float4 x0 = a0[q], x1 = a1[q], x2 = a2[q], x3 = a3[q];
+          const float r0 = r[4 * q], r1 = r[4 * q + 1], r2 = r[4 * q + 2], r3 = r[4 * q + 3];
+          d0 = __fadd_rn(d0, __fmul_rn(x0.x, r0)); d1 = __fadd_rn(d1, __fmul_rn(x1.x, r0));
+          d2 = __fadd_rn(d2, __fmul_rn(x2.x, r0)); d3 = __fadd_rn(d3, __fmul_rn(x3.x, r0));
+          d0 = __fadd_rn(d0, __fmul_rn(x0.y, r1)); d1 = __fadd_rn(d1, __fmul_rn(x1.y, r1));
+          d2 = __fadd_rn(d2, __fmul_rn(x2.y, r1)); d3 = __fadd_rn(d3, __fmul_rn(x3.y, r1));
+          d0 = __fadd_rn(d0, __fmul_rn(x0.z, r2)); d1 = __fadd_rn(d1, __fmul_rn(x1.z, r2));
+          d2 = __fadd_rn(d2, __fmul_rn(x2.z, r2)); d3 = __fadd_rn(d3, __fmul_rn(x3.z, r2));
+          d0 = __fadd_rn(d0, __fmul_rn(x0.w, r3)); d1 = __fadd_rn(d1, __fmul_rn(x1.w, r3));
+          d2 = __fadd_rn(d2, __fmul_rn(x2.w, r3)); d3 = __fadd_rn(d3, __fmul_rn(x3.w, r3));
+        }
+    } else {
+      for (int q = 0; q < nq; ++q) {
+        const float4 rv = SM ? reinterpret_cast<const float4*>(rowp)[q] : __ldcg(reinterpret_cast<const float4*>(rowp) + q);
+        const float4 x0 = a0[q], x1 = a1[q], x2 = a2[q], x3 = a3[q];
+        d0 = __fadd_rn(d0, __fmul_rn(x0.x, rv.x)); d1 = __fadd_rn(d1, __fmul_rn(x1.x, rv.x));
+        d2 = __fadd_rn(d2, __fmul_rn(x2.x, rv.x)); d3 = __fadd_rn(d3, __fmul_rn(x3.x, rv.x));
+        d0 = __fadd_rn(d0, __fmul_rn(x0.y, rv.y)); d1 = __fadd_rn(d1, __fmul_rn(x1.y, rv.y));
+        d2 = __fadd_rn(d2, __fmul_rn(x2.y, rv.y)); d3 = __fadd_rn(d3, __fmul_rn(x3.y, rv.y));
+        d0 = __fadd_rn(d0, __fmul_rn(x0.z, rv.z)); d1 = __fadd_rn(d1, __fmul_rn(x1.z, rv.z));
+        d2 = __fadd_rn(d2, __fmul_rn(x2.z, rv.z)); d3 = __fadd_rn(d3, __fmul_rn(x3.z, rv.z));
+        d0 = __fadd_rn(d0, __fmul_rn(x0.w, rv.w)); d1 = __fadd_rn(d1, __fmul_rn(x1.w, rv.w));
+        d2 = __fadd_rn(d2, __fmul_rn(x2.w, rv.w)); d3 = __fadd_rn(d3, __fmul_rn(x3.w, rv.w));
+      }
+    }
+    if (t0 + 0 < te && t0 + 0 != skip_t && pair_match(d0, s.cnorm[t0 + 0], rn, threshold, thr_lo)) hit(t0 + 0);
+    if (t0 + 1 < te && t0 + 1 != skip_t && pair_match(d1, s.cnorm[t0 + 1], rn, threshold, thr_lo)) hit(t0 + 1);
+    if (t0 + 2 < te && t0 + 2 != skip_t && pair_match(d2, s.cnorm[t0 + 2], rn, threshold, thr_lo)) hit(t0 + 2);
+    if (t0 + 3 < te && t0 + 3 != skip_t && pair_match(d3, s.cnorm[t0 + 3], rn, threshold, thr_lo)) hit(t0 + 3);
+  }
+}
+
+// ---- the resolver: warp 0 of the team's leader CTA ---------------------------------------------------
+// Lane e owns dirty-cache entry e: its position, member count and a 64-bit mask of the window
+// candidates that match the entry's CURRENT value (recomputed, for all unexamined candidates at once,
+// whenever the entry changes; the new norm comes out of the same pass).  Examining a candidate is
+// then a handful of bit tests; the floating-point work happens once per merge.  Member-chain
+// splices and the swap-remove writes are independent of the decisions, so they are logged and
+// applied in parallel when the window ends.
+template <int TEAM>
+__device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm, TeamCtl* ctl, Smem& s, int W, int wf,
+                               int wb, bool tail_mode, uint32_t i0, uint32_t size0) {
+  const int D = A.D, ld = A.ld, nq = ld >> 2;
+  const uint32_t lane = lane_id();
+  int nd = 0, a = 0, fi = 0, bi = 0, merges = 0;
+  uint32_t i = i0, size = size0;
+  bool from_back = false, back_exhausted = false;
+  int dbg_undec = 0, dbg_full = 0;
+  uint32_t accd_lo = 0, accd_hi = 0;  // accepted-in-window candidates that have since been modified
+  uint32_t accm_lo = 0, accm_hi = 0;  // accepted-in-window candidates (tile indices)
+  uint32_t my_dpos = kInf, my_dm_lo = 0, my_dm_hi = 0;  // this lane's dirty entry
+  int my_dcnt = 0, my_last = -1;                        // its member count; last candidate merged into it
+  // The entry modified by the latest merge keeps an INVALID mask: runs of candidates merging into the
+  // same representative (the common shape of a merge-heavy bucket) then cost one exact comparison
+  // each instead of a whole-window mask rebuild.  The mask is rebuilt when another entry is modified
+  // or a candidate is accepted.
+  int pend = -1;
+  // which unexamined candidates match entry e's current value; its norm falls out of the same pass
+  auto validate = [&](int e) {
+    const float4* r4 = reinterpret_cast<const float4*>(s.dvals + (size_t)e * s.ts);
+    const int nfront = tail_mode ? max(0, wf - fi - bi) : (wf - fi);
+    const int nback = tail_mode ? 0 : (wb - bi);
+    const int nun = nfront + nback;
+    uint32_t w0 = 0, w1 = 0;
+    float rn = 0.f;
+    for (int base = 0; base < max(nun, 1); base += 32) {
+      const int k = base + (int)lane;
+      const bool act = k < nun;
+      const int tc = act ? (k < nfront ? fi + k : wf + bi + (k - nfront)) : 0;
+      const float4* c4 = reinterpret_cast<const float4*>(s.tile + (size_t)tc * s.ts);
+      float dot = 0.f, nn = 0.f;
+#pragma unroll 4
+      for (int q = 0; q < nq; ++q) {
+        const float4 x = c4[q], y = r4[q];
+        dot = __fadd_rn(dot, __fmul_rn(x.x, y.x)); nn = __fadd_rn(nn, __fmul_rn(y.x, y.x));
+        dot = __fadd_rn(dot, __fmul_rn(x.y, y.y)); nn = __fadd_rn(nn, __fmul_rn(y.y, y.y));
+        dot = __fadd_rn(dot, __fmul_rn(x.z, y.z)); nn = __fadd_rn(nn, __fmul_rn(y.z, y.z));
+        dot = __fadd_rn(dot, __fmul_rn(x.w, y.w)); nn = __fadd_rn(nn, __fmul_rn(y.w, y.w));
+      }
+      rn = __fsqrt_rn(nn);
+      const bool mt = act && cos_match(dot, s.cnorm[tc], rn, A.threshold);
+      const uint32_t blo = (mt && tc < 32) ? (1u << tc) : 0u, bhi = (mt && tc >= 32) ? (1u << (tc - 32)) : 0u;
+      w0 |= __reduce_or_sync(0xffffffffu, blo);
+      w1 |= __reduce_or_sync(0xffffffffu, bhi);
+    }
+    if ((int)lane == e) {
+      my_dm_lo = w0;
+      my_dm_hi = w1;
+    }
+    if (lane == 0) s.dnorm[e] = rn;
+  };
+  // s.pair is dead once a candidate has been examined; reuse the per-candidate slots s.acc/... no:
+  // the merge log lives in s.pridx (prefetch row index, dead after the entry was allocated) as
+  // "previous candidate merged into the same entry" (kInf: none) and s.pcnt as the entry index.
+  while (i < size) {
+    int t;
+    if (from_back) {
+      if (!tail_mode && bi >= wb) { back_exhausted = true; break; }
+      t = tail_mode ? (wf - 1 - bi) : (wf + bi);
+      ++bi;
+    } else {
+      if (!tail_mode && fi >= wf) break;
+      t = fi;
+      ++fi;
+    }
+    const uint32_t fpos = s.s_f[t];
+    const uint32_t plo = s.pair[2 * t], phi = s.pair[2 * t + 1];
+    const uint32_t tbit_lo = (t < 32) ? (1u << t) : 0u, tbit_hi = (t < 32) ? 0u : (1u << (t - 32));
+    uint32_t best = kInf;
+    if (nd > 0) {
+      // (a) representatives modified in this window: match bits against their current values; the
+      // entry with an invalid mask is compared exactly (every lane computes the same comparison)
+      bool hit = ((my_dm_lo & tbit_lo) | (my_dm_hi & tbit_hi)) != 0u;
+      if (pend >= 0) {
+        const float4* r4 = reinterpret_cast<const float4*>(s.dvals + (size_t)pend * s.ts);
+        const float4* c4 = reinterpret_cast<const float4*>(s.tile + (size_t)t * s.ts);
+        float dot = 0.f, nn = 0.f;
+#pragma unroll 4
+        for (int q = 0; q < nq; ++q) {
+          const float4 x = c4[q], y = r4[q];
+          dot = __fadd_rn(dot, __fmul_rn(x.x, y.x)); nn = __fadd_rn(nn, __fmul_rn(y.x, y.x));
+          dot = __fadd_rn(dot, __fmul_rn(x.y, y.y)); nn = __fadd_rn(nn, __fmul_rn(y.y, y.y));
+          dot = __fadd_rn(dot, __fmul_rn(x.z, y.z)); nn = __fadd_rn(nn, __fmul_rn(y.z, y.z));
+          dot = __fadd_rn(dot, __fmul_rn(x.w, y.w)); nn = __fadd_rn(nn, __fmul_rn(y.w, y.w));
+        }
+        const bool mt = cos_match(dot, s.cnorm[t], __fsqrt_rn(nn), A.threshold);
+        if ((int)lane == pend) hit = mt;
+      }
+      best = __reduce_min_sync(0xffffffffu, hit ? my_dpos : kInf);
+    }
+    // (b) first matching old representative as of the window start
+    if (fpos != kInf) {
+      const bool is_dirty = nd > 0 && __any_sync(0xffffffffu, my_dpos == fpos);
+      if (!is_dirty) {
+        best = min(best, fpos);
+      } else if (best > fpos) {
+        // fpos changed since the window start and no modified representative at or before it
+        // matches: a clean match between fpos and `best` cannot be ruled out -> next window
+        if (from_back) --bi; else --fi;
+        dbg_undec = 1;
+        break;
+      }
+    }
+    // (c) representatives accepted in this window and not modified since: precomputed pair bits
+    if (best >= i0 && (((plo & accm_lo & ~accd_lo) | (phi & accm_hi & ~accd_hi)) != 0u)) {
+      __syncwarp();  // s.acc[] is written by lane 0
+      for (int k0 = 0; k0 < a; k0 += 32) {
+        const int k = k0 + (int)lane;
+        bool ok = false;
+        if (k < a) {
+          const uint32_t u = s.acc[k];
+          const bool bit = (u < 32) ? ((plo >> u) & 1u) : ((phi >> (u - 32)) & 1u);
+          const bool dirty = (u < 32) ? ((accd_lo >> u) & 1u) : ((accd_hi >> (u - 32)) & 1u);
+          ok = bit && !dirty;
+        }
+        const uint32_t m = __ballot_sync(0xffffffffu, ok);
+        if (m) {
+          best = min(best, i0 + (uint32_t)k0 + (uint32_t)(__ffs(m) - 1));
+          break;
+        }
+      }
+    }
+    if (best == kInf) {
+      // no merge: the candidate becomes representative i (its norm is published with the flush)
+      if (pend >= 0) {
+        validate(pend);
+        pend = -1;
+      }
+      if (lane == 0) s.acc[a] = (uint32_t)t;
+      accm_lo |= tbit_lo;
+      accm_hi |= tbit_hi;
+      ++a;
+      ++i;
+      from_back = false;
+      continue;
+    }
+    // merge the candidate into the representative at position `best`
+    const uint32_t p = best;
+    int e;
+    {
+      const uint32_t m = __ballot_sync(0xffffffffu, my_dpos == p);
+      if (m) {
+        e = __ffs(m) - 1;
+      } else {
+        e = nd++;
+        float* dst = s.dvals + (size_t)e * s.ts;
+        int cnt_e;
+        if (p < i0) {
+          // an old representative enters the cache only as this candidate's precomputed first match
+          // (any other old position in `best` is already dirty), so its row was prefetched
+          const float* src = s.pre + (size_t)t * s.ts;
+          for (int d = lane; d < ld; d += 32) dst[d] = src[d];
+          cnt_e = s.pcnt[t];
+          if (lane == 0) {
+            s.dridx[e] = s.pridx[t];
+            s.dhead[e] = s.phead[t];
+            s.dtail[e] = s.ptail[t];
+          }
+        } else {
+          __syncwarp();
+          const uint32_t u = s.acc[p - i0];
+          const float* src = s.tile + (size_t)u * s.ts;
+          for (int d = lane; d < ld; d += 32) dst[d] = src[d];
+          cnt_e = s.ccnt[u];
+          if (lane == 0) {
+            s.dridx[e] = s.ridx[u];
+            s.dhead[e] = s.chead[u];
+            s.dtail[e] = s.ctail[u];
+          }
+          if (u < 32) accd_lo |= 1u << u; else accd_hi |= 1u << (u - 32);
+        }
+        if (lane == 0) s.dpos[e] = p;
+        if ((int)lane == e) {
+          my_dpos = p;
+          my_dcnt = cnt_e;
+          my_last = -1;
+        }
+        __syncwarp();
+      }
+    }
+    const int c1 = s.ccnt[t];
+    const int c2 = __shfl_sync(0xffffffffu, my_dcnt, e);
+    {
+      const float* c = s.tile + (size_t)t * s.ts;
+      float* r = s.dvals + (size_t)e * s.ts;
+      for (int d = lane; d < D; d += 32) r[d] = consensus1(c[d], c1, r[d], c2);
+    }
+    // merge log: which candidate was merged into this entry just before t (applied at window end)
+    {
+      const int prev = __shfl_sync(0xffffffffu, my_last, e);
+      if (lane == 0) {
+        s.mprev[t] = prev;
+        s.ment[t] = e;
+      }
+      if ((int)lane == e) {
+        my_dcnt = c1 + c2;
+        if (s.ctail[t] >= 0) my_last = t;  // only candidates that carry ids take part in the chain
+      }
+    }
+    --size;
+    ++merges;
+    from_back = true;
+    __syncwarp();
+    if (pend >= 0 && pend != e) validate(pend);
+    pend = e;
+    if (nd == kKD) { dbg_full = 1; break; }  // dirty cache full: flush and start a new window
+  }
+  __syncwarp();
+  if (pend >= 0) validate(pend);  // publishes the entry's norm
+  __syncwarp();
+  // ---- apply the window's effects to global memory, in parallel ----
+  // accepted candidates: positions i0.. in acceptance order (row index + norm)
+  for (int k = lane; k < a; k += 32) {
+    const uint32_t u = s.acc[k];
+    seg[i0 + k] = s.ridx[u];
+    pos_nrm[i0 + k] = s.cnorm[u];
+  }
+  // a moved tail element waiting at position i (the window ended right after a merge)
+  if (from_back && i < size && lane == 0) {
+    uint32_t moved;
+    if (tail_mode) moved = s.ridx[wf - 1 - bi];
+    else if (bi < wb) moved = s.ridx[wf + bi];
+    else moved = __ldcg(seg + size);  // the element that was at the old tail position
+    seg[i] = moved;
+  }
+  __syncwarp();
+  for (uint32_t k = size + lane; k < size0; k += 32) seg[k] = KLSH_SENTINEL;
+  // member chains: ids(current) ++ ids(candidate) for every logged merge
+  for (int round = 0; round < 2; ++round) {
+    const int t = round * 32 + (int)lane;
+    if (t < W) {
+      const bool examined_merge = s.ment[t] >= 0;
+      if (examined_merge) {
+        const int e = s.ment[t], prev = s.mprev[t];
+        const int t1 = s.ctail[t];
+        if (t1 >= 0) A.next[t1] = (prev < 0) ? s.dhead[e] : s.chead[prev];
+      }
+    }
+  }
+  __syncwarp();
+  // modified representatives: values, count, head, tail, norm
+  {
+    const int e = (int)lane;
+    if (e < nd) {
+      const uint32_t rr = s.dridx[e];
+      A.cnt[rr] = my_dcnt;
+      // each merge prepends the candidate's members: the chain now starts with the LAST merged
+      // candidate that carried ids
+      if (my_last >= 0) A.head[rr] = s.chead[my_last];
+      if (s.dtail[e] < 0 && my_last >= 0) {  // the representative had no ids: its tail is the EARLIEST such candidate's
+        int first_t = my_last;
+        for (int tt = s.mprev[my_last]; tt >= 0; tt = s.mprev[tt]) first_t = tt;
+        A.tail[rr] = s.ctail[first_t];
+      }
+      pos_nrm[my_dpos] = s.dnorm[e];
+    }
+  }
+  for (int e = 0; e < nd; ++e) {
+    float* dst = A.vals + (uint64_t)s.dridx[e] * ld;
+    const float* src = s.dvals + (size_t)e * s.ts;
+    for (int d = lane; d < D; d += 32) dst[d] = src[d];
+  }
+  if (lane == 0) {
+    ctl->i = i;
+    ctl->size = size;
+    ctl->wb = back_exhausted ? (uint32_t)min(kWbMax, wb * 2) : (uint32_t)min(kWbMax, max(2, merges + merges / 2 + 2));
+    if (A.dbg) {
+      atomicAdd(A.dbg + 0, 1ull);
+      atomicAdd(A.dbg + 1, (unsigned long long)(fi + bi));
+      atomicAdd(A.dbg + 2, (unsigned long long)merges);
+      atomicAdd(A.dbg + 3, (unsigned long long)dbg_undec);
+      atomicAdd(A.dbg + 4, (unsigned long long)dbg_full);
+      atomicAdd(A.dbg + 5, (unsigned long long)(back_exhausted ? 1 : 0));
+      atomicAdd(A.dbg + 6, (unsigned long long)a);
+    }
+  }
+  __syncwarp();
+}
+
+// ---- one bucket, one team.  Returns true if the bucket was handed on to the next team. -----------------
+template <int TEAM, int DR>
+__device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i, uint32_t start_size, TeamCtl* ctl, Smem& s) {
+  const int ld = A.ld, nq = ld >> 2;
+  const int tid = threadIdx.x;
+  const uint32_t lane = lane_id(), warp = tid >> 5;
+  const bool leader = Team<TEAM>::rank() == 0;
+  const uint32_t st = A.bstart[bucket];
+  uint32_t* seg = A.rows_sorted + st;
+  float* pos_nrm = A.pos_nrm + st;
+  // every CTA must have left the previous bucket's loop before the control block is reused
+  if (TEAM == 2) Team<TEAM>::sync();
+  if (leader && warp == 0) {
+    if (start_i == 0) {  // fresh bucket: representative 0 is the first row
+      const uint32_t r0 = seg[0];
+      const float* src = A.vals + (uint64_t)r0 * ld;
+      for (int d = lane; d < ld; d += 32) s.dvals[d] = src[d];
+      __syncwarp();
+      if (lane == 0) {
+        pos_nrm[0] = norm_seq(reinterpret_cast<const float4*>(s.dvals), nq);
+        ctl->i = 1;
+        ctl->size = A.bstart[bucket + 1] - st;
+        ctl->wb = 4;
+      }
+    } else if (lane == 0) {
+      ctl->i = start_i;
+      ctl->size = start_size;
+      ctl->wb = 4;
+    }
+    if (TEAM != 0)
+      for (int t = lane; t < kW; t += 32) ctl->f[t] = kInf;
+  }
+  __threadfence();
+  Team<TEAM>::sync();
+  for (;;) {
+    const uint32_t i0 = __ldcg(&ctl->i), size0 = __ldcg(&ctl->size);
+    if (i0 >= size0) return false;
+    const uint32_t remaining = size0 - i0;
+    if (i0 > A.max_reps && A.esc_list) {  // more compare work than this team should carry: hand on
+      if (leader && tid == 0) {
+        const uint32_t k = atomicAdd(A.esc_count, 1u);
+        A.esc_list[3 * k] = bucket;
+        A.esc_list[3 * k + 1] = i0;
+        A.esc_list[3 * k + 2] = size0;
+        if (A.dbg) atomicAdd(A.dbg + 7, 1ull);
+      }
+      return true;
+    }
+    bool tail_mode;
+    int wf, wb;
+    if (remaining <= (uint32_t)kW) {
+      tail_mode = true;
+      wf = (int)remaining;
+      wb = 0;
+    } else {
+      tail_mode = false;
+      wb = (int)min(__ldcg(&ctl->wb), (uint32_t)kWbMax);
+      wf = kW - wb;
+    }
+    const int W = wf + wb;
+    long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tk5 = 0;
+    const bool prof = A.dbg && leader && tid == 0;
+    if (prof) tk0 = clock64();
+    // ---- stage the window: rows, metadata, norms ----
+    if (tid < W) {
+      const int t = tid;
+      const uint32_t pos = (t < wf) ? (i0 + t) : (size0 - 1 - (uint32_t)(t - wf));
+      const uint32_t r = __ldcg(seg + pos);
+      s.ridx[t] = r;
+      if (leader) {
+        s.ccnt[t] = A.cnt[r];
+        s.chead[t] = A.head[r];
+        s.ctail[t] = A.tail[r];
+      }
+    }
+    __syncthreads();
+    for (int v = tid; v < W * nq; v += kMT) {
+      const int t = v / nq, q = v - t * nq;
+      reinterpret_cast<float4*>(s.tile + (size_t)t * s.ts)[q] =
+          __ldcg(reinterpret_cast<const float4*>(A.vals + (uint64_t)s.ridx[t] * ld) + q);
+    }
+    if (tid < kW) {
+      s.s_f[tid] = kInf;
+      s.pair[2 * tid] = 0u;
+      s.pair[2 * tid + 1] = 0u;
+      s.ment[tid] = -1;
+      s.mprev[tid] = -1;
+    }
+    __syncthreads();
+    if (tid < W) s.cnorm[tid] = norm_seq(reinterpret_cast<const float4*>(s.tile + (size_t)tid * s.ts), nq);
+    __syncthreads();
+    if (prof) tk1 = clock64();
+    // ---- parallel phase: old representatives [0, i0) across the team ----
+    {
+      const uint32_t gstride = Team<TEAM>::ncta() * kMT;
+      for (uint32_t j = Team<TEAM>::rank() * kMT + tid; j < i0; j += gstride) {
+        const uint32_t rr = __ldcg(seg + j);
+        const float rn = __ldcg(pos_nrm + j);
+        compare_rep<DR, false>(A.vals + (uint64_t)rr * ld, rn, s, 0, W, nq, A.threshold, A.thr_lo, -1, j,
+                               [&](int t) { atomicMin(&s.s_f[t], j); });
+      }
+      if (leader) {  // candidate x candidate match bits: 4 threads per candidate row, 16 columns each
+        const int u = tid & (kW - 1), part = tid >> 6;
+        const int tb = part * (kW / 4), te = min(W, tb + kW / 4);
+        if (u < W && tb < te)
+          compare_rep<DR, true>(s.tile + (size_t)u * s.ts, s.cnorm[u], s, tb, te, nq, A.threshold, A.thr_lo, u, 0u,
+                                [&](int t) { atomicOr(&s.pair[2 * t + (u >> 5)], 1u << (u & 31)); });
+      }
+    }
+    __syncthreads();
+    if (prof) tk2 = clock64();
+    if (TEAM != 0) {
+      if (tid < W && s.s_f[tid] != kInf) atomicMin(&ctl->f[tid], s.s_f[tid]);
+      __threadfence();
+      Team<TEAM>::sync();
+    }
+    if (prof) tk3 = clock64();
+    if (leader) {
+      if (TEAM != 0) {
+        if (tid < W) {
+          s.s_f[tid] = __ldcg(&ctl->f[tid]);
+          ctl->f[tid] = kInf;
+        }
+        __syncthreads();
+      }
+      // prefetch every candidate's first-match representative (row + member metadata) in parallel
+      if (tid < W) {
+        const uint32_t p = s.s_f[tid];
+        if (p != kInf) {
+          const uint32_t rr = __ldcg(seg + p);
+          s.pridx[tid] = rr;
+          s.pcnt[tid] = A.cnt[rr];
+          s.phead[tid] = A.head[rr];
+          s.ptail[tid] = A.tail[rr];
+        }
+      }
+      __syncthreads();
+      for (int v = tid; v < W * nq; v += kMT) {
+        const int t = v / nq, q = v - t * nq;
+        if (s.s_f[t] != kInf)
+          reinterpret_cast<float4*>(s.pre + (size_t)t * s.ts)[q] =
+              __ldcg(reinterpret_cast<const float4*>(A.vals + (uint64_t)s.pridx[t] * ld) + q);
+      }
+      __syncthreads();
+      if (prof) tk4 = clock64();
+      if (warp == 0) resolve_window<TEAM>(A, seg, pos_nrm, ctl, s, W, wf, wb, tail_mode, i0, size0);
+      if (prof) tk5 = clock64();
+    }
+    __threadfence();
+    Team<TEAM>::sync();
+    if (prof) {
+      const long long tk6 = clock64();
+      atomicAdd(A.dbg + 8, (unsigned long long)(tk1 - tk0));
+      atomicAdd(A.dbg + 9, (unsigned long long)(tk2 - tk1));
+      atomicAdd(A.dbg + 10, (unsigned long long)(tk3 - tk2));
+      atomicAdd(A.dbg + 11, (unsigned long long)(tk4 - tk3));
+      atomicAdd(A.dbg + 12, (unsigned long long)(tk5 - tk4));
+      atomicAdd(A.dbg + 13, (unsigned long long)(tk6 - tk5));
+    }
+  }
+}
+
+template <int TEAM, int DR>
+__global__ void __launch_bounds__(kMT, 2) k_merge_window(MergeArgs A) {
+  extern __shared__ __align__(16) float smem_raw[];
+  __shared__ uint32_t s_work;
+  Smem s;
+  carve(s, smem_raw, A.ld);
+  TeamCtl* ctl = A.ctl + Team<TEAM>::id();
+  const uint32_t na = A.n_a ? *A.n_a : 0u, nb = A.n_b ? *A.n_b : 0u;
+  if (TEAM == 2) {  // the grid walks the lists together
+    for (uint32_t w = 0; w < na + nb; ++w) {
+      const uint32_t* it = (w < na) ? (A.list_a + 3 * (size_t)w) : (A.list_b + 3 * (size_t)(w - na));
+      merge_team<TEAM, DR>(A, it[0], it[1], it[2], ctl, s);
+    }
+    return;
+  }
+  for (;;) {
+    uint32_t w;
+    if (TEAM == 0) {
+      if (threadIdx.x == 0) s_work = atomicAdd(A.cursor, 1u);
+      __syncthreads();
+      w = s_work;
+      __syncthreads();
+    } else {
+      if (Team<TEAM>::rank() == 0 && threadIdx.x == 0) ctl->work = atomicAdd(A.cursor, 1u);
+      __threadfence();
+      Team<TEAM>::sync();
+      w = __ldcg(&ctl->work);
+      Team<TEAM>::sync();
+    }
+    if (w >= na + nb) break;
+    const uint32_t* it = (w < na) ? (A.list_a + 3 * (size_t)w) : (A.list_b + 3 * (size_t)(w - na));
+    merge_team<TEAM, DR>(A, it[0], it[1], it[2], ctl, s);
+  }
+}
+
+template <int TEAM>
+const void* kernel_for(int ld) {
+  if (ld <= 32) return (const void*)k_merge_window<TEAM, 32>;
+  if (ld <= 64) return (const void*)k_merge_window<TEAM, 64>;
+  return (const void*)k_merge_window<TEAM, 0>;
+}
+
+}  // namespace
+
+// ================================================================================================
+// Launch: stage 0 (CTA teams) over the classified lists, then the escalation stages.
+// ================================================================================================
+static int launch_stage(klsh_ctx* ctx, int team, int csize, MergeArgs& A, uint32_t host_items /* upper bound, 0 = unknown */) {
+  const int ld = ctx->ld;
+  const size_t smem = smem_bytes_for(ld);
+  if (smem > (size_t)ctx->max_smem_optin)
+    return klsh_fail(ctx, KLSH_ERR_ARG, "dimension %d needs %zu bytes of shared memory per CTA (limit %d)", ctx->D, smem,
+                     ctx->max_smem_optin);
+  const void* fn = team == 0 ? kernel_for<0>(ld) : team == 1 ? kernel_for<1>(ld) : kernel_for<2>(ld);
+  KCUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  if (team == 1 && csize > 8) {
+    if (cudaFuncSetAttribute(fn, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      (void)cudaGetLastError();
+      csize = 8;
+    }
+  }
+  int per_sm = 1;
+  KCUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kMT, smem));
+  if (per_sm < 1) per_sm = 1;
+  uint32_t grid, nteams;
+  if (team == 0) {
+    nteams = (uint32_t)ctx->sm_count * std::min(per_sm, 4);
+    if (host_items) nteams = std::min(nteams, host_items);
+    grid = nteams;
+  } else if (team == 1) {
+    nteams = (uint32_t)std::max(1, ctx->sm_count * std::min(per_sm, 2) / csize);
+    if (host_items) nteams = std::min(nteams, host_items);
+    grid = nteams * csize;
+  } else {
+    nteams = 1;
+    grid = (uint32_t)ctx->sm_count * std::min(per_sm, 2);
+  }
+  KTRY(dev_reserve(ctx, ctx->team_ctl, sizeof(TeamCtl) * (size_t)std::max<uint32_t>(nteams, 1)));
+  A.ctl = ctx->team_ctl.as<TeamCtl>();
+
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kMT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  cfg.attrs = attr;
+  cfg.numAttrs = 0;
+  if (team == 1) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)csize;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.numAttrs = 1;
+  } else if (team == 2) {
+    attr[0].id = cudaLaunchAttributeCooperative;
+    attr[0].val.cooperative = 1;
+    cfg.numAttrs = 1;
+  }
+  std::chrono::high_resolution_clock::time_point t0;
+  if (ctx->debug) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemset(ctx->dbg.p, 0, sizeof(unsigned long long) * 24);
+    t0 = std::chrono::high_resolution_clock::now();
+  }
+  void* args[] = {&A};
+  cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
+  ctx->launches++;
+  if (e != cudaSuccess)
+    return klsh_fail(ctx, KLSH_ERR_CUDA, "merge kernel launch (team %d, grid %u, smem %zu) failed: %s", team, grid, smem,
+                     cudaGetErrorString(e));
+  if (ctx->debug) {  // KLSH_DEBUG=1: per-stage timing and window statistics on stderr
+    unsigned long long h[24];
+    cudaStreamSynchronize(ctx->stream);
+    double ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+    cudaMemcpy(h, ctx->dbg.p, sizeof h, cudaMemcpyDeviceToHost);
+    if (h[0])
+      fprintf(stderr,
+              "[klsh] merge team=%d csize=%d grid=%u: %.3f ms; windows %llu cands %llu merges %llu accepted %llu escalated %llu | trunc: "
+              "undecidable %llu cache_full %llu back_exhausted %llu\n",
+              team, csize, grid, ms, h[0], h[1], h[2], h[6], h[7], h[3], h[4], h[5]);
+    if (h[0])
+      fprintf(stderr, "[klsh]   leader kcycles/window: stage %.1f parallel %.1f sync1 %.1f prefetch %.1f resolve %.1f sync2 %.1f\n",
+              h[8] / 1e3 / h[0], h[9] / 1e3 / h[0], h[10] / 1e3 / h[0], h[11] / 1e3 / h[0], h[12] / 1e3 / h[0], h[13] / 1e3 / h[0]);
+
+  }
+  return KLSH_OK;
+}
+
+// Work items {bucket, 0, 0} come from k_classify (list_big first, then list_large); their counts
+// live in the pass counters on the device.
+int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, uint32_t n_items_host,
+                        uint32_t bucket_max_host) {
+  if (n_items_host == 0) return KLSH_OK;
+  PassCounters* dc = s.counters.as<PassCounters>();
+  // escalation lists: every large bucket can escalate at most once per stage
+  KTRY(dev_reserve(ctx, s.esc1, sizeof(uint32_t) * 3 * ((size_t)n_items_host + 1)));
+  KTRY(dev_reserve(ctx, s.esc2, sizeof(uint32_t) * 3 * ((size_t)n_items_host + 1)));
+  KTRY(dev_reserve(ctx, s.esc3, sizeof(uint32_t) * 3 * ((size_t)n_items_host + 1)));
+  if (ctx->debug) KTRY(dev_reserve(ctx, ctx->dbg, sizeof(unsigned long long) * 24));
+
+  MergeArgs A;
+  A.vals = ctx->cur.vals.as<float>();
+  A.D = ctx->D;
+  A.ld = ctx->ld;
+  A.cnt = ctx->cur.cnt.as<int32_t>();
+  A.head = ctx->cur.head.as<int32_t>();
+  A.tail = ctx->cur.tail.as<int32_t>();
+  A.next = ctx->cur.next.as<int32_t>();
+  A.rows_sorted = rows_sorted;
+  A.bstart = s.bstart.as<uint32_t>();
+  A.pos_nrm = s.pos_nrm.as<float>();
+  A.dbg = ctx->debug ? ctx->dbg.as<unsigned long long>() : nullptr;
+  A.threshold = threshold;
+  A.thr_lo = threshold - 2e-6f;
+
+  // stage 0: one CTA per bucket, biggest buckets first
+  A.list_a = s.list_big.as<uint32_t>();
+  A.n_a = &dc->n_big;
+  A.list_b = s.list_large.as<uint32_t>();
+  A.n_b = &dc->n_large;
+  A.cursor = &dc->large_cursor;
+  A.esc_list = s.esc1.as<uint32_t>();
+  A.esc_count = &dc->n_esc1;
+  A.max_reps = ctx->cta_max;
+  KTRY(launch_stage(ctx, 0, 1, A, n_items_host));
+  if (bucket_max_host <= ctx->cta_max) return KLSH_OK;  // nothing can have escalated
+
+  // stage 1: one cluster per escalated bucket
+  A.list_a = s.esc1.as<uint32_t>();
+  A.n_a = &dc->n_esc1;
+  A.list_b = nullptr;
+  A.n_b = nullptr;
+  A.cursor = &dc->cluster_cursor;
+  A.esc_list = s.esc2.as<uint32_t>();
+  A.esc_count = &dc->n_esc2;
+  A.max_reps = ctx->cluster_max;
+  KTRY(launch_stage(ctx, 1, ctx->cluster_size, A, 0));
+  if (bucket_max_host <= ctx->cluster_max) return KLSH_OK;
+
+  // stage 2: one large cluster per bucket
+  A.list_a = s.esc2.as<uint32_t>();
+  A.n_a = &dc->n_esc2;
+  A.cursor = &dc->cluster2_cursor;
+  A.esc_list = s.esc3.as<uint32_t>();
+  A.esc_count = &dc->n_esc3;
+  A.max_reps = ctx->cluster2_max;
+  KTRY(launch_stage(ctx, 1, ctx->cluster2_size, A, 0));
+  if (bucket_max_host <= ctx->cluster2_max) return KLSH_OK;
+
+  // stage 3: the whole grid per bucket
+  A.list_a = s.esc3.as<uint32_t>();
+  A.n_a = &dc->n_esc3;
+  A.cursor = nullptr;
+  A.esc_list = nullptr;
+  A.esc_count = nullptr;
+  A.max_reps = 0xFFFFFFFFu;
+  KTRY(launch_stage(ctx, 2, 1, A, 0));
+  return KLSH_OK;
+}

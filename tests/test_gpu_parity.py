@@ -200,3 +200,47 @@ def test_save_files(gpu, oracle, tmp_path):
     gpu.load_cluster_file(str(tmp_path / "g.bin"), 8)
     back = oracle.read_cluster(str(tmp_path / "o.bin"), 8)
     assert_rows_equal(gpu.get_rows(), back.export())
+
+
+@pytest.mark.parametrize("cta_max,cluster_max,cluster2_max,csize", [(8, 64, 200, 8), (1, 1, 1, 8), (2, 1000000, 1000000, 4), (16, 100, 150, 16),
+                                                                  (4, 4, 1000000, 8), (1000000, 1000000, 1000000, 8)])
+def test_merge_team_variants(oracle, monkeypatch, cta_max, cluster_max, cluster2_max, csize):
+    """The windowed merge with the escalation thresholds (representatives per team) forced low, so
+    that small test buckets travel CTA -> cluster -> large cluster -> cooperative grid, against the oracle."""
+    from kmerlsh_b200 import Context
+
+    monkeypatch.setenv("KLSH_CTA_MAX", str(cta_max))
+    monkeypatch.setenv("KLSH_CLUSTER_MAX", str(cluster_max))
+    monkeypatch.setenv("KLSH_CLUSTER2_MAX", str(cluster2_max))
+    monkeypatch.setenv("KLSH_CLUSTER_SIZE", str(csize))
+    cases = [(40000, 4, 4, 6, 0.85, 100000, 7), (120000, 10, 10, 4, 0.80, 1000, 4), (30000, 16, 16, 5, 0.9, 100000, 5),
+             (8000, 40, 40, 3, 0.8, 100000, 9)]
+    with Context(0) as ctx:
+        for n, sa, sb, iters, minsim, thr, seed in cases:
+            _, _, values, ids = synth_rows(oracle, n, sa, sb, 60 + seed)
+            rows = oracle.rows(values)
+            rows.cluster(minsim, iters, thr, oracle.planes(seed))
+            ctx.set_seed(seed)
+            ctx.set_rows(values)
+            ctx.cluster(minsim, iters, thr)
+            assert_rows_equal(ctx.get_rows(), rows.export(), "n=%d D=%d" % (n, sa + sb))
+        for name, values in sorted(_bucket_cases().items()):
+            for thr in (0.95, 0.5):
+                rows = oracle.rows(values)
+                rows.p_cluster(thr)
+                ctx.set_rows(values)
+                ctx.p_cluster(thr)
+                assert_rows_equal(ctx.get_rows(), rows.export(), name)
+
+
+def test_merge_v1_kernel(oracle, monkeypatch):
+    from kmerlsh_b200 import Context
+
+    monkeypatch.setenv("KLSH_MERGE_V1", "1")
+    _, _, values, ids = synth_rows(oracle, 60000, 6, 6, 71)
+    rows = oracle.rows(values)
+    rows.cluster(0.8, 5, 500, oracle.planes(3))
+    with Context(0, seed=3) as ctx:
+        ctx.set_rows(values)
+        ctx.cluster(0.8, 5, 500)
+        assert_rows_equal(ctx.get_rows(), rows.export())
