@@ -124,6 +124,7 @@ int klsh_create(int device, klsh_ctx** out) {
   if (const char* e = std::getenv("KLSH_CLUSTER_SIZE")) ctx->cluster_size = std::atoi(e);
   if (const char* e = std::getenv("KLSH_CLUSTER2_MAX")) ctx->cluster2_max = (uint32_t)std::strtoul(e, nullptr, 10);
   if (const char* e = std::getenv("KLSH_CLUSTER2_SIZE")) ctx->cluster2_size = std::atoi(e);
+  if (const char* e = std::getenv("KLSH_CLUSTER_CTAS_PER_SM")) ctx->cluster_ctas_per_sm = std::max(1, std::atoi(e));
   if (ctx->cta_max < 1) ctx->cta_max = 1;
   if (ctx->cluster_max < ctx->cta_max) ctx->cluster_max = ctx->cta_max;
   if (ctx->cluster2_max < ctx->cluster_max) ctx->cluster2_max = ctx->cluster_max;

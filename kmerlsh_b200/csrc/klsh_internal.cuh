@@ -93,6 +93,7 @@ struct klsh_ctx {
   // cta_max representatives, and the cluster for the whole grid above cluster_max
   uint32_t cta_max = 512, cluster_max = 8192, cluster2_max = 65536;
   int cluster_size = 8, cluster2_size = 16;
+  int cluster_ctas_per_sm = 2;
   bool debug = false;     // KLSH_DEBUG=1
   DevBuf dbg;
   bool merge_v1 = false;  // KLSH_MERGE_V1=1: first-generation block-per-bucket kernel (A/B checks)

@@ -37,7 +37,8 @@ namespace {
 
 constexpr int kW = 64;    // window capacity
 constexpr int kKD = 32;   // dirty-cache entries
-constexpr int kMT = 256;  // threads per CTA
+constexpr int kMT = 256;  // threads per CTA (128 x 4 per SM measured slower on C2)
+constexpr int kCtasPerSm = 2;
 constexpr int kWbMax = 62;
 constexpr uint32_t kInf = 0x7fffffffu;
 
@@ -75,12 +76,14 @@ __device__ __forceinline__ bool cos_match(float dot, float nl, float nr, float t
   float dist = __fsub_rn(1.f, sim);
   return __fsub_rn(1.f, dist) >= threshold;
 }
-// cheap conservative reject: a match implies dot >= den*(thr - 2^-21) when den > 0;
-// thr_lo = thr - 2e-6 leaves room for the rounding of den*thr_lo.  NaN/0/inf fall through to the
-// exact test or are rejected correctly.
-__device__ __forceinline__ bool pair_match(float dot, float nl, float nr, float threshold, float thr_lo) {
-  if (dot < __fmul_rn(__fmul_rn(nl, nr), thr_lo)) return false;
-  return cos_match(dot, nl, nr, threshold);
+// Conservative reject used by the parallel phase.  `dot_fast` is the dot
+// product accumulated with fused multiply-adds: it differs from the reference's mul-then-add sum by
+// at most 2*D*2^-24 * sum|a_i b_i| <= 2*D*2^-24 * |a||b|.  A match implies
+// dot_exact >= den*(thr - 2^-21) (den = |a||b| > 0), hence dot_fast >= den*(thr - 2^-21 - 2*D*2^-24);
+// thr_lo = thr - 2e-6 - 4*D*2^-24 leaves room for the rounding of den*thr_lo.  Everything that passes
+// is re-evaluated exactly; NaN/0/inf fall through to the exact test or are rejected correctly.
+__device__ __forceinline__ bool fast_reject(float dot_fast, float nl, float nr, float thr_lo) {
+  return dot_fast < __fmul_rn(__fmul_rn(nl, nr), thr_lo);
 }
 __device__ __forceinline__ float consensus1(float cur, int c1, float cand, int c2) {
   const float fa = __int2float_rn(c1 + c2);
@@ -237,33 +240,39 @@ __device__ __forceinline__ void compare_rep(const float* rowp, float rn, const S
         if (q < nq) {
           const float4 x0 = a0[q], x1 = a1[q], x2 = a2[q], x3 = a3[q];
           const float r0 = r[4 * q], r1 = r[4 * q + 1], r2 = r[4 * q + 2], r3 = r[4 * q + 3];
-          d0 = __fadd_rn(d0, __fmul_rn(x0.x, r0)); d1 = __fadd_rn(d1, __fmul_rn(x1.x, r0));
-          d2 = __fadd_rn(d2, __fmul_rn(x2.x, r0)); d3 = __fadd_rn(d3, __fmul_rn(x3.x, r0));
-          d0 = __fadd_rn(d0, __fmul_rn(x0.y, r1)); d1 = __fadd_rn(d1, __fmul_rn(x1.y, r1));
-          d2 = __fadd_rn(d2, __fmul_rn(x2.y, r1)); d3 = __fadd_rn(d3, __fmul_rn(x3.y, r1));
-          d0 = __fadd_rn(d0, __fmul_rn(x0.z, r2)); d1 = __fadd_rn(d1, __fmul_rn(x1.z, r2));
-          d2 = __fadd_rn(d2, __fmul_rn(x2.z, r2)); d3 = __fadd_rn(d3, __fmul_rn(x3.z, r2));
-          d0 = __fadd_rn(d0, __fmul_rn(x0.w, r3)); d1 = __fadd_rn(d1, __fmul_rn(x1.w, r3));
-          d2 = __fadd_rn(d2, __fmul_rn(x2.w, r3)); d3 = __fadd_rn(d3, __fmul_rn(x3.w, r3));
+          d0 = __fmaf_rn(x0.x, r0, d0); d1 = __fmaf_rn(x1.x, r0, d1); d2 = __fmaf_rn(x2.x, r0, d2); d3 = __fmaf_rn(x3.x, r0, d3);
+          d0 = __fmaf_rn(x0.y, r1, d0); d1 = __fmaf_rn(x1.y, r1, d1); d2 = __fmaf_rn(x2.y, r1, d2); d3 = __fmaf_rn(x3.y, r1, d3);
+          d0 = __fmaf_rn(x0.z, r2, d0); d1 = __fmaf_rn(x1.z, r2, d1); d2 = __fmaf_rn(x2.z, r2, d2); d3 = __fmaf_rn(x3.z, r2, d3);
+          d0 = __fmaf_rn(x0.w, r3, d0); d1 = __fmaf_rn(x1.w, r3, d1); d2 = __fmaf_rn(x2.w, r3, d2); d3 = __fmaf_rn(x3.w, r3, d3);
         }
     } else {
       for (int q = 0; q < nq; ++q) {
         const float4 rv = SM ? reinterpret_cast<const float4*>(rowp)[q] : __ldcg(reinterpret_cast<const float4*>(rowp) + q);
         const float4 x0 = a0[q], x1 = a1[q], x2 = a2[q], x3 = a3[q];
-        d0 = __fadd_rn(d0, __fmul_rn(x0.x, rv.x)); d1 = __fadd_rn(d1, __fmul_rn(x1.x, rv.x));
-        d2 = __fadd_rn(d2, __fmul_rn(x2.x, rv.x)); d3 = __fadd_rn(d3, __fmul_rn(x3.x, rv.x));
-        d0 = __fadd_rn(d0, __fmul_rn(x0.y, rv.y)); d1 = __fadd_rn(d1, __fmul_rn(x1.y, rv.y));
-        d2 = __fadd_rn(d2, __fmul_rn(x2.y, rv.y)); d3 = __fadd_rn(d3, __fmul_rn(x3.y, rv.y));
-        d0 = __fadd_rn(d0, __fmul_rn(x0.z, rv.z)); d1 = __fadd_rn(d1, __fmul_rn(x1.z, rv.z));
-        d2 = __fadd_rn(d2, __fmul_rn(x2.z, rv.z)); d3 = __fadd_rn(d3, __fmul_rn(x3.z, rv.z));
-        d0 = __fadd_rn(d0, __fmul_rn(x0.w, rv.w)); d1 = __fadd_rn(d1, __fmul_rn(x1.w, rv.w));
-        d2 = __fadd_rn(d2, __fmul_rn(x2.w, rv.w)); d3 = __fadd_rn(d3, __fmul_rn(x3.w, rv.w));
+        d0 = __fmaf_rn(x0.x, rv.x, d0); d1 = __fmaf_rn(x1.x, rv.x, d1); d2 = __fmaf_rn(x2.x, rv.x, d2); d3 = __fmaf_rn(x3.x, rv.x, d3);
+        d0 = __fmaf_rn(x0.y, rv.y, d0); d1 = __fmaf_rn(x1.y, rv.y, d1); d2 = __fmaf_rn(x2.y, rv.y, d2); d3 = __fmaf_rn(x3.y, rv.y, d3);
+        d0 = __fmaf_rn(x0.z, rv.z, d0); d1 = __fmaf_rn(x1.z, rv.z, d1); d2 = __fmaf_rn(x2.z, rv.z, d2); d3 = __fmaf_rn(x3.z, rv.z, d3);
+        d0 = __fmaf_rn(x0.w, rv.w, d0); d1 = __fmaf_rn(x1.w, rv.w, d1); d2 = __fmaf_rn(x2.w, rv.w, d2); d3 = __fmaf_rn(x3.w, rv.w, d3);
       }
     }
-    if (t0 + 0 < te && t0 + 0 != skip_t && pair_match(d0, s.cnorm[t0 + 0], rn, threshold, thr_lo)) hit(t0 + 0);
-    if (t0 + 1 < te && t0 + 1 != skip_t && pair_match(d1, s.cnorm[t0 + 1], rn, threshold, thr_lo)) hit(t0 + 1);
-    if (t0 + 2 < te && t0 + 2 != skip_t && pair_match(d2, s.cnorm[t0 + 2], rn, threshold, thr_lo)) hit(t0 + 2);
-    if (t0 + 3 < te && t0 + 3 != skip_t && pair_match(d3, s.cnorm[t0 + 3], rn, threshold, thr_lo)) hit(t0 + 3);
+    // survivors of the filter (rare): the reference's exact mul-then-add sum decides
+    auto exact = [&](int t) {
+      const float4* c4 = t4 + (size_t)t * ts4;
+      float dx = 0.f;
+      for (int q = 0; q < nq; ++q) {
+        const float4 x = c4[q];
+        const float4 y = SM ? reinterpret_cast<const float4*>(rowp)[q] : __ldcg(reinterpret_cast<const float4*>(rowp) + q);
+        dx = __fadd_rn(dx, __fmul_rn(x.x, y.x));
+        dx = __fadd_rn(dx, __fmul_rn(x.y, y.y));
+        dx = __fadd_rn(dx, __fmul_rn(x.z, y.z));
+        dx = __fadd_rn(dx, __fmul_rn(x.w, y.w));
+      }
+      if (cos_match(dx, s.cnorm[t], rn, threshold)) hit(t);
+    };
+    if (t0 + 0 < te && t0 + 0 != skip_t && !fast_reject(d0, s.cnorm[t0 + 0], rn, thr_lo)) exact(t0 + 0);
+    if (t0 + 1 < te && t0 + 1 != skip_t && !fast_reject(d1, s.cnorm[t0 + 1], rn, thr_lo)) exact(t0 + 1);
+    if (t0 + 2 < te && t0 + 2 != skip_t && !fast_reject(d2, s.cnorm[t0 + 2], rn, thr_lo)) exact(t0 + 2);
+    if (t0 + 3 < te && t0 + 3 != skip_t && !fast_reject(d3, s.cnorm[t0 + 3], rn, thr_lo)) exact(t0 + 3);
   }
 }
 
@@ -291,7 +300,8 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
   // same representative (the common shape of a merge-heavy bucket) then cost one exact comparison
   // each instead of a whole-window mask rebuild.  The mask is rebuilt when another entry is modified
   // or a candidate is accepted.
-  int pend = -1;
+  uint32_t inval = 0;  // entries whose match mask is stale (modified since it was built)
+  int pend = -1;       // the entry whose norm is stale too (modified by the latest merge)
   // which unexamined candidates match entry e's current value; its norm falls out of the same pass
   auto validate = [&](int e) {
     const float4* r4 = reinterpret_cast<const float4*>(s.dvals + (size_t)e * s.ts);
@@ -348,8 +358,11 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
       // (a) representatives modified in this window: match bits against their current values; the
       // entry with an invalid mask is compared exactly (every lane computes the same comparison)
       bool hit = ((my_dm_lo & tbit_lo) | (my_dm_hi & tbit_hi)) != 0u;
-      if (pend >= 0) {
-        const float4* r4 = reinterpret_cast<const float4*>(s.dvals + (size_t)pend * s.ts);
+      if (inval != 0u) {
+        // entries with a stale mask: lane e compares the candidate with entry e's current value
+        const bool mine = (inval >> lane) & 1u;
+        const int er = mine ? (int)lane : 0;
+        const float4* r4 = reinterpret_cast<const float4*>(s.dvals + (size_t)er * s.ts);
         const float4* c4 = reinterpret_cast<const float4*>(s.tile + (size_t)t * s.ts);
         float dot = 0.f, nn = 0.f;
 #pragma unroll 4
@@ -360,8 +373,12 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
           dot = __fadd_rn(dot, __fmul_rn(x.z, y.z)); nn = __fadd_rn(nn, __fmul_rn(y.z, y.z));
           dot = __fadd_rn(dot, __fmul_rn(x.w, y.w)); nn = __fadd_rn(nn, __fmul_rn(y.w, y.w));
         }
-        const bool mt = cos_match(dot, s.cnorm[t], __fsqrt_rn(nn), A.threshold);
-        if ((int)lane == pend) hit = mt;
+        const float rn = __fsqrt_rn(nn);
+        if (mine) {
+          hit = cos_match(dot, s.cnorm[t], rn, A.threshold);
+          if ((int)lane == pend) s.dnorm[lane] = rn;
+        }
+        pend = -1;  // the latest entry's norm is now published
       }
       best = __reduce_min_sync(0xffffffffu, hit ? my_dpos : kInf);
     }
@@ -399,10 +416,14 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
     }
     if (best == kInf) {
       // no merge: the candidate becomes representative i (its norm is published with the flush)
-      if (pend >= 0) {
-        validate(pend);
-        pend = -1;
+      // an accept usually means more accepts follow: rebuild the stale masks once so that the
+      // following candidates are decided by bit tests alone
+      while (inval != 0u) {
+        const int e2 = __ffs(inval) - 1;
+        inval &= inval - 1;
+        validate(e2);
       }
+      pend = -1;
       if (lane == 0) s.acc[a] = (uint32_t)t;
       accm_lo |= tbit_lo;
       accm_hi |= tbit_hi;
@@ -478,12 +499,12 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
     ++merges;
     from_back = true;
     __syncwarp();
-    if (pend >= 0 && pend != e) validate(pend);
+    inval |= 1u << e;
     pend = e;
     if (nd == kKD) { dbg_full = 1; break; }  // dirty cache full: flush and start a new window
   }
   __syncwarp();
-  if (pend >= 0) validate(pend);  // publishes the entry's norm
+  if (pend >= 0) validate(pend);  // publishes the latest entry's norm
   __syncwarp();
   // ---- apply the window's effects to global memory, in parallel ----
   // accepted candidates: positions i0.. in acceptance order (row index + norm)
@@ -655,9 +676,10 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
         compare_rep<DR, false>(A.vals + (uint64_t)rr * ld, rn, s, 0, W, nq, A.threshold, A.thr_lo, -1, j,
                                [&](int t) { atomicMin(&s.s_f[t], j); });
       }
-      if (leader) {  // candidate x candidate match bits: 4 threads per candidate row, 16 columns each
-        const int u = tid & (kW - 1), part = tid >> 6;
-        const int tb = part * (kW / 4), te = min(W, tb + kW / 4);
+      if (leader) {  // candidate x candidate match bits: kMT/kW threads per candidate row
+        constexpr int kParts = kMT / kW;  // threads per candidate row
+        const int u = tid & (kW - 1), part = tid / kW;
+        const int tb = part * (kW / kParts), te = min(W, tb + kW / kParts);
         if (u < W && tb < te)
           compare_rep<DR, true>(s.tile + (size_t)u * s.ts, s.cnorm[u], s, tb, te, nq, A.threshold, A.thr_lo, u, 0u,
                                 [&](int t) { atomicOr(&s.pair[2 * t + (u >> 5)], 1u << (u & 31)); });
@@ -717,7 +739,7 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
 }
 
 template <int TEAM, int DR>
-__global__ void __launch_bounds__(kMT, 2) k_merge_window(MergeArgs A) {
+__global__ void __launch_bounds__(kMT, kCtasPerSm) k_merge_window(MergeArgs A) {
   extern __shared__ __align__(16) float smem_raw[];
   __shared__ uint32_t s_work;
   Smem s;
@@ -782,16 +804,16 @@ static int launch_stage(klsh_ctx* ctx, int team, int csize, MergeArgs& A, uint32
   if (per_sm < 1) per_sm = 1;
   uint32_t grid, nteams;
   if (team == 0) {
-    nteams = (uint32_t)ctx->sm_count * std::min(per_sm, 4);
+    nteams = (uint32_t)ctx->sm_count * std::min(per_sm, kCtasPerSm);
     if (host_items) nteams = std::min(nteams, host_items);
     grid = nteams;
   } else if (team == 1) {
-    nteams = (uint32_t)std::max(1, ctx->sm_count * std::min(per_sm, 2) / csize);
+    nteams = (uint32_t)std::max(1, ctx->sm_count * std::min(per_sm, ctx->cluster_ctas_per_sm) / csize);
     if (host_items) nteams = std::min(nteams, host_items);
     grid = nteams * csize;
   } else {
     nteams = 1;
-    grid = (uint32_t)ctx->sm_count * std::min(per_sm, 2);
+    grid = (uint32_t)ctx->sm_count * std::min(per_sm, ctx->cluster_ctas_per_sm);
   }
   KTRY(dev_reserve(ctx, ctx->team_ctl, sizeof(TeamCtl) * (size_t)std::max<uint32_t>(nteams, 1)));
   A.ctl = ctx->team_ctl.as<TeamCtl>();
@@ -870,7 +892,7 @@ int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
   A.pos_nrm = s.pos_nrm.as<float>();
   A.dbg = ctx->debug ? ctx->dbg.as<unsigned long long>() : nullptr;
   A.threshold = threshold;
-  A.thr_lo = threshold - 2e-6f;
+  A.thr_lo = threshold - 2e-6f - 4.0f * (float)ctx->ld * 5.9604645e-8f;
 
   // stage 0: one CTA per bucket, biggest buckets first
   A.list_a = s.list_big.as<uint32_t>();
