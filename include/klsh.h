@@ -108,6 +108,30 @@ int klsh_restore(klsh_ctx* ctx);
 /* Block until all work queued on the context's stream is done. */
 int klsh_sync(klsh_ctx* ctx);
 
+/* ---- multi-GPU building blocks ------------------------------------------------------------------
+ * No reference counterpart (the reference is one process).  One context per rank; every rank holds
+ * the same row set (load it identically on all ranks) and the same hyperplane source.  Per LSH
+ * iteration of Cluster (function/cluster.cc:199-331) the caller runs, on every rank,
+ *   klsh_mg_pass_begin  sign + group ALL rows (replicated, no communication)
+ *   klsh_mg_plan        contiguous bucket ranges, one per rank, balanced by row count
+ *   klsh_mg_merge       p_cluster / nestedCluster on the rank's own bucket range; logs what changed
+ *   klsh_mg_export      survivors of the range + modified rows + member-chain writes -> device buffers
+ *   (all-gather of those buffers over NCCL — kmerlsh_b200/distributed.py)
+ *   klsh_mg_apply       replay the other ranks' logs on this replica
+ *   klsh_mg_set_alive   new working set = survivor lists concatenated in rank order
+ * Results are identical to klsh_cluster on one GPU.  d_* arguments are DEVICE pointers. */
+int klsh_row_stride(const klsh_ctx* ctx); /* floats per row in exported/applied row blocks (D rounded up to 4) */
+int klsh_mg_pass_begin(klsh_ctx* ctx, uint64_t* n_rows, int32_t* H, uint64_t* n_buckets);
+int klsh_mg_plan(klsh_ctx* ctx, int world, uint32_t* splits_out /* host, world+1 bucket indices */);
+int klsh_mg_merge(klsh_ctx* ctx, uint32_t bucket_lo, uint32_t bucket_hi, float threshold, int64_t bucket_size_threshold,
+                  uint64_t* n_survivors, uint64_t* n_modified_rows, uint64_t* n_chain_writes);
+int klsh_mg_export(klsh_ctx* ctx, uint32_t* d_survivors, uint32_t* d_mod_rows, float* d_mod_vals /* [n][stride] */,
+                   int32_t* d_mod_meta /* [n][3] count, head, tail */, uint32_t* d_chain_slots, int32_t* d_chain_vals);
+int klsh_mg_apply(klsh_ctx* ctx, const uint32_t* d_mod_rows, const float* d_mod_vals, const int32_t* d_mod_meta,
+                  uint64_t n_modified_rows, const uint32_t* d_chain_slots, const int32_t* d_chain_vals,
+                  uint64_t n_chain_writes);
+int klsh_mg_set_alive(klsh_ctx* ctx, const uint32_t* d_alive, uint64_t n);
+
 #ifdef __cplusplus
 }
 #endif

@@ -72,6 +72,13 @@ SYMBOLS = [
     ("klsh_snapshot", C.c_int, [C.c_void_p]),
     ("klsh_restore", C.c_int, [C.c_void_p]),
     ("klsh_sync", C.c_int, [C.c_void_p]),
+    ("klsh_row_stride", C.c_int, [C.c_void_p]),
+    ("klsh_mg_pass_begin", C.c_int, [C.c_void_p, u64p, C.POINTER(C.c_int32), u64p]),
+    ("klsh_mg_plan", C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_uint32)]),
+    ("klsh_mg_merge", C.c_int, [C.c_void_p, C.c_uint32, C.c_uint32, C.c_float, i64, u64p, u64p, u64p]),
+    ("klsh_mg_export", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    ("klsh_mg_apply", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, u64, C.c_void_p, C.c_void_p, u64]),
+    ("klsh_mg_set_alive", C.c_int, [C.c_void_p, C.c_void_p, u64]),
 ]
 
 
@@ -228,6 +235,35 @@ class Context:
 
     def launch_count(self) -> int:
         return self.lib.klsh_launch_count(self.h)
+
+    # ---- multi-GPU building blocks (device pointers are passed as integers, e.g. tensor.data_ptr())
+    def row_stride(self) -> int:
+        return self.lib.klsh_row_stride(self.h)
+
+    def mg_pass_begin(self):
+        n, H, nb = u64(), C.c_int32(), u64()
+        self._ck(self.lib.klsh_mg_pass_begin(self.h, C.byref(n), C.byref(H), C.byref(nb)), "klsh_mg_pass_begin")
+        return n.value, H.value, nb.value
+
+    def mg_plan(self, world: int):
+        out = (C.c_uint32 * (world + 1))()
+        self._ck(self.lib.klsh_mg_plan(self.h, world, out), "klsh_mg_plan")
+        return list(out)
+
+    def mg_merge(self, b_lo: int, b_hi: int, threshold: float, bucket_size_threshold: int):
+        a, b, c = u64(), u64(), u64()
+        self._ck(self.lib.klsh_mg_merge(self.h, b_lo, b_hi, threshold, bucket_size_threshold, C.byref(a), C.byref(b), C.byref(c)),
+                 "klsh_mg_merge")
+        return a.value, b.value, c.value
+
+    def mg_export(self, d_surv, d_mod_rows, d_mod_vals, d_mod_meta, d_slots, d_vals):
+        self._ck(self.lib.klsh_mg_export(self.h, d_surv, d_mod_rows, d_mod_vals, d_mod_meta, d_slots, d_vals), "klsh_mg_export")
+
+    def mg_apply(self, d_mod_rows, d_mod_vals, d_mod_meta, n_mod, d_slots, d_vals, n_next):
+        self._ck(self.lib.klsh_mg_apply(self.h, d_mod_rows, d_mod_vals, d_mod_meta, n_mod, d_slots, d_vals, n_next), "klsh_mg_apply")
+
+    def mg_set_alive(self, d_alive, n: int):
+        self._ck(self.lib.klsh_mg_set_alive(self.h, d_alive, n), "klsh_mg_set_alive")
 
 
 def Cluster(rows, min_similarity, cluster_iteration, threads_to_use, dim, bucket_size_threshold, verbose=False,

@@ -147,6 +147,8 @@ void klsh_destroy(klsh_ctx* ctx) {
   dev_free(ctx->nested_out);
   dev_free(ctx->team_ctl);
   dev_free(ctx->dbg);
+  dev_free(ctx->mg_counts); dev_free(ctx->mg_mod_rows); dev_free(ctx->mg_next_slot); dev_free(ctx->mg_next_val);
+  dev_free(ctx->mg_splits); dev_free(ctx->mg_surv);
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
@@ -338,7 +340,8 @@ static int run_pass(klsh_ctx* ctx, PassScratch& s, const uint32_t* rows_in, uint
   if (timed) cudaEventRecord(ctx->ev[1], st);
   uint32_t *keys_sorted, *rows_sorted;
   KTRY(launch_sort_pairs(ctx, s, n, H, &keys_sorted, &rows_sorted));
-  KTRY(launch_bounds(ctx, s, keys_sorted, n, nest_threshold));
+  KTRY(launch_bounds(ctx, s, keys_sorted, n));
+  KTRY(launch_classify(ctx, s, n, nest_threshold, 0u, 0xFFFFFFFFu));
   PassCounters* hc = ctx->h_counters + (&s == &ctx->nested ? 1 : 0);
   KCUDA(ctx, cudaMemcpyAsync(hc, s.counters.p, sizeof(PassCounters), cudaMemcpyDeviceToHost, st));
   if (timed) cudaEventRecord(ctx->ev[2], st);
@@ -627,5 +630,190 @@ extern "C" int klsh_restore(klsh_ctx* ctx) {
   ctx->ids = ctx->snap_ids;
   ctx->id_base = ctx->snap_id_base;
   ctx->ids_implicit = ctx->snap_ids_implicit;
+  return KLSH_OK;
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Multi-GPU building blocks: one context per rank, REPLICATED row state,
+// PARTITIONED merge work.  Every rank signs, sorts and bounds all rows (cheap, and it keeps every
+// replica's view identical without communication); the buckets are split into `world` contiguous
+// ranges balanced by row count; each rank merges its range and logs what it changed; the logs and
+// the per-range survivor lists are exchanged by the caller (NCCL all-gather) and applied on every
+// replica.  Contiguous ranges in bucket order keep the reference's canonical row order: the new
+// working set is the concatenation of the ranks' survivor lists in rank order.
+// Pointers named d_* are DEVICE pointers owned by the caller.
+// ------------------------------------------------------------------------------------------------
+extern "C" int klsh_row_stride(const klsh_ctx* ctx) { return ctx ? ctx->ld : 0; }
+
+extern "C" int klsh_mg_pass_begin(klsh_ctx* ctx, uint64_t* n_rows, int32_t* H_out, uint64_t* n_buckets) {
+  if (!ctx || ctx->D <= 0) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_pass_begin: no rows loaded");
+  if (ctx->merge_v1) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_*: not available with KLSH_MERGE_V1");
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  const uint64_t n = ctx->cur.n_alive;
+  ctx->mg_n = n;
+  ctx->mg_nb = 0;
+  if (n_rows) *n_rows = n;
+  if (n == 0) {
+    if (H_out) *H_out = 0;
+    if (n_buckets) *n_buckets = 0;
+    return KLSH_OK;
+  }
+  const int H = floor_log2_u64(n);
+  ctx->mg_H = H;
+  PassScratch& s = ctx->top;
+  KTRY(reserve_scratch(ctx, s, n, H));
+  KTRY(upload_planes(ctx, s, H));
+  KTRY(launch_sign(ctx, ctx->cur.vals.as<float>(), ctx->D, ctx->ld, ctx->cur.alive.as<uint32_t>(), n, s.planes.as<float>(), H,
+                   s.keys_a.as<uint32_t>(), s.rows_a.as<uint32_t>()));
+  KTRY(launch_sort_pairs(ctx, s, n, H, &ctx->mg_keys_sorted, &ctx->mg_rows_sorted));
+  KTRY(launch_bounds(ctx, s, ctx->mg_keys_sorted, n));
+  KCUDA(ctx, cudaMemcpyAsync(ctx->h_counters, s.counters.p, sizeof(PassCounters), cudaMemcpyDeviceToHost, ctx->stream));
+  KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->mg_nb = ctx->h_counters->n_buckets;
+  if (H_out) *H_out = H;
+  if (n_buckets) *n_buckets = ctx->mg_nb;
+  return KLSH_OK;
+}
+
+extern "C" int klsh_mg_plan(klsh_ctx* ctx, int world, uint32_t* splits_out) {
+  if (!ctx || world < 1 || world > 63 || !splits_out) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_plan: bad argument");
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  if (ctx->mg_n == 0) {
+    for (int r = 0; r <= world; ++r) splits_out[r] = 0;
+    return KLSH_OK;
+  }
+  KTRY(dev_reserve(ctx, ctx->mg_splits, sizeof(uint32_t) * 64));
+  KTRY(launch_find_splits(ctx, ctx->top, ctx->mg_nb, ctx->mg_n, world, ctx->mg_splits.as<uint32_t>()));
+  KCUDA(ctx, cudaMemcpyAsync(splits_out, ctx->mg_splits.p, sizeof(uint32_t) * (world + 1), cudaMemcpyDeviceToHost, ctx->stream));
+  KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  splits_out[0] = 0;
+  return KLSH_OK;
+}
+
+extern "C" int klsh_mg_merge(klsh_ctx* ctx, uint32_t b_lo, uint32_t b_hi, float threshold, int64_t bucket_size_threshold,
+                             uint64_t* n_surv, uint64_t* n_mod, uint64_t* n_next) {
+  if (!ctx || b_lo > b_hi) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_merge: bad argument");
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  const uint64_t n = ctx->mg_n;
+  if (n_surv) *n_surv = 0;
+  if (n_mod) *n_mod = 0;
+  if (n_next) *n_next = 0;
+  if (n == 0) return KLSH_OK;
+  cudaStream_t st = ctx->stream;
+  PassScratch& s = ctx->top;
+  uint32_t* rows_sorted = ctx->mg_rows_sorted;
+  // logs: a row is logged once per window flush, a chain pointer once per merge -> both bounded by n
+  KTRY(dev_reserve(ctx, ctx->mg_counts, sizeof(uint32_t) * 4));
+  KTRY(dev_reserve(ctx, ctx->mg_mod_rows, sizeof(uint32_t) * (n + 1)));
+  KTRY(dev_reserve(ctx, ctx->mg_next_slot, sizeof(uint32_t) * (n + 1)));
+  KTRY(dev_reserve(ctx, ctx->mg_next_val, sizeof(int32_t) * (n + 1)));
+  KTRY(dev_reserve(ctx, ctx->mg_surv, sizeof(uint32_t) * (n + 1)));
+  KCUDA(ctx, cudaMemsetAsync(ctx->mg_counts.p, 0, sizeof(uint32_t) * 4, st));
+  ctx->mg.counts = ctx->mg_counts.as<uint32_t>();
+  ctx->mg.mod_rows = ctx->mg_mod_rows.as<uint32_t>();
+  ctx->mg.next_slot = ctx->mg_next_slot.as<uint32_t>();
+  ctx->mg.next_val = ctx->mg_next_val.as<int32_t>();
+  struct Reset {
+    klsh_ctx* c;
+    ~Reset() { c->mg = MgLog(); }
+  } reset{ctx};
+
+  const int64_t nest = bucket_size_threshold < 0 ? -1 : bucket_size_threshold;
+  KTRY(launch_classify(ctx, s, n, nest, b_lo, b_hi));
+  KCUDA(ctx, cudaMemcpyAsync(ctx->h_counters, s.counters.p, sizeof(PassCounters), cudaMemcpyDeviceToHost, st));
+  KCUDA(ctx, cudaStreamSynchronize(st));
+  const PassCounters c = *ctx->h_counters;
+  KTRY(launch_merge(ctx, s, rows_sorted, threshold, c));
+  if (c.n_nested) {
+    // every rank draws the table of every oversized bucket, in bucket order, to stay in step with
+    // the single-process hyperplane stream; only the owner runs the nested pass
+    std::vector<uint32_t> nb(c.n_nested);
+    KCUDA(ctx, cudaMemcpyAsync(nb.data(), s.list_nested.p, sizeof(uint32_t) * c.n_nested, cudaMemcpyDeviceToHost, st));
+    KCUDA(ctx, cudaStreamSynchronize(st));
+    std::sort(nb.begin(), nb.end());
+    uint32_t bs[2];
+    std::vector<float> discard;
+    for (uint32_t b : nb) {
+      KCUDA(ctx, cudaMemcpyAsync(bs, s.bstart.as<uint32_t>() + b, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, st));
+      KCUDA(ctx, cudaStreamSynchronize(st));
+      const uint64_t seg_n = bs[1] - bs[0];
+      const int H2 = floor_log2_u64(seg_n);
+      if (b < b_lo || b >= b_hi) {
+        discard.resize((size_t)H2 * ctx->D + 1);
+        planes_draw(ctx->planes, H2, ctx->D, discard.data());
+        continue;
+      }
+      uint32_t* seg = rows_sorted + bs[0];
+      uint64_t kept = 0;
+      KTRY(reserve_scratch(ctx, ctx->nested, seg_n, H2));
+      KTRY(dev_reserve(ctx, ctx->nested_out, sizeof(uint32_t) * (seg_n + 2)));
+      uint32_t* tmp_out = ctx->nested_out.as<uint32_t>();
+      KTRY(run_pass(ctx, ctx->nested, seg, seg_n, H2, threshold, -1, tmp_out, &kept, nullptr, false));
+      KCUDA(ctx, cudaMemcpyAsync(seg, tmp_out, sizeof(uint32_t) * kept, cudaMemcpyDeviceToDevice, st));
+      KTRY(launch_fill_tail(ctx, seg, kept, seg_n));
+    }
+  }
+  // survivors of my range, in order
+  uint32_t pr[2] = {0, 0};
+  KCUDA(ctx, cudaMemcpyAsync(&pr[0], s.bstart.as<uint32_t>() + b_lo, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  KCUDA(ctx, cudaMemcpyAsync(&pr[1], s.bstart.as<uint32_t>() + b_hi, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+  KCUDA(ctx, cudaStreamSynchronize(st));
+  if (b_lo >= ctx->mg_nb) pr[0] = (uint32_t)n;
+  if (b_hi >= ctx->mg_nb) pr[1] = (uint32_t)n;
+  uint64_t surv = 0;
+  if (pr[1] > pr[0]) {
+    KTRY(launch_compact(ctx, s, rows_sorted + pr[0], pr[1] - pr[0], ctx->mg_surv.as<uint32_t>()));
+    KCUDA(ctx, cudaMemcpyAsync(&ctx->h_counters->n_out, &s.counters.as<PassCounters>()->n_out, sizeof(uint32_t), cudaMemcpyDeviceToHost, st));
+    KCUDA(ctx, cudaStreamSynchronize(st));
+    surv = ctx->h_counters->n_out;
+  }
+  uint32_t counts[2];
+  KCUDA(ctx, cudaMemcpyAsync(counts, ctx->mg_counts.p, sizeof counts, cudaMemcpyDeviceToHost, st));
+  KCUDA(ctx, cudaStreamSynchronize(st));
+  if (n_surv) *n_surv = surv;
+  if (n_mod) *n_mod = counts[0];
+  if (n_next) *n_next = counts[1];
+  ctx->h_counters[1].n_out = (uint32_t)surv;  // remembered for klsh_mg_export
+  ctx->h_counters[1].n_small = counts[0];
+  ctx->h_counters[1].n_large = counts[1];
+  return KLSH_OK;
+}
+
+extern "C" int klsh_mg_export(klsh_ctx* ctx, uint32_t* d_surv, uint32_t* d_mod_rows, float* d_mod_vals, int32_t* d_mod_meta,
+                              uint32_t* d_next_slot, int32_t* d_next_val) {
+  if (!ctx) return KLSH_ERR_ARG;
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const uint32_t surv = ctx->h_counters[1].n_out, nmod = ctx->h_counters[1].n_small, nnext = ctx->h_counters[1].n_large;
+  if (surv) KCUDA(ctx, cudaMemcpyAsync(d_surv, ctx->mg_surv.p, sizeof(uint32_t) * surv, cudaMemcpyDeviceToDevice, st));
+  if (nmod) {
+    KCUDA(ctx, cudaMemcpyAsync(d_mod_rows, ctx->mg_mod_rows.p, sizeof(uint32_t) * nmod, cudaMemcpyDeviceToDevice, st));
+    KTRY(launch_gather_mod(ctx, ctx->mg_mod_rows.as<uint32_t>(), nmod, d_mod_vals, d_mod_meta));
+  }
+  if (nnext) {
+    KCUDA(ctx, cudaMemcpyAsync(d_next_slot, ctx->mg_next_slot.p, sizeof(uint32_t) * nnext, cudaMemcpyDeviceToDevice, st));
+    KCUDA(ctx, cudaMemcpyAsync(d_next_val, ctx->mg_next_val.p, sizeof(int32_t) * nnext, cudaMemcpyDeviceToDevice, st));
+  }
+  KCUDA(ctx, cudaStreamSynchronize(st));
+  return KLSH_OK;
+}
+
+extern "C" int klsh_mg_apply(klsh_ctx* ctx, const uint32_t* d_mod_rows, const float* d_mod_vals, const int32_t* d_mod_meta,
+                             uint64_t n_mod, const uint32_t* d_next_slot, const int32_t* d_next_val, uint64_t n_next) {
+  if (!ctx) return KLSH_ERR_ARG;
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  KTRY(launch_apply_mod(ctx, d_mod_rows, (uint32_t)n_mod, d_mod_vals, d_mod_meta, d_next_slot, d_next_val, (uint32_t)n_next));
+  KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return KLSH_OK;
+}
+
+extern "C" int klsh_mg_set_alive(klsh_ctx* ctx, const uint32_t* d_alive, uint64_t n) {
+  if (!ctx || n > ctx->n_born) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_set_alive: bad argument");
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  KTRY(dev_reserve(ctx, ctx->cur.alive, sizeof(uint32_t) * (n + 1)));
+  if (n) KCUDA(ctx, cudaMemcpyAsync(ctx->cur.alive.p, d_alive, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, ctx->stream));
+  KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->cur.n_alive = n;
   return KLSH_OK;
 }

@@ -6,6 +6,7 @@
 // FMA (SURVEY.md section 7 hard part 2).  This file is compiled with -fmad=false and uses the
 // explicit-rounding intrinsics (__fmul_rn, __fadd_rn, __fdiv_rn, __fsqrt_rn), which ptxas never
 // contracts.
+#include <cstddef>
 #include <cstring>
 
 #include "klsh_internal.cuh"
@@ -359,12 +360,17 @@ __device__ __forceinline__ void warp_append_item(bool pred, uint32_t* counter, u
   }
 }
 
-__global__ void k_classify(uint32_t* bstart, uint64_t n, long long nest_threshold, PassCounters* counters,
-                           uint32_t* list_small, uint32_t* list_large, uint32_t* list_big, uint32_t* list_nested) {
+// Only buckets in [b_lo, b_hi) are queued for merging (multi-GPU: each rank owns a contiguous
+// range); oversized buckets are listed regardless of the range because every rank has to draw their
+// hash tables to keep the hyperplane stream in step.
+__global__ void k_classify(uint32_t* bstart, uint64_t n, long long nest_threshold, uint32_t b_lo, uint32_t b_hi,
+                           PassCounters* counters, uint32_t* list_small, uint32_t* list_large, uint32_t* list_big,
+                           uint32_t* list_nested) {
   const uint32_t nb = counters->n_buckets;
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b == 0) bstart[nb] = (uint32_t)n;
   uint32_t size = 0;
+  const bool mine = b >= b_lo && b < b_hi;
   if (b < nb) {
     const uint32_t s = bstart[b];
     const uint32_t e = (b + 1 < nb) ? bstart[b + 1] : (uint32_t)n;
@@ -373,9 +379,9 @@ __global__ void k_classify(uint32_t* bstart, uint64_t n, long long nest_threshol
   const uint32_t wmax = __reduce_max_sync(0xffffffffu, size);
   if (lane_id() == 0 && wmax > 0) atomicMax(&counters->bucket_max, wmax);
   const bool nested = nest_threshold >= 0 && (long long)size > nest_threshold && size >= 2;
-  const bool small = !nested && size >= 2 && size <= KLSH_SMALL_MAX;
-  const bool large = !nested && size > KLSH_SMALL_MAX && size < KLSH_BIG;
-  const bool big = !nested && size >= KLSH_BIG;
+  const bool small = mine && !nested && size >= 2 && size <= KLSH_SMALL_MAX;
+  const bool large = mine && !nested && size > KLSH_SMALL_MAX && size < KLSH_BIG;
+  const bool big = mine && !nested && size >= KLSH_BIG;
   warp_append(nested, &counters->n_nested, list_nested, b);
   warp_append(small, &counters->n_small, list_small, b);
   warp_append_item(large, &counters->n_large, list_large, b);
@@ -420,7 +426,7 @@ __global__ void __launch_bounds__(128)
 k_merge_small(float* __restrict__ vals, int D, int ld, int32_t* __restrict__ cnt, int32_t* __restrict__ head,
               int32_t* __restrict__ tail, int32_t* __restrict__ next, uint32_t* __restrict__ rows_sorted,
               const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ list, const PassCounters* counters,
-              float threshold) {
+              float threshold, MgLog mg) {
   extern __shared__ float smem[];
   const int stride = ld + 1;
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
@@ -483,6 +489,11 @@ k_merge_small(float* __restrict__ vals, int D, int ld, int32_t* __restrict__ cnt
         // ids(current) ++ ids(candidate): current's chain goes first
         if (t1 >= 0) {
           next[t1] = h2;
+          if (mg.counts) {
+            const uint32_t k = atomicAdd(mg.counts + 1, 1u);
+            mg.next_slot[k] = (uint32_t)t1;
+            mg.next_val[k] = h2;
+          }
           my_head = h1;
           if (my_tail < 0) my_tail = t1;
         }
@@ -506,6 +517,7 @@ k_merge_small(float* __restrict__ vals, int D, int ld, int32_t* __restrict__ cnt
       cnt[ridx] = my_cnt;
       head[ridx] = my_head;
       tail[ridx] = my_tail;
+      if (mg.counts) mg.mod_rows[atomicAdd(mg.counts, 1u)] = ridx;
     }
     uint32_t dm = dirty;
     while (dm) {
@@ -824,7 +836,7 @@ int launch_sort_pairs(klsh_ctx* ctx, PassScratch& s, uint64_t n, int bits, uint3
   return KLSH_OK;
 }
 
-int launch_bounds(klsh_ctx* ctx, PassScratch& s, const uint32_t* keys_sorted, uint64_t n, int64_t nest_threshold) {
+int launch_bounds(klsh_ctx* ctx, PassScratch& s, const uint32_t* keys_sorted, uint64_t n) {
   uint32_t nblk = cdiv64(n, kScanTile);
   KTRY(dev_reserve(ctx, s.blkcnt, sizeof(uint32_t) * (nblk + 1)));
   KTRY(dev_reserve(ctx, s.bstart, sizeof(uint32_t) * (n + 2)));
@@ -842,11 +854,94 @@ int launch_bounds(klsh_ctx* ctx, PassScratch& s, const uint32_t* keys_sorted, ui
   KTRY(scan_blkcnt(ctx, blk, nblk, &dc->n_buckets));
   k_heads_write<<<nblk, 256, 0, ctx->stream>>>(keys_sorted, n, blk, s.bstart.as<uint32_t>());
   KLAUNCH(ctx);
+  return KLSH_OK;
+}
+
+// Size classes of the buckets in [b_lo, b_hi) (everything after n_buckets in the counters is reset).
+int launch_classify(klsh_ctx* ctx, PassScratch& s, uint64_t n, int64_t nest_threshold, uint32_t b_lo, uint32_t b_hi) {
+  PassCounters* dc = s.counters.as<PassCounters>();
+  KCUDA(ctx, cudaMemsetAsync(&dc->n_small, 0, sizeof(PassCounters) - offsetof(PassCounters, n_small), ctx->stream));
   // bucket count is on the device; launch enough threads for the worst case (n buckets)
-  k_classify<<<cdiv64(n, 256), 256, 0, ctx->stream>>>(s.bstart.as<uint32_t>(), n, (long long)nest_threshold, dc,
+  k_classify<<<cdiv64(n, 256), 256, 0, ctx->stream>>>(s.bstart.as<uint32_t>(), n, (long long)nest_threshold, b_lo, b_hi, dc,
                                                       s.list_small.as<uint32_t>(), s.list_large.as<uint32_t>(),
                                                       s.list_big.as<uint32_t>(), s.list_nested.as<uint32_t>());
   KLAUNCH(ctx);
+  return KLSH_OK;
+}
+
+// ================================================================================================
+// Multi-GPU helpers: bucket range splits, update export / apply
+// ================================================================================================
+namespace {
+// splits[r] = first bucket whose start offset is >= r*n/world (buckets are never split)
+__global__ void k_find_splits(const uint32_t* __restrict__ bstart, uint32_t nb, uint64_t n, int world, uint32_t* splits) {
+  const int r = threadIdx.x;
+  if (r > world) return;
+  if (r == world) { splits[r] = nb; return; }
+  const uint64_t target = (uint64_t)r * n / (uint64_t)world;
+  uint32_t lo = 0, hi = nb;
+  while (lo < hi) {
+    const uint32_t mid = lo + (hi - lo) / 2;
+    if ((uint64_t)bstart[mid] < target) lo = mid + 1; else hi = mid;
+  }
+  splits[r] = lo;
+}
+__global__ void k_gather_mod(const float* __restrict__ vals, int ld, const int32_t* __restrict__ cnt,
+                             const int32_t* __restrict__ head, const int32_t* __restrict__ tail,
+                             const uint32_t* __restrict__ rows, uint32_t n, float* out_vals, int32_t* out_meta) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
+  if (w >= n) return;
+  const uint32_t r = rows[w];
+  for (int d = lane; d < ld; d += 32) out_vals[(uint64_t)w * ld + d] = vals[(uint64_t)r * ld + d];
+  if (lane == 0) {
+    out_meta[3 * (uint64_t)w] = cnt[r];
+    out_meta[3 * (uint64_t)w + 1] = head[r];
+    out_meta[3 * (uint64_t)w + 2] = tail[r];
+  }
+}
+__global__ void k_apply_mod(float* vals, int ld, int32_t* cnt, int32_t* head, int32_t* tail, const uint32_t* __restrict__ rows,
+                            uint32_t n, const float* __restrict__ in_vals, const int32_t* __restrict__ in_meta) {
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
+  if (w >= n) return;
+  const uint32_t r = rows[w];
+  for (int d = lane; d < ld; d += 32) vals[(uint64_t)r * ld + d] = in_vals[(uint64_t)w * ld + d];
+  if (lane == 0) {
+    cnt[r] = in_meta[3 * (uint64_t)w];
+    head[r] = in_meta[3 * (uint64_t)w + 1];
+    tail[r] = in_meta[3 * (uint64_t)w + 2];
+  }
+}
+__global__ void k_apply_next(int32_t* next, const uint32_t* __restrict__ slots, const int32_t* __restrict__ v, uint32_t n) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) next[slots[i]] = v[i];
+}
+}  // namespace
+
+int launch_find_splits(klsh_ctx* ctx, PassScratch& s, uint32_t nb, uint64_t n, int world, uint32_t* d_splits) {
+  k_find_splits<<<1, 64, 0, ctx->stream>>>(s.bstart.as<uint32_t>(), nb, n, world, d_splits);
+  KLAUNCH(ctx);
+  return KLSH_OK;
+}
+int launch_gather_mod(klsh_ctx* ctx, const uint32_t* rows, uint32_t n, float* out_vals, int32_t* out_meta) {
+  if (!n) return KLSH_OK;
+  k_gather_mod<<<cdiv64((uint64_t)n * 32, 256), 256, 0, ctx->stream>>>(ctx->cur.vals.as<float>(), ctx->ld, ctx->cur.cnt.as<int32_t>(),
+                                                                     ctx->cur.head.as<int32_t>(), ctx->cur.tail.as<int32_t>(), rows, n,
+                                                                     out_vals, out_meta);
+  KLAUNCH(ctx);
+  return KLSH_OK;
+}
+int launch_apply_mod(klsh_ctx* ctx, const uint32_t* rows, uint32_t n, const float* in_vals, const int32_t* in_meta,
+                     const uint32_t* slots, const int32_t* nvals, uint32_t n_next) {
+  if (n) {
+    k_apply_mod<<<cdiv64((uint64_t)n * 32, 256), 256, 0, ctx->stream>>>(ctx->cur.vals.as<float>(), ctx->ld, ctx->cur.cnt.as<int32_t>(),
+                                                                      ctx->cur.head.as<int32_t>(), ctx->cur.tail.as<int32_t>(), rows, n,
+                                                                      in_vals, in_meta);
+    KLAUNCH(ctx);
+  }
+  if (n_next) {
+    k_apply_next<<<cdiv64(n_next, 256), 256, 0, ctx->stream>>>(ctx->cur.next.as<int32_t>(), slots, nvals, n_next);
+    KLAUNCH(ctx);
+  }
   return KLSH_OK;
 }
 
@@ -889,7 +984,7 @@ int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float thr
     uint32_t grid = std::min<uint32_t>((n_small + wpb - 1) / wpb, (uint32_t)ctx->sm_count * 32);
     k_merge_small<<<grid, wpb * 32, smem, ctx->stream>>>(vals, D, ld, cnt, head, tail, next, rows_sorted,
                                                          s.bstart.as<uint32_t>(), s.list_small.as<uint32_t>(), dc,
-                                                         threshold);
+                                                         threshold, ctx->mg);
     KLAUNCH(ctx);
   }
   if (!n_large) return KLSH_OK;

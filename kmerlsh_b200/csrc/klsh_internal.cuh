@@ -54,6 +54,15 @@ struct PassCounters {  // lives in device memory, mirrored to pinned host memory
   uint32_t pad[3];
 };
 
+// Multi-GPU update logs (all null in single-GPU runs): rows whose values/metadata changed and the
+// member-chain pointer writes, appended by the merge kernels.  counts[0] = rows, counts[1] = next writes.
+struct MgLog {
+  uint32_t* counts = nullptr;
+  uint32_t* mod_rows = nullptr;
+  uint32_t* next_slot = nullptr;
+  int32_t* next_val = nullptr;
+};
+
 struct RowState {  // everything klsh_snapshot copies
   DevBuf vals, cnt, head, tail, next, alive;
   uint64_t n_alive = 0;
@@ -89,6 +98,13 @@ struct klsh_ctx {
   DevBuf alive_alt;   // the other half of the alive-list ping-pong
   DevBuf nested_out;  // survivors of one nested pass
   DevBuf team_ctl;    // per-team control blocks of the windowed merge
+  MgLog mg;           // multi-GPU update logs (null pointers unless a sharded pass is running)
+  DevBuf mg_counts, mg_mod_rows, mg_next_slot, mg_next_val, mg_splits, mg_surv;
+  uint32_t* mg_keys_sorted = nullptr;  // state of the sharded pass between klsh_mg_* calls
+  uint32_t* mg_rows_sorted = nullptr;
+  uint64_t mg_n = 0;
+  uint32_t mg_nb = 0;
+  int mg_H = 0;
   // escalation of the windowed merge: a bucket leaves its CTA for a cluster once it has more than
   // cta_max representatives, and the cluster for the whole grid above cluster_max
   uint32_t cta_max = 512, cluster_max = 8192, cluster2_max = 65536;
@@ -140,7 +156,12 @@ int launch_sign(klsh_ctx* ctx, const float* vals, int D, int ld, const uint32_t*
                 const float* d_planes, int H, uint32_t* keys_out, uint32_t* rows_out);
 int launch_sort_pairs(klsh_ctx* ctx, PassScratch& s, uint64_t n, int bits, uint32_t** keys_sorted,
                       uint32_t** rows_sorted);
-int launch_bounds(klsh_ctx* ctx, PassScratch& s, const uint32_t* keys_sorted, uint64_t n, int64_t nest_threshold);
+int launch_bounds(klsh_ctx* ctx, PassScratch& s, const uint32_t* keys_sorted, uint64_t n);
+int launch_classify(klsh_ctx* ctx, PassScratch& s, uint64_t n, int64_t nest_threshold, uint32_t b_lo, uint32_t b_hi);
+int launch_find_splits(klsh_ctx* ctx, PassScratch& s, uint32_t nb, uint64_t n, int world, uint32_t* d_splits);
+int launch_gather_mod(klsh_ctx* ctx, const uint32_t* rows, uint32_t n, float* out_vals, int32_t* out_meta);
+int launch_apply_mod(klsh_ctx* ctx, const uint32_t* rows, uint32_t n, const float* in_vals, const int32_t* in_meta,
+                     const uint32_t* slots, const int32_t* nvals, uint32_t n_next);
 int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, const PassCounters& c);
 int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, uint32_t n_items_host,
                         uint32_t bucket_max_host);

@@ -141,6 +141,7 @@ struct MergeArgs {
   uint32_t max_reps;
   float* pos_nrm;  // norm of the representative at each sorted position (scratch, N floats)
   TeamCtl* ctl;
+  MgLog mg;
   unsigned long long* dbg;  // [16] (8..13: leader cycles in stage/parallel/sync1/prefetch/resolve/sync2) windows, candidates, merges, undecidable, cache_full, back_exhausted, accepted, escalated
   float threshold, thr_lo;
 };
@@ -531,7 +532,15 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
       if (examined_merge) {
         const int e = s.ment[t], prev = s.mprev[t];
         const int t1 = s.ctail[t];
-        if (t1 >= 0) A.next[t1] = (prev < 0) ? s.dhead[e] : s.chead[prev];
+        if (t1 >= 0) {
+          const int nv = (prev < 0) ? s.dhead[e] : s.chead[prev];
+          A.next[t1] = nv;
+          if (A.mg.counts) {
+            const uint32_t k = atomicAdd(A.mg.counts + 1, 1u);
+            A.mg.next_slot[k] = (uint32_t)t1;
+            A.mg.next_val[k] = nv;
+          }
+        }
       }
     }
   }
@@ -541,6 +550,7 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
     const int e = (int)lane;
     if (e < nd) {
       const uint32_t rr = s.dridx[e];
+      if (A.mg.counts) A.mg.mod_rows[atomicAdd(A.mg.counts, 1u)] = rr;
       A.cnt[rr] = my_dcnt;
       // each merge prepends the candidate's members: the chain now starts with the LAST merged
       // candidate that carried ids
@@ -891,6 +901,7 @@ int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
   A.bstart = s.bstart.as<uint32_t>();
   A.pos_nrm = s.pos_nrm.as<float>();
   A.dbg = ctx->debug ? ctx->dbg.as<unsigned long long>() : nullptr;
+  A.mg = ctx->mg;
   A.threshold = threshold;
   A.thr_lo = threshold - 2e-6f - 4.0f * (float)ctx->ld * 5.9604645e-8f;
 

@@ -244,3 +244,32 @@ def test_merge_v1_kernel(oracle, monkeypatch):
         ctx.set_rows(values)
         ctx.cluster(0.8, 5, 500)
         assert_rows_equal(ctx.get_rows(), rows.export())
+
+
+@pytest.mark.parametrize("world,n,sa,sb,iters,nest", [(2, 60000, 4, 4, 5, 100000), (3, 60000, 4, 4, 3, 60), (4, 150000, 10, 10, 4, 1000)])
+def test_sharded_cluster_in_process(oracle, world, n, sa, sb, iters, nest):
+    """The multi-GPU protocol (replicated rows, partitioned bucket ranges, exchanged update logs) with
+    `world` contexts stepped in lockstep on one GPU: every replica must end bit-identical to the
+    oracle's single-process Cluster."""
+    import torch
+
+    from kmerlsh_b200 import Context
+    from kmerlsh_b200 import distributed as kd
+
+    _, _, values, ids = synth_rows(oracle, n, sa, sb, 91)
+    rows = oracle.rows(values)
+    ost = rows.cluster(0.82, iters, nest, oracle.planes(17))
+    want = rows.export()
+    ctxs = [Context(0, seed=17) for _ in range(world)]
+    try:
+        for c in ctxs:
+            c.set_rows(values)
+        stats = []
+        kd.run_in_process([kd.TorchBackend(c, torch.device("cuda:0")) for c in ctxs], 0.82, iters, nest, stats)
+        assert [s["rows_out"] for s in stats] == [s.rows_out for s in ost]
+        assert all(s["my_buckets"] < s["buckets"] for s in stats if s["buckets"] > world)
+        for c in ctxs:
+            assert_rows_equal(c.get_rows(), want)
+    finally:
+        for c in ctxs:
+            c.close()
