@@ -162,7 +162,7 @@ def reference_arm(args, rank, world):
         sample_rows, args.workload, sa + sb, iters, cores)
     print(json.dumps({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": workload_config(args, n, sa, sb, world),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "reference", "sample": sample},
@@ -174,8 +174,9 @@ def workload_config(args, n, sa, sb, world):
     return {
         "workload": "%s: mode C on synthetic %d k-mers x %d samples (%d A + %d B), phase 1 I=1 + phase 2 I=%d, N=%.2f" % (
             args.workload, n, sa + sb, sa, sb, args.iters, args.min_similarity),
-        "rows_per_gpu": n, "dim": sa + sb, "iterations": 1 + args.iters, "min_similarity": args.min_similarity,
-        "parallelism": "1 GPU" if world == 1 else "%d independent row shards (one mode-C job per GPU, no data-path collective)" % world,
+        "rows": n, "dim": sa + sb, "iterations": 1 + args.iters, "min_similarity": args.min_similarity,
+        "parallelism": "1 GPU" if world == 1 else ("%d GPUs: replicated rows, bucket ranges partitioned over ranks, per-iteration NCCL "
+                                                   "all-gather of survivors + modified rows (kmerlsh_b200/distributed.py)" % world),
         "l2_policy": "inputs larger than L2 (row arena %.1f GB per GPU); no flush" % (n * (sa + sb) * 4 / 1e9),
         "state_reset": "untimed device-to-device restore between steps",
     }
@@ -220,21 +221,41 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- inputs (each rank its own shard: generator seed offset by rank) --------------------------
-    n, sa, sb, gseed = synth.CONFIGS[args.workload]
-    if world > 1:
-        synth.CONFIGS[args.workload] = (n, sa, sb, gseed + 1000 * rank)
+    # ---- inputs: the SAME matrix on every rank (the multi-GPU path replicates the rows and
+    # partitions the merge work, so total work is fixed as N grows: strong scaling) ----------------
     n, sa, sb, counts, cov, vk, _keep = make_inputs(args.workload, args.rows, "cuda:%d" % local_rank)
     d = sa + sb
     torch.cuda.empty_cache()
+    if world > 1:
+        chk = torch.tensor([float(cov.sum()), float(counts[:, :: max(1, n // 4096)].astype(np.float64).sum())], device="cuda", dtype=torch.float64)
+        lo, hi = chk.clone(), chk.clone()
+        dist.all_reduce(lo, op=dist.ReduceOp.MIN)
+        dist.all_reduce(hi, op=dist.ReduceOp.MAX)
+        if not torch.equal(lo, hi):
+            raise SystemExit("synthetic inputs differ between ranks; the replicated multi-GPU path needs identical rows")
 
     ctx = Context(local_rank, seed=42)
     p1_thr, p2_thr = 100000, 1000000
 
+    class _S:  # the fields of klsh_iter_stats this script reads, for the sharded path
+        def __init__(self, d_):
+            self.rows_in, self.rows_out = d_["rows_in"], d_["rows_out"]
+            self.ms_sign = self.ms_group = self.ms_merge = self.ms_compact = self.ms_total = 0.0
+
+    if world > 1:
+        from kmerlsh_b200 import distributed as kd
+
+        backend = kd.TorchBackend(ctx, torch.device("cuda", local_rank))
+
     def one_pass():
-        st = ctx.cluster(args.min_similarity, 1, p1_thr)
-        st += ctx.cluster(args.min_similarity, args.iters, p2_thr)
-        return st
+        if world == 1:
+            st = ctx.cluster(args.min_similarity, 1, p1_thr)
+            st += ctx.cluster(args.min_similarity, args.iters, p2_thr)
+            return st
+        raw = []
+        kd.run_with_torch_distributed(backend, args.min_similarity, 1, p1_thr, raw)
+        kd.run_with_torch_distributed(backend, args.min_similarity, args.iters, p2_thr, raw)
+        return [_S(x) for x in raw]
 
     # ---- device-resident arm ------------------------------------------------------------------------
     ctx.load_counts(counts, vk, 0)
@@ -287,10 +308,10 @@ def main():
     if world > 1:
         tt = torch.tensor([t_total, e_total], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        rr = torch.tensor([rows_total, erows_total, float(launches)], device="cuda", dtype=torch.float64)
+        rr = torch.tensor([float(launches)], device="cuda", dtype=torch.float64)
         dist.all_reduce(rr, op=dist.ReduceOp.SUM)
         t_total, e_total = tt.tolist()
-        rows_total, erows_total, launches = rr.tolist()
+        launches = rr.tolist()[0]  # rows are NOT summed: every rank iterates over the same (whole) row set
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -315,14 +336,17 @@ def main():
             job_bytes += s.rows_in * b_alg(d, surv)
     dom = max(fam, key=fam.get)
     dev_total_ms = sum(fam.values())
+    if world > 1:  # per-family event times exist only on the single-GPU path; use the step time
+        dev_total_ms = t_total * 1e3
     achieved = merge_bytes / (fam["merge"] * 1e-3) / 1e9 if fam["merge"] > 0 else 0.0
     job_achieved = job_bytes / (dev_total_ms * 1e-3) / 1e9 if dev_total_ms > 0 else 0.0
     roofline = {
         "bound": "hbm", "kernel": "k_merge_* (in-bucket greedy merge, per iteration)", "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
-        "share_of_step": fam["merge"] / dev_total_ms if dev_total_ms else None, "dominant_family": dom,
-        "family_ms_per_step": {k: v / args.steps for k, v in fam.items()},
-        "job": {"achieved": job_achieved, "frac": job_achieved / peak, "bytes_per_row_iter": "8D+32+s(4D+12)"},
+        "share_of_step": (fam["merge"] / dev_total_ms if dev_total_ms else None) if world == 1 else None, "dominant_family": dom,
+        "family_ms_per_step": {k: v / args.steps for k, v in fam.items()} if world == 1 else None,
+        "job": {"achieved": job_achieved, "frac": job_achieved / (peak * world), "bytes_per_row_iter": "8D+32+s(4D+12)",
+                "peak_all_gpus": peak * world},
     }
 
     cpu = None
@@ -338,7 +362,7 @@ def main():
 
     out = {
         "metric": METRIC, "value": rows_total / t_total, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": t_total / args.steps * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "config": workload_config(args, n, sa, sb, world),
         "clocks": sampler.summary(),
         "e2e": {"value": erows_total / e_total, "unit": UNIT, "h2d_bytes_per_step": int(h2d_bytes), "d2h_bytes_per_step": int(d2h_bytes),
@@ -346,8 +370,8 @@ def main():
         "gpu_launches": int(launches),
         "roofline": roofline,
         "cpu_baseline": cpu,
-        "device_ms_per_step": float(np.mean(dev_ms)),
-        "rows_iterations_per_step": rows_total / args.steps / world,
+        "device_ms_per_step": float(np.mean(dev_ms)) if world == 1 else None,
+        "rows_iterations_per_step": rows_total / args.steps,
         "final_clusters": int(all_stats[-1][-1].rows_out),
     }
     print(json.dumps(out))

@@ -69,7 +69,6 @@ class TorchBackend:
         self.torch = torch
         self.ctx = ctx
         self.device = device
-        self.stride = ctx.row_stride()
 
     def mg_pass_begin(self):
         return self.ctx.mg_pass_begin()
@@ -83,10 +82,11 @@ class TorchBackend:
     def mg_export(self, n_surv, n_mod, n_chain):
         t = self.torch
         dev = self.device
+        stride = self.ctx.row_stride()  # known once rows are loaded
         counts = t.tensor([n_surv, n_mod, n_chain], dtype=t.int64, device=dev)
         surv = t.empty(max(n_surv, 1), dtype=t.int32, device=dev)
         mod_rows = t.empty(max(n_mod, 1), dtype=t.int32, device=dev)
-        mod_vals = t.empty((max(n_mod, 1), self.stride), dtype=t.float32, device=dev)
+        mod_vals = t.empty((max(n_mod, 1), stride), dtype=t.float32, device=dev)
         mod_meta = t.empty((max(n_mod, 1), 3), dtype=t.int32, device=dev)
         slots = t.empty(max(n_chain, 1), dtype=t.int32, device=dev)
         vals = t.empty(max(n_chain, 1), dtype=t.int32, device=dev)
