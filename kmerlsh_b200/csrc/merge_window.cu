@@ -25,6 +25,7 @@
 // Every decision and every centroid is bit-identical to the sequential algorithm (DESIGN.md
 // "Windowed merge: why it is exact").
 #include <cooperative_groups.h>
+#include <cuda_fp16.h>
 
 #include <chrono>
 #include <cstdio>
@@ -92,6 +93,25 @@ __device__ __forceinline__ float consensus1(float cur, int c1, float cand, int c
   return __fadd_rn(a, b);
 }
 
+// ---- tensor-core prefilter ----------------------------------------------------------------------------
+// The parallel phase is a contraction (window candidates x representatives x D).  Its exact form is
+// bound by FP32 issue, so it is screened on the tensor cores first: rows are scaled to unit norm,
+// rounded to fp16 and multiplied with mma.sync (fp32 accumulate).  With unit-norm inputs the result
+// approximates the cosine with absolute error < 1.1e-3 (fp16 input rounding 2*2^-11 per product,
+// Cauchy-Schwarz; accumulation and the reference's own fp32 rounding are orders of magnitude below).
+// A match needs cos >= thr - 2^-21, so only pairs with approx >= thr - 2e-3 can match: those few are
+// re-evaluated with the reference's exact arithmetic and nothing else decides anything.  Zero, NaN or
+// infinite norms give NaN/inf fragments, which never compare "below" and therefore reach the exact test.
+__device__ __forceinline__ uint32_t pack_half2(float a, float b) {
+  const __half2 h = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&h);
+}
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
 // ---- teams -----------------------------------------------------------------------------------------
 template <int TEAM>
 struct Team;
@@ -152,6 +172,8 @@ struct Smem {
   float* pre;    // [kW][ts]  row of each candidate's first-match representative, prefetched for the resolver
   float* cnorm;  // [kW]
   float* dnorm;  // [kKD]
+  __half* htile; // [kW][hs] unit-norm fp16 copy of the window (tensor-core prefilter)
+  int hs;
   uint32_t* ridx;   // [kW]
   int32_t* ccnt;    // [kW]
   int32_t* chead;   // [kW]
@@ -173,8 +195,13 @@ struct Smem {
   int ts;
 };
 
+// width (halfs) of the fp16 window copy: the k extent the kernel variant for this ld multiplies over
+__host__ __device__ inline int tc_width(int ld) { return ld <= 32 ? 32 : (ld <= 64 ? 64 : 16); }
+
 __host__ __device__ inline size_t smem_bytes_for(int ld) {
-  return sizeof(float) * ((size_t)(2 * kW + kKD) * (ld + 4) + kW + kKD) + sizeof(uint32_t) * (kW * 14 + kKD * 5) + 64;
+  const int hs = tc_width(ld) + 8;
+  return sizeof(float) * ((size_t)(2 * kW + kKD) * (ld + 4) + kW + kKD) + sizeof(uint32_t) * (kW * 14 + kKD * 5) + 64 +
+         sizeof(__half) * (size_t)kW * hs;
 }
 
 __device__ __forceinline__ void carve(Smem& s, float* base, int ld) {
@@ -202,7 +229,9 @@ __device__ __forceinline__ void carve(Smem& s, float* base, int ld) {
   s.phead = reinterpret_cast<int32_t*>(u); u += kW;
   s.ptail = reinterpret_cast<int32_t*>(u); u += kW;
   s.mprev = reinterpret_cast<int32_t*>(u); u += kW;
-  s.ment = reinterpret_cast<int32_t*>(u);
+  s.ment = reinterpret_cast<int32_t*>(u); u += kW;
+  s.hs = tc_width(ld) + 8;  // +8 halfs: rows 16 bytes apart modulo 128 -> conflict-free fragment loads
+  s.htile = reinterpret_cast<__half*>(u + 4);
 }
 
 // Compare one representative (row at rowp, norm rn) with window candidates [tb, te); call hit(t) on
@@ -274,6 +303,95 @@ __device__ __forceinline__ void compare_rep(const float* rowp, float rn, const S
     if (t0 + 1 < te && t0 + 1 != skip_t && !fast_reject(d1, s.cnorm[t0 + 1], rn, thr_lo)) exact(t0 + 1);
     if (t0 + 2 < te && t0 + 2 != skip_t && !fast_reject(d2, s.cnorm[t0 + 2], rn, thr_lo)) exact(t0 + 2);
     if (t0 + 3 < te && t0 + 3 != skip_t && !fast_reject(d3, s.cnorm[t0 + 3], rn, thr_lo)) exact(t0 + 3);
+  }
+}
+
+// Exact evaluation of one (candidate t, representative) pair that survived a prefilter.
+template <bool SM>
+__device__ __forceinline__ bool exact_pair(const Smem& s, int t, const float* rowp, float rn, int nq, float threshold) {
+  const float4* c4 = reinterpret_cast<const float4*>(s.tile + (size_t)t * s.ts);
+  float dx = 0.f;
+  for (int q = 0; q < nq; ++q) {
+    const float4 x = c4[q];
+    const float4 y = SM ? reinterpret_cast<const float4*>(rowp)[q] : __ldcg(reinterpret_cast<const float4*>(rowp) + q);
+    dx = __fadd_rn(dx, __fmul_rn(x.x, y.x));
+    dx = __fadd_rn(dx, __fmul_rn(x.y, y.y));
+    dx = __fadd_rn(dx, __fmul_rn(x.z, y.z));
+    dx = __fadd_rn(dx, __fmul_rn(x.w, y.w));
+  }
+  return cos_match(dx, s.cnorm[t], rn, threshold);
+}
+
+// Tensor-core screened comparison of the window with representatives [j_begin, j_end) (SELF == false)
+// or with the window's own rows (SELF == true: candidate x candidate bits).  One warp handles 8
+// representatives per step; KS16 = number of 16-wide k steps (rows are zero-padded to 16*KS16).
+template <int KS16, bool SELF>
+__device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* seg, const float* pos_nrm, Smem& s, int W,
+                                           uint32_t j_begin, uint32_t j_end, uint32_t warp_rank, uint32_t n_warps, int nq) {
+  const uint32_t lane = lane_id(), g = lane >> 2, tg = lane & 3;
+  const float thr_tc = A.threshold - 2e-3f;
+  const int ld = A.ld;
+  // A fragments of the whole window stay in registers: 4 row tiles x KS16 k-steps
+  uint32_t af[4][KS16][4];
+#pragma unroll
+  for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < KS16; ++ks) {
+      const __half* r0 = s.htile + (size_t)(mt * 16 + g) * s.hs + ks * 16 + tg * 2;
+      const __half* r1 = r0 + 8 * s.hs;
+      af[mt][ks][0] = *reinterpret_cast<const uint32_t*>(r0);
+      af[mt][ks][1] = *reinterpret_cast<const uint32_t*>(r1);
+      af[mt][ks][2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
+      af[mt][ks][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
+    }
+  for (uint32_t jb = j_begin + warp_rank * 8; jb < j_end; jb += n_warps * 8) {
+    const uint32_t j = jb + g;  // this thread group's representative
+    const bool valid = j < j_end;
+    uint32_t bf[KS16][2];
+    if (SELF) {
+      const __half* hr = s.htile + (size_t)(valid ? j : 0) * s.hs + tg * 2;
+#pragma unroll
+      for (int ks = 0; ks < KS16; ++ks) {
+        bf[ks][0] = *reinterpret_cast<const uint32_t*>(hr + ks * 16);
+        bf[ks][1] = *reinterpret_cast<const uint32_t*>(hr + ks * 16 + 8);
+      }
+    } else {
+      const uint32_t rr = valid ? __ldcg(seg + j) : 0u;
+      const float inv = valid ? __fdividef(1.f, __ldcg(pos_nrm + j)) : 0.f;
+      const float* row = A.vals + (uint64_t)rr * ld + tg * 2;
+#pragma unroll
+      for (int ks = 0; ks < KS16; ++ks) {
+        float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
+        if (valid && ks * 16 + tg * 2 < ld) v0 = __ldcg(reinterpret_cast<const float2*>(row + ks * 16));
+        if (valid && ks * 16 + 8 + tg * 2 < ld) v1 = __ldcg(reinterpret_cast<const float2*>(row + ks * 16 + 8));
+        bf[ks][0] = pack_half2(v0.x * inv, v0.y * inv);
+        bf[ks][1] = pack_half2(v1.x * inv, v1.y * inv);
+      }
+    }
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt) {
+      float c[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int ks = 0; ks < KS16; ++ks) mma_16816(c, af[mt][ks], bf[ks][0], bf[ks][1]);
+      // c[0],c[1]: candidate mt*16+g vs representatives jb+2*tg, +1 ; c[2],c[3]: candidate +8
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        if (c[e] < thr_tc) continue;  // NaN/inf do not compare below and go to the exact test
+        const int t = mt * 16 + (int)g + ((e & 2) ? 8 : 0);
+        const uint32_t jj = jb + tg * 2 + (e & 1);
+        if (t >= W || jj >= j_end) continue;
+        if (SELF) {
+          if ((int)jj == t) continue;
+          if (exact_pair<true>(s, t, s.tile + (size_t)jj * s.ts, s.cnorm[jj], nq, A.threshold))
+            atomicOr(&s.pair[2 * t + (jj >> 5)], 1u << (jj & 31));
+        } else {
+          if (s.s_f[t] < jj) continue;  // an earlier match is already recorded
+          const uint32_t rr2 = __ldcg(seg + jj);
+          if (exact_pair<false>(s, t, A.vals + (uint64_t)rr2 * ld, __ldcg(pos_nrm + jj), nq, A.threshold))
+            atomicMin(&s.s_f[t], jj);
+        }
+      }
+    }
   }
 }
 
@@ -676,9 +794,26 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
     __syncthreads();
     if (tid < W) s.cnorm[tid] = norm_seq(reinterpret_cast<const float4*>(s.tile + (size_t)tid * s.ts), nq);
     __syncthreads();
+    constexpr bool kUseTc = DR > 0;  // rows of up to 64 floats: tensor-core prefilter
+    if (kUseTc) {
+      // unit-norm fp16 copy of the window, zero-padded to the k-step width
+      const int kw = s.hs - 8;
+      for (int v = tid; v < kW * kw; v += kMT) {
+        const int t = v / kw, d = v - t * kw;
+        float x = 0.f;
+        if (t < W && d < ld) x = __fdividef(s.tile[(size_t)t * s.ts + d], s.cnorm[t]);
+        s.htile[(size_t)t * s.hs + d] = __float2half_rn(x);
+      }
+      __syncthreads();
+    }
     if (prof) tk1 = clock64();
     // ---- parallel phase: old representatives [0, i0) across the team ----
-    {
+    if (kUseTc) {
+      constexpr int KS16 = DR > 0 ? DR / 16 : 1;
+      tc_compare<KS16, false>(A, seg, pos_nrm, s, W, 0u, i0, Team<TEAM>::rank() * (kMT / 32) + warp,
+                              Team<TEAM>::ncta() * (kMT / 32), nq);
+      if (leader) tc_compare<KS16, true>(A, seg, pos_nrm, s, W, 0u, (uint32_t)W, warp, kMT / 32, nq);
+    } else {
       const uint32_t gstride = Team<TEAM>::ncta() * kMT;
       for (uint32_t j = Team<TEAM>::rank() * kMT + tid; j < i0; j += gstride) {
         const uint32_t rr = __ldcg(seg + j);

@@ -273,3 +273,29 @@ def test_sharded_cluster_in_process(oracle, world, n, sa, sb, iters, nest):
     finally:
         for c in ctxs:
             c.close()
+
+
+def test_prefilter_boundaries(gpu, oracle):
+    """The tensor-core / FMA prefilters may only drop pairs the exact test would drop: thresholds set
+    exactly on (and one ulp either side of) similarities that occur in the bucket, rows scaled to
+    tiny and huge magnitudes (fp16 copies are taken of unit-norm rows), a zero row and a NaN row."""
+    rng = np.random.default_rng(123)
+    base = rng.standard_normal((1, 24)).astype(np.float32)
+    x = (base + np.float32(0.35) * rng.standard_normal((400, 24))).astype(np.float32)
+    sims = np.array([np.float32(1) - oracle.cosine_distance(x[i], x[0]) for i in range(1, 60)], dtype=np.float32)
+    thrs = []
+    for s_ in np.sort(sims)[[5, 20, 40]]:
+        thrs += [float(np.nextafter(s_, np.float32(-1))), float(s_), float(np.nextafter(s_, np.float32(2)))]
+    scaled = x.copy()
+    scaled[::3] *= np.float32(1e-18)
+    scaled[1::3] *= np.float32(1e15)
+    odd = x.copy()
+    odd[7] = 0.0
+    odd[11, 3] = np.nan
+    for values in (x, scaled, odd):
+        for thr in thrs[:6] if values is not x else thrs:
+            rows = oracle.rows(values)
+            rows.p_cluster(thr)
+            gpu.set_rows(values)
+            gpu.p_cluster(thr)
+            assert_rows_equal(gpu.get_rows(), rows.export(), "thr=%r" % thr)
