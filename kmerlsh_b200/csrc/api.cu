@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <thread>
 
 #include "klsh_internal.cuh"
 
@@ -539,13 +540,29 @@ static int export_rows(klsh_ctx* ctx, std::vector<float>* values, std::vector<ui
   for (uint64_t r = 0; r < n; ++r) offs[r + 1] = offs[r] + (uint64_t)cnt[r];
   if (ids) {
     ids->resize(offs[n]);
-    for (uint64_t r = 0; r < n; ++r) {
-      uint64_t o = offs[r];
-      const uint64_t end = offs[r + 1];
-      for (int32_t s = head[r]; s >= 0 && o < end; s = next[s])
-        (*ids)[o++] = ctx->ids_implicit ? ctx->id_base + (uint64_t)s : ctx->ids[s];
-      if (o != end) return klsh_fail(ctx, KLSH_ERR_ARG, "internal: member chain of row %llu is inconsistent", (unsigned long long)r);
-    }
+    // Walking the member chains is pointer chasing through next[] (one dependent load per id): split the
+    // clusters over host threads, balanced by id count.
+    const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
+    const unsigned nt = (unsigned)std::min<uint64_t>(hw, std::max<uint64_t>(1, offs[n] / 65536));
+    std::vector<uint64_t> bad(nt, UINT64_MAX);
+    auto work = [&](unsigned w) {
+      const uint64_t id_lo = offs[n] / nt * w, id_hi = (w + 1 == nt) ? offs[n] : offs[n] / nt * (w + 1);
+      uint64_t r = std::lower_bound(offs.begin(), offs.begin() + n, id_lo) - offs.begin();
+      for (; r < n && offs[r] < id_hi; ++r) {
+        uint64_t o = offs[r];
+        const uint64_t end = offs[r + 1];
+        for (int32_t s = head[r]; s >= 0 && o < end; s = next[s])
+          (*ids)[o++] = ctx->ids_implicit ? ctx->id_base + (uint64_t)s : ctx->ids[s];
+        if (o != end && bad[w] == UINT64_MAX) bad[w] = r;
+      }
+    };
+    std::vector<std::thread> pool;
+    for (unsigned w = 1; w < nt; ++w) pool.emplace_back(work, w);
+    work(0);
+    for (auto& t : pool) t.join();
+    for (unsigned w = 0; w < nt; ++w)
+      if (bad[w] != UINT64_MAX)
+        return klsh_fail(ctx, KLSH_ERR_ARG, "internal: member chain of row %llu is inconsistent", (unsigned long long)bad[w]);
   }
   return KLSH_OK;
 }
