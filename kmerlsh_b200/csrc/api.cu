@@ -147,6 +147,7 @@ void klsh_destroy(klsh_ctx* ctx) {
   dev_free(ctx->alive_alt);
   dev_free(ctx->nested_out);
   dev_free(ctx->team_ctl);
+  dev_free(ctx->eps_counter);
   dev_free(ctx->dbg);
   dev_free(ctx->mg_counts); dev_free(ctx->mg_mod_rows); dev_free(ctx->mg_next_slot); dev_free(ctx->mg_next_val);
   dev_free(ctx->mg_splits); dev_free(ctx->mg_surv);
@@ -408,6 +409,9 @@ extern "C" int klsh_cluster(klsh_ctx* ctx, float min_similarity, int iterations,
   float max_similarity = 0.95f;
   float sim_step = (max_similarity - min_similarity) / iterations;
   float threshold = max_similarity;
+  KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long)));
+  KCUDA(ctx, cudaMemsetAsync(ctx->eps_counter.p, 0, sizeof(unsigned long long), ctx->stream));
+  unsigned long long eps_prev = 0;
   for (int iter = 1; iter <= iterations; ++iter) {
     const uint64_t n = ctx->cur.n_alive;
     if (n == 0) break;  // the reference takes log2(0) here (undefined); an empty set stays empty
@@ -429,7 +433,11 @@ extern "C" int klsh_cluster(klsh_ctx* ctx, float min_similarity, int iterations,
       s.buckets = info.buckets;
       s.bucket_max = info.bucket_max;
       s.nested_calls = info.nested_calls;
-      s.eps_margin_rows = 0;
+      unsigned long long eps_now = 0;
+      KCUDA(ctx, cudaMemcpyAsync(&eps_now, ctx->eps_counter.p, sizeof eps_now, cudaMemcpyDeviceToHost, ctx->stream));
+      KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      s.eps_margin_rows = eps_now - eps_prev;  // includes the signing passes of nested buckets
+      eps_prev = eps_now;
       s.ms_sign = info.ms_sign;
       s.ms_group = info.ms_group;
       s.ms_merge = info.ms_merge;

@@ -147,19 +147,37 @@ __global__ void k_fill_i32(int32_t* p, uint64_t n, int32_t v) {
 // ================================================================================================
 constexpr int kSignWarps = 4;
 
+// Fast path: the sum is first accumulated with fused multiply-adds (half the instructions of the
+// reference's mul-then-add chain; the exact chain makes this kernel FP32-issue bound at 0.09*H
+// times its HBM time).  |s_fma - s_exact| <= 2*D*2^-24 * sum|w_i x_i| <= 2*D*2^-24 * |w||x|, so if
+// |s_fma| exceeds eps = (2.5*D+2)*2^-24*|w||x| both sums are non-zero with the same sign.  Otherwise —
+// the north star's "projection magnitude below eps" set — the (row, plane) sum is re-evaluated with
+// the reference's exact arithmetic, so every key bit is the reference's; such rows are counted.
+// DR > 0: the row is held in registers (ld <= DR) and the planes are read as broadcast float4; DR == 0:
+// any width, row read from the shared-memory tile.
+template <int DR>
 __global__ void __launch_bounds__(kSignWarps * 32)
 k_sign(const float* __restrict__ vals, int D, int ld, const uint32_t* __restrict__ rows, uint64_t n,
-       const float* __restrict__ planes, int H, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ rows_out) {
-  extern __shared__ float smem[];
+       const float* __restrict__ planes, int H, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ rows_out,
+       unsigned long long* eps_rows) {
+  extern __shared__ __align__(16) float smem[];
   float* sp = smem;                      // planes [H][ld]
+  float* pn = smem + (size_t)H * ld;     // eps factor per plane: |w_h| * (2.5*D+2)*2^-24   [H rounded up to 4]
   const int stride = ld + 1;             // odd
-  float* tiles = smem + (size_t)H * ld;  // [kSignWarps][32][stride]
+  float* tiles = pn + ((H + 3) & ~3);    // [kSignWarps][32][stride]
   for (int i = threadIdx.x; i < H * ld; i += blockDim.x) sp[i] = planes[i];
+  __syncthreads();
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float m = 0.f;
+    for (int i = 0; i < D; ++i) m = __fmaf_rn(sp[h * ld + i], sp[h * ld + i], m);
+    pn[h] = sqrtf(m) * ((2.5f * (float)D + 2.f) * 5.9604645e-8f);
+  }
   __syncthreads();
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   float* tile = tiles + (size_t)warp * 32 * stride;
   const uint64_t nwarps_total = (uint64_t)gridDim.x * kSignWarps;
   const int vec_per_row = ld >> 2;
+  uint32_t my_eps = 0;
   for (uint64_t t0 = ((uint64_t)blockIdx.x * kSignWarps + warp) * 32; t0 < n; t0 += nwarps_total * 32) {
     uint64_t t = t0 + lane;
     uint32_t r = (t < n) ? (rows ? rows[t] : (uint32_t)t) : 0u;
@@ -180,16 +198,76 @@ k_sign(const float* __restrict__ vals, int D, int ld, const uint32_t* __restrict
     if (t < n) {
       const float* x = tile + lane * stride;
       uint32_t key = 0;
-      for (int h = 0; h < H; ++h) {
-        const float* w = sp + h * ld;
-        float sum = 0.f;
-        for (int i = 0; i < D; ++i) sum = __fadd_rn(sum, __fmul_rn(w[i], x[i]));
-        key = key * 2u + (sum >= 0.f ? 1u : 0u);
+      bool slow = false;
+      if (DR > 0) {
+        float xr[DR > 0 ? DR : 1];
+#pragma unroll
+        for (int i = 0; i < DR; ++i) xr[i] = (i < ld) ? x[i] : 0.f;  // padding (i >= D) is zero in the arena
+        float xx = 0.f;
+#pragma unroll
+        for (int i = 0; i < DR; ++i) xx = __fmaf_rn(xr[i], xr[i], xx);
+        const float xn = sqrtf(xx);
+        // two planes per step, four independent accumulators each: short dependency chains
+        for (int h = 0; h < H; h += 2) {
+          const bool two = h + 1 < H;
+          const float4* wa = reinterpret_cast<const float4*>(sp + h * ld);
+          const float4* wb = reinterpret_cast<const float4*>(sp + (two ? h + 1 : h) * ld);
+          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
+#pragma unroll
+          for (int q = 0; q < DR / 4; ++q)
+            if (q < vec_per_row) {
+              const float4 u = wa[q], v = wb[q];
+              a0 = __fmaf_rn(u.x, xr[4 * q], a0);     b0 = __fmaf_rn(v.x, xr[4 * q], b0);
+              a1 = __fmaf_rn(u.y, xr[4 * q + 1], a1); b1 = __fmaf_rn(v.y, xr[4 * q + 1], b1);
+              a2 = __fmaf_rn(u.z, xr[4 * q + 2], a2); b2 = __fmaf_rn(v.z, xr[4 * q + 2], b2);
+              a3 = __fmaf_rn(u.w, xr[4 * q + 3], a3); b3 = __fmaf_rn(v.w, xr[4 * q + 3], b3);
+            }
+          float sums[2] = {(a0 + a1) + (a2 + a3), (b0 + b1) + (b2 + b3)};
+#pragma unroll
+          for (int p = 0; p < 2; ++p) {
+            if (p == 1 && !two) break;
+            float sum = sums[p];
+            if (!(fabsf(sum) > pn[h + p] * xn) || !(fabsf(sum) <= 3.0e38f)) {
+              // reference arithmetic: sum = fl(sum + fl(w_i * x_i)), i ascending (hash/lshash.cc:44-51)
+              const float* w = sp + (h + p) * ld;
+              sum = 0.f;
+              for (int j = 0; j < D; ++j) sum = __fadd_rn(sum, __fmul_rn(w[j], x[j]));
+              slow = true;
+            }
+            key = key * 2u + (sum >= 0.f ? 1u : 0u);
+          }
+        }
+      } else {
+        float xx = 0.f;
+        for (int i = 0; i < D; ++i) xx = __fmaf_rn(x[i], x[i], xx);
+        const float xn = sqrtf(xx);
+        for (int h = 0; h < H; ++h) {
+          const float* w = sp + h * ld;
+          float s0 = 0.f, s1 = 0.f;
+          int i = 0;
+          for (; i + 1 < D; i += 2) {
+            s0 = __fmaf_rn(w[i], x[i], s0);
+            s1 = __fmaf_rn(w[i + 1], x[i + 1], s1);
+          }
+          if (i < D) s0 = __fmaf_rn(w[i], x[i], s0);
+          float sum = s0 + s1;
+          if (!(fabsf(sum) > pn[h] * xn) || !(fabsf(sum) <= 3.0e38f)) {
+            sum = 0.f;
+            for (int j = 0; j < D; ++j) sum = __fadd_rn(sum, __fmul_rn(w[j], x[j]));
+            slow = true;
+          }
+          key = key * 2u + (sum >= 0.f ? 1u : 0u);
+        }
       }
       keys_out[t] = key;
       rows_out[t] = r;
+      my_eps += slow ? 1u : 0u;
     }
     __syncwarp();
+  }
+  if (eps_rows) {
+    const uint32_t tot = __reduce_add_sync(0xffffffffu, my_eps);
+    if (lane == 0 && tot) atomicAdd(eps_rows, (unsigned long long)tot);
   }
 }
 
@@ -241,12 +319,13 @@ __global__ void __launch_bounds__(kRadixWarps * 32)
 k_radix_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ rows, uint64_t n, int shift,
                 const uint32_t* __restrict__ hist, const uint32_t* __restrict__ dtot, uint32_t nblk,
                 uint32_t* __restrict__ keys_out, uint32_t* __restrict__ rows_out) {
-  __shared__ uint32_t wc[kRadixWarps][256];
-  __shared__ uint32_t dbase[256];
+  __shared__ uint32_t wc[kRadixWarps][256];  // per warp and digit: count, then exclusive prefix over warps
+  __shared__ uint32_t dbase[256];            // global position of this block's first element of each digit
+  __shared__ uint32_t tstart[256];           // position of each digit's run inside the block's sorted tile
+  __shared__ uint32_t skey[kRadixTile], srow[kRadixTile];
   __shared__ uint32_t ws[33];
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
   for (int w = 0; w < kRadixWarps; ++w) wc[w][threadIdx.x] = 0;
-  // exclusive scan of the 256 digit totals (256 threads)
   {
     uint32_t tot;
     uint32_t ex = block_exclusive_scan(dtot[threadIdx.x], ws, &tot);
@@ -255,7 +334,8 @@ k_radix_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ 
   __syncthreads();
   uint32_t k[kRadixRounds], r[kRadixRounds];
   uint16_t rank[kRadixRounds];
-  const uint64_t base = (uint64_t)blockIdx.x * kRadixTile + (uint64_t)warp * (kRadixRounds * 32);
+  const uint64_t tile_base = (uint64_t)blockIdx.x * kRadixTile;
+  const uint64_t base = tile_base + (uint64_t)warp * (kRadixRounds * 32);
 #pragma unroll
   for (int rd = 0; rd < kRadixRounds; ++rd) {
     uint64_t i = base + (uint64_t)rd * 32 + lane;
@@ -278,25 +358,42 @@ k_radix_scatter(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ 
     __syncwarp();
   }
   __syncthreads();
-  // per digit: exclusive prefix over warps, plus the block's global base
+  // per digit: exclusive prefix over warps (input order inside the tile is warp-major) and the tile total
+  uint32_t tile_cnt;
   {
-    uint32_t run = dbase[threadIdx.x];
+    uint32_t run = 0;
     for (int w = 0; w < kRadixWarps; ++w) {
       uint32_t c = wc[w][threadIdx.x];
       wc[w][threadIdx.x] = run;
       run += c;
     }
+    tile_cnt = run;
+  }
+  {
+    uint32_t tot;
+    tstart[threadIdx.x] = block_exclusive_scan(tile_cnt, ws, &tot);
   }
   __syncthreads();
+  // stage the tile in digit order in shared memory ...
 #pragma unroll
   for (int rd = 0; rd < kRadixRounds; ++rd) {
     uint64_t i = base + (uint64_t)rd * 32 + lane;
     if (i < n) {
       uint32_t d = (k[rd] >> shift) & 255u;
-      uint32_t dst = wc[warp][d] + rank[rd];
-      keys_out[dst] = k[rd];
-      rows_out[dst] = r[rd];
+      uint32_t lp = tstart[d] + wc[warp][d] + rank[rd];
+      skey[lp] = k[rd];
+      srow[lp] = r[rd];
     }
+  }
+  __syncthreads();
+  // ... and write every digit's run to its global position with consecutive threads
+  const uint32_t tile_n = (uint32_t)min((uint64_t)kRadixTile, n - tile_base);
+  for (uint32_t i = threadIdx.x; i < tile_n; i += kRadixWarps * 32) {
+    const uint32_t kk = skey[i];
+    const uint32_t d = (kk >> shift) & 255u;
+    const uint32_t dst = dbase[d] + (i - tstart[d]);
+    keys_out[dst] = kk;
+    rows_out[dst] = srow[i];
   }
 }
 
@@ -367,25 +464,30 @@ __global__ void k_classify(uint32_t* bstart, uint64_t n, long long nest_threshol
                            PassCounters* counters, uint32_t* list_small, uint32_t* list_large, uint32_t* list_big,
                            uint32_t* list_nested) {
   const uint32_t nb = counters->n_buckets;
-  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b == 0) bstart[nb] = (uint32_t)n;
-  uint32_t size = 0;
-  const bool mine = b >= b_lo && b < b_hi;
-  if (b < nb) {
-    const uint32_t s = bstart[b];
-    const uint32_t e = (b + 1 < nb) ? bstart[b + 1] : (uint32_t)n;
-    size = e - s;
+  if (blockIdx.x == 0 && threadIdx.x == 0) bstart[nb] = (uint32_t)n;
+  uint32_t tmax = 0;
+  // grid-stride over the buckets (their number is only known on the device); whole warps iterate together
+  for (uint32_t b0 = blockIdx.x * blockDim.x; b0 < nb; b0 += gridDim.x * blockDim.x) {
+    const uint32_t b = b0 + threadIdx.x;
+    uint32_t size = 0;
+    const bool mine = b >= b_lo && b < b_hi;
+    if (b < nb) {
+      const uint32_t s = bstart[b];
+      const uint32_t e = (b + 1 < nb) ? bstart[b + 1] : (uint32_t)n;
+      size = e - s;
+    }
+    tmax = max(tmax, size);
+    const bool nested = nest_threshold >= 0 && (long long)size > nest_threshold && size >= 2;
+    const bool small = mine && !nested && size >= 2 && size <= KLSH_SMALL_MAX;
+    const bool large = mine && !nested && size > KLSH_SMALL_MAX && size < KLSH_BIG;
+    const bool big = mine && !nested && size >= KLSH_BIG;
+    warp_append(nested, &counters->n_nested, list_nested, b);
+    warp_append(small, &counters->n_small, list_small, b);
+    warp_append_item(large, &counters->n_large, list_large, b);
+    warp_append_item(big, &counters->n_big, list_big, b);
   }
-  const uint32_t wmax = __reduce_max_sync(0xffffffffu, size);
+  const uint32_t wmax = __reduce_max_sync(0xffffffffu, tmax);
   if (lane_id() == 0 && wmax > 0) atomicMax(&counters->bucket_max, wmax);
-  const bool nested = nest_threshold >= 0 && (long long)size > nest_threshold && size >= 2;
-  const bool small = mine && !nested && size >= 2 && size <= KLSH_SMALL_MAX;
-  const bool large = mine && !nested && size > KLSH_SMALL_MAX && size < KLSH_BIG;
-  const bool big = mine && !nested && size >= KLSH_BIG;
-  warp_append(nested, &counters->n_nested, list_nested, b);
-  warp_append(small, &counters->n_small, list_small, b);
-  warp_append_item(large, &counters->n_large, list_large, b);
-  warp_append_item(big, &counters->n_big, list_big, b);
 }
 
 // ================================================================================================
@@ -796,15 +898,14 @@ int launch_transform(klsh_ctx* ctx, const uint16_t* d_counts, const float* d_vk,
 int launch_sign(klsh_ctx* ctx, const float* vals, int D, int ld, const uint32_t* rows, uint64_t n,
                 const float* d_planes, int H, uint32_t* keys_out, uint32_t* rows_out) {
   if (!n) return KLSH_OK;
-  size_t smem = sizeof(float) * ((size_t)H * ld + (size_t)kSignWarps * 32 * (ld + 1));
-  static size_t configured = 0;
-  if (smem > 48 * 1024 && smem > configured) {
-    KCUDA(ctx, cudaFuncSetAttribute(k_sign, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = smem;
-  }
+  KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long)));
+  size_t smem = sizeof(float) * ((size_t)H * ld + ((H + 3) & ~3) + (size_t)kSignWarps * 32 * (ld + 1));
+  auto fn = ld <= 32 ? k_sign<32> : (ld <= 64 ? k_sign<64> : k_sign<0>);
+  if (smem > 48 * 1024) KCUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   uint64_t want = (n + kSignWarps * 32 - 1) / (kSignWarps * 32);
   uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * 16);
-  k_sign<<<grid, kSignWarps * 32, smem, ctx->stream>>>(vals, D, ld, rows, n, d_planes, H, keys_out, rows_out);
+  fn<<<grid, kSignWarps * 32, smem, ctx->stream>>>(vals, D, ld, rows, n, d_planes, H, keys_out, rows_out,
+                                                   ctx->eps_counter.as<unsigned long long>());
   KLAUNCH(ctx);
   return KLSH_OK;
 }
@@ -862,7 +963,7 @@ int launch_classify(klsh_ctx* ctx, PassScratch& s, uint64_t n, int64_t nest_thre
   PassCounters* dc = s.counters.as<PassCounters>();
   KCUDA(ctx, cudaMemsetAsync(&dc->n_small, 0, sizeof(PassCounters) - offsetof(PassCounters, n_small), ctx->stream));
   // bucket count is on the device; launch enough threads for the worst case (n buckets)
-  k_classify<<<cdiv64(n, 256), 256, 0, ctx->stream>>>(s.bstart.as<uint32_t>(), n, (long long)nest_threshold, b_lo, b_hi, dc,
+  k_classify<<<std::min<uint32_t>(cdiv64(n, 256), (uint32_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(s.bstart.as<uint32_t>(), n, (long long)nest_threshold, b_lo, b_hi, dc,
                                                       s.list_small.as<uint32_t>(), s.list_large.as<uint32_t>(),
                                                       s.list_big.as<uint32_t>(), s.list_nested.as<uint32_t>());
   KLAUNCH(ctx);

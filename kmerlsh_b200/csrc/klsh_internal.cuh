@@ -98,6 +98,7 @@ struct klsh_ctx {
   DevBuf alive_alt;   // the other half of the alive-list ping-pong
   DevBuf nested_out;  // survivors of one nested pass
   DevBuf team_ctl;    // per-team control blocks of the windowed merge
+  DevBuf eps_counter; // rows whose key needed the exact re-evaluation of at least one plane (cumulative)
   MgLog mg;           // multi-GPU update logs (null pointers unless a sharded pass is running)
   DevBuf mg_counts, mg_mod_rows, mg_next_slot, mg_next_val, mg_splits, mg_surv;
   uint32_t* mg_keys_sorted = nullptr;  // state of the sharded pass between klsh_mg_* calls
