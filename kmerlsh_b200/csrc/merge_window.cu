@@ -344,6 +344,17 @@ __device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* s
       af[mt][ks][2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
       af[mt][ks][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
     }
+  // the row index and norm of the NEXT step's representative are fetched one step ahead, so that a
+  // step waits for one L2 round trip (the row), not two dependent ones
+  uint32_t rr_n = 0u;
+  float nrm_n = 1.f;
+  if (!SELF) {
+    const uint32_t j0 = j_begin + warp_rank * 8 + g;
+    if (j0 < j_end) {
+      rr_n = __ldcg(seg + j0);
+      nrm_n = __ldcg(pos_nrm + j0);
+    }
+  }
   for (uint32_t jb = j_begin + warp_rank * 8; jb < j_end; jb += n_warps * 8) {
     const uint32_t j = jb + g;  // this thread group's representative
     const bool valid = j < j_end;
@@ -356,16 +367,28 @@ __device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* s
         bf[ks][1] = *reinterpret_cast<const uint32_t*>(hr + ks * 16 + 8);
       }
     } else {
-      const uint32_t rr = valid ? __ldcg(seg + j) : 0u;
-      const float inv = valid ? __fdividef(1.f, __ldcg(pos_nrm + j)) : 0.f;
+      const uint32_t rr = rr_n;
+      const float inv = valid ? __fdividef(1.f, nrm_n) : 0.f;
       const float* row = A.vals + (uint64_t)rr * ld + tg * 2;
+      float2 v0[KS16], v1[KS16];
 #pragma unroll
       for (int ks = 0; ks < KS16; ++ks) {
-        float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
-        if (valid && ks * 16 + tg * 2 < ld) v0 = __ldcg(reinterpret_cast<const float2*>(row + ks * 16));
-        if (valid && ks * 16 + 8 + tg * 2 < ld) v1 = __ldcg(reinterpret_cast<const float2*>(row + ks * 16 + 8));
-        bf[ks][0] = pack_half2(v0.x * inv, v0.y * inv);
-        bf[ks][1] = pack_half2(v1.x * inv, v1.y * inv);
+        v0[ks] = make_float2(0.f, 0.f);
+        v1[ks] = make_float2(0.f, 0.f);
+        if (valid && ks * 16 + tg * 2 < ld) v0[ks] = __ldcg(reinterpret_cast<const float2*>(row + ks * 16));
+        if (valid && ks * 16 + 8 + tg * 2 < ld) v1[ks] = __ldcg(reinterpret_cast<const float2*>(row + ks * 16 + 8));
+      }
+      {
+        const uint32_t jn = j + n_warps * 8;
+        if (jn < j_end) {
+          rr_n = __ldcg(seg + jn);
+          nrm_n = __ldcg(pos_nrm + jn);
+        }
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS16; ++ks) {
+        bf[ks][0] = pack_half2(v0[ks].x * inv, v0[ks].y * inv);
+        bf[ks][1] = pack_half2(v1[ks].x * inv, v1[ks].y * inv);
       }
     }
 #pragma unroll
