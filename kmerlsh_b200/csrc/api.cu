@@ -359,24 +359,85 @@ static int run_pass(klsh_ctx* ctx, PassScratch& s, const uint32_t* rows_in, uint
     KCUDA(ctx, cudaMemcpyAsync(nb.data(), s.list_nested.p, sizeof(uint32_t) * c.n_nested, cudaMemcpyDeviceToHost, st));
     KCUDA(ctx, cudaStreamSynchronize(st));
     std::sort(nb.begin(), nb.end());
-    std::vector<uint32_t> bs(2);
-    for (uint32_t b : nb) {
-      KCUDA(ctx, cudaMemcpyAsync(bs.data(), s.bstart.as<uint32_t>() + b, sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, st));
+    if (&s == &ctx->nested) return klsh_fail(ctx, KLSH_ERR_ARG, "internal: nested pass may not nest");
+    std::vector<uint32_t> bs(2 * nb.size());
+    for (size_t k = 0; k < nb.size(); ++k)
+      KCUDA(ctx, cudaMemcpyAsync(&bs[2 * k], s.bstart.as<uint32_t>() + nb[k], sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, st));
+    KCUDA(ctx, cudaStreamSynchronize(st));
+    // All oversized buckets go through ONE combined nested pass: bucket k's rows are signed with
+    // bucket k's own fresh table (drawn in bucket order, like the reference's serial loop) and get
+    // the key prefix k, so one sort / bounds / merge handles every sub-bucket of every nested bucket
+    // and their greedy chains run side by side.  The merged, still sentinel-holed, row lists are
+    // copied back over the parent's segments; the parent's compaction drops the sentinels.
+    int Hmax = 0, pb = 0;
+    uint64_t total = 0;
+    std::vector<int> H2(nb.size());
+    for (size_t k = 0; k < nb.size(); ++k) {
+      const uint64_t seg_n = bs[2 * k + 1] - bs[2 * k];
+      H2[k] = floor_log2_u64(seg_n);
+      Hmax = std::max(Hmax, H2[k]);
+      total += seg_n;
+    }
+    while ((1ull << pb) < nb.size()) ++pb;
+    const bool combined = Hmax + pb <= 32 && total < 0xFFFFFFF0ull;
+    if (combined) {
+      PassScratch& ns = ctx->nested;
+      const int D = ctx->D, ld = ctx->ld;
+      KTRY(reserve_scratch(ctx, ns, total, Hmax));
+      size_t plane_floats = 0;
+      for (int h : H2) plane_floats += (size_t)h * ld;
+      KTRY(dev_reserve(ctx, ns.planes, sizeof(float) * (plane_floats + 4)));
+      std::vector<float> padded(plane_floats + 1, 0.f), t;
+      size_t po = 0;
+      for (size_t k = 0; k < nb.size(); ++k) {  // hyperplane stream order = bucket order
+        t.resize((size_t)H2[k] * D + 1);
+        planes_draw(ctx->planes, H2[k], D, t.data());
+        for (int h = 0; h < H2[k]; ++h) std::memcpy(&padded[po + (size_t)h * ld], &t[(size_t)h * D], sizeof(float) * D);
+        po += (size_t)H2[k] * ld;
+      }
+      if (plane_floats) {
+        KCUDA(ctx, cudaMemcpyAsync(ns.planes.p, padded.data(), sizeof(float) * plane_floats, cudaMemcpyHostToDevice, st));
+        KCUDA(ctx, cudaStreamSynchronize(st));
+      }
+      uint64_t off = 0;
+      po = 0;
+      for (size_t k = 0; k < nb.size(); ++k) {
+        const uint64_t seg_n = bs[2 * k + 1] - bs[2 * k];
+        KTRY(launch_sign(ctx, ctx->cur.vals.as<float>(), D, ld, rows_sorted + bs[2 * k], seg_n, ns.planes.as<float>() + po, H2[k],
+                         ns.keys_a.as<uint32_t>() + off, ns.rows_a.as<uint32_t>() + off,
+                         Hmax >= 32 ? 0u : (uint32_t)(k << Hmax)));
+        off += seg_n;
+        po += (size_t)H2[k] * ld;
+      }
+      uint32_t *nkeys, *nrows;
+      KTRY(launch_sort_pairs(ctx, ns, total, Hmax + pb, &nkeys, &nrows));
+      KTRY(launch_bounds(ctx, ns, nkeys, total));
+      KTRY(launch_classify(ctx, ns, total, -1, 0u, 0xFFFFFFFFu));
+      PassCounters* hc2 = ctx->h_counters + 1;
+      KCUDA(ctx, cudaMemcpyAsync(hc2, ns.counters.p, sizeof(PassCounters), cudaMemcpyDeviceToHost, st));
       KCUDA(ctx, cudaStreamSynchronize(st));
-      const uint64_t seg_n = bs[1] - bs[0];
-      uint32_t* seg = rows_sorted + bs[0];
-      const int H2 = floor_log2_u64(seg_n);
-      if (&s == &ctx->nested) return klsh_fail(ctx, KLSH_ERR_ARG, "internal: nested pass may not nest");
-      // survivors of the sub-pass go to a side buffer ...
-      uint64_t kept = 0;
-      KTRY(reserve_scratch(ctx, ctx->nested, seg_n, H2));
-      KTRY(dev_reserve(ctx, ctx->nested_out, sizeof(uint32_t) * (seg_n + 2)));
-      uint32_t* tmp_out = ctx->nested_out.as<uint32_t>();
-      KTRY(run_pass(ctx, ctx->nested, seg, seg_n, H2, threshold, -1, tmp_out, &kept, nullptr, false));
-      // ... and back to the front of the segment, sentinels behind
-      KCUDA(ctx, cudaMemcpyAsync(seg, tmp_out, sizeof(uint32_t) * kept, cudaMemcpyDeviceToDevice, st));
-      KTRY(launch_fill_tail(ctx, seg, kept, seg_n));
-      ++nested_calls;
+      const PassCounters c2 = *hc2;
+      KTRY(launch_merge(ctx, ns, nrows, threshold, c2));
+      off = 0;
+      for (size_t k = 0; k < nb.size(); ++k) {
+        const uint64_t seg_n = bs[2 * k + 1] - bs[2 * k];
+        KCUDA(ctx, cudaMemcpyAsync(rows_sorted + bs[2 * k], nrows + off, sizeof(uint32_t) * seg_n, cudaMemcpyDeviceToDevice, st));
+        off += seg_n;
+      }
+      nested_calls = nb.size();
+    } else {
+      for (size_t k = 0; k < nb.size(); ++k) {
+        const uint64_t seg_n = bs[2 * k + 1] - bs[2 * k];
+        uint32_t* seg = rows_sorted + bs[2 * k];
+        uint64_t kept = 0;
+        KTRY(reserve_scratch(ctx, ctx->nested, seg_n, H2[k]));
+        KTRY(dev_reserve(ctx, ctx->nested_out, sizeof(uint32_t) * (seg_n + 2)));
+        uint32_t* tmp_out = ctx->nested_out.as<uint32_t>();
+        KTRY(run_pass(ctx, ctx->nested, seg, seg_n, H2[k], threshold, -1, tmp_out, &kept, nullptr, false));
+        KCUDA(ctx, cudaMemcpyAsync(seg, tmp_out, sizeof(uint32_t) * kept, cudaMemcpyDeviceToDevice, st));
+        KTRY(launch_fill_tail(ctx, seg, kept, seg_n));
+        ++nested_calls;
+      }
     }
   }
   if (timed) cudaEventRecord(ctx->ev[3], st);

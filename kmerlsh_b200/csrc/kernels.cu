@@ -159,7 +159,7 @@ template <int DR>
 __global__ void __launch_bounds__(kSignWarps * 32)
 k_sign(const float* __restrict__ vals, int D, int ld, const uint32_t* __restrict__ rows, uint64_t n,
        const float* __restrict__ planes, int H, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ rows_out,
-       unsigned long long* eps_rows) {
+       unsigned long long* eps_rows, uint32_t key_or) {
   extern __shared__ __align__(16) float smem[];
   float* sp = smem;                      // planes [H][ld]
   float* pn = smem + (size_t)H * ld;     // eps factor per plane: |w_h| * (2.5*D+2)*2^-24   [H rounded up to 4]
@@ -259,7 +259,7 @@ k_sign(const float* __restrict__ vals, int D, int ld, const uint32_t* __restrict
           key = key * 2u + (sum >= 0.f ? 1u : 0u);
         }
       }
-      keys_out[t] = key;
+      keys_out[t] = key | key_or;
       rows_out[t] = r;
       my_eps += slow ? 1u : 0u;
     }
@@ -896,7 +896,7 @@ int launch_transform(klsh_ctx* ctx, const uint16_t* d_counts, const float* d_vk,
 }
 
 int launch_sign(klsh_ctx* ctx, const float* vals, int D, int ld, const uint32_t* rows, uint64_t n,
-                const float* d_planes, int H, uint32_t* keys_out, uint32_t* rows_out) {
+                const float* d_planes, int H, uint32_t* keys_out, uint32_t* rows_out, uint32_t key_or) {
   if (!n) return KLSH_OK;
   KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long)));
   size_t smem = sizeof(float) * ((size_t)H * ld + ((H + 3) & ~3) + (size_t)kSignWarps * 32 * (ld + 1));
@@ -905,7 +905,7 @@ int launch_sign(klsh_ctx* ctx, const float* vals, int D, int ld, const uint32_t*
   uint64_t want = (n + kSignWarps * 32 - 1) / (kSignWarps * 32);
   uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * 16);
   fn<<<grid, kSignWarps * 32, smem, ctx->stream>>>(vals, D, ld, rows, n, d_planes, H, keys_out, rows_out,
-                                                   ctx->eps_counter.as<unsigned long long>());
+                                                   ctx->eps_counter.as<unsigned long long>(), key_or);
   KLAUNCH(ctx);
   return KLSH_OK;
 }

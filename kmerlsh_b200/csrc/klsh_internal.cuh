@@ -154,7 +154,7 @@ int io_read_cluster(const char* bin_path, int D, uint64_t start_line, uint64_t n
 int launch_transform(klsh_ctx* ctx, const uint16_t* d_counts, const float* d_vk, uint64_t batch,
                      uint64_t* kept_out);
 int launch_sign(klsh_ctx* ctx, const float* vals, int D, int ld, const uint32_t* rows, uint64_t n,
-                const float* d_planes, int H, uint32_t* keys_out, uint32_t* rows_out);
+                const float* d_planes, int H, uint32_t* keys_out, uint32_t* rows_out, uint32_t key_or = 0);
 int launch_sort_pairs(klsh_ctx* ctx, PassScratch& s, uint64_t n, int bits, uint32_t** keys_sorted,
                       uint32_t** rows_sorted);
 int launch_bounds(klsh_ctx* ctx, PassScratch& s, const uint32_t* keys_sorted, uint64_t n);
