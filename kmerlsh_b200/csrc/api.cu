@@ -147,6 +147,10 @@ void klsh_destroy(klsh_ctx* ctx) {
   dev_free(ctx->alive_alt);
   dev_free(ctx->nested_out);
   dev_free(ctx->team_ctl);
+  dev_free(ctx->exp_vals); dev_free(ctx->exp_cnt); dev_free(ctx->exp_head);
+  if (ctx->h_cnt.p) cudaFreeHost(ctx->h_cnt.p);
+  if (ctx->h_head.p) cudaFreeHost(ctx->h_head.p);
+  if (ctx->h_next.p) cudaFreeHost(ctx->h_next.p);
   dev_free(ctx->eps_counter);
   dev_free(ctx->dbg);
   dev_free(ctx->mg_counts); dev_free(ctx->mg_mod_rows); dev_free(ctx->mg_next_slot); dev_free(ctx->mg_next_val);
@@ -578,51 +582,94 @@ extern "C" int klsh_nested_cluster(klsh_ctx* ctx, float threshold) {
 // ------------------------------------------------------------------------------------------------
 // Rows out
 // ------------------------------------------------------------------------------------------------
-static int export_rows(klsh_ctx* ctx, std::vector<float>* values, std::vector<uint64_t>& offs, std::vector<uint64_t>* ids) {
+// Grow-only pinned host buffer (export staging: D2H at full PCIe rate, no page faults per call).
+static int host_reserve(klsh_ctx* ctx, HostBuf& b, size_t bytes) {
+  if (bytes <= b.bytes) return KLSH_OK;
+  if (b.p) cudaFreeHost(b.p);
+  b.p = nullptr;
+  b.bytes = 0;
+  size_t want = (bytes + (bytes >> 3) + 4095) & ~(size_t)4095;
+  if (cudaMallocHost(&b.p, want) != cudaSuccess) {
+    (void)cudaGetLastError();
+    return klsh_fail(ctx, KLSH_ERR_NOMEM, "cudaMallocHost(%zu bytes) failed", want);
+  }
+  b.bytes = want;
+  return KLSH_OK;
+}
+
+// Survivors in order.  values_out / ids_out may be NULL; offs_out has n_alive+1 entries.
+static int export_rows(klsh_ctx* ctx, float* values_out, uint64_t* offs_out, uint64_t* ids_out) {
   const uint64_t n = ctx->cur.n_alive;
   const int D = ctx->D;
-  offs.assign(n + 1, 0);
-  if (values) values->resize(n * (uint64_t)D);
-  if (!n) {
-    if (ids) ids->clear();
-    return KLSH_OK;
-  }
-  DevBuf dv, dc, dh;
-  int rc = KLSH_OK;
-  std::vector<int32_t> cnt(n), head(n), next(ctx->n_slots);
-  do {
-    if ((rc = dev_reserve(ctx, dv, sizeof(float) * n * (uint64_t)D))) break;
-    if ((rc = dev_reserve(ctx, dc, sizeof(int32_t) * n))) break;
-    if ((rc = dev_reserve(ctx, dh, sizeof(int32_t) * n))) break;
-    if ((rc = launch_gather_rows(ctx, ctx->cur.alive.as<uint32_t>(), n, dv.as<float>(), dc.as<int32_t>(), dh.as<int32_t>())))
-      break;
-    if (values) cudaMemcpyAsync(values->data(), dv.p, sizeof(float) * n * (uint64_t)D, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaMemcpyAsync(cnt.data(), dc.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaMemcpyAsync(head.data(), dh.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
-    if (ids && ctx->n_slots)
-      cudaMemcpyAsync(next.data(), ctx->cur.next.p, sizeof(int32_t) * ctx->n_slots, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) rc = klsh_fail(ctx, KLSH_ERR_CUDA, "export: %s", cudaGetErrorString(e));
-  } while (0);
-  dev_free(dv); dev_free(dc); dev_free(dh);
-  if (rc != KLSH_OK) return rc;
-  for (uint64_t r = 0; r < n; ++r) offs[r + 1] = offs[r] + (uint64_t)cnt[r];
-  if (ids) {
-    ids->resize(offs[n]);
+  offs_out[0] = 0;
+  if (!n) return KLSH_OK;
+  cudaStream_t st = ctx->stream;
+  KTRY(dev_reserve(ctx, ctx->exp_vals, sizeof(float) * n * (uint64_t)D));
+  KTRY(dev_reserve(ctx, ctx->exp_cnt, sizeof(int32_t) * n));
+  KTRY(dev_reserve(ctx, ctx->exp_head, sizeof(int32_t) * n));
+  KTRY(host_reserve(ctx, ctx->h_cnt, sizeof(int32_t) * n));
+  KTRY(host_reserve(ctx, ctx->h_head, sizeof(int32_t) * n));
+  if (ids_out) KTRY(host_reserve(ctx, ctx->h_next, sizeof(int32_t) * (ctx->n_slots + 1)));
+  KTRY(launch_gather_rows(ctx, ctx->cur.alive.as<uint32_t>(), n, ctx->exp_vals.as<float>(), ctx->exp_cnt.as<int32_t>(),
+                          ctx->exp_head.as<int32_t>()));
+  KCUDA(ctx, cudaMemcpyAsync(ctx->h_cnt.p, ctx->exp_cnt.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  KCUDA(ctx, cudaMemcpyAsync(ctx->h_head.p, ctx->exp_head.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
+  if (ids_out && ctx->n_slots)
+    KCUDA(ctx, cudaMemcpyAsync(ctx->h_next.p, ctx->cur.next.p, sizeof(int32_t) * ctx->n_slots, cudaMemcpyDeviceToHost, st));
+  if (values_out)
+    KCUDA(ctx, cudaMemcpyAsync(values_out, ctx->exp_vals.p, sizeof(float) * n * (uint64_t)D, cudaMemcpyDeviceToHost, st));
+  KCUDA(ctx, cudaStreamSynchronize(st));
+  const int32_t* cnt = static_cast<const int32_t*>(ctx->h_cnt.p);
+  const int32_t* head = static_cast<const int32_t*>(ctx->h_head.p);
+  const int32_t* next = static_cast<const int32_t*>(ctx->h_next.p);
+  for (uint64_t r = 0; r < n; ++r) offs_out[r + 1] = offs_out[r] + (uint64_t)cnt[r];
+  if (ids_out) {
     // Walking the member chains is pointer chasing through next[] (one dependent load per id): split the
     // clusters over host threads, balanced by id count.
+    const uint64_t total = offs_out[n];
     const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-    const unsigned nt = (unsigned)std::min<uint64_t>(hw, std::max<uint64_t>(1, offs[n] / 65536));
+    const unsigned nt = (unsigned)std::min<uint64_t>(hw, std::max<uint64_t>(1, total / 65536));
     std::vector<uint64_t> bad(nt, UINT64_MAX);
     auto work = [&](unsigned w) {
-      const uint64_t id_lo = offs[n] / nt * w, id_hi = (w + 1 == nt) ? offs[n] : offs[n] / nt * (w + 1);
-      uint64_t r = std::lower_bound(offs.begin(), offs.begin() + n, id_lo) - offs.begin();
-      for (; r < n && offs[r] < id_hi; ++r) {
-        uint64_t o = offs[r];
-        const uint64_t end = offs[r + 1];
-        for (int32_t s = head[r]; s >= 0 && o < end; s = next[s])
-          (*ids)[o++] = ctx->ids_implicit ? ctx->id_base + (uint64_t)s : ctx->ids[s];
-        if (o != end && bad[w] == UINT64_MAX) bad[w] = r;
+      const uint64_t id_lo = total / nt * w, id_hi = (w + 1 == nt) ? total : total / nt * (w + 1);
+      uint64_t r = std::lower_bound(offs_out, offs_out + n, id_lo) - offs_out;
+      // kWalk chains are advanced in turn so that their cache misses overlap
+      constexpr int kWalk = 16;
+      int32_t cur[kWalk];
+      uint64_t pos[kWalk], end[kWalk], row[kWalk];
+      int active = 0;
+      auto refill = [&](int k) {
+        while (r < n && offs_out[r] < id_hi) {
+          const uint64_t rr = r++;
+          if (offs_out[rr + 1] == offs_out[rr] && head[rr] < 0) continue;  // no members
+          cur[k] = head[rr];
+          pos[k] = offs_out[rr];
+          end[k] = offs_out[rr + 1];
+          row[k] = rr;
+          if (cur[k] >= 0) __builtin_prefetch(next + cur[k]);
+          return true;
+        }
+        return false;
+      };
+      bool live[kWalk];
+      for (int k = 0; k < kWalk; ++k) {
+        live[k] = refill(k);
+        active += live[k] ? 1 : 0;
+      }
+      while (active) {
+        for (int k = 0; k < kWalk; ++k) {
+          if (!live[k]) continue;
+          const int32_t s = cur[k];
+          if (s >= 0 && pos[k] < end[k]) {
+            ids_out[pos[k]++] = ctx->ids_implicit ? ctx->id_base + (uint64_t)s : ctx->ids[s];
+            cur[k] = next[s];
+            if (cur[k] >= 0) __builtin_prefetch(next + cur[k]);
+          } else {
+            if (pos[k] != end[k] && bad[w] == UINT64_MAX) bad[w] = row[k];
+            live[k] = refill(k);
+            if (!live[k]) --active;
+          }
+        }
       }
     };
     std::vector<std::thread> pool;
@@ -641,9 +688,14 @@ extern "C" int klsh_row_count(klsh_ctx* ctx, uint64_t* n_rows, uint64_t* n_ids) 
   KCUDA(ctx, cudaSetDevice(ctx->device));
   if (n_rows) *n_rows = ctx->cur.n_alive;
   if (n_ids) {
-    std::vector<uint64_t> offs;
-    KTRY(export_rows(ctx, nullptr, offs, nullptr));
-    *n_ids = offs.back();
+    // sum of the survivors' member counts
+    const uint64_t n = ctx->cur.n_alive;
+    *n_ids = 0;
+    if (n) {
+      std::vector<uint64_t> offs(n + 1);
+      KTRY(export_rows(ctx, nullptr, offs.data(), nullptr));
+      *n_ids = offs[n];
+    }
   }
   return KLSH_OK;
 }
@@ -651,22 +703,19 @@ extern "C" int klsh_row_count(klsh_ctx* ctx, uint64_t* n_rows, uint64_t* n_ids) 
 extern "C" int klsh_get_rows(klsh_ctx* ctx, float* values, uint64_t* id_offsets, uint64_t* ids) {
   if (!ctx || !id_offsets) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_get_rows: bad argument");
   KCUDA(ctx, cudaSetDevice(ctx->device));
-  std::vector<float> v;
-  std::vector<uint64_t> offs, idv;
-  KTRY(export_rows(ctx, values ? &v : nullptr, offs, ids ? &idv : nullptr));
-  if (values && !v.empty()) std::memcpy(values, v.data(), sizeof(float) * v.size());
-  std::memcpy(id_offsets, offs.data(), sizeof(uint64_t) * offs.size());
-  if (ids && !idv.empty()) std::memcpy(ids, idv.data(), sizeof(uint64_t) * idv.size());
-  return KLSH_OK;
+  return export_rows(ctx, values, id_offsets, ids);
 }
 
 extern "C" int klsh_save(klsh_ctx* ctx, const char* bin_path, int delfile, int64_t ignore_small) {
   if (!ctx || !bin_path) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_save: bad argument");
   KCUDA(ctx, cudaSetDevice(ctx->device));
-  std::vector<float> v;
-  std::vector<uint64_t> offs, idv;
-  KTRY(export_rows(ctx, &v, offs, &idv));
-  int rc = io_save(bin_path, delfile, ignore_small, v.data(), ctx->D, offs.data(), idv.data(), ctx->cur.n_alive);
+  const uint64_t n = ctx->cur.n_alive;
+  std::vector<uint64_t> offs(n + 1, 0);
+  KTRY(export_rows(ctx, nullptr, offs.data(), nullptr));
+  std::vector<float> v(n * (uint64_t)ctx->D + 1);
+  std::vector<uint64_t> idv(offs[n] + 1);
+  KTRY(export_rows(ctx, v.data(), offs.data(), idv.data()));
+  int rc = io_save(bin_path, delfile, ignore_small, v.data(), ctx->D, offs.data(), idv.data(), n);
   if (rc != KLSH_OK) return klsh_fail(ctx, rc, "cannot write %s(.clust)", bin_path);
   return KLSH_OK;
 }

@@ -14,6 +14,11 @@
 
 struct PlaneSource;  // planes.cc
 
+struct HostBuf {  // grow-only pinned host buffer
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
 // Grow-only device buffer.
 struct DevBuf {
   void* p = nullptr;
@@ -98,6 +103,8 @@ struct klsh_ctx {
   DevBuf alive_alt;   // the other half of the alive-list ping-pong
   DevBuf nested_out;  // survivors of one nested pass
   DevBuf team_ctl;    // per-team control blocks of the windowed merge
+  DevBuf exp_vals, exp_cnt, exp_head;  // export staging (device)
+  HostBuf h_cnt, h_head, h_next;       // export staging (pinned host)
   DevBuf eps_counter; // rows whose key needed the exact re-evaluation of at least one plane (cumulative)
   MgLog mg;           // multi-GPU update logs (null pointers unless a sharded pass is running)
   DevBuf mg_counts, mg_mod_rows, mg_next_slot, mg_next_val, mg_splits, mg_surv;
