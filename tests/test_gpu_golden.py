@@ -102,3 +102,21 @@ def test_mode_c_cli_matches_reference_binary(tag, tmp_path):
     assert md5(os.path.join(work, "tmp", "0.bin.clust")) == m["tmp_clust_md5"]
     assert md5(out) == m["bin_md5"]
     assert md5(out + ".clust") == m["clust_md5"]
+
+
+def test_mode_c_cli_two_batches(oracle, tmp_path):
+    """--batch smaller than the input: independent phase-1 batches appended to tmp/0.bin, the
+    re-batch loop (similarity -= 0.001, 5 iterations per batch) while survivors exceed the batch
+    size, then the -I iterations — byte-identical to the oracle's mode C with the same batch size
+    (the reference hard-codes 100 M rows per batch, app/kmerLSH.cc:285)."""
+    work = str(tmp_path)
+    synth.write_mode_c_inputs(work, 30000, 3, 3, 99)
+    out = os.path.join(work, "oracle_result.txt")
+    os.makedirs(os.path.join(work, "otmp"))
+    oracle.mode_c(work, 6, 0.85, 4, out, 17, batch_thresh=8000, tmp_dir=os.path.join(work, "otmp") + "/")
+    exe = os.path.join(ROOT, "kmerlsh_b200", "kmerLSH_b200")
+    subprocess.run([exe, "-a", "A.txt", "-b", "B.txt", "-o", "oa", "-p", "ob", "-M", "C", "--only", "-I", "4", "-N", "0.85",
+                    "-T", "1", "--seed=17", "--batch=8000"], cwd=work, check=True, stdout=subprocess.DEVNULL)
+    res = os.path.join(work, "clustering_result.txt")
+    assert md5(res) == md5(out)
+    assert md5(res + ".clust") == md5(out + ".clust")

@@ -299,3 +299,46 @@ def test_prefilter_boundaries(gpu, oracle):
             gpu.set_rows(values)
             gpu.p_cluster(thr)
             assert_rows_equal(gpu.get_rows(), rows.export(), "thr=%r" % thr)
+
+
+def test_degenerate_inputs(gpu, oracle):
+    """Empty row set, everything dropped by the keep filter, a single column."""
+    gpu.set_rows(np.zeros((0, 5), np.float32), np.zeros(1, np.uint64), np.zeros(0, np.uint64))
+    st = gpu.cluster(0.8, 3, 1000)
+    assert st[0].rows_in == 0 and gpu.row_count() == (0, 0)
+    v, o, i = gpu.get_rows()
+    assert v.shape == (0, 5) and list(o) == [0] and len(i) == 0
+    gpu.load_counts(np.zeros((4, 100), np.uint16), np.ones(4, np.float32), 0)
+    assert gpu.row_count() == (0, 0)
+    gpu.cluster(0.8, 2, 1000)
+    rng = np.random.default_rng(2)
+    vals = rng.standard_normal((500, 1)).astype(np.float32)     # D = 1: cosine is +-1
+    rows = oracle.rows(vals)
+    rows.cluster(0.8, 3, 1000, oracle.planes(3))
+    gpu.set_seed(3)
+    gpu.set_rows(vals)
+    gpu.cluster(0.8, 3, 1000)
+    assert_rows_equal(gpu.get_rows(), rows.export())
+
+
+def test_eps_margin_rows_are_reported(gpu, oracle):
+    """Rows that needed the exact re-evaluation of a plane are counted (and still signed exactly)."""
+    rng = np.random.default_rng(5)
+    vals = rng.standard_normal((20000, 16)).astype(np.float32)
+    table = oracle.planes(1).table(14, 16)
+    # rows built to be (numerically) orthogonal to plane 0: their sum lands inside the eps margin
+    w = table[0].astype(np.float64)
+    ortho = vals[:200].astype(np.float64)
+    ortho -= np.outer(ortho @ w / (w @ w), w)
+    vals[:200] = ortho.astype(np.float32)
+    assert np.array_equal(gpu.sign(vals, table), oracle.sign(vals, table).astype(np.uint64))
+    src = oracle.planes(1)
+    rows = oracle.rows(vals)
+    rows.cluster(0.9, 1, 100000, oracle.planes(1))
+    gpu.set_plane_source(lambda H, D: src.table(H, D))
+    gpu.set_rows(vals)
+    st = gpu.cluster(0.9, 1, 100000)
+    gpu.set_seed(0)
+    assert st[0].eps_margin_rows >= 100   # most of the 200 constructed rows
+    assert st[0].eps_margin_rows < 2000
+    assert_rows_equal(gpu.get_rows(), rows.export())
