@@ -391,6 +391,8 @@ __device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* s
         bf[ks][1] = pack_half2(v1[ks].x * inv, v1[ks].y * inv);
       }
     }
+    // screen all 64 x 8 pairs of this step, remember the survivors as a 16-bit mask per lane ...
+    uint32_t pend = 0;
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
       float c[4] = {0.f, 0.f, 0.f, 0.f};
@@ -398,20 +400,27 @@ __device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* s
       for (int ks = 0; ks < KS16; ++ks) mma_16816(c, af[mt][ks], bf[ks][0], bf[ks][1]);
       // c[0],c[1]: candidate mt*16+g vs representatives jb+2*tg, +1 ; c[2],c[3]: candidate +8
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        if (c[e] < thr_tc) continue;  // NaN/inf do not compare below and go to the exact test
+      for (int e = 0; e < 4; ++e)
+        if (!(c[e] < thr_tc)) pend |= 1u << (mt * 4 + e);  // NaN/inf do not compare below: they go to the exact test
+    }
+    // ... then every lane works through its own survivors: the exact evaluations of different lanes
+    // run side by side instead of one (row tile, element) slot after the other
+    while (__any_sync(0xffffffffu, pend != 0u)) {
+      if (pend != 0u) {
+        const int slot = __ffs(pend) - 1;
+        pend &= pend - 1;
+        const int mt = slot >> 2, e = slot & 3;
         const int t = mt * 16 + (int)g + ((e & 2) ? 8 : 0);
         const uint32_t jj = jb + tg * 2 + (e & 1);
-        if (t >= W || jj >= j_end) continue;
-        if (SELF) {
-          if ((int)jj == t) continue;
-          if (exact_pair<true>(s, t, s.tile + (size_t)jj * s.ts, s.cnorm[jj], nq, A.threshold))
-            atomicOr(&s.pair[2 * t + (jj >> 5)], 1u << (jj & 31));
-        } else {
-          if (s.s_f[t] < jj) continue;  // an earlier match is already recorded
-          const uint32_t rr2 = __ldcg(seg + jj);
-          if (exact_pair<false>(s, t, A.vals + (uint64_t)rr2 * ld, __ldcg(pos_nrm + jj), nq, A.threshold))
-            atomicMin(&s.s_f[t], jj);
+        if (t < W && jj < j_end) {
+          if (SELF) {
+            if ((int)jj != t && exact_pair<true>(s, t, s.tile + (size_t)jj * s.ts, s.cnorm[jj], nq, A.threshold))
+              atomicOr(&s.pair[2 * t + (jj >> 5)], 1u << (jj & 31));
+          } else if (!(s.s_f[t] < jj)) {  // skip when an earlier match is already recorded
+            const uint32_t rr2 = __ldcg(seg + jj);
+            if (exact_pair<false>(s, t, A.vals + (uint64_t)rr2 * ld, __ldcg(pos_nrm + jj), nq, A.threshold))
+              atomicMin(&s.s_f[t], jj);
+          }
         }
       }
     }
