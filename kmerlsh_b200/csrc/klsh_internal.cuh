@@ -115,7 +115,7 @@ struct klsh_ctx {
   int mg_H = 0;
   // escalation of the windowed merge: a bucket leaves its CTA for a cluster once it has more than
   // cta_max representatives, and the cluster for the whole grid above cluster_max
-  uint32_t cta_max = 512, cluster_max = 8192, cluster2_max = 65536;
+  uint32_t cta_max = 4096, cluster_max = 65536, cluster2_max = 1000000;  // measured on C2 (profiles/README.md)
   int cluster_size = 8, cluster2_size = 16;
   int cluster_ctas_per_sm = 2;
   bool debug = false;     // KLSH_DEBUG=1
