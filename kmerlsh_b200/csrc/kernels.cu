@@ -153,8 +153,7 @@ constexpr int kSignWarps = 4;
 // |s_fma| exceeds eps = (2.5*D+2)*2^-24*|w||x| both sums are non-zero with the same sign.  Otherwise —
 // the north star's "projection magnitude below eps" set — the (row, plane) sum is re-evaluated with
 // the reference's exact arithmetic, so every key bit is the reference's; such rows are counted.
-// DR > 0: the row is held in registers (ld <= DR) and the planes are read as broadcast float4; DR == 0:
-// any width, row read from the shared-memory tile.
+// The row is held in registers (ld <= DR) and the planes are read as broadcast float4.
 template <int DR>
 __global__ void __launch_bounds__(kSignWarps * 32)
 k_sign(const float* __restrict__ vals, int D, int ld, const uint32_t* __restrict__ rows, uint64_t n,
@@ -199,8 +198,8 @@ k_sign(const float* __restrict__ vals, int D, int ld, const uint32_t* __restrict
       const float* x = tile + lane * stride;
       uint32_t key = 0;
       bool slow = false;
-      if (DR > 0) {
-        float xr[DR > 0 ? DR : 1];
+      {
+        float xr[DR];
 #pragma unroll
         for (int i = 0; i < DR; ++i) xr[i] = (i < ld) ? x[i] : 0.f;  // padding (i >= D) is zero in the arena
         float xx = 0.f;
@@ -237,33 +236,109 @@ k_sign(const float* __restrict__ vals, int D, int ld, const uint32_t* __restrict
             key = key * 2u + (sum >= 0.f ? 1u : 0u);
           }
         }
-      } else {
-        float xx = 0.f;
-        for (int i = 0; i < D; ++i) xx = __fmaf_rn(x[i], x[i], xx);
-        const float xn = sqrtf(xx);
-        for (int h = 0; h < H; ++h) {
-          const float* w = sp + h * ld;
-          float s0 = 0.f, s1 = 0.f;
-          int i = 0;
-          for (; i + 1 < D; i += 2) {
-            s0 = __fmaf_rn(w[i], x[i], s0);
-            s1 = __fmaf_rn(w[i + 1], x[i + 1], s1);
-          }
-          if (i < D) s0 = __fmaf_rn(w[i], x[i], s0);
-          float sum = s0 + s1;
-          if (!(fabsf(sum) > pn[h] * xn) || !(fabsf(sum) <= 3.0e38f)) {
-            sum = 0.f;
-            for (int j = 0; j < D; ++j) sum = __fadd_rn(sum, __fmul_rn(w[j], x[j]));
-            slow = true;
-          }
-          key = key * 2u + (sum >= 0.f ? 1u : 0u);
-        }
       }
       keys_out[t] = key | key_or;
       rows_out[t] = r;
       my_eps += slow ? 1u : 0u;
     }
     __syncwarp();
+  }
+  if (eps_rows) {
+    const uint32_t tot = __reduce_add_sync(0xffffffffu, my_eps);
+    if (lane == 0 && tot) atomicAdd(eps_rows, (unsigned long long)tot);
+  }
+}
+
+// Rows wider than 64 floats: the warp stages its 32 rows 32 columns at a time (4 KB per warp instead
+// of a whole-row tile, so occupancy does not collapse at D = 256), one fused accumulator per plane.
+__global__ void __launch_bounds__(kSignWarps * 32)
+k_sign_wide(const float* __restrict__ vals, int D, int ld, const uint32_t* __restrict__ rows, uint64_t n,
+            const float* __restrict__ planes, int H, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ rows_out,
+            unsigned long long* eps_rows, uint32_t key_or) {
+  extern __shared__ __align__(16) float smem[];
+  float* sp = smem;                     // planes [H][ld]
+  float* pn = smem + (size_t)H * ld;    // eps factor per plane
+  float* tiles = pn + ((H + 3) & ~3);   // [kSignWarps][32][33]
+  for (int i = threadIdx.x; i < H * ld; i += blockDim.x) sp[i] = planes[i];
+  __syncthreads();
+  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+    float m = 0.f;
+    for (int i = 0; i < D; ++i) m = __fmaf_rn(sp[h * ld + i], sp[h * ld + i], m);
+    pn[h] = sqrtf(m) * ((2.5f * (float)D + 2.f) * 5.9604645e-8f);
+  }
+  __syncthreads();
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
+  float* tile = tiles + (size_t)warp * 32 * 33;
+  const uint64_t nwarps_total = (uint64_t)gridDim.x * kSignWarps;
+  uint32_t my_eps = 0;
+  for (uint64_t t0 = ((uint64_t)blockIdx.x * kSignWarps + warp) * 32; t0 < n; t0 += nwarps_total * 32) {
+    const uint64_t t = t0 + lane;
+    const uint32_t r = (t < n) ? (rows ? rows[t] : (uint32_t)t) : 0u;
+    const int nrow = (int)min((uint64_t)32, n - t0);
+    float acc[32];
+#pragma unroll
+    for (int h = 0; h < 32; ++h) acc[h] = 0.f;
+    float xx = 0.f;
+    for (int c0 = 0; c0 < ld; c0 += 32) {
+      // 32 rows x 32 columns: 8 lanes fetch one row's 128 bytes
+      for (int v0 = 0; v0 < nrow * 8; v0 += 32) {
+        const int v = v0 + (int)lane;
+        const int rr = min(v, nrow * 8 - 1) >> 3, cc = v & 7;
+        const uint32_t ri = __shfl_sync(0xffffffffu, r, rr);
+        if (v < nrow * 8) {
+          float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (c0 + cc * 4 < ld) q = __ldg(reinterpret_cast<const float4*>(vals + (uint64_t)ri * ld + c0) + cc);
+          float* d = tile + rr * 33 + cc * 4;
+          d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+        }
+      }
+      __syncwarp();
+      if (t < n) {
+        float xr[32];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xr[i] = tile[lane * 33 + i];
+#pragma unroll
+        for (int i = 0; i < 32; ++i) xx = __fmaf_rn(xr[i], xr[i], xx);
+#pragma unroll
+        for (int h = 0; h < 32; ++h)
+          if (h < H) {
+            const float4* w4 = reinterpret_cast<const float4*>(sp + h * ld + c0);
+            float s0 = acc[h], s1 = 0.f;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+              if (c0 + 4 * q < ld) {
+                const float4 w = w4[q];
+                s0 = __fmaf_rn(w.x, xr[4 * q], s0);
+                s1 = __fmaf_rn(w.y, xr[4 * q + 1], s1);
+                s0 = __fmaf_rn(w.z, xr[4 * q + 2], s0);
+                s1 = __fmaf_rn(w.w, xr[4 * q + 3], s1);
+              }
+            acc[h] = s0 + s1;
+          }
+      }
+      __syncwarp();
+    }
+    if (t < n) {
+      const float xn = sqrtf(xx);
+      const float* x = vals + (uint64_t)r * ld;  // exact re-evaluation reads the row again (rare)
+      uint32_t key = 0;
+      bool slow = false;
+#pragma unroll
+      for (int h = 0; h < 32; ++h)
+        if (h < H) {
+          float sum = acc[h];
+          if (!(fabsf(sum) > pn[h] * xn) || !(fabsf(sum) <= 3.0e38f)) {
+            const float* w = sp + h * ld;
+            sum = 0.f;
+            for (int j = 0; j < D; ++j) sum = __fadd_rn(sum, __fmul_rn(w[j], __ldg(x + j)));
+            slow = true;
+          }
+          key = key * 2u + (sum >= 0.f ? 1u : 0u);
+        }
+      keys_out[t] = key | key_or;
+      rows_out[t] = r;
+      my_eps += slow ? 1u : 0u;
+    }
   }
   if (eps_rows) {
     const uint32_t tot = __reduce_add_sync(0xffffffffu, my_eps);
@@ -899,8 +974,9 @@ int launch_sign(klsh_ctx* ctx, const float* vals, int D, int ld, const uint32_t*
                 const float* d_planes, int H, uint32_t* keys_out, uint32_t* rows_out, uint32_t key_or) {
   if (!n) return KLSH_OK;
   KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long)));
-  size_t smem = sizeof(float) * ((size_t)H * ld + ((H + 3) & ~3) + (size_t)kSignWarps * 32 * (ld + 1));
-  auto fn = ld <= 32 ? k_sign<32> : (ld <= 64 ? k_sign<64> : k_sign<0>);
+  const bool wide = ld > 64;
+  size_t smem = sizeof(float) * ((size_t)H * ld + ((H + 3) & ~3) + (size_t)kSignWarps * 32 * (wide ? 33 : (ld + 1)));
+  auto fn = ld <= 32 ? k_sign<32> : (ld <= 64 ? k_sign<64> : k_sign_wide);
   if (smem > 48 * 1024) KCUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   uint64_t want = (n + kSignWarps * 32 - 1) / (kSignWarps * 32);
   uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * 16);

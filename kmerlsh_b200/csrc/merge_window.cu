@@ -48,18 +48,6 @@ __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
 // ---- exact arithmetic ---------------------------------------------------------------------------------
 // Rows are padded with zeros to a multiple of 4 floats; the padded products are +0 and x + (+0) == x
 // (a running sum that starts at +0 is never -0), so walking quads gives the reference's D-term sums.
-__device__ __forceinline__ float dot_seq(const float4* a, const float4* b, int nq) {
-  float s = 0.f;
-#pragma unroll 4
-  for (int q = 0; q < nq; ++q) {
-    const float4 x = a[q], y = b[q];
-    s = __fadd_rn(s, __fmul_rn(x.x, y.x));
-    s = __fadd_rn(s, __fmul_rn(x.y, y.y));
-    s = __fadd_rn(s, __fmul_rn(x.z, y.z));
-    s = __fadd_rn(s, __fmul_rn(x.w, y.w));
-  }
-  return s;
-}
 __device__ __forceinline__ float norm_seq(const float4* a, int nq) {  // sqrt(sum v_i^2), Distance::cosine's magnitudes
   float s = 0.f;
 #pragma unroll 4
@@ -76,15 +64,6 @@ __device__ __forceinline__ bool cos_match(float dot, float nl, float nr, float t
   float sim = __fdiv_rn(dot, __fmul_rn(nl, nr));
   float dist = __fsub_rn(1.f, sim);
   return __fsub_rn(1.f, dist) >= threshold;
-}
-// Conservative reject used by the parallel phase.  `dot_fast` is the dot
-// product accumulated with fused multiply-adds: it differs from the reference's mul-then-add sum by
-// at most 2*D*2^-24 * sum|a_i b_i| <= 2*D*2^-24 * |a||b|.  A match implies
-// dot_exact >= den*(thr - 2^-21) (den = |a||b| > 0), hence dot_fast >= den*(thr - 2^-21 - 2*D*2^-24);
-// thr_lo = thr - 2e-6 - 4*D*2^-24 leaves room for the rounding of den*thr_lo.  Everything that passes
-// is re-evaluated exactly; NaN/0/inf fall through to the exact test or are rejected correctly.
-__device__ __forceinline__ bool fast_reject(float dot_fast, float nl, float nr, float thr_lo) {
-  return dot_fast < __fmul_rn(__fmul_rn(nl, nr), thr_lo);
 }
 __device__ __forceinline__ float consensus1(float cur, int c1, float cand, int c2) {
   const float fa = __int2float_rn(c1 + c2);
@@ -163,7 +142,7 @@ struct MergeArgs {
   TeamCtl* ctl;
   MgLog mg;
   unsigned long long* dbg;  // [16] (8..13: leader cycles in stage/parallel/sync1/prefetch/resolve/sync2) windows, candidates, merges, undecidable, cache_full, back_exhausted, accepted, escalated
-  float threshold, thr_lo;
+  float threshold;
 };
 
 struct Smem {
@@ -196,7 +175,7 @@ struct Smem {
 };
 
 // width (halfs) of the fp16 window copy: the k extent the kernel variant for this ld multiplies over
-__host__ __device__ inline int tc_width(int ld) { return ld <= 32 ? 32 : (ld <= 64 ? 64 : 16); }
+__host__ __device__ inline int tc_width(int ld) { return ld <= 32 ? 32 : (ld <= 64 ? 64 : ((ld + 15) & ~15)); }
 
 __host__ __device__ inline size_t smem_bytes_for(int ld) {
   const int hs = tc_width(ld) + 8;
@@ -232,78 +211,6 @@ __device__ __forceinline__ void carve(Smem& s, float* base, int ld) {
   s.ment = reinterpret_cast<int32_t*>(u); u += kW;
   s.hs = tc_width(ld) + 8;  // +8 halfs: rows 16 bytes apart modulo 128 -> conflict-free fragment loads
   s.htile = reinterpret_cast<__half*>(u + 4);
-}
-
-// Compare one representative (row at rowp, norm rn) with window candidates [tb, te); call hit(t) on
-// a match.  DR > 0: the row is held in registers (ld <= DR); DR == 0: read through the pointer.
-// SM: rowp points to shared memory, else to global memory (read through L2: another CTA may have
-// rewritten the row in the previous window).
-// Candidates whose recorded first match (this CTA's view, s_f) already lies before position j cannot
-// be improved by representative j and are skipped in groups of four.
-template <int DR, bool SM, typename Hit>
-__device__ __forceinline__ void compare_rep(const float* rowp, float rn, const Smem& s, int tb, int te, int nq,
-                                            float threshold, float thr_lo, int skip_t, uint32_t j, Hit hit) {
-  float r[DR > 0 ? DR : 4];
-  if (DR > 0) {
-#pragma unroll
-    for (int q = 0; q < DR / 4; ++q)
-      if (q < nq) {
-        const float4 v = SM ? reinterpret_cast<const float4*>(rowp)[q] : __ldcg(reinterpret_cast<const float4*>(rowp) + q);
-        r[4 * q] = v.x; r[4 * q + 1] = v.y; r[4 * q + 2] = v.z; r[4 * q + 3] = v.w;
-      }
-  }
-  const float4* t4 = reinterpret_cast<const float4*>(s.tile);
-  const int ts4 = s.ts >> 2;
-  for (int t0 = tb; t0 < te; t0 += 4) {  // rows t0..t0+3 always lie inside the kW-row tile
-    if (!SM) {
-      const uint4 f4 = *reinterpret_cast<const uint4*>(s.s_f + t0);
-      if (f4.x < j && f4.y < j && f4.z < j && f4.w < j) continue;
-    }
-    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-    const float4* a0 = t4 + (size_t)(t0 + 0) * ts4;
-    const float4* a1 = t4 + (size_t)(t0 + 1) * ts4;
-    const float4* a2 = t4 + (size_t)(t0 + 2) * ts4;
-    const float4* a3 = t4 + (size_t)(t0 + 3) * ts4;
-    if (DR > 0) {
-#pragma unroll
-      for (int q = 0; q < DR / 4; ++q)
-        if (q < nq) {
-          const float4 x0 = a0[q], x1 = a1[q], x2 = a2[q], x3 = a3[q];
-          const float r0 = r[4 * q], r1 = r[4 * q + 1], r2 = r[4 * q + 2], r3 = r[4 * q + 3];
-          d0 = __fmaf_rn(x0.x, r0, d0); d1 = __fmaf_rn(x1.x, r0, d1); d2 = __fmaf_rn(x2.x, r0, d2); d3 = __fmaf_rn(x3.x, r0, d3);
-          d0 = __fmaf_rn(x0.y, r1, d0); d1 = __fmaf_rn(x1.y, r1, d1); d2 = __fmaf_rn(x2.y, r1, d2); d3 = __fmaf_rn(x3.y, r1, d3);
-          d0 = __fmaf_rn(x0.z, r2, d0); d1 = __fmaf_rn(x1.z, r2, d1); d2 = __fmaf_rn(x2.z, r2, d2); d3 = __fmaf_rn(x3.z, r2, d3);
-          d0 = __fmaf_rn(x0.w, r3, d0); d1 = __fmaf_rn(x1.w, r3, d1); d2 = __fmaf_rn(x2.w, r3, d2); d3 = __fmaf_rn(x3.w, r3, d3);
-        }
-    } else {
-      for (int q = 0; q < nq; ++q) {
-        const float4 rv = SM ? reinterpret_cast<const float4*>(rowp)[q] : __ldcg(reinterpret_cast<const float4*>(rowp) + q);
-        const float4 x0 = a0[q], x1 = a1[q], x2 = a2[q], x3 = a3[q];
-        d0 = __fmaf_rn(x0.x, rv.x, d0); d1 = __fmaf_rn(x1.x, rv.x, d1); d2 = __fmaf_rn(x2.x, rv.x, d2); d3 = __fmaf_rn(x3.x, rv.x, d3);
-        d0 = __fmaf_rn(x0.y, rv.y, d0); d1 = __fmaf_rn(x1.y, rv.y, d1); d2 = __fmaf_rn(x2.y, rv.y, d2); d3 = __fmaf_rn(x3.y, rv.y, d3);
-        d0 = __fmaf_rn(x0.z, rv.z, d0); d1 = __fmaf_rn(x1.z, rv.z, d1); d2 = __fmaf_rn(x2.z, rv.z, d2); d3 = __fmaf_rn(x3.z, rv.z, d3);
-        d0 = __fmaf_rn(x0.w, rv.w, d0); d1 = __fmaf_rn(x1.w, rv.w, d1); d2 = __fmaf_rn(x2.w, rv.w, d2); d3 = __fmaf_rn(x3.w, rv.w, d3);
-      }
-    }
-    // survivors of the filter (rare): the reference's exact mul-then-add sum decides
-    auto exact = [&](int t) {
-      const float4* c4 = t4 + (size_t)t * ts4;
-      float dx = 0.f;
-      for (int q = 0; q < nq; ++q) {
-        const float4 x = c4[q];
-        const float4 y = SM ? reinterpret_cast<const float4*>(rowp)[q] : __ldcg(reinterpret_cast<const float4*>(rowp) + q);
-        dx = __fadd_rn(dx, __fmul_rn(x.x, y.x));
-        dx = __fadd_rn(dx, __fmul_rn(x.y, y.y));
-        dx = __fadd_rn(dx, __fmul_rn(x.z, y.z));
-        dx = __fadd_rn(dx, __fmul_rn(x.w, y.w));
-      }
-      if (cos_match(dx, s.cnorm[t], rn, threshold)) hit(t);
-    };
-    if (t0 + 0 < te && t0 + 0 != skip_t && !fast_reject(d0, s.cnorm[t0 + 0], rn, thr_lo)) exact(t0 + 0);
-    if (t0 + 1 < te && t0 + 1 != skip_t && !fast_reject(d1, s.cnorm[t0 + 1], rn, thr_lo)) exact(t0 + 1);
-    if (t0 + 2 < te && t0 + 2 != skip_t && !fast_reject(d2, s.cnorm[t0 + 2], rn, thr_lo)) exact(t0 + 2);
-    if (t0 + 3 < te && t0 + 3 != skip_t && !fast_reject(d3, s.cnorm[t0 + 3], rn, thr_lo)) exact(t0 + 3);
-  }
 }
 
 // Exact evaluation of one (candidate t, representative) pair that survived a prefilter.
@@ -417,6 +324,86 @@ __device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* s
             if ((int)jj != t && exact_pair<true>(s, t, s.tile + (size_t)jj * s.ts, s.cnorm[jj], nq, A.threshold))
               atomicOr(&s.pair[2 * t + (jj >> 5)], 1u << (jj & 31));
           } else if (!(s.s_f[t] < jj)) {  // skip when an earlier match is already recorded
+            const uint32_t rr2 = __ldcg(seg + jj);
+            if (exact_pair<false>(s, t, A.vals + (uint64_t)rr2 * ld, __ldcg(pos_nrm + jj), nq, A.threshold))
+              atomicMin(&s.s_f[t], jj);
+          }
+        }
+      }
+    }
+  }
+}
+
+// Same screen for rows wider than 64 floats: the window's fragments are re-read from shared memory
+// per k-step instead of living in registers (ks16 = number of 16-wide k steps, run time).
+template <bool SELF>
+__device__ __forceinline__ void tc_compare_wide(const MergeArgs& A, const uint32_t* seg, const float* pos_nrm, Smem& s, int W,
+                                                uint32_t j_begin, uint32_t j_end, uint32_t warp_rank, uint32_t n_warps, int nq,
+                                                int ks16) {
+  const uint32_t lane = lane_id(), g = lane >> 2, tg = lane & 3;
+  const float thr_tc = A.threshold - 2e-3f;
+  const int ld = A.ld;
+  for (uint32_t jb = j_begin + warp_rank * 8; jb < j_end; jb += n_warps * 8) {
+    const uint32_t j = jb + g;
+    const bool valid = j < j_end;
+    const float* row = nullptr;
+    const __half* hrow = nullptr;
+    float inv = 0.f;
+    if (SELF) {
+      hrow = s.htile + (size_t)(valid ? j : 0) * s.hs + tg * 2;
+    } else {
+      const uint32_t rr = valid ? __ldcg(seg + j) : 0u;
+      inv = valid ? __fdividef(1.f, __ldcg(pos_nrm + j)) : 0.f;
+      row = A.vals + (uint64_t)rr * ld + tg * 2;
+    }
+    float c[4][4];
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) c[mt][e] = 0.f;
+#pragma unroll 2
+    for (int ks = 0; ks < ks16; ++ks) {
+      uint32_t b0, b1;
+      if (SELF) {
+        b0 = *reinterpret_cast<const uint32_t*>(hrow + ks * 16);
+        b1 = *reinterpret_cast<const uint32_t*>(hrow + ks * 16 + 8);
+      } else {
+        float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
+        if (valid && ks * 16 + (int)tg * 2 < ld) v0 = __ldcg(reinterpret_cast<const float2*>(row + ks * 16));
+        if (valid && ks * 16 + 8 + (int)tg * 2 < ld) v1 = __ldcg(reinterpret_cast<const float2*>(row + ks * 16 + 8));
+        b0 = pack_half2(v0.x * inv, v0.y * inv);
+        b1 = pack_half2(v1.x * inv, v1.y * inv);
+      }
+#pragma unroll
+      for (int mt = 0; mt < 4; ++mt) {
+        const __half* r0 = s.htile + (size_t)(mt * 16 + g) * s.hs + ks * 16 + tg * 2;
+        const __half* r1 = r0 + 8 * s.hs;
+        uint32_t af[4];
+        af[0] = *reinterpret_cast<const uint32_t*>(r0);
+        af[1] = *reinterpret_cast<const uint32_t*>(r1);
+        af[2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
+        af[3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
+        mma_16816(c[mt], af, b0, b1);
+      }
+    }
+    uint32_t pend = 0;
+#pragma unroll
+    for (int mt = 0; mt < 4; ++mt)
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (!(c[mt][e] < thr_tc)) pend |= 1u << (mt * 4 + e);
+    while (__any_sync(0xffffffffu, pend != 0u)) {
+      if (pend != 0u) {
+        const int slot = __ffs(pend) - 1;
+        pend &= pend - 1;
+        const int mt = slot >> 2, e = slot & 3;
+        const int t = mt * 16 + (int)g + ((e & 2) ? 8 : 0);
+        const uint32_t jj = jb + tg * 2 + (e & 1);
+        if (t < W && jj < j_end) {
+          if (SELF) {
+            if ((int)jj != t && exact_pair<true>(s, t, s.tile + (size_t)jj * s.ts, s.cnorm[jj], nq, A.threshold))
+              atomicOr(&s.pair[2 * t + (jj >> 5)], 1u << (jj & 31));
+          } else if (!(s.s_f[t] < jj)) {
             const uint32_t rr2 = __ldcg(seg + jj);
             if (exact_pair<false>(s, t, A.vals + (uint64_t)rr2 * ld, __ldcg(pos_nrm + jj), nq, A.threshold))
               atomicMin(&s.s_f[t], jj);
@@ -826,9 +813,8 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
     __syncthreads();
     if (tid < W) s.cnorm[tid] = norm_seq(reinterpret_cast<const float4*>(s.tile + (size_t)tid * s.ts), nq);
     __syncthreads();
-    constexpr bool kUseTc = DR > 0;  // rows of up to 64 floats: tensor-core prefilter
-    if (kUseTc) {
-      // unit-norm fp16 copy of the window, zero-padded to the k-step width
+    {
+      // unit-norm fp16 copy of the window, zero-padded to the k-step width (tensor-core screen)
       const int kw = s.hs - 8;
       for (int v = tid; v < kW * kw; v += kMT) {
         const int t = v / kw, d = v - t * kw;
@@ -839,28 +825,17 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
       __syncthreads();
     }
     if (prof) tk1 = clock64();
-    // ---- parallel phase: old representatives [0, i0) across the team ----
-    if (kUseTc) {
+    // ---- parallel phase: old representatives [0, i0) across the team, then candidate x candidate bits ----
+    if (DR > 0) {
       constexpr int KS16 = DR > 0 ? DR / 16 : 1;
       tc_compare<KS16, false>(A, seg, pos_nrm, s, W, 0u, i0, Team<TEAM>::rank() * (kMT / 32) + warp,
                               Team<TEAM>::ncta() * (kMT / 32), nq);
       if (leader) tc_compare<KS16, true>(A, seg, pos_nrm, s, W, 0u, (uint32_t)W, warp, kMT / 32, nq);
     } else {
-      const uint32_t gstride = Team<TEAM>::ncta() * kMT;
-      for (uint32_t j = Team<TEAM>::rank() * kMT + tid; j < i0; j += gstride) {
-        const uint32_t rr = __ldcg(seg + j);
-        const float rn = __ldcg(pos_nrm + j);
-        compare_rep<DR, false>(A.vals + (uint64_t)rr * ld, rn, s, 0, W, nq, A.threshold, A.thr_lo, -1, j,
-                               [&](int t) { atomicMin(&s.s_f[t], j); });
-      }
-      if (leader) {  // candidate x candidate match bits: kMT/kW threads per candidate row
-        constexpr int kParts = kMT / kW;  // threads per candidate row
-        const int u = tid & (kW - 1), part = tid / kW;
-        const int tb = part * (kW / kParts), te = min(W, tb + kW / kParts);
-        if (u < W && tb < te)
-          compare_rep<DR, true>(s.tile + (size_t)u * s.ts, s.cnorm[u], s, tb, te, nq, A.threshold, A.thr_lo, u, 0u,
-                                [&](int t) { atomicOr(&s.pair[2 * t + (u >> 5)], 1u << (u & 31)); });
-      }
+      const int ks16 = (s.hs - 8) >> 4;
+      tc_compare_wide<false>(A, seg, pos_nrm, s, W, 0u, i0, Team<TEAM>::rank() * (kMT / 32) + warp,
+                             Team<TEAM>::ncta() * (kMT / 32), nq, ks16);
+      if (leader) tc_compare_wide<true>(A, seg, pos_nrm, s, W, 0u, (uint32_t)W, warp, kMT / 32, nq, ks16);
     }
     __syncthreads();
     if (prof) tk2 = clock64();
@@ -1070,7 +1045,6 @@ int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
   A.dbg = ctx->debug ? ctx->dbg.as<unsigned long long>() : nullptr;
   A.mg = ctx->mg;
   A.threshold = threshold;
-  A.thr_lo = threshold - 2e-6f - 4.0f * (float)ctx->ld * 5.9604645e-8f;
 
   // stage 0: one CTA per bucket, biggest buckets first
   A.list_a = s.list_big.as<uint32_t>();
