@@ -212,11 +212,21 @@ class Context:
         self._ck(self.lib.klsh_row_count(self.h, C.byref(n), C.byref(m) if with_ids else None), "klsh_row_count")
         return n.value, m.value
 
-    def get_rows(self):
+    def get_rows(self, out=None):
+        """Clusters out: (values[n][D], id_offsets[n+1], ids).  `out` = (values, id_offsets, ids) caller-owned
+        host arrays (e.g. pinned, reused across calls) large enough for the result; views of them are returned."""
         n, m = self.row_count()
-        values = np.empty((n, self.D), dtype=np.float32)
-        offs = np.empty(n + 1, dtype=np.uint64)
-        ids = np.empty(max(m, 1), dtype=np.uint64)
+        if out is None:
+            values = np.empty((n, self.D), dtype=np.float32)
+            offs = np.empty(n + 1, dtype=np.uint64)
+            ids = np.empty(max(m, 1), dtype=np.uint64)
+        else:
+            bv, bo, bi = out
+            if bv.size < n * self.D or bo.size < n + 1 or bi.size < max(m, 1):
+                raise KlshError("get_rows: output buffers too small (%d rows, %d ids)" % (n, m))
+            values = bv.reshape(-1)[: n * self.D].reshape(n, self.D)
+            offs = bo.reshape(-1)[: n + 1]
+            ids = bi.reshape(-1)[: max(m, 1)]
         self._ck(self.lib.klsh_get_rows(self.h, _p(values, f32p), _p(offs, u64p), _p(ids, u64p)), "klsh_get_rows")
         return values, offs, ids[:m]
 

@@ -14,6 +14,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <chrono>
 #include <thread>
 
 #include "klsh_internal.cuh"
@@ -148,9 +149,10 @@ void klsh_destroy(klsh_ctx* ctx) {
   dev_free(ctx->nested_out);
   dev_free(ctx->team_ctl);
   dev_free(ctx->exp_vals); dev_free(ctx->exp_cnt); dev_free(ctx->exp_head);
+  dev_free(ctx->rank_buf); dev_free(ctx->exp_offs); dev_free(ctx->exp_slots);
+  if (ctx->h_slots.p) cudaFreeHost(ctx->h_slots.p);
   if (ctx->h_cnt.p) cudaFreeHost(ctx->h_cnt.p);
   if (ctx->h_head.p) cudaFreeHost(ctx->h_head.p);
-  if (ctx->h_next.p) cudaFreeHost(ctx->h_next.p);
   dev_free(ctx->eps_counter);
   dev_free(ctx->dbg);
   dev_free(ctx->mg_counts); dev_free(ctx->mg_mod_rows); dev_free(ctx->mg_next_slot); dev_free(ctx->mg_next_val);
@@ -604,72 +606,48 @@ static int export_rows(klsh_ctx* ctx, float* values_out, uint64_t* offs_out, uin
   offs_out[0] = 0;
   if (!n) return KLSH_OK;
   cudaStream_t st = ctx->stream;
+  const auto t_begin = std::chrono::high_resolution_clock::now();
   KTRY(dev_reserve(ctx, ctx->exp_vals, sizeof(float) * n * (uint64_t)D));
   KTRY(dev_reserve(ctx, ctx->exp_cnt, sizeof(int32_t) * n));
   KTRY(dev_reserve(ctx, ctx->exp_head, sizeof(int32_t) * n));
   KTRY(host_reserve(ctx, ctx->h_cnt, sizeof(int32_t) * n));
   KTRY(host_reserve(ctx, ctx->h_head, sizeof(int32_t) * n));
-  if (ids_out) KTRY(host_reserve(ctx, ctx->h_next, sizeof(int32_t) * (ctx->n_slots + 1)));
   KTRY(launch_gather_rows(ctx, ctx->cur.alive.as<uint32_t>(), n, ctx->exp_vals.as<float>(), ctx->exp_cnt.as<int32_t>(),
                           ctx->exp_head.as<int32_t>()));
   KCUDA(ctx, cudaMemcpyAsync(ctx->h_cnt.p, ctx->exp_cnt.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-  KCUDA(ctx, cudaMemcpyAsync(ctx->h_head.p, ctx->exp_head.p, sizeof(int32_t) * n, cudaMemcpyDeviceToHost, st));
-  if (ids_out && ctx->n_slots)
-    KCUDA(ctx, cudaMemcpyAsync(ctx->h_next.p, ctx->cur.next.p, sizeof(int32_t) * ctx->n_slots, cudaMemcpyDeviceToHost, st));
   if (values_out)
     KCUDA(ctx, cudaMemcpyAsync(values_out, ctx->exp_vals.p, sizeof(float) * n * (uint64_t)D, cudaMemcpyDeviceToHost, st));
   KCUDA(ctx, cudaStreamSynchronize(st));
+  const auto t_copied = std::chrono::high_resolution_clock::now();
   const int32_t* cnt = static_cast<const int32_t*>(ctx->h_cnt.p);
-  const int32_t* head = static_cast<const int32_t*>(ctx->h_head.p);
-  const int32_t* next = static_cast<const int32_t*>(ctx->h_next.p);
   for (uint64_t r = 0; r < n; ++r) offs_out[r + 1] = offs_out[r] + (uint64_t)cnt[r];
   if (ids_out) {
-    // Walking the member chains is pointer chasing through next[] (one dependent load per id): split the
-    // clusters over host threads, balanced by id count.
     const uint64_t total = offs_out[n];
+    if (total >= 0xFFFFFFF0ull) return klsh_fail(ctx, KLSH_ERR_ARG, "too many member ids for one export (%llu)", (unsigned long long)total);
+    // flat member order on the device (pointer jumping over the chains), then one streaming map slot -> id
+    std::vector<uint32_t> offs32(n + 1);
+    for (uint64_t r = 0; r <= n; ++r) offs32[r] = (uint32_t)offs_out[r];
+    KTRY(dev_reserve(ctx, ctx->exp_offs, sizeof(uint32_t) * (n + 1)));
+    KTRY(dev_reserve(ctx, ctx->exp_slots, sizeof(uint32_t) * (total + 1)));
+    KTRY(host_reserve(ctx, ctx->h_slots, sizeof(uint32_t) * (total + 1)));
+    KCUDA(ctx, cudaMemcpyAsync(ctx->exp_offs.p, offs32.data(), sizeof(uint32_t) * (n + 1), cudaMemcpyHostToDevice, st));
+    KCUDA(ctx, cudaMemsetAsync(ctx->exp_slots.p, 0xFF, sizeof(uint32_t) * total, st));
+    KTRY(launch_rank_chains(ctx, n, ctx->exp_offs.as<uint32_t>(), ctx->exp_slots.as<uint32_t>()));
+    KCUDA(ctx, cudaMemcpyAsync(ctx->h_slots.p, ctx->exp_slots.p, sizeof(uint32_t) * total, cudaMemcpyDeviceToHost, st));
+    KCUDA(ctx, cudaStreamSynchronize(st));
+    const uint32_t* slots = static_cast<const uint32_t*>(ctx->h_slots.p);
     const unsigned hw = std::max(1u, std::min(32u, std::thread::hardware_concurrency()));
-    const unsigned nt = (unsigned)std::min<uint64_t>(hw, std::max<uint64_t>(1, total / 65536));
+    const unsigned nt = (unsigned)std::min<uint64_t>(hw, std::max<uint64_t>(1, total / 1048576));
     std::vector<uint64_t> bad(nt, UINT64_MAX);
     auto work = [&](unsigned w) {
-      const uint64_t id_lo = total / nt * w, id_hi = (w + 1 == nt) ? total : total / nt * (w + 1);
-      uint64_t r = std::lower_bound(offs_out, offs_out + n, id_lo) - offs_out;
-      // kWalk chains are advanced in turn so that their cache misses overlap
-      constexpr int kWalk = 16;
-      int32_t cur[kWalk];
-      uint64_t pos[kWalk], end[kWalk], row[kWalk];
-      int active = 0;
-      auto refill = [&](int k) {
-        while (r < n && offs_out[r] < id_hi) {
-          const uint64_t rr = r++;
-          if (offs_out[rr + 1] == offs_out[rr] && head[rr] < 0) continue;  // no members
-          cur[k] = head[rr];
-          pos[k] = offs_out[rr];
-          end[k] = offs_out[rr + 1];
-          row[k] = rr;
-          if (cur[k] >= 0) __builtin_prefetch(next + cur[k]);
-          return true;
+      const uint64_t lo = total / nt * w, hi = (w + 1 == nt) ? total : total / nt * (w + 1);
+      for (uint64_t i = lo; i < hi; ++i) {
+        const uint32_t s = slots[i];
+        if (s == 0xFFFFFFFFu) {
+          if (bad[w] == UINT64_MAX) bad[w] = i;
+          continue;
         }
-        return false;
-      };
-      bool live[kWalk];
-      for (int k = 0; k < kWalk; ++k) {
-        live[k] = refill(k);
-        active += live[k] ? 1 : 0;
-      }
-      while (active) {
-        for (int k = 0; k < kWalk; ++k) {
-          if (!live[k]) continue;
-          const int32_t s = cur[k];
-          if (s >= 0 && pos[k] < end[k]) {
-            ids_out[pos[k]++] = ctx->ids_implicit ? ctx->id_base + (uint64_t)s : ctx->ids[s];
-            cur[k] = next[s];
-            if (cur[k] >= 0) __builtin_prefetch(next + cur[k]);
-          } else {
-            if (pos[k] != end[k] && bad[w] == UINT64_MAX) bad[w] = row[k];
-            live[k] = refill(k);
-            if (!live[k]) --active;
-          }
-        }
+        ids_out[i] = ctx->ids_implicit ? ctx->id_base + (uint64_t)s : ctx->ids[s];
       }
     };
     std::vector<std::thread> pool;
@@ -678,7 +656,14 @@ static int export_rows(klsh_ctx* ctx, float* values_out, uint64_t* offs_out, uin
     for (auto& t : pool) t.join();
     for (unsigned w = 0; w < nt; ++w)
       if (bad[w] != UINT64_MAX)
-        return klsh_fail(ctx, KLSH_ERR_ARG, "internal: member chain of row %llu is inconsistent", (unsigned long long)bad[w]);
+        return klsh_fail(ctx, KLSH_ERR_ARG, "internal: member chains are inconsistent (output position %llu unfilled)",
+                         (unsigned long long)bad[w]);
+    if (ctx->debug) {
+      const auto t_end = std::chrono::high_resolution_clock::now();
+      fprintf(stderr, "[klsh] export: gather+D2H %.1f ms, offsets+chain ranking+id map %.1f ms (%u threads, %llu ids)\n",
+              std::chrono::duration<double, std::milli>(t_copied - t_begin).count(),
+              std::chrono::duration<double, std::milli>(t_end - t_copied).count(), nt, (unsigned long long)total);
+    }
   }
   return KLSH_OK;
 }

@@ -1094,6 +1094,93 @@ __global__ void k_apply_next(int32_t* next, const uint32_t* __restrict__ slots, 
 }
 }  // namespace
 
+// ================================================================================================
+// Member chains -> flat id order on the device (export).  A host walk of next[] is one dependent
+// cache miss per id and cannot be split inside one chain (clusters grow to millions of members), so
+// the chains are ranked by pointer jumping: after ceil(log2(longest chain)) rounds every member slot
+// knows its distance to the chain's tail and the tail itself; the tail identifies the cluster, and
+// the distance gives the member's position inside the cluster's id list.
+// ================================================================================================
+namespace {
+__global__ void k_rank_init(const int32_t* __restrict__ next, uint32_t m, int32_t* succ, uint32_t* dist, uint32_t* tailof) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= m) return;
+  succ[s] = next[s];
+  dist[s] = 1u;
+  tailof[s] = s;
+}
+__global__ void k_rank_step(const int32_t* __restrict__ succ_in, const uint32_t* __restrict__ dist_in,
+                            const uint32_t* __restrict__ tail_in, uint32_t m, int32_t* succ_out, uint32_t* dist_out,
+                            uint32_t* tail_out, uint32_t* changed) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= m) return;
+  const int32_t q = succ_in[s];
+  if (q >= 0) {
+    dist_out[s] = dist_in[s] + dist_in[q];
+    tail_out[s] = tail_in[q];
+    succ_out[s] = succ_in[q];
+    *changed = 1u;  // benign race: everybody writes the same value
+  } else {
+    dist_out[s] = dist_in[s];
+    tail_out[s] = tail_in[s];
+    succ_out[s] = -1;
+  }
+}
+__global__ void k_rank_owner(const int32_t* __restrict__ tail, const uint32_t* __restrict__ alive, uint32_t n, int32_t* owner) {
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  const int32_t t = tail[alive[r]];
+  if (t >= 0) owner[t] = (int32_t)r;
+}
+__global__ void k_rank_emit(const uint32_t* __restrict__ dist, const uint32_t* __restrict__ tailof,
+                            const int32_t* __restrict__ owner, const uint32_t* __restrict__ offs /* n+1 */, uint32_t m,
+                            uint32_t* slot_out) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= m) return;
+  const int32_t r = owner[tailof[s]];
+  if (r < 0) return;  // slot of a row that never entered the set (dropped by the keep filter)
+  const uint32_t end = offs[r + 1];
+  const uint32_t d = dist[s];
+  if (d <= end - offs[r]) slot_out[end - d] = s;
+}
+}  // namespace
+
+// slot_out[0 .. total_ids): member slots in output order (cluster after cluster, chain order inside).
+// d_offs: exclusive prefix of the survivors' member counts (n+1 entries, uint32) on the device.
+int launch_rank_chains(klsh_ctx* ctx, uint64_t n, const uint32_t* d_offs, uint32_t* slot_out) {
+  const uint32_t m = (uint32_t)ctx->n_slots;
+  if (!m || !n) return KLSH_OK;
+  KTRY(dev_reserve(ctx, ctx->rank_buf, sizeof(uint32_t) * ((size_t)m * 7 + 64)));
+  uint32_t* base = ctx->rank_buf.as<uint32_t>();
+  int32_t* succ[2] = {reinterpret_cast<int32_t*>(base), reinterpret_cast<int32_t*>(base + (size_t)m)};
+  uint32_t* dist[2] = {base + (size_t)2 * m, base + (size_t)3 * m};
+  uint32_t* tl[2] = {base + (size_t)4 * m, base + (size_t)5 * m};
+  int32_t* owner = reinterpret_cast<int32_t*>(base + (size_t)6 * m);
+  uint32_t* changed = base + (size_t)7 * m;
+  const uint32_t grid = cdiv64(m, 256);
+  k_rank_init<<<grid, 256, 0, ctx->stream>>>(ctx->cur.next.as<int32_t>(), m, succ[0], dist[0], tl[0]);
+  KLAUNCH(ctx);
+  KCUDA(ctx, cudaMemsetAsync(owner, 0xFF, sizeof(int32_t) * m, ctx->stream));
+  k_rank_owner<<<cdiv64(n, 256), 256, 0, ctx->stream>>>(ctx->cur.tail.as<int32_t>(), ctx->cur.alive.as<uint32_t>(), (uint32_t)n, owner);
+  KLAUNCH(ctx);
+  int cur = 0;
+  for (int round = 0; round < 34; ++round) {
+    KCUDA(ctx, cudaMemsetAsync(changed, 0, sizeof(uint32_t), ctx->stream));
+    k_rank_step<<<grid, 256, 0, ctx->stream>>>(succ[cur], dist[cur], tl[cur], m, succ[cur ^ 1], dist[cur ^ 1], tl[cur ^ 1], changed);
+    KLAUNCH(ctx);
+    cur ^= 1;
+    if ((round & 3) == 3) {  // look at the flag every fourth round only (each look is a host sync)
+      uint32_t h = 0;
+      KCUDA(ctx, cudaMemcpyAsync(&h, changed, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+      KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+      if (!h) break;
+    }
+  }
+  k_rank_emit<<<grid, 256, 0, ctx->stream>>>(dist[cur], tl[cur], owner, d_offs, m, slot_out);
+  KLAUNCH(ctx);
+  return KLSH_OK;
+}
+
 int launch_find_splits(klsh_ctx* ctx, PassScratch& s, uint32_t nb, uint64_t n, int world, uint32_t* d_splits) {
   k_find_splits<<<1, 64, 0, ctx->stream>>>(s.bstart.as<uint32_t>(), nb, n, world, d_splits);
   KLAUNCH(ctx);

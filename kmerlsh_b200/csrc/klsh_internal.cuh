@@ -104,7 +104,9 @@ struct klsh_ctx {
   DevBuf nested_out;  // survivors of one nested pass
   DevBuf team_ctl;    // per-team control blocks of the windowed merge
   DevBuf exp_vals, exp_cnt, exp_head;  // export staging (device)
-  HostBuf h_cnt, h_head, h_next;       // export staging (pinned host)
+  DevBuf rank_buf, exp_offs, exp_slots; // chain ranking scratch, offsets and flat slot order (device)
+  HostBuf h_slots;                     // flat slot order (pinned host)
+  HostBuf h_cnt, h_head;               // export staging (pinned host)
   DevBuf eps_counter; // rows whose key needed the exact re-evaluation of at least one plane (cumulative)
   MgLog mg;           // multi-GPU update logs (null pointers unless a sharded pass is running)
   DevBuf mg_counts, mg_mod_rows, mg_next_slot, mg_next_val, mg_splits, mg_surv;
@@ -166,6 +168,7 @@ int launch_sort_pairs(klsh_ctx* ctx, PassScratch& s, uint64_t n, int bits, uint3
                       uint32_t** rows_sorted);
 int launch_bounds(klsh_ctx* ctx, PassScratch& s, const uint32_t* keys_sorted, uint64_t n);
 int launch_classify(klsh_ctx* ctx, PassScratch& s, uint64_t n, int64_t nest_threshold, uint32_t b_lo, uint32_t b_hi);
+int launch_rank_chains(klsh_ctx* ctx, uint64_t n, const uint32_t* d_offs, uint32_t* slot_out);
 int launch_find_splits(klsh_ctx* ctx, PassScratch& s, uint32_t nb, uint64_t n, int world, uint32_t* d_splits);
 int launch_gather_mod(klsh_ctx* ctx, const uint32_t* rows, uint32_t n, float* out_vals, int32_t* out_meta);
 int launch_apply_mod(klsh_ctx* ctx, const uint32_t* rows, uint32_t n, const float* in_vals, const int32_t* in_meta,
