@@ -356,6 +356,23 @@ static int run_pass(klsh_ctx* ctx, PassScratch& s, const uint32_t* rows_in, uint
   KCUDA(ctx, cudaStreamSynchronize(st));
   const PassCounters c = *hc;
   ctx->h_counters->bucket_max = c.bucket_max;  // launch_merge sizes its spill slab from slot 0
+  if (ctx->debug && c.n_buckets) {  // KLSH_DEBUG=1: bucket-size histogram (rows per power-of-two size class)
+    std::vector<uint32_t> hb(c.n_buckets + 1);
+    cudaMemcpy(hb.data(), s.bstart.p, sizeof(uint32_t) * (c.n_buckets + 1), cudaMemcpyDeviceToHost);
+    uint64_t nb_h[33] = {0}, rows_h[33] = {0};
+    for (uint32_t b = 0; b < c.n_buckets; ++b) {
+      const uint32_t sz = hb[b + 1] - hb[b];
+      int k = 0;
+      while ((1u << k) < sz) ++k;  // size in (2^(k-1), 2^k]
+      nb_h[k]++;
+      rows_h[k] += sz;
+    }
+    fprintf(stderr, "[klsh] pass n=%llu H=%d buckets=%u small=%u large=%u big=%u nested=%u | size<=2^k: buckets/rows",
+            (unsigned long long)n, H, c.n_buckets, c.n_small, c.n_large, c.n_big, c.n_nested);
+    for (int k = 0; k < 33; ++k)
+      if (nb_h[k]) fprintf(stderr, " %d:%llu/%llu", k, (unsigned long long)nb_h[k], (unsigned long long)rows_h[k]);
+    fprintf(stderr, "\n");
+  }
   KTRY(launch_merge(ctx, s, rows_sorted, threshold, c));
   uint64_t nested_calls = 0;
   if (c.n_nested) {

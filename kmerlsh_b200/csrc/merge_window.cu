@@ -441,7 +441,12 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
   uint32_t inval = 0;  // entries whose match mask is stale (modified since it was built)
   int pend = -1;       // the entry whose norm is stale too (modified by the latest merge)
   // which unexamined candidates match entry e's current value; its norm falls out of the same pass
+  long long pv = 0, pa = 0, pm = 0;
+  int nval = 0;
+  const bool rprof = A.dbg != nullptr;
   auto validate = [&](int e) {
+    const long long tv0 = rprof ? clock64() : 0;
+    ++nval;
     const float4* r4 = reinterpret_cast<const float4*>(s.dvals + (size_t)e * s.ts);
     const int nfront = tail_mode ? max(0, wf - fi - bi) : (wf - fi);
     const int nback = tail_mode ? 0 : (wb - bi);
@@ -473,11 +478,44 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
       my_dm_hi = w1;
     }
     if (lane == 0) s.dnorm[e] = rn;
+    if (rprof) pv += clock64() - tv0;
   };
   // s.pair is dead once a candidate has been examined; reuse the per-candidate slots s.acc/... no:
   // the merge log lives in s.pridx (prefetch row index, dead after the entry was allocated) as
   // "previous candidate merged into the same entry" (kInf: none) and s.pcnt as the entry index.
+  // Candidates with no old match and no match bit against any other window row ("easy") can only merge
+  // into a representative modified in this window; while every dirty mask is valid that is one bit
+  // test, so whole runs of them are accepted at once instead of one loop trip each.
+  uint32_t easy_lo, easy_hi;
+  {
+    const int t0 = (int)lane, t1 = (int)lane + 32;
+    const bool e0 = t0 < wf && s.s_f[t0] == kInf && (s.pair[2 * t0] | s.pair[2 * t0 + 1]) == 0u;
+    const bool e1 = t1 < wf && s.s_f[t1] == kInf && (s.pair[2 * t1] | s.pair[2 * t1 + 1]) == 0u;
+    easy_lo = __ballot_sync(0xffffffffu, e0);
+    easy_hi = __ballot_sync(0xffffffffu, e1);
+  }
   while (i < size) {
+    if (!from_back && inval == 0u && fi < wf) {
+      uint32_t any_lo = 0u, any_hi = 0u;
+      if (nd > 0) {
+        any_lo = __reduce_or_sync(0xffffffffu, my_dm_lo);
+        any_hi = __reduce_or_sync(0xffffffffu, my_dm_hi);
+      }
+      const unsigned long long ok = ((unsigned long long)(easy_hi & ~any_hi) << 32) | (unsigned long long)(easy_lo & ~any_lo);
+      const unsigned long long stop = ~(ok >> fi);
+      int k = stop ? (__ffsll((long long)stop) - 1) : 64;
+      k = min(k, min(wf - fi, (int)(size - i)));
+      if (k > 0) {
+        for (int j = (int)lane; j < k; j += 32) s.acc[a + j] = (uint32_t)(fi + j);
+        const unsigned long long bits = ((k >= 64) ? ~0ull : ((1ull << k) - 1ull)) << fi;
+        accm_lo |= (uint32_t)bits;
+        accm_hi |= (uint32_t)(bits >> 32);
+        a += k;
+        i += (uint32_t)k;
+        fi += k;
+        continue;
+      }
+    }
     int t;
     if (from_back) {
       if (!tail_mode && bi >= wb) { back_exhausted = true; break; }
@@ -571,6 +609,7 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
       continue;
     }
     // merge the candidate into the representative at position `best`
+    const long long tm0 = rprof ? clock64() : 0;
     const uint32_t p = best;
     int e;
     {
@@ -639,11 +678,13 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
     __syncwarp();
     inval |= 1u << e;
     pend = e;
+    if (rprof) pm += clock64() - tm0;
     if (nd == kKD) { dbg_full = 1; break; }  // dirty cache full: flush and start a new window
   }
   __syncwarp();
   if (pend >= 0) validate(pend);  // publishes the latest entry's norm
   __syncwarp();
+  const long long ta0 = rprof ? clock64() : 0;
   // ---- apply the window's effects to global memory, in parallel ----
   // accepted candidates: positions i0.. in acceptance order (row index + norm)
   for (int k = lane; k < a; k += 32) {
@@ -705,6 +746,7 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
     const float* src = s.dvals + (size_t)e * s.ts;
     for (int d = lane; d < D; d += 32) dst[d] = src[d];
   }
+  if (rprof) pa = clock64() - ta0;
   if (lane == 0) {
     ctl->i = i;
     ctl->size = size;
@@ -717,6 +759,10 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
       atomicAdd(A.dbg + 4, (unsigned long long)dbg_full);
       atomicAdd(A.dbg + 5, (unsigned long long)(back_exhausted ? 1 : 0));
       atomicAdd(A.dbg + 6, (unsigned long long)a);
+      atomicAdd(A.dbg + 14, (unsigned long long)pv);
+      atomicAdd(A.dbg + 15, (unsigned long long)pm);
+      atomicAdd(A.dbg + 16, (unsigned long long)pa);
+      atomicAdd(A.dbg + 17, (unsigned long long)nval);
     }
   }
   __syncwarp();
@@ -1014,6 +1060,9 @@ static int launch_stage(klsh_ctx* ctx, int team, int csize, MergeArgs& A, uint32
     if (h[0])
       fprintf(stderr, "[klsh]   leader kcycles/window: stage %.1f parallel %.1f sync1 %.1f prefetch %.1f resolve %.1f sync2 %.1f\n",
               h[8] / 1e3 / h[0], h[9] / 1e3 / h[0], h[10] / 1e3 / h[0], h[11] / 1e3 / h[0], h[12] / 1e3 / h[0], h[13] / 1e3 / h[0]);
+    if (h[0])
+      fprintf(stderr, "[klsh]   resolver kcycles/window: validate %.1f (%.2f calls) merge-step %.1f apply %.1f\n", h[14] / 1e3 / h[0],
+              (double)h[17] / h[0], h[15] / 1e3 / h[0], h[16] / 1e3 / h[0]);
 
   }
   return KLSH_OK;

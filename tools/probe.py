@@ -4,6 +4,8 @@ sys.path.insert(0, ".")
 import numpy as np
 from kmerlsh_b200 import Context, synth
 
+import os
+ALL = bool(os.environ.get('PROBE_ALL'))
 cfg = sys.argv[1] if len(sys.argv) > 1 else "C1"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 100
 n, sa, sb, seed = synth.CONFIGS[cfg]
@@ -23,7 +25,7 @@ def show(tag, st, wall):
     tot_rows = sum(s.rows_in for s in st); tot_ms = sum(s.ms_total for s in st)
     print("%s: wall %.3fs device %.1f ms rows_in %d -> %.3e rows/s (device), %.3e rows/s (wall)" % (tag, wall, tot_ms, tot_rows, tot_rows / tot_ms * 1e3, tot_rows / wall))
     for k, s in enumerate(st):
-        if k < 6 or k % 10 == 9:
+        if k < 6 or k % 10 == 9 or ALL:
             print("  it %3d in %9d out %9d H %2d nb %8d bmax %7d nest %d | sign %.3f group %.3f merge %.3f compact %.3f ms" % (
                 k + 1, s.rows_in, s.rows_out, s.H, s.buckets, s.bucket_max, s.nested_calls, s.ms_sign, s.ms_group, s.ms_merge, s.ms_compact))
 t = time.time(); st = ctx.cluster(0.80, 1, 100000); show("phase1", st, time.time() - t)
