@@ -68,7 +68,7 @@ static void free_scratch(PassScratch& s) {
   dev_free(s.keys_a); dev_free(s.keys_b); dev_free(s.rows_a); dev_free(s.rows_b);
   dev_free(s.hist); dev_free(s.blkcnt); dev_free(s.bstart);
   dev_free(s.list_small); dev_free(s.list_large); dev_free(s.list_big); dev_free(s.esc1); dev_free(s.esc2); dev_free(s.esc3); dev_free(s.list_nested);
-  dev_free(s.pos_nrm);
+  dev_free(s.pos_nrm); dev_free(s.pos_h);
   dev_free(s.planes); dev_free(s.counters);
 }
 

@@ -38,6 +38,7 @@ struct PassScratch {
   DevBuf list_big, list_large;      // windowed-merge work items {bucket, i, size}: >= KLSH_BIG rows / the rest
   DevBuf esc1, esc2, esc3;          // buckets handed on: CTA -> cluster -> large cluster -> grid
   DevBuf pos_nrm;   // norm of the representative at each sorted position (merge scratch)
+  DevBuf pos_h;     // unit-norm fp16 copy of the representative at each sorted position (merge scratch, D <= 64)
   DevBuf planes;    // H*ld floats
   DevBuf counters;  // device counters (see PassCounters)
 };

@@ -91,6 +91,29 @@ __device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4],
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+// Fragment-order fp16 copy of a unit-norm row.  Chunk c (16 bytes) holds what lane tg = c & 3 of an
+// mma B fragment needs for the k-steps 2*(c>>2) and 2*(c>>2)+1: halves {k0+2tg, k0+2tg+1, k0+8+2tg, ...}.
+__device__ __forceinline__ float unit_scale(float x, float nrm) { return __fdividef(x, nrm); }
+__device__ __forceinline__ uint4 h16_chunk_from_row(const float* row, int ld, float nrm, int c) {
+  const int tg = c & 3, k0 = (c >> 2) * 32;
+  uint32_t w[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int off = k0 + (q >> 1) * 16 + (q & 1) * 8 + tg * 2;
+    const float x0 = off < ld ? unit_scale(row[off], nrm) : 0.f;
+    const float x1 = off + 1 < ld ? unit_scale(row[off + 1], nrm) : 0.f;
+    w[q] = pack_half2(x0, x1);
+  }
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+__device__ __forceinline__ uint4 h16_chunk_from_htile(const __half* hrow, int c) {
+  const int tg = c & 3, k0 = (c >> 2) * 32;
+  uint32_t w[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) w[q] = *reinterpret_cast<const uint32_t*>(hrow + k0 + (q >> 1) * 16 + (q & 1) * 8 + tg * 2);
+  return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
 // ---- teams -----------------------------------------------------------------------------------------
 template <int TEAM>
 struct Team;
@@ -139,6 +162,10 @@ struct MergeArgs {
   uint32_t* esc_count;
   uint32_t max_reps;
   float* pos_nrm;  // norm of the representative at each sorted position (scratch, N floats)
+  // unit-norm fp16 copy of the representative at each sorted position, in tensor-core fragment order
+  // (D <= 64 only): the screen streams it with one coalesced 16-byte load per lane instead of chasing
+  // row index -> row and converting on the fly
+  uint4* pos_h;
   TeamCtl* ctl;
   MgLog mg;
   unsigned long long* dbg;  // [16] (8..13: leader cycles in stage/parallel/sync1/prefetch/resolve/sync2) windows, candidates, merges, undecidable, cache_full, back_exhausted, accepted, escalated
@@ -232,12 +259,18 @@ __device__ __forceinline__ bool exact_pair(const Smem& s, int t, const float* ro
 // Tensor-core screened comparison of the window with representatives [j_begin, j_end) (SELF == false)
 // or with the window's own rows (SELF == true: candidate x candidate bits).  One warp handles 8
 // representatives per step; KS16 = number of 16-wide k steps (rows are zero-padded to 16*KS16).
+// Representatives come from the fragment-order fp16 copy seg_h (KS16/2 16-byte chunks per lane and
+// step, coalesced), fetched several steps ahead so that the tensor pipe, not L2 latency, paces the loop.
 template <int KS16, bool SELF>
-__device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* seg, const float* pos_nrm, Smem& s, int W,
-                                           uint32_t j_begin, uint32_t j_end, uint32_t warp_rank, uint32_t n_warps, int nq) {
+__device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* seg, const float* pos_nrm, const uint4* seg_h,
+                                           Smem& s, int W, uint32_t j_begin, uint32_t j_end, uint32_t warp_rank,
+                                           uint32_t n_warps, int nq) {
   const uint32_t lane = lane_id(), g = lane >> 2, tg = lane & 3;
   const float thr_tc = A.threshold - 2e-3f;
   const int ld = A.ld;
+  constexpr int NV = KS16 / 2;      // 16-byte chunks per lane per step
+  constexpr int QH = KS16 * 2;      // 16-byte chunks per representative
+  constexpr int PF = KS16 == 2 ? 4 : 2;  // steps in flight
   // A fragments of the whole window stay in registers: 4 row tiles x KS16 k-steps
   uint32_t af[4][KS16][4];
 #pragma unroll
@@ -251,54 +284,9 @@ __device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* s
       af[mt][ks][2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
       af[mt][ks][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
     }
-  // the row index and norm of the NEXT step's representative are fetched one step ahead, so that a
-  // step waits for one L2 round trip (the row), not two dependent ones
-  uint32_t rr_n = 0u;
-  float nrm_n = 1.f;
-  if (!SELF) {
-    const uint32_t j0 = j_begin + warp_rank * 8 + g;
-    if (j0 < j_end) {
-      rr_n = __ldcg(seg + j0);
-      nrm_n = __ldcg(pos_nrm + j0);
-    }
-  }
-  for (uint32_t jb = j_begin + warp_rank * 8; jb < j_end; jb += n_warps * 8) {
-    const uint32_t j = jb + g;  // this thread group's representative
-    const bool valid = j < j_end;
-    uint32_t bf[KS16][2];
-    if (SELF) {
-      const __half* hr = s.htile + (size_t)(valid ? j : 0) * s.hs + tg * 2;
-#pragma unroll
-      for (int ks = 0; ks < KS16; ++ks) {
-        bf[ks][0] = *reinterpret_cast<const uint32_t*>(hr + ks * 16);
-        bf[ks][1] = *reinterpret_cast<const uint32_t*>(hr + ks * 16 + 8);
-      }
-    } else {
-      const uint32_t rr = rr_n;
-      const float inv = valid ? __fdividef(1.f, nrm_n) : 0.f;
-      const float* row = A.vals + (uint64_t)rr * ld + tg * 2;
-      float2 v0[KS16], v1[KS16];
-#pragma unroll
-      for (int ks = 0; ks < KS16; ++ks) {
-        v0[ks] = make_float2(0.f, 0.f);
-        v1[ks] = make_float2(0.f, 0.f);
-        if (valid && ks * 16 + tg * 2 < ld) v0[ks] = __ldcg(reinterpret_cast<const float2*>(row + ks * 16));
-        if (valid && ks * 16 + 8 + tg * 2 < ld) v1[ks] = __ldcg(reinterpret_cast<const float2*>(row + ks * 16 + 8));
-      }
-      {
-        const uint32_t jn = j + n_warps * 8;
-        if (jn < j_end) {
-          rr_n = __ldcg(seg + jn);
-          nrm_n = __ldcg(pos_nrm + jn);
-        }
-      }
-#pragma unroll
-      for (int ks = 0; ks < KS16; ++ks) {
-        bf[ks][0] = pack_half2(v0[ks].x * inv, v0[ks].y * inv);
-        bf[ks][1] = pack_half2(v1[ks].x * inv, v1[ks].y * inv);
-      }
-    }
-    // screen all 64 x 8 pairs of this step, remember the survivors as a 16-bit mask per lane ...
+  // screen all 64 x 8 pairs of one step, then every lane works through its own survivors: the exact
+  // evaluations of different lanes run side by side instead of one (row tile, element) slot after the other
+  auto screen = [&](const uint32_t (&bf)[KS16][2], uint32_t jb) {
     uint32_t pend = 0;
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt) {
@@ -310,8 +298,6 @@ __device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* s
       for (int e = 0; e < 4; ++e)
         if (!(c[e] < thr_tc)) pend |= 1u << (mt * 4 + e);  // NaN/inf do not compare below: they go to the exact test
     }
-    // ... then every lane works through its own survivors: the exact evaluations of different lanes
-    // run side by side instead of one (row tile, element) slot after the other
     while (__any_sync(0xffffffffu, pend != 0u)) {
       if (pend != 0u) {
         const int slot = __ffs(pend) - 1;
@@ -329,6 +315,49 @@ __device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* s
               atomicMin(&s.s_f[t], jj);
           }
         }
+      }
+    }
+  };
+  if (SELF) {
+    for (uint32_t jb = j_begin + warp_rank * 8; jb < j_end; jb += n_warps * 8) {
+      const uint32_t j = jb + g;
+      const __half* hr = s.htile + (size_t)(j < j_end ? j : 0) * s.hs + tg * 2;
+      uint32_t bf[KS16][2];
+#pragma unroll
+      for (int ks = 0; ks < KS16; ++ks) {
+        bf[ks][0] = *reinterpret_cast<const uint32_t*>(hr + ks * 16);
+        bf[ks][1] = *reinterpret_cast<const uint32_t*>(hr + ks * 16 + 8);
+      }
+      screen(bf, jb);
+    }
+    return;
+  }
+  const uint32_t stride = n_warps * 8;
+  const uint32_t jb0 = j_begin + warp_rank * 8;
+  uint4 buf[PF][NV];
+  auto fetch = [&](uint4 (&dst)[NV], uint32_t jb) {
+    const uint32_t j = jb + g;
+#pragma unroll
+    for (int v = 0; v < NV; ++v)
+      dst[v] = (j < j_end) ? __ldcg(seg_h + (size_t)j * QH + v * 4 + tg) : make_uint4(0u, 0u, 0u, 0u);
+  };
+#pragma unroll
+  for (int u = 0; u < PF; ++u) fetch(buf[u], jb0 + (uint32_t)u * stride);
+  for (uint32_t jb = jb0; jb < j_end; jb += stride * PF) {
+#pragma unroll
+    for (int u = 0; u < PF; ++u) {
+      const uint32_t jbu = jb + (uint32_t)u * stride;
+      if (jbu < j_end) {  // warp-uniform
+        uint32_t bf[KS16][2];
+#pragma unroll
+        for (int v = 0; v < NV; ++v) {
+          bf[2 * v][0] = buf[u][v].x;
+          bf[2 * v][1] = buf[u][v].y;
+          bf[2 * v + 1][0] = buf[u][v].z;
+          bf[2 * v + 1][1] = buf[u][v].w;
+        }
+        fetch(buf[u], jbu + stride * PF);
+        screen(bf, jbu);
       }
     }
   }
@@ -422,8 +451,8 @@ __device__ __forceinline__ void tc_compare_wide(const MergeArgs& A, const uint32
 // splices and the swap-remove writes are independent of the decisions, so they are logged and
 // applied in parallel when the window ends.
 template <int TEAM>
-__device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm, TeamCtl* ctl, Smem& s, int W, int wf,
-                               int wb, bool tail_mode, uint32_t i0, uint32_t size0) {
+__device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm, uint4* seg_h, int qh, TeamCtl* ctl, Smem& s,
+                               int W, int wf, int wb, bool tail_mode, uint32_t i0, uint32_t size0) {
   const int D = A.D, ld = A.ld, nq = ld >> 2;
   const uint32_t lane = lane_id();
   int nd = 0, a = 0, fi = 0, bi = 0, merges = 0;
@@ -692,6 +721,19 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
     seg[i0 + k] = s.ridx[u];
     pos_nrm[i0 + k] = s.cnorm[u];
   }
+  if (qh) {
+    // fp16 copies: accepted candidates take theirs from the window's fp16 tile, modified
+    // representatives are re-scaled from their current value and norm
+    for (int idx = lane; idx < a * qh; idx += 32) {
+      const int k = idx / qh, c = idx - k * qh;
+      seg_h[(size_t)(i0 + k) * qh + c] = h16_chunk_from_htile(s.htile + (size_t)s.acc[k] * s.hs, c);
+    }
+    __syncwarp();  // an accepted candidate modified later in the window is rewritten below
+    for (int idx = lane; idx < nd * qh; idx += 32) {
+      const int e = idx / qh, c = idx - e * qh;
+      seg_h[(size_t)s.dpos[e] * qh + c] = h16_chunk_from_row(s.dvals + (size_t)e * s.ts, ld, s.dnorm[e], c);
+    }
+  }
   // a moved tail element waiting at position i (the window ended right after a merge)
   if (from_back && i < size && lane == 0) {
     uint32_t moved;
@@ -778,6 +820,8 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
   const uint32_t st = A.bstart[bucket];
   uint32_t* seg = A.rows_sorted + st;
   float* pos_nrm = A.pos_nrm + st;
+  constexpr int QH = DR > 0 ? DR / 8 : 0;  // 16-byte chunks of the fp16 copy per representative (0: not kept)
+  uint4* seg_h = QH ? A.pos_h + (size_t)st * QH : nullptr;
   // every CTA must have left the previous bucket's loop before the control block is reused
   if (TEAM == 2) Team<TEAM>::sync();
   if (leader && warp == 0) {
@@ -786,8 +830,10 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
       const float* src = A.vals + (uint64_t)r0 * ld;
       for (int d = lane; d < ld; d += 32) s.dvals[d] = src[d];
       __syncwarp();
+      const float n0 = norm_seq(reinterpret_cast<const float4*>(s.dvals), nq);
+      if ((int)lane < QH) seg_h[lane] = h16_chunk_from_row(s.dvals, ld, n0, (int)lane);
       if (lane == 0) {
-        pos_nrm[0] = norm_seq(reinterpret_cast<const float4*>(s.dvals), nq);
+        pos_nrm[0] = n0;
         ctl->i = 1;
         ctl->size = A.bstart[bucket + 1] - st;
         ctl->wb = 4;
@@ -844,6 +890,8 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
       }
     }
     __syncthreads();
+    long long ts1 = 0, ts2 = 0, ts3 = 0;
+    if (prof) ts1 = clock64();
     for (int v = tid; v < W * nq; v += kMT) {
       const int t = v / nq, q = v - t * nq;
       reinterpret_cast<float4*>(s.tile + (size_t)t * s.ts)[q] =
@@ -857,8 +905,10 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
       s.mprev[tid] = -1;
     }
     __syncthreads();
+    if (prof) ts2 = clock64();
     if (tid < W) s.cnorm[tid] = norm_seq(reinterpret_cast<const float4*>(s.tile + (size_t)tid * s.ts), nq);
     __syncthreads();
+    if (prof) ts3 = clock64();
     {
       // unit-norm fp16 copy of the window, zero-padded to the k-step width (tensor-core screen)
       const int kw = s.hs - 8;
@@ -872,11 +922,11 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
     }
     if (prof) tk1 = clock64();
     // ---- parallel phase: old representatives [0, i0) across the team, then candidate x candidate bits ----
-    if (DR > 0) {
-      constexpr int KS16 = DR > 0 ? DR / 16 : 1;
-      tc_compare<KS16, false>(A, seg, pos_nrm, s, W, 0u, i0, Team<TEAM>::rank() * (kMT / 32) + warp,
+    if constexpr (DR > 0) {
+      constexpr int KS16 = DR / 16;
+      tc_compare<KS16, false>(A, seg, pos_nrm, seg_h, s, W, 0u, i0, Team<TEAM>::rank() * (kMT / 32) + warp,
                               Team<TEAM>::ncta() * (kMT / 32), nq);
-      if (leader) tc_compare<KS16, true>(A, seg, pos_nrm, s, W, 0u, (uint32_t)W, warp, kMT / 32, nq);
+      if (leader) tc_compare<KS16, true>(A, seg, pos_nrm, seg_h, s, W, 0u, (uint32_t)W, warp, kMT / 32, nq);
     } else {
       const int ks16 = (s.hs - 8) >> 4;
       tc_compare_wide<false>(A, seg, pos_nrm, s, W, 0u, i0, Team<TEAM>::rank() * (kMT / 32) + warp,
@@ -919,7 +969,7 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
       }
       __syncthreads();
       if (prof) tk4 = clock64();
-      if (warp == 0) resolve_window<TEAM>(A, seg, pos_nrm, ctl, s, W, wf, wb, tail_mode, i0, size0);
+      if (warp == 0) resolve_window<TEAM>(A, seg, pos_nrm, seg_h, QH, ctl, s, W, wf, wb, tail_mode, i0, size0);
       if (prof) tk5 = clock64();
     }
     __threadfence();
@@ -932,6 +982,10 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
       atomicAdd(A.dbg + 11, (unsigned long long)(tk4 - tk3));
       atomicAdd(A.dbg + 12, (unsigned long long)(tk5 - tk4));
       atomicAdd(A.dbg + 13, (unsigned long long)(tk6 - tk5));
+      atomicAdd(A.dbg + 18, (unsigned long long)(ts1 - tk0));
+      atomicAdd(A.dbg + 19, (unsigned long long)(ts2 - ts1));
+      atomicAdd(A.dbg + 20, (unsigned long long)(ts3 - ts2));
+      atomicAdd(A.dbg + 21, (unsigned long long)(tk1 - ts3));
     }
   }
 }
@@ -1061,6 +1115,9 @@ static int launch_stage(klsh_ctx* ctx, int team, int csize, MergeArgs& A, uint32
       fprintf(stderr, "[klsh]   leader kcycles/window: stage %.1f parallel %.1f sync1 %.1f prefetch %.1f resolve %.1f sync2 %.1f\n",
               h[8] / 1e3 / h[0], h[9] / 1e3 / h[0], h[10] / 1e3 / h[0], h[11] / 1e3 / h[0], h[12] / 1e3 / h[0], h[13] / 1e3 / h[0]);
     if (h[0])
+      fprintf(stderr, "[klsh]   stage kcycles/window: index+meta %.1f rows %.1f norms %.1f fp16 %.1f\n", h[18] / 1e3 / h[0],
+              h[19] / 1e3 / h[0], h[20] / 1e3 / h[0], h[21] / 1e3 / h[0]);
+    if (h[0])
       fprintf(stderr, "[klsh]   resolver kcycles/window: validate %.1f (%.2f calls) merge-step %.1f apply %.1f\n", h[14] / 1e3 / h[0],
               (double)h[17] / h[0], h[15] / 1e3 / h[0], h[16] / 1e3 / h[0]);
 
@@ -1091,6 +1148,7 @@ int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
   A.rows_sorted = rows_sorted;
   A.bstart = s.bstart.as<uint32_t>();
   A.pos_nrm = s.pos_nrm.as<float>();
+  A.pos_h = s.pos_h.as<uint4>();
   A.dbg = ctx->debug ? ctx->dbg.as<unsigned long long>() : nullptr;
   A.mg = ctx->mg;
   A.threshold = threshold;
