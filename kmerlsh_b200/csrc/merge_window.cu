@@ -32,14 +32,24 @@
 
 #include "klsh_internal.cuh"
 
+#ifndef KLSH_CTA_THREADS
+#define KLSH_CTA_THREADS 128
+#endif
+
 namespace cg = cooperative_groups;
 
 namespace {
 
 constexpr int kW = 64;    // window capacity
 constexpr int kKD = 32;   // dirty-cache entries
-constexpr int kMT = 256;  // threads per CTA (128 x 4 per SM measured slower on C2)
-constexpr int kCtasPerSm = 2;
+// Threads per CTA and CTAs per SM by team kind.  Single-CTA teams are paced by per-window latencies
+// (staging, the resolver warp), so more, smaller CTAs per SM raise throughput; cluster and grid teams
+// carry the compare-heavy buckets and keep the wider CTAs.
+template <int TEAM>
+struct Shape {
+  static constexpr int kMT = TEAM == 0 ? KLSH_CTA_THREADS : 256;
+  static constexpr int kCtasPerSm = TEAM == 0 ? (512 / KLSH_CTA_THREADS) : 2;
+};
 constexpr int kWbMax = 62;
 constexpr uint32_t kInf = 0x7fffffffu;
 
@@ -810,9 +820,19 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
   __syncwarp();
 }
 
+// Window staging.  Rows go global -> shared with cp.async (no registers, no wait until the whole
+// batch is in flight), so a stage costs two dependent round trips (row index -> row / metadata)
+// however many rows a thread moves.
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
 // ---- one bucket, one team.  Returns true if the bucket was handed on to the next team. -----------------
 template <int TEAM, int DR>
 __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i, uint32_t start_size, TeamCtl* ctl, Smem& s) {
+  constexpr int kMT = Shape<TEAM>::kMT;
   const int ld = A.ld, nq = ld >> 2;
   const int tid = threadIdx.x;
   const uint32_t lane = lane_id(), warp = tid >> 5;
@@ -878,24 +898,40 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
     const bool prof = A.dbg && leader && tid == 0;
     if (prof) tk0 = clock64();
     // ---- stage the window: rows, metadata, norms ----
-    if (tid < W) {
-      const int t = tid;
-      const uint32_t pos = (t < wf) ? (i0 + t) : (size0 - 1 - (uint32_t)(t - wf));
-      const uint32_t r = __ldcg(seg + pos);
-      s.ridx[t] = r;
-      if (leader) {
-        s.ccnt[t] = A.cnt[r];
-        s.chead[t] = A.head[r];
-        s.ctail[t] = A.tail[r];
-      }
-    }
-    __syncthreads();
+    // Every load is issued before the first result is used, so the staging costs two dependent
+    // round trips (row index -> row / metadata) however many rows a thread moves.
     long long ts1 = 0, ts2 = 0, ts3 = 0;
-    if (prof) ts1 = clock64();
-    for (int v = tid; v < W * nq; v += kMT) {
-      const int t = v / nq, q = v - t * nq;
-      reinterpret_cast<float4*>(s.tile + (size_t)t * s.ts)[q] =
-          __ldcg(reinterpret_cast<const float4*>(A.vals + (uint64_t)s.ridx[t] * ld) + q);
+    {
+      auto pos_of = [&](int t) { return (t < wf) ? (i0 + (uint32_t)t) : (size0 - 1 - (uint32_t)(t - wf)); };
+      uint32_t mr = 0u;
+      if (tid < W) mr = __ldcg(seg + pos_of(tid));
+      const int items = W * nq;
+      for (int base = 0; base < items; base += 4 * kMT) {
+        uint32_t rr[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int v = base + u * kMT + tid;
+          rr[u] = (v < items) ? __ldcg(seg + pos_of(v / nq)) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+          const int v = base + u * kMT + tid;
+          if (v < items) {
+            const int t = v / nq, q = v - t * nq;
+            cp_async16(reinterpret_cast<float4*>(s.tile + (size_t)t * s.ts) + q,
+                       reinterpret_cast<const float4*>(A.vals + (uint64_t)rr[u] * ld) + q);
+          }
+        }
+      }
+      if (tid < W) {
+        s.ridx[tid] = mr;
+        if (leader) {
+          s.ccnt[tid] = A.cnt[mr];
+          s.chead[tid] = A.head[mr];
+          s.ctail[tid] = A.tail[mr];
+        }
+      }
+      cp_async_wait_all();
     }
     if (tid < kW) {
       s.s_f[tid] = kInf;
@@ -905,18 +941,29 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
       s.mprev[tid] = -1;
     }
     __syncthreads();
-    if (prof) ts2 = clock64();
+    if (prof) ts1 = clock64();
+    if (prof) ts2 = ts1;
     if (tid < W) s.cnorm[tid] = norm_seq(reinterpret_cast<const float4*>(s.tile + (size_t)tid * s.ts), nq);
     __syncthreads();
     if (prof) ts3 = clock64();
     {
-      // unit-norm fp16 copy of the window, zero-padded to the k-step width (tensor-core screen)
-      const int kw = s.hs - 8;
-      for (int v = tid; v < kW * kw; v += kMT) {
-        const int t = v / kw, d = v - t * kw;
-        float x = 0.f;
-        if (t < W && d < ld) x = __fdividef(s.tile[(size_t)t * s.ts + d], s.cnorm[t]);
-        s.htile[(size_t)t * s.hs + d] = __float2half_rn(x);
+      // unit-norm fp16 copy of the window, zero-padded to the k-step width (tensor-core screen);
+      // one thread converts 8 consecutive elements and stores them with one 16-byte write
+      const int kw = DR > 0 ? DR : s.hs - 8;
+      const int cpr = kw >> 3;
+      for (int v = tid; v < kW * cpr; v += kMT) {
+        const int t = v / cpr, d0 = (v - t * cpr) * 8;
+        const float nrm = t < W ? s.cnorm[t] : 1.f;
+        const float* src = s.tile + (size_t)t * s.ts + d0;
+        uint32_t w[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int d = d0 + 2 * q;
+          const float x0 = (t < W && d < ld) ? unit_scale(src[2 * q], nrm) : 0.f;
+          const float x1 = (t < W && d + 1 < ld) ? unit_scale(src[2 * q + 1], nrm) : 0.f;
+          w[q] = pack_half2(x0, x1);
+        }
+        *reinterpret_cast<uint4*>(s.htile + (size_t)t * s.hs + d0) = make_uint4(w[0], w[1], w[2], w[3]);
       }
       __syncthreads();
     }
@@ -950,22 +997,36 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
         __syncthreads();
       }
       // prefetch every candidate's first-match representative (row + member metadata) in parallel
-      if (tid < W) {
-        const uint32_t p = s.s_f[tid];
-        if (p != kInf) {
-          const uint32_t rr = __ldcg(seg + p);
-          s.pridx[tid] = rr;
-          s.pcnt[tid] = A.cnt[rr];
-          s.phead[tid] = A.head[rr];
-          s.ptail[tid] = A.tail[rr];
+      {
+        const bool has = tid < W && s.s_f[tid] != kInf;
+        uint32_t mr = 0u;
+        if (has) mr = __ldcg(seg + s.s_f[tid]);
+        const int items = W * nq;
+        for (int base = 0; base < items; base += 4 * kMT) {
+          uint32_t rr[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int v = base + u * kMT + tid;
+            const uint32_t p = (v < items) ? s.s_f[v / nq] : kInf;
+            rr[u] = (p != kInf) ? __ldcg(seg + p) : 0xFFFFFFFFu;
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            const int v = base + u * kMT + tid;
+            if (rr[u] != 0xFFFFFFFFu) {
+              const int t = v / nq, q = v - t * nq;
+              cp_async16(reinterpret_cast<float4*>(s.pre + (size_t)t * s.ts) + q,
+                         reinterpret_cast<const float4*>(A.vals + (uint64_t)rr[u] * ld) + q);
+            }
+          }
         }
-      }
-      __syncthreads();
-      for (int v = tid; v < W * nq; v += kMT) {
-        const int t = v / nq, q = v - t * nq;
-        if (s.s_f[t] != kInf)
-          reinterpret_cast<float4*>(s.pre + (size_t)t * s.ts)[q] =
-              __ldcg(reinterpret_cast<const float4*>(A.vals + (uint64_t)s.pridx[t] * ld) + q);
+        if (has) {
+          s.pridx[tid] = mr;
+          s.pcnt[tid] = A.cnt[mr];
+          s.phead[tid] = A.head[mr];
+          s.ptail[tid] = A.tail[mr];
+        }
+        cp_async_wait_all();
       }
       __syncthreads();
       if (prof) tk4 = clock64();
@@ -991,7 +1052,7 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
 }
 
 template <int TEAM, int DR>
-__global__ void __launch_bounds__(kMT, kCtasPerSm) k_merge_window(MergeArgs A) {
+__global__ void __launch_bounds__(Shape<TEAM>::kMT, Shape<TEAM>::kCtasPerSm) k_merge_window(MergeArgs A) {
   extern __shared__ __align__(16) float smem_raw[];
   __shared__ uint32_t s_work;
   Smem s;
@@ -1051,6 +1112,8 @@ static int launch_stage(klsh_ctx* ctx, int team, int csize, MergeArgs& A, uint32
       csize = 8;
     }
   }
+  const int kMT = team == 0 ? Shape<0>::kMT : Shape<1>::kMT;
+  const int kCtasPerSm = Shape<0>::kCtasPerSm;
   int per_sm = 1;
   KCUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kMT, smem));
   if (per_sm < 1) per_sm = 1;
