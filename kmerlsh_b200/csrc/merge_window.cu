@@ -559,15 +559,29 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
     if (from_back) {
       if (!tail_mode && bi >= wb) { back_exhausted = true; break; }
       t = tail_mode ? (wf - 1 - bi) : (wf + bi);
-      ++bi;
     } else {
       if (!tail_mode && fi >= wf) break;
       t = fi;
-      ++fi;
     }
     const uint32_t fpos = s.s_f[t];
     const uint32_t plo = s.pair[2 * t], phi = s.pair[2 * t + 1];
     const uint32_t tbit_lo = (t < 32) ? (1u << t) : 0u, tbit_hi = (t < 32) ? 0u : (1u << (t - 32));
+    if (inval != 0u) {
+      // Stale masks still predict well.  If nothing suggests that t merges, it will be accepted and the
+      // masks would be rebuilt right after its exact comparisons: rebuild them first (t is still in
+      // the unexamined set, so its bits come out of the same pass) and skip those comparisons.
+      const bool stale_hit = ((my_dm_lo & tbit_lo) | (my_dm_hi & tbit_hi)) != 0u;
+      const bool likely = fpos != kInf || ((plo & accm_lo) | (phi & accm_hi)) != 0u || __any_sync(0xffffffffu, stale_hit);
+      if (!likely) {
+        while (inval != 0u) {
+          const int e2 = __ffs(inval) - 1;
+          inval &= inval - 1;
+          validate(e2);
+        }
+        pend = -1;
+      }
+    }
+    if (from_back) ++bi; else ++fi;
     uint32_t best = kInf;
     if (nd > 0) {
       // (a) representatives modified in this window: match bits against their current values; the
