@@ -51,6 +51,8 @@ struct Shape {
   static constexpr int kCtasPerSm = TEAM == 0 ? (512 / KLSH_CTA_THREADS) : 2;
 };
 constexpr int kWbMax = 62;
+constexpr int kSurvCap = 1023;  // deferred screen survivors per CTA and window
+constexpr int kRing = 8;  // representative groups in flight per warp in the screen (cp.async ring)
 constexpr uint32_t kInf = 0x7fffffffu;
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
@@ -124,6 +126,15 @@ __device__ __forceinline__ uint4 h16_chunk_from_htile(const __half* hrow, int c)
   return make_uint4(w[0], w[1], w[2], w[3]);
 }
 
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 // ---- teams -----------------------------------------------------------------------------------------
 template <int TEAM>
 struct Team;
@@ -189,6 +200,8 @@ struct Smem {
   float* cnorm;  // [kW]
   float* dnorm;  // [kKD]
   __half* htile; // [kW][hs] unit-norm fp16 copy of the window (tensor-core prefilter)
+  uint32_t* surv;  // [kSurvCap + 1] deferred (representative << 6 | candidate) pairs that passed the screen; [kSurvCap] = count
+  uint4* ring;   // per warp: kRing slots x 32 lanes x (width/32) 16-byte chunks of representative fp16 copies in flight
   int hs;
   uint32_t* ridx;   // [kW]
   int32_t* ccnt;    // [kW]
@@ -214,10 +227,13 @@ struct Smem {
 // width (halfs) of the fp16 window copy: the k extent the kernel variant for this ld multiplies over
 __host__ __device__ inline int tc_width(int ld) { return ld <= 32 ? 32 : (ld <= 64 ? 64 : ((ld + 15) & ~15)); }
 
-__host__ __device__ inline size_t smem_bytes_for(int ld) {
+__host__ __device__ inline size_t ring_bytes_for(int ld, int threads) {
+  return ld <= 64 ? (size_t)(threads / 32) * kRing * 32 * (tc_width(ld) / 32) * 16 : 0;
+}
+__host__ __device__ inline size_t smem_bytes_for(int ld, int threads) {
   const int hs = tc_width(ld) + 8;
   return sizeof(float) * ((size_t)(2 * kW + kKD) * (ld + 4) + kW + kKD) + sizeof(uint32_t) * (kW * 14 + kKD * 5) + 64 +
-         sizeof(__half) * (size_t)kW * hs;
+         sizeof(__half) * (size_t)kW * hs + 16 + sizeof(uint32_t) * (kSurvCap + 1) + ring_bytes_for(ld, threads);
 }
 
 __device__ __forceinline__ void carve(Smem& s, float* base, int ld) {
@@ -248,6 +264,8 @@ __device__ __forceinline__ void carve(Smem& s, float* base, int ld) {
   s.ment = reinterpret_cast<int32_t*>(u); u += kW;
   s.hs = tc_width(ld) + 8;  // +8 halfs: rows 16 bytes apart modulo 128 -> conflict-free fragment loads
   s.htile = reinterpret_cast<__half*>(u + 4);
+  s.surv = reinterpret_cast<uint32_t*>(s.htile + (size_t)kW * s.hs);  // kW*hs halves: a multiple of 16 bytes
+  s.ring = reinterpret_cast<uint4*>(s.surv + kSurvCap + 1);
 }
 
 // Exact evaluation of one (candidate t, representative) pair that survived a prefilter.
@@ -280,7 +298,6 @@ __device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* s
   const int ld = A.ld;
   constexpr int NV = KS16 / 2;      // 16-byte chunks per lane per step
   constexpr int QH = KS16 * 2;      // 16-byte chunks per representative
-  constexpr int PF = KS16 == 2 ? 4 : 2;  // steps in flight
   // A fragments of the whole window stay in registers: 4 row tiles x KS16 k-steps
   uint32_t af[4][KS16][4];
 #pragma unroll
@@ -320,9 +337,17 @@ __device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* s
             if ((int)jj != t && exact_pair<true>(s, t, s.tile + (size_t)jj * s.ts, s.cnorm[jj], nq, A.threshold))
               atomicOr(&s.pair[2 * t + (jj >> 5)], 1u << (jj & 31));
           } else if (!(s.s_f[t] < jj)) {  // skip when an earlier match is already recorded
-            const uint32_t rr2 = __ldcg(seg + jj);
-            if (exact_pair<false>(s, t, A.vals + (uint64_t)rr2 * ld, __ldcg(pos_nrm + jj), nq, A.threshold))
-              atomicMin(&s.s_f[t], jj);
+            // The exact test needs the representative's fp32 row (two dependent global round trips):
+            // park the pair and test all parked pairs of the CTA together after the streaming loop.
+            uint32_t k = kSurvCap;
+            if (jj < (1u << 26)) k = atomicAdd(&s.surv[kSurvCap], 1u);
+            if (k < (uint32_t)kSurvCap) {
+              s.surv[k] = (jj << 6) | (uint32_t)t;
+            } else {
+              const uint32_t rr2 = __ldcg(seg + jj);
+              if (exact_pair<false>(s, t, A.vals + (uint64_t)rr2 * ld, __ldcg(pos_nrm + jj), nq, A.threshold))
+                atomicMin(&s.s_f[t], jj);
+            }
           }
         }
       }
@@ -342,35 +367,41 @@ __device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* s
     }
     return;
   }
+  // The fp16 copies travel global -> shared with cp.async through a ring private to the warp (every
+  // lane copies and later reads its own 16-byte chunks, so no barrier is involved): kRing steps are in
+  // flight per warp without holding registers.
   const uint32_t stride = n_warps * 8;
   const uint32_t jb0 = j_begin + warp_rank * 8;
-  uint4 buf[PF][NV];
-  auto fetch = [&](uint4 (&dst)[NV], uint32_t jb) {
+  uint4* ring = s.ring + (size_t)(threadIdx.x >> 5) * (kRing * 32 * NV) + lane;
+  auto fetch = [&](int slot, uint32_t jb) {
     const uint32_t j = jb + g;
 #pragma unroll
-    for (int v = 0; v < NV; ++v)
-      dst[v] = (j < j_end) ? __ldcg(seg_h + (size_t)j * QH + v * 4 + tg) : make_uint4(0u, 0u, 0u, 0u);
+    for (int v = 0; v < NV; ++v) {
+      uint4* dst = ring + (slot * NV + v) * 32;
+      if (j < j_end) cp_async16(dst, seg_h + (size_t)j * QH + v * 4 + tg);
+      else *dst = make_uint4(0u, 0u, 0u, 0u);
+    }
+    cp_async_commit();
   };
 #pragma unroll
-  for (int u = 0; u < PF; ++u) fetch(buf[u], jb0 + (uint32_t)u * stride);
-  for (uint32_t jb = jb0; jb < j_end; jb += stride * PF) {
+  for (int u = 0; u < kRing; ++u) fetch(u, jb0 + (uint32_t)u * stride);
+  int slot = 0;
+  for (uint32_t jb = jb0; jb < j_end; jb += stride) {
+    cp_async_wait_group<kRing - 1>();
+    uint32_t bf[KS16][2];
 #pragma unroll
-    for (int u = 0; u < PF; ++u) {
-      const uint32_t jbu = jb + (uint32_t)u * stride;
-      if (jbu < j_end) {  // warp-uniform
-        uint32_t bf[KS16][2];
-#pragma unroll
-        for (int v = 0; v < NV; ++v) {
-          bf[2 * v][0] = buf[u][v].x;
-          bf[2 * v][1] = buf[u][v].y;
-          bf[2 * v + 1][0] = buf[u][v].z;
-          bf[2 * v + 1][1] = buf[u][v].w;
-        }
-        fetch(buf[u], jbu + stride * PF);
-        screen(bf, jbu);
-      }
+    for (int v = 0; v < NV; ++v) {
+      const uint4 x = ring[(slot * NV + v) * 32];
+      bf[2 * v][0] = x.x;
+      bf[2 * v][1] = x.y;
+      bf[2 * v + 1][0] = x.z;
+      bf[2 * v + 1][1] = x.w;
     }
+    screen(bf, jb);
+    fetch(slot, jb + stride * kRing);  // after the screen: the slot's values have been consumed
+    slot = (slot + 1 == kRing) ? 0 : slot + 1;
   }
+  cp_async_wait_all();
 }
 
 // Same screen for rows wider than 64 floats: the window's fragments are re-read from shared memory
@@ -837,11 +868,6 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
 // Window staging.  Rows go global -> shared with cp.async (no registers, no wait until the whole
 // batch is in flight), so a stage costs two dependent round trips (row index -> row / metadata)
 // however many rows a thread moves.
-__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
-  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
 // ---- one bucket, one team.  Returns true if the bucket was handed on to the next team. -----------------
 template <int TEAM, int DR>
@@ -947,6 +973,7 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
       }
       cp_async_wait_all();
     }
+    if (tid == 0) s.surv[kSurvCap] = 0u;
     if (tid < kW) {
       s.s_f[tid] = kInf;
       s.pair[2 * tid] = 0u;
@@ -995,6 +1022,32 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
       if (leader) tc_compare_wide<true>(A, seg, pos_nrm, s, W, 0u, (uint32_t)W, warp, kMT / 32, nq, ks16);
     }
     __syncthreads();
+    {
+      // exact tests of the pairs the screen parked: all of the CTA's threads at once, so the
+      // dependent row fetches of different pairs overlap
+      const uint32_t ns = min(s.surv[kSurvCap], (uint32_t)kSurvCap);
+      for (uint32_t k0 = 0; k0 < ns; k0 += 2 * kMT) {
+        uint32_t ent[2], rr2[2];
+        bool on[2];
+#pragma unroll
+        for (int u = 0; u < 2; ++u) {
+          const uint32_t k = k0 + u * kMT + tid;
+          on[u] = k < ns;
+          ent[u] = on[u] ? s.surv[k] : 0u;
+          on[u] = on[u] && !(s.s_f[ent[u] & 63u] < (ent[u] >> 6));
+          rr2[u] = on[u] ? __ldcg(seg + (ent[u] >> 6)) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+          if (on[u]) {
+            const uint32_t jj = ent[u] >> 6;
+            const int t = (int)(ent[u] & 63u);
+            if (exact_pair<false>(s, t, A.vals + (uint64_t)rr2[u] * ld, __ldcg(pos_nrm + jj), nq, A.threshold))
+              atomicMin(&s.s_f[t], jj);
+          }
+      }
+      if (ns) __syncthreads();
+    }
     if (prof) tk2 = clock64();
     if (TEAM != 0) {
       if (tid < W && s.s_f[tid] != kInf) atomicMin(&ctl->f[tid], s.s_f[tid]);
@@ -1114,7 +1167,7 @@ const void* kernel_for(int ld) {
 // ================================================================================================
 static int launch_stage(klsh_ctx* ctx, int team, int csize, MergeArgs& A, uint32_t host_items /* upper bound, 0 = unknown */) {
   const int ld = ctx->ld;
-  const size_t smem = smem_bytes_for(ld);
+  const size_t smem = smem_bytes_for(ld, team == 0 ? Shape<0>::kMT : Shape<1>::kMT);
   if (smem > (size_t)ctx->max_smem_optin)
     return klsh_fail(ctx, KLSH_ERR_ARG, "dimension %d needs %zu bytes of shared memory per CTA (limit %d)", ctx->D, smem,
                      ctx->max_smem_optin);
