@@ -249,6 +249,224 @@ k_sign(const float* __restrict__ vals, int D, int ld, const uint32_t* __restrict
   }
 }
 
+// Tensor-core signing (rows of at most 64 floats).  ncu on the FMA kernel above at C2 scale: issue
+// slots 59 % busy at 44 % occupancy, 2.7 k warp instructions per 32 rows, 1.08 TB/s — contraction
+// bound, H*D fused multiply-adds per row against 4*D bytes (profiles/).  The projection is a
+// [rows x D] x [D x H] product, so it goes to the tensor cores as 3xTF32: every operand is split
+// into hi = tf32(v) and lo = tf32(v - hi) and the sum hi*hi + hi*lo + lo*hi is accumulated in fp32
+// (mma.sync.m16n8k8).  The products are exact; what is dropped (lo*lo and the split residue) is below
+// 3*2^-22 per term and the accumulation adds at most a few 2^-23 per mma, together under
+// 64*2^-24 * sum|w_i x_i|.  With the reference chain's own D*2^-24 the margin
+//     eps = (2.5*D + 64) * 2^-24 * |w| * |x|
+// guarantees that a sum outside it has the sign of the reference's mul-then-add chain; a sum inside it
+// is re-evaluated with the reference's exact arithmetic (and the row counted), so every key bit is
+// the reference's.  A warp owns 32 rows: cp.async gathers them into a double-buffered shared tile
+// (the next tile is in flight while this one is multiplied), planes sit in shared memory already
+// split and in B-fragment order (one 16-byte load per k-step and 8 planes).
+__device__ __forceinline__ uint32_t tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ void sign_cp_async16(void* smem_dst, const void* gsrc) {
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+
+template <int KS8>  // 8-wide k steps: 4 for rows of up to 32 floats, 8 for up to 64
+__global__ void __launch_bounds__(kSignWarps * 32)
+k_sign_tc(const float* __restrict__ vals, int D, int ld, const uint32_t* __restrict__ rows, uint64_t n,
+          const float* __restrict__ planes, int H, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ rows_out,
+          unsigned long long* eps_rows, uint32_t key_or) {
+  constexpr int KW = KS8 * 8;     // padded row width
+  constexpr int TS = KW + 4;      // tile row stride: fragment loads and per-row float4 walks are conflict-free
+  extern __shared__ __align__(16) float smem[];
+  float* sp = smem;                                          // planes [32][KW] fp32, zero padded (exact path)
+  float* pn = sp + 32 * KW;                                  // eps factor per plane [32]
+  uint4* bfrag = reinterpret_cast<uint4*>(pn + 32);          // [KS8][4][32] {hi b0, hi b1, lo b0, lo b1}
+  float* tiles = reinterpret_cast<float*>(bfrag + KS8 * 4 * 32);  // [kSignWarps][2][32][TS]
+  for (int i = threadIdx.x; i < 32 * KW; i += blockDim.x) {
+    const int h = i / KW, c = i - h * KW;
+    sp[i] = (h < H && c < ld) ? planes[h * ld + c] : 0.f;
+  }
+  for (int i = threadIdx.x; i < kSignWarps * 2 * 32 * TS; i += blockDim.x) tiles[i] = 0.f;  // padding columns stay zero
+  __syncthreads();
+  for (int h = threadIdx.x; h < 32; h += blockDim.x) {
+    float m = 0.f;
+    for (int i = 0; i < D; ++i) m = __fmaf_rn(sp[h * KW + i], sp[h * KW + i], m);
+    pn[h] = sqrtf(m) * ((2.5f * (float)D + 64.f) * 5.9604645e-8f);
+  }
+  for (int i = threadIdx.x; i < KS8 * 4 * 32; i += blockDim.x) {
+    const int l = i & 31, nt = (i >> 5) & 3, ks = i >> 7;
+    const int h = nt * 8 + (l >> 2), k0 = ks * 8 + (l & 3);
+    const float w0 = sp[h * KW + k0], w1 = sp[h * KW + k0 + 4];
+    const uint32_t h0 = tf32_rna(w0), h1 = tf32_rna(w1);
+    bfrag[i] = make_uint4(h0, h1, tf32_rna(w0 - __uint_as_float(h0)), tf32_rna(w1 - __uint_as_float(h1)));
+  }
+  __syncthreads();
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3;
+  float* wt = tiles + (size_t)warp * 2 * 32 * TS;
+  const uint64_t nwarps_total = (uint64_t)gridDim.x * kSignWarps;
+  const int vec_per_row = ld >> 2;
+  const int rr_lane = (int)lane / vec_per_row, cc_lane = (int)lane - rr_lane * vec_per_row;
+  const int rr_step = 32 / vec_per_row, cc_step = 32 - rr_step * vec_per_row;
+  uint32_t my_eps = 0;
+  // this lane's 8 planes (nt*8 + 2*tg + e): eps factors and which of them exist
+  float pnr[8];
+  uint32_t vmask = 0u;
+#pragma unroll
+  for (int q = 0; q < 8; ++q) {
+    const int h = (q >> 1) * 8 + 2 * (int)tg + (q & 1);
+    pnr[q] = pn[h];
+    if (h < H) vmask |= 1u << q;
+  }
+  // gather the 32 rows of the tile starting at t0 into buffer b; returns this lane's row index
+  auto issue = [&](uint64_t t0, int b) -> uint32_t {
+    uint32_t r = 0u;
+    if (t0 < n) {
+      const uint64_t t = t0 + lane;
+      r = (t < n) ? (rows ? rows[t] : (uint32_t)t) : 0u;
+      const int nrow = (int)min((uint64_t)32, n - t0);
+      const int total = nrow * vec_per_row;
+      float* tile = wt + (size_t)b * 32 * TS;
+      int rr = rr_lane, cc = cc_lane;  // (row, 16-byte chunk) of element v = v0 + lane, advanced without dividing
+      for (int v0 = 0; v0 < total; v0 += 32) {
+        const uint32_t ri = __shfl_sync(0xffffffffu, r, min(rr, 31));
+        if (v0 + (int)lane < total) sign_cp_async16(tile + rr * TS + cc * 4, vals + (uint64_t)ri * ld + cc * 4);
+        rr += rr_step;
+        cc += cc_step;
+        if (cc >= vec_per_row) {
+          cc -= vec_per_row;
+          ++rr;
+        }
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    return r;
+  };
+  uint64_t t0 = ((uint64_t)blockIdx.x * kSignWarps + warp) * 32;
+  int buf = 0;
+  uint32_t r_cur = issue(t0, 0);
+  for (; t0 < n; t0 += nwarps_total * 32, buf ^= 1) {
+    const uint32_t r_next = issue(t0 + nwarps_total * 32, buf ^ 1);
+    asm volatile("cp.async.wait_group 1;" ::: "memory");
+    __syncwarp();
+    const float* tile = wt + (size_t)buf * 32 * TS;
+    // |x| of this lane's own row
+    float xx = 0.f;
+    {
+      const float4* x4 = reinterpret_cast<const float4*>(tile + lane * TS);
+#pragma unroll
+      for (int q = 0; q < KS8 * 2; ++q) {
+        const float4 x = x4[q];
+        xx = __fmaf_rn(x.x, x.x, xx);
+        xx = __fmaf_rn(x.y, x.y, xx);
+        xx = __fmaf_rn(x.z, x.z, xx);
+        xx = __fmaf_rn(x.w, x.w, xx);
+      }
+    }
+    const float xn = sqrtf(xx);
+    float c[2][4][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[m][nt][e] = 0.f;
+#pragma unroll
+    for (int ks = 0; ks < KS8; ++ks) {
+      uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+      for (int m = 0; m < 2; ++m) {
+        const float* p0 = tile + (m * 16 + g) * TS + ks * 8 + tg;
+        const float a0 = p0[0], a1 = p0[8 * TS], a2 = p0[4], a3 = p0[8 * TS + 4];
+        ahi[m][0] = tf32_rna(a0); alo[m][0] = tf32_rna(a0 - __uint_as_float(ahi[m][0]));
+        ahi[m][1] = tf32_rna(a1); alo[m][1] = tf32_rna(a1 - __uint_as_float(ahi[m][1]));
+        ahi[m][2] = tf32_rna(a2); alo[m][2] = tf32_rna(a2 - __uint_as_float(ahi[m][2]));
+        ahi[m][3] = tf32_rna(a3); alo[m][3] = tf32_rna(a3 - __uint_as_float(ahi[m][3]));
+      }
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+        if (nt * 8 < H) {  // warp-uniform
+          const uint4 b = bfrag[(ks * 4 + nt) * 32 + lane];
+#pragma unroll
+          for (int m = 0; m < 2; ++m) {
+            mma_tf32(c[m][nt], alo[m], b.x, b.y);
+            mma_tf32(c[m][nt], ahi[m], b.z, b.w);
+            mma_tf32(c[m][nt], ahi[m], b.x, b.y);
+          }
+        }
+    }
+    // c[m][nt][2*half + e]: row m*16 + half*8 + g, plane nt*8 + 2*tg + e.  Branch-free: sign bits and
+    // "inside the margin" flags for the lane's 4 rows x 8 planes, then one rare pass over the flagged.
+    uint32_t part[4];
+    uint32_t slow = 0u;
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int row = m * 16 + half * 8 + (int)g;
+        const float xnr = __shfl_sync(0xffffffffu, xn, row);
+        uint32_t bits = 0u, flag = 0u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float sum = c[m][q >> 1][2 * half + (q & 1)];
+          const float a = fabsf(sum);
+          bits |= (sum >= 0.f ? 1u : 0u) << q;
+          flag |= ((a > pnr[q] * xnr && a <= 3.0e38f) ? 0u : 1u) << q;
+        }
+        flag &= vmask;
+        while (flag) {  // reference arithmetic: sum = fl(sum + fl(w_i * x_i)), i ascending (hash/lshash.cc:44-51)
+          const int q = __ffs(flag) - 1;
+          flag &= flag - 1;
+          const float* w = sp + ((q >> 1) * 8 + 2 * (int)tg + (q & 1)) * KW;
+          const float* x = tile + row * TS;
+          float sum = 0.f;
+          for (int j = 0; j < D; ++j) sum = __fadd_rn(sum, __fmul_rn(w[j], x[j]));
+          bits = (bits & ~(1u << q)) | ((sum >= 0.f ? 1u : 0u) << q);
+          slow |= 1u << (m * 2 + half);
+        }
+        bits &= vmask;
+        // bit q = (nt, e) -> plane h = nt*8 + 2*tg + e -> key bit H-1-h (plane 0 is the most significant)
+        uint32_t byplane = 0u;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) byplane |= ((bits >> (2 * nt)) & 3u) << (nt * 8);
+        byplane <<= 2 * tg;  // bit h set <=> plane h non-negative
+        part[m * 2 + half] = H ? (__brev(byplane) >> (32 - H)) : 0u;
+      }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      part[q] |= __shfl_xor_sync(0xffffffffu, part[q], 1);
+      part[q] |= __shfl_xor_sync(0xffffffffu, part[q], 2);
+    }
+    slow |= __shfl_xor_sync(0xffffffffu, slow, 1);
+    slow |= __shfl_xor_sync(0xffffffffu, slow, 2);
+    {
+      // lane (g, tg) writes row slot tg of its group: rows g, g+8, g+16, g+24
+      const uint32_t key = tg == 0 ? part[0] : (tg == 1 ? part[1] : (tg == 2 ? part[2] : part[3]));
+      const uint64_t t = t0 + tg * 8 + g;
+      if (t < n) {
+        keys_out[t] = key | key_or;
+        my_eps += (slow >> tg) & 1u;
+      }
+      const uint64_t tl = t0 + lane;
+      if (tl < n) rows_out[tl] = r_cur;
+    }
+    r_cur = r_next;
+    __syncwarp();
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+  if (eps_rows) {
+    const uint32_t tot = __reduce_add_sync(0xffffffffu, my_eps);
+    if (lane == 0 && tot) atomicAdd(eps_rows, (unsigned long long)tot);
+  }
+}
+
 // Rows wider than 64 floats: the warp stages its 32 rows 32 columns at a time (4 KB per warp instead
 // of a whole-row tile, so occupancy does not collapse at D = 256), one fused accumulator per plane.
 __global__ void __launch_bounds__(kSignWarps * 32)
@@ -974,9 +1192,23 @@ int launch_sign(klsh_ctx* ctx, const float* vals, int D, int ld, const uint32_t*
                 const float* d_planes, int H, uint32_t* keys_out, uint32_t* rows_out, uint32_t key_or) {
   if (!n) return KLSH_OK;
   KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long)));
-  const bool wide = ld > 64;
-  size_t smem = sizeof(float) * ((size_t)H * ld + ((H + 3) & ~3) + (size_t)kSignWarps * 32 * (wide ? 33 : (ld + 1)));
-  auto fn = ld <= 32 ? k_sign<32> : (ld <= 64 ? k_sign<64> : k_sign_wide);
+  if (ld <= 64) {
+    const int ks8 = ld <= 32 ? 4 : 8, kw = ks8 * 8;
+    const size_t smem = sizeof(float) * ((size_t)32 * kw + 32) + 16 * (size_t)ks8 * 4 * 32 +
+                        sizeof(float) * (size_t)kSignWarps * 2 * 32 * (kw + 4);
+    auto fn = ld <= 32 ? k_sign_tc<4> : k_sign_tc<8>;
+    KCUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 1;
+    KCUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSignWarps * 32, smem));
+    const uint64_t want = (n + kSignWarps * 32 - 1) / (kSignWarps * 32);
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * std::max(per_sm, 1));
+    fn<<<grid, kSignWarps * 32, smem, ctx->stream>>>(vals, D, ld, rows, n, d_planes, H, keys_out, rows_out,
+                                                     ctx->eps_counter.as<unsigned long long>(), key_or);
+    KLAUNCH(ctx);
+    return KLSH_OK;
+  }
+  size_t smem = sizeof(float) * ((size_t)H * ld + ((H + 3) & ~3) + (size_t)kSignWarps * 32 * 33);
+  auto fn = k_sign_wide;
   if (smem > 48 * 1024) KCUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   uint64_t want = (n + kSignWarps * 32 - 1) / (kSignWarps * 32);
   uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * 16);
