@@ -1254,7 +1254,7 @@ int launch_bounds(klsh_ctx* ctx, PassScratch& s, const uint32_t* keys_sorted, ui
   KTRY(dev_reserve(ctx, s.list_big, sizeof(uint32_t) * 3 * (n / KLSH_BIG + 2)));
   KTRY(dev_reserve(ctx, s.list_nested, sizeof(uint32_t) * (n / 2 + 2)));
   KTRY(dev_reserve(ctx, s.pos_nrm, sizeof(float) * (n + 2)));
-  KTRY(dev_reserve(ctx, s.pos_h, ctx->ld <= 64 ? (size_t)(ctx->ld <= 32 ? 64 : 128) * (n + 2) : 64));
+  KTRY(dev_reserve(ctx, s.pos_h, (size_t)(ctx->ld <= 32 ? 64 : (ctx->ld <= 64 ? 128 : 2 * ((ctx->ld + 31) & ~31))) * (n + 2)));
   KTRY(dev_reserve(ctx, s.counters, sizeof(PassCounters)));
   PassCounters* dc = s.counters.as<PassCounters>();
   KCUDA(ctx, cudaMemsetAsync(dc, 0, sizeof(PassCounters), ctx->stream));
@@ -1508,7 +1508,7 @@ int launch_merge_one(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, uint6
   KTRY(dev_reserve(ctx, s.counters, sizeof(PassCounters)));
   if (!ctx->merge_v1) {
     KTRY(dev_reserve(ctx, s.pos_nrm, sizeof(float) * (n + 2)));
-    KTRY(dev_reserve(ctx, s.pos_h, ctx->ld <= 64 ? (size_t)(ctx->ld <= 32 ? 64 : 128) * (n + 2) : 64));
+    KTRY(dev_reserve(ctx, s.pos_h, (size_t)(ctx->ld <= 32 ? 64 : (ctx->ld <= 64 ? 128 : 2 * ((ctx->ld + 31) & ~31))) * (n + 2)));
     KTRY(dev_reserve(ctx, s.bstart, sizeof(uint32_t) * 4));
     KTRY(dev_reserve(ctx, s.list_big, sizeof(uint32_t) * 4));
     KTRY(dev_reserve(ctx, s.list_large, sizeof(uint32_t) * 4));

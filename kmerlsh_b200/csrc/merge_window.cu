@@ -183,8 +183,8 @@ struct MergeArgs {
   uint32_t* esc_count;
   uint32_t max_reps;
   float* pos_nrm;  // norm of the representative at each sorted position (scratch, N floats)
-  // unit-norm fp16 copy of the representative at each sorted position, in tensor-core fragment order
-  // (D <= 64 only): the screen streams it with one coalesced 16-byte load per lane instead of chasing
+  // unit-norm fp16 copy of the representative at each sorted position, in tensor-core fragment order:
+  // the screen streams it with one coalesced 16-byte load per lane instead of chasing
   // row index -> row and converting on the fly
   uint4* pos_h;
   TeamCtl* ctl;
@@ -225,7 +225,7 @@ struct Smem {
 };
 
 // width (halfs) of the fp16 window copy: the k extent the kernel variant for this ld multiplies over
-__host__ __device__ inline int tc_width(int ld) { return ld <= 32 ? 32 : (ld <= 64 ? 64 : ((ld + 15) & ~15)); }
+__host__ __device__ inline int tc_width(int ld) { return ld <= 32 ? 32 : (ld <= 64 ? 64 : ((ld + 31) & ~31)); }
 
 __host__ __device__ inline size_t ring_bytes_for(int ld, int threads) {
   return ld <= 64 ? (size_t)(threads / 32) * kRing * 32 * (tc_width(ld) / 32) * 16 : 0;
@@ -407,53 +407,50 @@ __device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* s
 // Same screen for rows wider than 64 floats: the window's fragments are re-read from shared memory
 // per k-step instead of living in registers (ks16 = number of 16-wide k steps, run time).
 template <bool SELF>
-__device__ __forceinline__ void tc_compare_wide(const MergeArgs& A, const uint32_t* seg, const float* pos_nrm, Smem& s, int W,
-                                                uint32_t j_begin, uint32_t j_end, uint32_t warp_rank, uint32_t n_warps, int nq,
-                                                int ks16) {
+__device__ __forceinline__ void tc_compare_wide(const MergeArgs& A, const uint32_t* seg, const float* pos_nrm, const uint4* seg_h,
+                                                Smem& s, int W, uint32_t j_begin, uint32_t j_end, uint32_t warp_rank,
+                                                uint32_t n_warps, int nq, int ks16) {
   const uint32_t lane = lane_id(), g = lane >> 2, tg = lane & 3;
   const float thr_tc = A.threshold - 2e-3f;
   const int ld = A.ld;
+  const int qh = ks16 * 2;  // 16-byte chunks of the fp16 copy per representative (ks16 is even)
   for (uint32_t jb = j_begin + warp_rank * 8; jb < j_end; jb += n_warps * 8) {
     const uint32_t j = jb + g;
     const bool valid = j < j_end;
-    const float* row = nullptr;
-    const __half* hrow = nullptr;
-    float inv = 0.f;
-    if (SELF) {
-      hrow = s.htile + (size_t)(valid ? j : 0) * s.hs + tg * 2;
-    } else {
-      const uint32_t rr = valid ? __ldcg(seg + j) : 0u;
-      inv = valid ? __fdividef(1.f, __ldcg(pos_nrm + j)) : 0.f;
-      row = A.vals + (uint64_t)rr * ld + tg * 2;
-    }
+    const __half* hrow = SELF ? s.htile + (size_t)(valid ? j : 0) * s.hs + tg * 2 : nullptr;
+    const uint4* hp = SELF ? nullptr : seg_h + (size_t)(valid ? j : 0) * qh + tg;
     float c[4][4];
 #pragma unroll
     for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
       for (int e = 0; e < 4; ++e) c[mt][e] = 0.f;
 #pragma unroll 2
-    for (int ks = 0; ks < ks16; ++ks) {
-      uint32_t b0, b1;
+    for (int ks2 = 0; ks2 < (ks16 >> 1); ++ks2) {
+      uint32_t b[2][2];
       if (SELF) {
-        b0 = *reinterpret_cast<const uint32_t*>(hrow + ks * 16);
-        b1 = *reinterpret_cast<const uint32_t*>(hrow + ks * 16 + 8);
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          b[h][0] = *reinterpret_cast<const uint32_t*>(hrow + (2 * ks2 + h) * 16);
+          b[h][1] = *reinterpret_cast<const uint32_t*>(hrow + (2 * ks2 + h) * 16 + 8);
+        }
       } else {
-        float2 v0 = make_float2(0.f, 0.f), v1 = make_float2(0.f, 0.f);
-        if (valid && ks * 16 + (int)tg * 2 < ld) v0 = __ldcg(reinterpret_cast<const float2*>(row + ks * 16));
-        if (valid && ks * 16 + 8 + (int)tg * 2 < ld) v1 = __ldcg(reinterpret_cast<const float2*>(row + ks * 16 + 8));
-        b0 = pack_half2(v0.x * inv, v0.y * inv);
-        b1 = pack_half2(v1.x * inv, v1.y * inv);
+        const uint4 x = valid ? __ldcg(hp + ks2 * 4) : make_uint4(0u, 0u, 0u, 0u);
+        b[0][0] = x.x; b[0][1] = x.y; b[1][0] = x.z; b[1][1] = x.w;
       }
 #pragma unroll
-      for (int mt = 0; mt < 4; ++mt) {
-        const __half* r0 = s.htile + (size_t)(mt * 16 + g) * s.hs + ks * 16 + tg * 2;
-        const __half* r1 = r0 + 8 * s.hs;
-        uint32_t af[4];
-        af[0] = *reinterpret_cast<const uint32_t*>(r0);
-        af[1] = *reinterpret_cast<const uint32_t*>(r1);
-        af[2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
-        af[3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
-        mma_16816(c[mt], af, b0, b1);
+      for (int h = 0; h < 2; ++h) {
+        const int ks = 2 * ks2 + h;
+#pragma unroll
+        for (int mt = 0; mt < 4; ++mt) {
+          const __half* r0 = s.htile + (size_t)(mt * 16 + g) * s.hs + ks * 16 + tg * 2;
+          const __half* r1 = r0 + 8 * s.hs;
+          uint32_t af[4];
+          af[0] = *reinterpret_cast<const uint32_t*>(r0);
+          af[1] = *reinterpret_cast<const uint32_t*>(r1);
+          af[2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
+          af[3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
+          mma_16816(c[mt], af, b[h][0], b[h][1]);
+        }
       }
     }
     uint32_t pend = 0;
@@ -474,9 +471,15 @@ __device__ __forceinline__ void tc_compare_wide(const MergeArgs& A, const uint32
             if ((int)jj != t && exact_pair<true>(s, t, s.tile + (size_t)jj * s.ts, s.cnorm[jj], nq, A.threshold))
               atomicOr(&s.pair[2 * t + (jj >> 5)], 1u << (jj & 31));
           } else if (!(s.s_f[t] < jj)) {
-            const uint32_t rr2 = __ldcg(seg + jj);
-            if (exact_pair<false>(s, t, A.vals + (uint64_t)rr2 * ld, __ldcg(pos_nrm + jj), nq, A.threshold))
-              atomicMin(&s.s_f[t], jj);
+            uint32_t k = kSurvCap;
+            if (jj < (1u << 26)) k = atomicAdd(&s.surv[kSurvCap], 1u);
+            if (k < (uint32_t)kSurvCap) {
+              s.surv[k] = (jj << 6) | (uint32_t)t;
+            } else {
+              const uint32_t rr2 = __ldcg(seg + jj);
+              if (exact_pair<false>(s, t, A.vals + (uint64_t)rr2 * ld, __ldcg(pos_nrm + jj), nq, A.threshold))
+                atomicMin(&s.s_f[t], jj);
+            }
           }
         }
       }
@@ -880,8 +883,8 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
   const uint32_t st = A.bstart[bucket];
   uint32_t* seg = A.rows_sorted + st;
   float* pos_nrm = A.pos_nrm + st;
-  constexpr int QH = DR > 0 ? DR / 8 : 0;  // 16-byte chunks of the fp16 copy per representative (0: not kept)
-  uint4* seg_h = QH ? A.pos_h + (size_t)st * QH : nullptr;
+  const int QH = DR > 0 ? DR / 8 : (s.hs - 8) / 8;  // 16-byte chunks of the fp16 copy per representative
+  uint4* seg_h = A.pos_h + (size_t)st * QH;
   // every CTA must have left the previous bucket's loop before the control block is reused
   if (TEAM == 2) Team<TEAM>::sync();
   if (leader && warp == 0) {
@@ -891,7 +894,7 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
       for (int d = lane; d < ld; d += 32) s.dvals[d] = src[d];
       __syncwarp();
       const float n0 = norm_seq(reinterpret_cast<const float4*>(s.dvals), nq);
-      if ((int)lane < QH) seg_h[lane] = h16_chunk_from_row(s.dvals, ld, n0, (int)lane);
+      for (int c = (int)lane; c < QH; c += 32) seg_h[c] = h16_chunk_from_row(s.dvals, ld, n0, c);
       if (lane == 0) {
         pos_nrm[0] = n0;
         ctl->i = 1;
@@ -1017,9 +1020,9 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
       if (leader) tc_compare<KS16, true>(A, seg, pos_nrm, seg_h, s, W, 0u, (uint32_t)W, warp, kMT / 32, nq);
     } else {
       const int ks16 = (s.hs - 8) >> 4;
-      tc_compare_wide<false>(A, seg, pos_nrm, s, W, 0u, i0, Team<TEAM>::rank() * (kMT / 32) + warp,
+      tc_compare_wide<false>(A, seg, pos_nrm, seg_h, s, W, 0u, i0, Team<TEAM>::rank() * (kMT / 32) + warp,
                              Team<TEAM>::ncta() * (kMT / 32), nq, ks16);
-      if (leader) tc_compare_wide<true>(A, seg, pos_nrm, s, W, 0u, (uint32_t)W, warp, kMT / 32, nq, ks16);
+      if (leader) tc_compare_wide<true>(A, seg, pos_nrm, seg_h, s, W, 0u, (uint32_t)W, warp, kMT / 32, nq, ks16);
     }
     __syncthreads();
     {
