@@ -342,13 +342,26 @@ def main():
     dev_total_ms = sum(fam.values())
     if world > 1:  # per-family event times exist only on the single-GPU path; use the step time
         dev_total_ms = t_total * 1e3
+    sign_bytes = sum(s.rows_in * (4.0 * d + 8.0) for st in all_stats for s in st if s.rows_in)
+    sign_achieved = sign_bytes / (fam["sign"] * 1e-3) / 1e9 if fam["sign"] > 0 else 0.0
+    # DRAM traffic of the merge family for one step of this workload, from the committed ncu capture
+    traffic, traffic_src = None, None
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01c_dram_traffic_C2.json")
+    if args.workload == "C2" and not args.rows and world == 1 and os.path.exists(tpath):
+        with open(tpath) as fh:
+            tj = json.load(fh)
+        traffic = tj["families"]["merge"]["dram_GB"] * 1e9
+        traffic_src = "bytes per step over the family's launches, " + tj["source"]
     achieved = merge_bytes / (fam["merge"] * 1e-3) / 1e9 if fam["merge"] > 0 else 0.0
     job_achieved = job_bytes / (dev_total_ms * 1e-3) / 1e9 if dev_total_ms > 0 else 0.0
     roofline = {
         "bound": "hbm", "kernel": "k_merge_* (in-bucket greedy merge, per iteration)", "achieved": achieved, "peak": peak,
-        "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+        "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_src,
+        "algorithmic_bytes_per_step": merge_bytes / args.steps, "peak_source": peak_src,
         "share_of_step": (fam["merge"] / dev_total_ms if dev_total_ms else None) if world == 1 else None, "dominant_family": dom,
         "family_ms_per_step": {k: v / args.steps for k, v in fam.items()} if world == 1 else None,
+        "streaming": ({"kernel": "k_sign_tc (3xTF32 projection + key packing)", "achieved": sign_achieved, "unit": "GB/s",
+                       "frac": sign_achieved / peak, "bytes_per_row": "4D+8"} if world == 1 else None),
         "job": {"achieved": job_achieved, "frac": job_achieved / (peak * world), "bytes_per_row_iter": "8D+32+s(4D+12)",
                 "peak_all_gpus": peak * world},
     }
