@@ -7,6 +7,11 @@
 // members.  All clustering goes through the C ABI in include/klsh.h; there is no CPU path.
 // Additions: --seed=N (seeded hyperplanes; default draws a seed from std::random_device like the
 // reference), --device=N, --batch=N (rows per phase-1 batch, reference constant 100000000).
+// When the whole input is ONE batch, the phase-1 survivors stay resident on the device for the -I
+// iterations instead of being re-read from the spill files (the rows, their order and their member
+// lists are the same either way, so the results are too — SURVEY.md section 8f item 3); the spill
+// files are still written for compatibility.  --reload-tmp forces the reference's file round trip,
+// --no-tmp-files skips writing the spill when it is not needed.
 // Modes K, B and E are outside this tool.
 #include <getopt.h>
 
@@ -38,6 +43,7 @@ struct Params {
   uint64_t seed = 0;
   int device = 0;
   uint64_t batch = 100000000ull;
+  bool reload_tmp = false, no_tmp_files = false;
 };
 
 int count_lines(const std::string& path) {  // GetInput, reference io/ioHT.cc:3-19
@@ -112,6 +118,8 @@ int main(int argc, char** argv) {
                                          {"seed", required_argument, 0, 1000},
                                          {"device", required_argument, 0, 1001},
                                          {"batch", required_argument, 0, 1002},
+                                         {"reload-tmp", no_argument, 0, 1003},
+                                         {"no-tmp-files", no_argument, 0, 1004},
                                          {0, 0, 0, 0}};
   for (;;) {
     int idx = 0;
@@ -131,6 +139,8 @@ int main(int argc, char** argv) {
       case 1000: p.have_seed = true; p.seed = strtoull(optarg, 0, 10); break;
       case 1001: p.device = atoi(optarg); break;
       case 1002: p.batch = strtoull(optarg, 0, 10); break;
+      case 1003: p.reload_tmp = true; break;
+      case 1004: p.no_tmp_files = true; break;
       default: break;  // -H -X -C -K -S -P -V: accepted, meaningless for mode C
     }
   }
@@ -194,7 +204,7 @@ int main(int argc, char** argv) {
     return 1;
   }
   uint64_t batch_offset = 0, total_size = 0;
-  int tmp = 0;
+  int tmp = 0, batches_run = 0;
   int iter = (int)(kmap_size / batch_thresh);
   std::cout << "iteration : " << iter << " kmap_size : " << kmap_size << std::endl;
   std::string write_tmp = p.tmp_dir + std::to_string(tmp++) + ".bin";
@@ -213,10 +223,14 @@ int main(int argc, char** argv) {
     uint64_t rows = 0;
     CK(ctx, klsh_row_count(ctx, &rows, nullptr));
     total_size += rows;
-    CK(ctx, klsh_save(ctx, write_tmp.c_str(), i == 0, 0));
+    ++batches_run;
+    // a single batch that needs no re-batching stays on the device; its spill is optional then
+    const bool resident_ok = !p.reload_tmp && iter == 0 && rows <= batch_thresh;
+    if (!(resident_ok && p.no_tmp_files)) CK(ctx, klsh_save(ctx, write_tmp.c_str(), i == 0, 0));
     batch_offset += batch_size;
     if (p.verbose) std::cout << "# loaded kmers: " << batch_offset << std::endl;
   }
+  const bool resident = !p.reload_tmp && iter == 0 && batches_run == 1 && total_size <= batch_thresh;
   counts.clear();
   counts.shrink_to_fit();
   inStream.close();
@@ -249,7 +263,7 @@ int main(int argc, char** argv) {
     if (std::remove(rc.c_str()) != 0) perror("The temporary file deletion failed");
     else std::cout << rc << "file are removed" << std::endl;
   }
-  CK(ctx, klsh_load_cluster_file(ctx, write_tmp.c_str(), tot_sample, 0, 0));
+  if (!resident) CK(ctx, klsh_load_cluster_file(ctx, write_tmp.c_str(), tot_sample, 0, 0));
 
   // ---- the -I iterations, reference app/kmerLSH.cc:490 -----------------------------------------
   if (cluster_logged(ctx, p.min_similarity, p.cluster_iteration, 1000000, tot_sample, p.verbose)) return 1;

@@ -84,10 +84,13 @@ def test_cluster_kats(gpu, tag):
     assert np.array_equal(o, g[tag + "_offs"]) and np.array_equal(i, g[tag + "_ids"])
 
 
-@pytest.mark.parametrize("tag", ["modec_small", "modec_C1"])
-def test_mode_c_cli_matches_reference_binary(tag, tmp_path):
+@pytest.mark.parametrize("tag,extra", [("modec_small", []), ("modec_C1", []), ("modec_small", ["--reload-tmp"]),
+                                       ("modec_small", ["--no-tmp-files"])])
+def test_mode_c_cli_matches_reference_binary(tag, extra, tmp_path):
     """kmerLSH_b200 -M C --only ... in a directory laid out like the reference's: the output files
-    and the phase-1 spill are byte-identical to the seeded T=1 reference run."""
+    and the phase-1 spill are byte-identical to the seeded T=1 reference run — with the phase-1
+    survivors kept on the device (default for a single batch), with the reference's re-read of the
+    spill files (--reload-tmp), and without writing the spill at all (--no-tmp-files)."""
     m = json.load(open(os.path.join(G, "golden.json")))[tag]
     work = str(tmp_path)
     synth.write_mode_c_inputs(work, m["n"], m["sa"], m["sb"], m["gen_seed"])
@@ -95,11 +98,14 @@ def test_mode_c_cli_matches_reference_binary(tag, tmp_path):
         pytest.skip("numpy generator stream differs from the one the golden run used")
     exe = os.path.join(ROOT, "kmerlsh_b200", "kmerLSH_b200")
     subprocess.run([exe, "-a", "A.txt", "-b", "B.txt", "-o", "oa", "-p", "ob", "-M", "C", "--only", "-I", str(m["iters"]),
-                    "-N", str(m["min_similarity"]), "-K", "23", "-T", "1", "--seed=%d" % m["klsh_seed"]], cwd=work, check=True,
-                   stdout=subprocess.DEVNULL)
+                    "-N", str(m["min_similarity"]), "-K", "23", "-T", "1", "--seed=%d" % m["klsh_seed"]] + extra, cwd=work,
+                   check=True, stdout=subprocess.DEVNULL)
     out = os.path.join(work, "clustering_result.txt")
-    assert md5(os.path.join(work, "tmp", "0.bin")) == m["tmp_bin_md5"]
-    assert md5(os.path.join(work, "tmp", "0.bin.clust")) == m["tmp_clust_md5"]
+    if "--no-tmp-files" in extra:
+        assert not os.path.exists(os.path.join(work, "tmp", "0.bin"))
+    else:
+        assert md5(os.path.join(work, "tmp", "0.bin")) == m["tmp_bin_md5"]
+        assert md5(os.path.join(work, "tmp", "0.bin.clust")) == m["tmp_clust_md5"]
     assert md5(out) == m["bin_md5"]
     assert md5(out + ".clust") == m["clust_md5"]
 
