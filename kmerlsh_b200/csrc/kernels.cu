@@ -140,116 +140,13 @@ __global__ void k_fill_i32(int32_t* p, uint64_t n, int32_t v) {
 // Signing (reference LSH::random_projection, hash/lshash.cc:44-59):
 //   bit_h = (sum_h >= 0), sum_h = fl(fl(... fl(0 + fl(w_h0*x_0)) ...) + fl(w_h,D-1 * x_D-1))
 //   key = ((bit_0*2 + bit_1)*2 + ...) — plane 0 is the most significant bit.
-// One thread per row.  A warp stages its 32 rows through shared memory with coalesced 16-byte
-// loads (rows are gathered by index: the row arena never moves, DESIGN.md "Layout"), then every
-// lane walks its own row (odd stride -> conflict-free) against the planes held in shared memory
-// (broadcast reads).
+// D <= 64: k_sign_tc (tensor cores, below).  D > 64: k_sign_tc_wide (the same product walked in 64-column
+// chunks).  Both decide every bit with the reference's exact mul-then-add chain whenever the fast sum is
+// inside its error margin, and count those rows.
 // ================================================================================================
 constexpr int kSignWarps = 4;
 
-// Fast path: the sum is first accumulated with fused multiply-adds (half the instructions of the
-// reference's mul-then-add chain; the exact chain makes this kernel FP32-issue bound at 0.09*H
-// times its HBM time).  |s_fma - s_exact| <= 2*D*2^-24 * sum|w_i x_i| <= 2*D*2^-24 * |w||x|, so if
-// |s_fma| exceeds eps = (2.5*D+2)*2^-24*|w||x| both sums are non-zero with the same sign.  Otherwise —
-// the north star's "projection magnitude below eps" set — the (row, plane) sum is re-evaluated with
-// the reference's exact arithmetic, so every key bit is the reference's; such rows are counted.
-// The row is held in registers (ld <= DR) and the planes are read as broadcast float4.
-template <int DR>
-__global__ void __launch_bounds__(kSignWarps * 32)
-k_sign(const float* __restrict__ vals, int D, int ld, const uint32_t* __restrict__ rows, uint64_t n,
-       const float* __restrict__ planes, int H, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ rows_out,
-       unsigned long long* eps_rows, uint32_t key_or) {
-  extern __shared__ __align__(16) float smem[];
-  float* sp = smem;                      // planes [H][ld]
-  float* pn = smem + (size_t)H * ld;     // eps factor per plane: |w_h| * (2.5*D+2)*2^-24   [H rounded up to 4]
-  const int stride = ld + 1;             // odd
-  float* tiles = pn + ((H + 3) & ~3);    // [kSignWarps][32][stride]
-  for (int i = threadIdx.x; i < H * ld; i += blockDim.x) sp[i] = planes[i];
-  __syncthreads();
-  for (int h = threadIdx.x; h < H; h += blockDim.x) {
-    float m = 0.f;
-    for (int i = 0; i < D; ++i) m = __fmaf_rn(sp[h * ld + i], sp[h * ld + i], m);
-    pn[h] = sqrtf(m) * ((2.5f * (float)D + 2.f) * 5.9604645e-8f);
-  }
-  __syncthreads();
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  float* tile = tiles + (size_t)warp * 32 * stride;
-  const uint64_t nwarps_total = (uint64_t)gridDim.x * kSignWarps;
-  const int vec_per_row = ld >> 2;
-  uint32_t my_eps = 0;
-  for (uint64_t t0 = ((uint64_t)blockIdx.x * kSignWarps + warp) * 32; t0 < n; t0 += nwarps_total * 32) {
-    uint64_t t = t0 + lane;
-    uint32_t r = (t < n) ? (rows ? rows[t] : (uint32_t)t) : 0u;
-    int nrow = (int)min((uint64_t)32, n - t0);
-    // coalesced staging: consecutive lanes fetch consecutive float4 of the same row
-    const int total = nrow * vec_per_row;
-    for (int v0 = 0; v0 < total; v0 += 32) {
-      const int v = v0 + (int)lane;
-      const int rr = min(v, total - 1) / vec_per_row, cc = v - rr * vec_per_row;
-      const uint32_t ri = __shfl_sync(0xffffffffu, r, rr);
-      if (v < total) {
-        float4 q = __ldg(reinterpret_cast<const float4*>(vals + (uint64_t)ri * ld) + cc);
-        float* d = tile + rr * stride + cc * 4;
-        d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
-      }
-    }
-    __syncwarp();
-    if (t < n) {
-      const float* x = tile + lane * stride;
-      uint32_t key = 0;
-      bool slow = false;
-      {
-        float xr[DR];
-#pragma unroll
-        for (int i = 0; i < DR; ++i) xr[i] = (i < ld) ? x[i] : 0.f;  // padding (i >= D) is zero in the arena
-        float xx = 0.f;
-#pragma unroll
-        for (int i = 0; i < DR; ++i) xx = __fmaf_rn(xr[i], xr[i], xx);
-        const float xn = sqrtf(xx);
-        // two planes per step, four independent accumulators each: short dependency chains
-        for (int h = 0; h < H; h += 2) {
-          const bool two = h + 1 < H;
-          const float4* wa = reinterpret_cast<const float4*>(sp + h * ld);
-          const float4* wb = reinterpret_cast<const float4*>(sp + (two ? h + 1 : h) * ld);
-          float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, b0 = 0.f, b1 = 0.f, b2 = 0.f, b3 = 0.f;
-#pragma unroll
-          for (int q = 0; q < DR / 4; ++q)
-            if (q < vec_per_row) {
-              const float4 u = wa[q], v = wb[q];
-              a0 = __fmaf_rn(u.x, xr[4 * q], a0);     b0 = __fmaf_rn(v.x, xr[4 * q], b0);
-              a1 = __fmaf_rn(u.y, xr[4 * q + 1], a1); b1 = __fmaf_rn(v.y, xr[4 * q + 1], b1);
-              a2 = __fmaf_rn(u.z, xr[4 * q + 2], a2); b2 = __fmaf_rn(v.z, xr[4 * q + 2], b2);
-              a3 = __fmaf_rn(u.w, xr[4 * q + 3], a3); b3 = __fmaf_rn(v.w, xr[4 * q + 3], b3);
-            }
-          float sums[2] = {(a0 + a1) + (a2 + a3), (b0 + b1) + (b2 + b3)};
-#pragma unroll
-          for (int p = 0; p < 2; ++p) {
-            if (p == 1 && !two) break;
-            float sum = sums[p];
-            if (!(fabsf(sum) > pn[h + p] * xn) || !(fabsf(sum) <= 3.0e38f)) {
-              // reference arithmetic: sum = fl(sum + fl(w_i * x_i)), i ascending (hash/lshash.cc:44-51)
-              const float* w = sp + (h + p) * ld;
-              sum = 0.f;
-              for (int j = 0; j < D; ++j) sum = __fadd_rn(sum, __fmul_rn(w[j], x[j]));
-              slow = true;
-            }
-            key = key * 2u + (sum >= 0.f ? 1u : 0u);
-          }
-        }
-      }
-      keys_out[t] = key | key_or;
-      rows_out[t] = r;
-      my_eps += slow ? 1u : 0u;
-    }
-    __syncwarp();
-  }
-  if (eps_rows) {
-    const uint32_t tot = __reduce_add_sync(0xffffffffu, my_eps);
-    if (lane == 0 && tot) atomicAdd(eps_rows, (unsigned long long)tot);
-  }
-}
-
-// Tensor-core signing (rows of at most 64 floats).  ncu on the FMA kernel above at C2 scale: issue
+// Tensor-core signing (rows of at most 64 floats).  ncu on the FMA kernel this replaced, at C2 scale: issue
 // slots 59 % busy at 44 % occupancy, 2.7 k warp instructions per 32 rows, 1.08 TB/s — contraction
 // bound, H*D fused multiply-adds per row against 4*D bytes (profiles/).  The projection is a
 // [rows x D] x [D x H] product, so it goes to the tensor cores as 3xTF32: every operand is split
@@ -467,97 +364,186 @@ k_sign_tc(const float* __restrict__ vals, int D, int ld, const uint32_t* __restr
   }
 }
 
-// Rows wider than 64 floats: the warp stages its 32 rows 32 columns at a time (4 KB per warp instead
-// of a whole-row tile, so occupancy does not collapse at D = 256), one fused accumulator per plane.
-__global__ void __launch_bounds__(kSignWarps * 32)
-k_sign_wide(const float* __restrict__ vals, int D, int ld, const uint32_t* __restrict__ rows, uint64_t n,
-            const float* __restrict__ planes, int H, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ rows_out,
-            unsigned long long* eps_rows, uint32_t key_or) {
+// Rows wider than 64 floats: the same 3xTF32 product, walked in chunks of 64 columns.  The accumulators
+// stay in registers across the chunks, the 32 x 64 chunk tiles are double-buffered through cp.async
+// (chunk after chunk, tile after tile, one flat sequence), and the split planes for the whole width
+// sit in shared memory in B-fragment order.  The exact re-evaluation reads row and plane from global
+// memory (rare).
+__global__ void __launch_bounds__(256)
+k_sign_tc_wide(const float* __restrict__ vals, int D, int ld, const uint32_t* __restrict__ rows, uint64_t n,
+               const float* __restrict__ planes, int H, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ rows_out,
+               unsigned long long* eps_rows, uint32_t key_or) {
+  constexpr int CW = 64, TS = CW + 4, KS8 = CW / 8;
+  const int nch = (ld + CW - 1) / CW;
+  const int nwarp = blockDim.x >> 5;
   extern __shared__ __align__(16) float smem[];
-  float* sp = smem;                     // planes [H][ld]
-  float* pn = smem + (size_t)H * ld;    // eps factor per plane
-  float* tiles = pn + ((H + 3) & ~3);   // [kSignWarps][32][33]
-  for (int i = threadIdx.x; i < H * ld; i += blockDim.x) sp[i] = planes[i];
-  __syncthreads();
-  for (int h = threadIdx.x; h < H; h += blockDim.x) {
+  float* pn = smem;                                            // eps factor per plane [32]
+  uint4* bfrag = reinterpret_cast<uint4*>(pn + 32);            // [nch][KS8][4][32] {hi b0, hi b1, lo b0, lo b1}
+  float* tiles = reinterpret_cast<float*>(bfrag + (size_t)nch * KS8 * 4 * 32);  // [nwarp][2][32][TS]
+  for (int i = threadIdx.x; i < nwarp * 2 * 32 * TS; i += blockDim.x) tiles[i] = 0.f;
+  for (int h = threadIdx.x; h < 32; h += blockDim.x) {
     float m = 0.f;
-    for (int i = 0; i < D; ++i) m = __fmaf_rn(sp[h * ld + i], sp[h * ld + i], m);
-    pn[h] = sqrtf(m) * ((2.5f * (float)D + 2.f) * 5.9604645e-8f);
+    if (h < H)
+      for (int i = 0; i < D; ++i) m = __fmaf_rn(planes[h * ld + i], planes[h * ld + i], m);
+    pn[h] = sqrtf(m) * ((2.5f * (float)D + 64.f) * 5.9604645e-8f);
+  }
+  for (int i = threadIdx.x; i < nch * KS8 * 4 * 32; i += blockDim.x) {
+    const int l = i & 31, nt = (i >> 5) & 3, ks = i >> 7;  // ks runs over the whole width
+    const int h = nt * 8 + (l >> 2), k0 = ks * 8 + (l & 3);
+    const float w0 = (h < H && k0 < ld) ? planes[h * ld + k0] : 0.f;
+    const float w1 = (h < H && k0 + 4 < ld) ? planes[h * ld + k0 + 4] : 0.f;
+    const uint32_t h0 = tf32_rna(w0), h1 = tf32_rna(w1);
+    bfrag[i] = make_uint4(h0, h1, tf32_rna(w0 - __uint_as_float(h0)), tf32_rna(w1 - __uint_as_float(h1)));
   }
   __syncthreads();
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5;
-  float* tile = tiles + (size_t)warp * 32 * 33;
-  const uint64_t nwarps_total = (uint64_t)gridDim.x * kSignWarps;
+  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3;
+  float* wt = tiles + (size_t)warp * 2 * 32 * TS;
+  const uint64_t nwarps_total = (uint64_t)gridDim.x * nwarp;
   uint32_t my_eps = 0;
-  for (uint64_t t0 = ((uint64_t)blockIdx.x * kSignWarps + warp) * 32; t0 < n; t0 += nwarps_total * 32) {
-    const uint64_t t = t0 + lane;
-    const uint32_t r = (t < n) ? (rows ? rows[t] : (uint32_t)t) : 0u;
-    const int nrow = (int)min((uint64_t)32, n - t0);
-    float acc[32];
+  float pnr[8];
+  uint32_t vmask = 0u;
 #pragma unroll
-    for (int h = 0; h < 32; ++h) acc[h] = 0.f;
-    float xx = 0.f;
-    for (int c0 = 0; c0 < ld; c0 += 32) {
-      // 32 rows x 32 columns: 8 lanes fetch one row's 128 bytes
-      for (int v0 = 0; v0 < nrow * 8; v0 += 32) {
-        const int v = v0 + (int)lane;
-        const int rr = min(v, nrow * 8 - 1) >> 3, cc = v & 7;
-        const uint32_t ri = __shfl_sync(0xffffffffu, r, rr);
-        if (v < nrow * 8) {
-          float4 q = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (c0 + cc * 4 < ld) q = __ldg(reinterpret_cast<const float4*>(vals + (uint64_t)ri * ld + c0) + cc);
-          float* d = tile + rr * 33 + cc * 4;
-          d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
-        }
-      }
-      __syncwarp();
-      if (t < n) {
-        float xr[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) xr[i] = tile[lane * 33 + i];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) xx = __fmaf_rn(xr[i], xr[i], xx);
-#pragma unroll
-        for (int h = 0; h < 32; ++h)
-          if (h < H) {
-            const float4* w4 = reinterpret_cast<const float4*>(sp + h * ld + c0);
-            float s0 = acc[h], s1 = 0.f;
-#pragma unroll
-            for (int q = 0; q < 8; ++q)
-              if (c0 + 4 * q < ld) {
-                const float4 w = w4[q];
-                s0 = __fmaf_rn(w.x, xr[4 * q], s0);
-                s1 = __fmaf_rn(w.y, xr[4 * q + 1], s1);
-                s0 = __fmaf_rn(w.z, xr[4 * q + 2], s0);
-                s1 = __fmaf_rn(w.w, xr[4 * q + 3], s1);
-              }
-            acc[h] = s0 + s1;
-          }
-      }
-      __syncwarp();
-    }
-    if (t < n) {
-      const float xn = sqrtf(xx);
-      const float* x = vals + (uint64_t)r * ld;  // exact re-evaluation reads the row again (rare)
-      uint32_t key = 0;
-      bool slow = false;
-#pragma unroll
-      for (int h = 0; h < 32; ++h)
-        if (h < H) {
-          float sum = acc[h];
-          if (!(fabsf(sum) > pn[h] * xn) || !(fabsf(sum) <= 3.0e38f)) {
-            const float* w = sp + h * ld;
-            sum = 0.f;
-            for (int j = 0; j < D; ++j) sum = __fadd_rn(sum, __fmul_rn(w[j], __ldg(x + j)));
-            slow = true;
-          }
-          key = key * 2u + (sum >= 0.f ? 1u : 0u);
-        }
-      keys_out[t] = key | key_or;
-      rows_out[t] = r;
-      my_eps += slow ? 1u : 0u;
-    }
+  for (int q = 0; q < 8; ++q) {
+    const int h = (q >> 1) * 8 + 2 * (int)tg + (q & 1);
+    pnr[q] = pn[h];
+    if (h < H) vmask |= 1u << q;
   }
+  // gather chunk ch of the tile starting at t0 into buffer b (r = this lane's row index)
+  auto issue = [&](uint64_t t0, uint32_t r, int ch, int b) {
+    if (t0 < n) {
+      const int nrow = (int)min((uint64_t)32, n - t0);
+      const int c0 = ch * CW;
+      const int vpr = min(CW, ld - c0) >> 2;  // 16-byte pieces per row in this chunk
+      const int total = nrow * vpr;
+      float* tile = wt + (size_t)b * 32 * TS;
+      for (int v0 = 0; v0 < total; v0 += 32) {
+        const int v = v0 + (int)lane;
+        const int rr = min(v, total - 1) / vpr, cc = v - rr * vpr;
+        const uint32_t ri = __shfl_sync(0xffffffffu, r, rr);
+        if (v < total) sign_cp_async16(tile + rr * TS + cc * 4, vals + (uint64_t)ri * ld + c0 + cc * 4);
+      }
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  auto row_of = [&](uint64_t t0) -> uint32_t {
+    const uint64_t t = t0 + lane;
+    return (t < n) ? (rows ? rows[t] : (uint32_t)t) : 0u;
+  };
+  uint64_t t0 = ((uint64_t)blockIdx.x * nwarp + warp) * 32;
+  uint32_t r_cur = row_of(t0);
+  int buf = 0;
+  issue(t0, r_cur, 0, 0);
+  for (; t0 < n; t0 += nwarps_total * 32) {
+    const uint64_t t0n = t0 + nwarps_total * 32;
+    const uint32_t r_next = row_of(t0n);
+    float c[2][4][4];
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+        for (int e = 0; e < 4; ++e) c[m][nt][e] = 0.f;
+    float xx = 0.f;
+    for (int ch = 0; ch < nch; ++ch, buf ^= 1) {
+      if (ch + 1 < nch) issue(t0, r_cur, ch + 1, buf ^ 1);
+      else issue(t0n, r_next, 0, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+      __syncwarp();
+      const float* tile = wt + (size_t)buf * 32 * TS;
+      {
+        const float4* x4 = reinterpret_cast<const float4*>(tile + lane * TS);
+        const int nq = min(CW, ld - ch * CW) >> 2;
+        for (int q = 0; q < nq; ++q) {
+          const float4 x = x4[q];
+          xx = __fmaf_rn(x.x, x.x, xx);
+          xx = __fmaf_rn(x.y, x.y, xx);
+          xx = __fmaf_rn(x.z, x.z, xx);
+          xx = __fmaf_rn(x.w, x.w, xx);
+        }
+      }
+#pragma unroll
+      for (int ks = 0; ks < KS8; ++ks) {
+        uint32_t ahi[2][4], alo[2][4];
+#pragma unroll
+        for (int m = 0; m < 2; ++m) {
+          const float* p0 = tile + (m * 16 + g) * TS + ks * 8 + tg;
+          const float a0 = p0[0], a1 = p0[8 * TS], a2 = p0[4], a3 = p0[8 * TS + 4];
+          ahi[m][0] = tf32_rna(a0); alo[m][0] = tf32_rna(a0 - __uint_as_float(ahi[m][0]));
+          ahi[m][1] = tf32_rna(a1); alo[m][1] = tf32_rna(a1 - __uint_as_float(ahi[m][1]));
+          ahi[m][2] = tf32_rna(a2); alo[m][2] = tf32_rna(a2 - __uint_as_float(ahi[m][2]));
+          ahi[m][3] = tf32_rna(a3); alo[m][3] = tf32_rna(a3 - __uint_as_float(ahi[m][3]));
+        }
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+          if (nt * 8 < H) {  // warp-uniform
+            const uint4 b = bfrag[((size_t)(ch * KS8 + ks) * 4 + nt) * 32 + lane];
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+              mma_tf32(c[m][nt], alo[m], b.x, b.y);
+              mma_tf32(c[m][nt], ahi[m], b.z, b.w);
+              mma_tf32(c[m][nt], ahi[m], b.x, b.y);
+            }
+          }
+      }
+      __syncwarp();
+    }
+    const float xn = sqrtf(xx);
+    uint32_t part[4];
+    uint32_t slow = 0u;
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        const int row = m * 16 + half * 8 + (int)g;
+        const float xnr = __shfl_sync(0xffffffffu, xn, row);
+        const uint32_t rrow = __shfl_sync(0xffffffffu, r_cur, row);
+        uint32_t bits = 0u, flag = 0u;
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+          const float sum = c[m][q >> 1][2 * half + (q & 1)];
+          const float a = fabsf(sum);
+          bits |= (sum >= 0.f ? 1u : 0u) << q;
+          flag |= ((a > pnr[q] * xnr && a <= 3.0e38f) ? 0u : 1u) << q;
+        }
+        flag &= vmask;
+        if (t0 + row >= n) flag = 0u;  // rows past the end of the last tile hold stale data
+        while (flag) {  // reference arithmetic: sum = fl(sum + fl(w_i * x_i)), i ascending (hash/lshash.cc:44-51)
+          const int q = __ffs(flag) - 1;
+          flag &= flag - 1;
+          const float* w = planes + ((q >> 1) * 8 + 2 * (int)tg + (q & 1)) * ld;
+          const float* x = vals + (uint64_t)rrow * ld;
+          float sum = 0.f;
+          for (int j = 0; j < D; ++j) sum = __fadd_rn(sum, __fmul_rn(__ldg(w + j), __ldg(x + j)));
+          bits = (bits & ~(1u << q)) | ((sum >= 0.f ? 1u : 0u) << q);
+          slow |= 1u << (m * 2 + half);
+        }
+        bits &= vmask;
+        uint32_t byplane = 0u;
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt) byplane |= ((bits >> (2 * nt)) & 3u) << (nt * 8);
+        byplane <<= 2 * tg;
+        part[m * 2 + half] = H ? (__brev(byplane) >> (32 - H)) : 0u;
+      }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      part[q] |= __shfl_xor_sync(0xffffffffu, part[q], 1);
+      part[q] |= __shfl_xor_sync(0xffffffffu, part[q], 2);
+    }
+    slow |= __shfl_xor_sync(0xffffffffu, slow, 1);
+    slow |= __shfl_xor_sync(0xffffffffu, slow, 2);
+    {
+      const uint32_t key = tg == 0 ? part[0] : (tg == 1 ? part[1] : (tg == 2 ? part[2] : part[3]));
+      const uint64_t t = t0 + tg * 8 + g;
+      if (t < n) {
+        keys_out[t] = key | key_or;
+        my_eps += (slow >> tg) & 1u;
+      }
+      const uint64_t tl = t0 + lane;
+      if (tl < n) rows_out[tl] = r_cur;
+    }
+    r_cur = r_next;
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
   if (eps_rows) {
     const uint32_t tot = __reduce_add_sync(0xffffffffu, my_eps);
     if (lane == 0 && tot) atomicAdd(eps_rows, (unsigned long long)tot);
@@ -1207,13 +1193,18 @@ int launch_sign(klsh_ctx* ctx, const float* vals, int D, int ld, const uint32_t*
     KLAUNCH(ctx);
     return KLSH_OK;
   }
-  size_t smem = sizeof(float) * ((size_t)H * ld + ((H + 3) & ~3) + (size_t)kSignWarps * 32 * 33);
-  auto fn = k_sign_wide;
-  if (smem > 48 * 1024) KCUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  uint64_t want = (n + kSignWarps * 32 - 1) / (kSignWarps * 32);
-  uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * 16);
-  fn<<<grid, kSignWarps * 32, smem, ctx->stream>>>(vals, D, ld, rows, n, d_planes, H, keys_out, rows_out,
-                                                   ctx->eps_counter.as<unsigned long long>(), key_or);
+  const int nch = (ld + 63) / 64;
+  const size_t fixed = sizeof(float) * 32 + 16 * (size_t)nch * 8 * 4 * 32;
+  const size_t per_warp = sizeof(float) * 2 * 32 * 68;
+  int warps = 8;
+  while (warps > 1 && fixed + per_warp * warps > (size_t)ctx->max_smem_optin) warps >>= 1;
+  const size_t smem = fixed + per_warp * warps;
+  if (smem > (size_t)ctx->max_smem_optin) return klsh_fail(ctx, KLSH_ERR_ARG, "dimension %d too large for the signing kernel", D);
+  KCUDA(ctx, cudaFuncSetAttribute(k_sign_tc_wide, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const uint64_t want = (n + (uint64_t)warps * 32 - 1) / ((uint64_t)warps * 32);
+  const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count);
+  k_sign_tc_wide<<<grid, warps * 32, smem, ctx->stream>>>(vals, D, ld, rows, n, d_planes, H, keys_out, rows_out,
+                                                          ctx->eps_counter.as<unsigned long long>(), key_or);
   KLAUNCH(ctx);
   return KLSH_OK;
 }

@@ -9,10 +9,11 @@ from helpers import assert_rows_equal, synth_rows
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("D,H", [(1, 0), (1, 3), (7, 5), (20, 19), (32, 25), (64, 29), (256, 27), (12, 32)])
+@pytest.mark.parametrize("D,H", [(1, 0), (1, 3), (7, 5), (20, 19), (32, 25), (64, 29), (256, 27), (12, 32),
+                                 (65, 9), (100, 20), (130, 31), (200, 24)])
 def test_sign_keys(gpu, oracle, D, H):
     rng = np.random.default_rng(100 + D + H)
-    n = 5000 if D < 256 else 1500
+    n = 5000 if D < 100 else 1500
     rows = rng.standard_normal((n, D)).astype(np.float32)
     rows[::17] = 0.0                      # zero rows: every sum is +0 -> bit 1
     rows[1::29] *= np.float32(1e-30)      # denormal products
