@@ -781,6 +781,18 @@ __global__ void k_classify(uint32_t* bstart, uint64_t n, long long nest_threshol
 // ================================================================================================
 
 // sqrt(sum v_i^2), accumulated in index order (the magnitude_* sums of Distance::cosine)
+__device__ __forceinline__ float row_norm4(const float* v, int nq) {  // zero-padded row walked in quads (+0 terms)
+  const float4* v4 = reinterpret_cast<const float4*>(v);
+  float m = 0.f;
+  for (int q = 0; q < nq; ++q) {
+    const float4 x = v4[q];
+    m = __fadd_rn(m, __fmul_rn(x.x, x.x));
+    m = __fadd_rn(m, __fmul_rn(x.y, x.y));
+    m = __fadd_rn(m, __fmul_rn(x.z, x.z));
+    m = __fadd_rn(m, __fmul_rn(x.w, x.w));
+  }
+  return __fsqrt_rn(m);
+}
 __device__ __forceinline__ float row_norm(const float* v, int D) {
   float m = 0.f;
   for (int i = 0; i < D; ++i) m = __fadd_rn(m, __fmul_rn(v[i], v[i]));
@@ -808,8 +820,9 @@ k_merge_small(float* __restrict__ vals, int D, int ld, int32_t* __restrict__ cnt
               int32_t* __restrict__ tail, int32_t* __restrict__ next, uint32_t* __restrict__ rows_sorted,
               const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ list, const PassCounters* counters,
               float threshold, MgLog mg) {
-  extern __shared__ float smem[];
-  const int stride = ld + 1;
+  extern __shared__ __align__(16) float smem[];
+  const int stride = ld + 4;  // rows 16 bytes apart modulo 128: per-lane float4 walks are conflict-free
+  const int nq = ld >> 2;
   const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, wpb = blockDim.x >> 5;
   float* tile = smem + (size_t)warp * KLSH_SMALL_MAX * stride;
   const uint32_t nlist = counters->n_small;
@@ -819,12 +832,19 @@ k_merge_small(float* __restrict__ vals, int D, int ld, int32_t* __restrict__ cnt
     const int n = (int)(bstart[b + 1] - s);
     // slot = lane: row index and metadata of the row originally at position `lane`
     uint32_t ridx = (lane < (uint32_t)n) ? rows_sorted[s + lane] : 0u;
-    for (int k = 0; k < n; ++k) {
-      uint32_t rk = __shfl_sync(0xffffffffu, ridx, k);
-      const float* src = vals + (uint64_t)rk * ld;
-      for (int d = lane; d < D; d += 32) tile[k * stride + d] = src[d];
+    // all rows of the bucket are requested before any is waited for (cp.async, 16 bytes per lane)
+    {
+      const int total = n * nq;
+      for (int v0 = 0; v0 < total; v0 += 32) {
+        const int v = v0 + (int)lane;
+        const int rr = min(v, total - 1) / nq, cc = v - rr * nq;
+        const uint32_t rk = __shfl_sync(0xffffffffu, ridx, rr);
+        if (v < total) {
+          const uint32_t dsts = (uint32_t)__cvta_generic_to_shared(tile + rr * stride + cc * 4);
+          asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dsts), "l"(vals + (uint64_t)rk * ld + cc * 4) : "memory");
+        }
+      }
     }
-    __syncwarp();
     int my_cnt = 0, my_head = -1, my_tail = -1;
     float my_nrm = 0.f;
     bool my_dirty = false;
@@ -832,8 +852,10 @@ k_merge_small(float* __restrict__ vals, int D, int ld, int32_t* __restrict__ cnt
       my_cnt = cnt[ridx];
       my_head = head[ridx];
       my_tail = tail[ridx];
-      my_nrm = row_norm(tile + lane * stride, D);
     }
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    if (lane < (uint32_t)n) my_nrm = row_norm4(tile + lane * stride, nq);
     int pos_slot = (int)lane;  // slot held by position `lane`
     int size = n, i = 1;
     while (i < size) {
@@ -842,10 +864,16 @@ k_merge_small(float* __restrict__ vals, int D, int ld, int32_t* __restrict__ cnt
       const float rn = __shfl_sync(0xffffffffu, my_nrm, pos_slot & 31);
       bool match = false;
       if ((int)lane < i) {
-        const float* c = tile + cs * stride;
-        const float* r = tile + pos_slot * stride;
+        const float4* c = reinterpret_cast<const float4*>(tile + cs * stride);
+        const float4* r = reinterpret_cast<const float4*>(tile + pos_slot * stride);
         float dot = 0.f;
-        for (int d = 0; d < D; ++d) dot = __fadd_rn(dot, __fmul_rn(c[d], r[d]));
+        for (int q = 0; q < nq; ++q) {  // padded products are +0: the D-term sum of the reference
+          const float4 x = c[q], y = r[q];
+          dot = __fadd_rn(dot, __fmul_rn(x.x, y.x));
+          dot = __fadd_rn(dot, __fmul_rn(x.y, y.y));
+          dot = __fadd_rn(dot, __fmul_rn(x.z, y.z));
+          dot = __fadd_rn(dot, __fmul_rn(x.w, y.w));
+        }
         match = cos_match(dot, cn, rn, threshold);
       }
       const uint32_t m = __ballot_sync(0xffffffffu, match);
@@ -879,7 +907,7 @@ k_merge_small(float* __restrict__ vals, int D, int ld, int32_t* __restrict__ cnt
           if (my_tail < 0) my_tail = t1;
         }
         my_cnt = c1 + c2;
-        my_nrm = row_norm(tile + rs * stride, D);
+        my_nrm = row_norm4(tile + rs * stride, nq);
         my_dirty = true;
       }
       // position i takes the tail position's slot
@@ -1459,7 +1487,7 @@ int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float thr
   PassCounters* dc = s.counters.as<PassCounters>();
   const uint32_t n_small = c.n_small, n_large = c.n_large + c.n_big;
   if (n_small) {
-    size_t per_warp = sizeof(float) * (size_t)KLSH_SMALL_MAX * (ld + 1);
+    size_t per_warp = sizeof(float) * (size_t)KLSH_SMALL_MAX * (ld + 4);
     int wpb = 4;
     while (wpb > 1 && per_warp * wpb > (size_t)ctx->max_smem_optin - 1024) wpb >>= 1;
     size_t smem = per_warp * wpb;
