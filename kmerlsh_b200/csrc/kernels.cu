@@ -1469,11 +1469,8 @@ static int large_smem_config(klsh_ctx* ctx, int ld, int* rep_cap, size_t* smem) 
   if (cap < 1) return klsh_fail(ctx, KLSH_ERR_ARG, "dimension %d too large for the merge kernel", ld);
   *rep_cap = cap;
   *smem = fixed + per_rep * (size_t)cap;
-  static size_t configured = 0;
-  if (*smem > configured) {
-    KCUDA(ctx, cudaFuncSetAttribute(k_merge_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
-    configured = *smem;
-  }
+  // function attributes are per device: set it on every call (cheap), never cache it process-wide
+  KCUDA(ctx, cudaFuncSetAttribute(k_merge_large, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)*smem));
   return KLSH_OK;
 }
 
@@ -1492,11 +1489,8 @@ int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float thr
     while (wpb > 1 && per_warp * wpb > (size_t)ctx->max_smem_optin - 1024) wpb >>= 1;
     size_t smem = per_warp * wpb;
     if (smem > (size_t)ctx->max_smem_optin) return klsh_fail(ctx, KLSH_ERR_ARG, "dimension %d too large", D);
-    static size_t configured = 0;
-    if (smem > 48 * 1024 && smem > configured) {
+    if (smem > 48 * 1024)  // per device, so not cached process-wide
       KCUDA(ctx, cudaFuncSetAttribute(k_merge_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-      configured = smem;
-    }
     uint32_t grid = std::min<uint32_t>((n_small + wpb - 1) / wpb, (uint32_t)ctx->sm_count * 32);
     k_merge_small<<<grid, wpb * 32, smem, ctx->stream>>>(vals, D, ld, cnt, head, tail, next, rows_sorted,
                                                          s.bstart.as<uint32_t>(), s.list_small.as<uint32_t>(), dc,
