@@ -850,7 +850,10 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
   if (lane == 0) {
     ctl->i = i;
     ctl->size = size;
-    ctl->wb = back_exhausted ? (uint32_t)min(kWbMax, wb * 2) : (uint32_t)min(kWbMax, max(2, merges + merges / 2 + 2));
+    // back candidates for the next window: grow fast when they ran out, shrink slowly otherwise (a
+    // window that runs out of them throws away the screen of its remaining front candidates)
+    ctl->wb = back_exhausted ? (uint32_t)min(kWbMax, max(wb * 2, 4))
+                             : (uint32_t)min(kWbMax, max(max(2, merges + merges / 2 + 2), wb - (wb + 3) / 4));
     if (A.dbg) {
       atomicAdd(A.dbg + 0, 1ull);
       atomicAdd(A.dbg + 1, (unsigned long long)(fi + bi));
