@@ -100,10 +100,12 @@ def make_inputs(workload, rows_override, device):
         counts, cov = synth.synth_counts(n, sa, sb, seed)
         import torch
 
-        pinned = torch.empty(counts.shape, dtype=torch.int16, pin_memory=True)
-        pinned.numpy().view(np.uint16)[:] = counts
-        counts = pinned.numpy().view(np.uint16)
-        keep = pinned
+        keep = None
+        if torch.cuda.is_available():  # pinned for the end-to-end arm; the reference arm needs no GPU
+            pinned = torch.empty(counts.shape, dtype=torch.int16, pin_memory=True)
+            pinned.numpy().view(np.uint16)[:] = counts
+            counts = pinned.numpy().view(np.uint16)
+            keep = pinned
     else:
         from kmerlsh_b200.synth_gpu import synth_counts_gpu
 

@@ -79,3 +79,24 @@ def test_floor_log2_matches_reference_formula():
     for k in range(1, 41):
         for n in (2 ** k - 1, 2 ** k, 2 ** k + 1):
             assert int(np.floor(np.log2(float(n)))) == n.bit_length() - 1
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the driver's reference arm) needs no GPU: it times the reference's own
+    binary on a bounded sample and prints one JSON line with the contract's keys."""
+    import json
+    import subprocess
+    import sys
+
+    ref_bin = os.path.join(ROOT, "oracle", "_ref", "kmerLSH_ref")
+    if not os.path.exists(ref_bin):
+        pytest.skip("oracle/_ref/kmerLSH_ref not built (needs /root/reference)")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--workload", "C1", "--steps", "1",
+                          "--warmup", "0", "--cpu-sample-rows", "30000", "--cpu-sample-iters", "3"], check=True,
+                         capture_output=True, text=True, cwd=ROOT).stdout.strip().splitlines()[-1]
+    line = json.loads(out)
+    assert line["impl"] == "reference" and line["unit"] == "rows/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["e2e"]["value"] == line["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
+    assert line["cpu_baseline"]["kind"] == "reference" and line["cpu_baseline"]["cores"] >= 1
+    assert line["config"]["workload"].startswith("C1")
