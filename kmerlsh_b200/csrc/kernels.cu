@@ -151,10 +151,13 @@ constexpr int kSignWarps = 4;
 // bound, H*D fused multiply-adds per row against 4*D bytes (profiles/).  The projection is a
 // [rows x D] x [D x H] product, so it goes to the tensor cores as 3xTF32: every operand is split
 // into hi = tf32(v) and lo = tf32(v - hi) and the sum hi*hi + hi*lo + lo*hi is accumulated in fp32
-// (mma.sync.m16n8k8).  The products are exact; what is dropped (lo*lo and the split residue) is below
-// 3*2^-22 per term and the accumulation adds at most a few 2^-23 per mma, together under
-// 64*2^-24 * sum|w_i x_i|.  With the reference chain's own D*2^-24 the margin
-//     eps = (2.5*D + 64) * 2^-24 * |w| * |x|
+// (mma.sync.m16n8k8).  Error budget in units of 2^-24 * sum|w_i x_i| (<= 2^-24 * |w| * |x|):
+//   12   the dropped lo*lo products and the split residues (3 * 2^-22 per term);
+//   10   per mma for the tensor core's truncating fp32 accumulation (alignment of the 8 products to the
+//        largest exponent with a few guard bits + the final truncation; a worst-case figure, the
+//        measured behaviour is far better), 3*ceil(D/8) mma per sum;
+//   D    the reference chain's own rounding (its sign is what has to be reproduced).
+// So   eps = (D + 16 + 30*ceil(D/8)) * 2^-24 * |w| * |x|   (D = 32: 168 * 2^-24 = 1.0e-5)
 // guarantees that a sum outside it has the sign of the reference's mul-then-add chain; a sum inside it
 // is re-evaluated with the reference's exact arithmetic (and the row counted), so every key bit is
 // the reference's.  A warp owns 32 rows: cp.async gathers them into a double-buffered shared tile
@@ -196,7 +199,7 @@ k_sign_tc(const float* __restrict__ vals, int D, int ld, const uint32_t* __restr
   for (int h = threadIdx.x; h < 32; h += blockDim.x) {
     float m = 0.f;
     for (int i = 0; i < D; ++i) m = __fmaf_rn(sp[h * KW + i], sp[h * KW + i], m);
-    pn[h] = sqrtf(m) * ((2.5f * (float)D + 64.f) * 5.9604645e-8f);
+    pn[h] = sqrtf(m) * (((float)D + 16.f + 30.f * (float)((D + 7) / 8)) * 5.9604645e-8f);
   }
   for (int i = threadIdx.x; i < KS8 * 4 * 32; i += blockDim.x) {
     const int l = i & 31, nt = (i >> 5) & 3, ks = i >> 7;
@@ -385,7 +388,7 @@ k_sign_tc_wide(const float* __restrict__ vals, int D, int ld, const uint32_t* __
     float m = 0.f;
     if (h < H)
       for (int i = 0; i < D; ++i) m = __fmaf_rn(planes[h * ld + i], planes[h * ld + i], m);
-    pn[h] = sqrtf(m) * ((2.5f * (float)D + 64.f) * 5.9604645e-8f);
+    pn[h] = sqrtf(m) * (((float)D + 16.f + 240.f + (float)nch) * 5.9604645e-8f);  // 24 mma per 64-column chunk
   }
   for (int i = threadIdx.x; i < nch * KS8 * 4 * 32; i += blockDim.x) {
     const int l = i & 31, nt = (i >> 5) & 3, ks = i >> 7;  // ks runs over the whole width
@@ -436,15 +439,23 @@ k_sign_tc_wide(const float* __restrict__ vals, int D, int ld, const uint32_t* __
   for (; t0 < n; t0 += nwarps_total * 32) {
     const uint64_t t0n = t0 + nwarps_total * 32;
     const uint32_t r_next = row_of(t0n);
-    float c[2][4][4];
+    // every chunk is accumulated from zero and added to the running sum in fp32: the tensor core's
+    // accumulation error is then relative to the chunk's own magnitude (24 mma), not to the whole row's
+    float c[2][4][4], ct[2][4][4];
 #pragma unroll
     for (int m = 0; m < 2; ++m)
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
 #pragma unroll
-        for (int e = 0; e < 4; ++e) c[m][nt][e] = 0.f;
+        for (int e = 0; e < 4; ++e) ct[m][nt][e] = 0.f;
     float xx = 0.f;
     for (int ch = 0; ch < nch; ++ch, buf ^= 1) {
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) c[m][nt][e] = 0.f;
       if (ch + 1 < nch) issue(t0, r_cur, ch + 1, buf ^ 1);
       else issue(t0n, r_next, 0, buf ^ 1);
       asm volatile("cp.async.wait_group 1;" ::: "memory");
@@ -485,6 +496,12 @@ k_sign_tc_wide(const float* __restrict__ vals, int D, int ld, const uint32_t* __
             }
           }
       }
+#pragma unroll
+      for (int m = 0; m < 2; ++m)
+#pragma unroll
+        for (int nt = 0; nt < 4; ++nt)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) ct[m][nt][e] = __fadd_rn(ct[m][nt][e], c[m][nt][e]);
       __syncwarp();
     }
     const float xn = sqrtf(xx);
@@ -500,7 +517,7 @@ k_sign_tc_wide(const float* __restrict__ vals, int D, int ld, const uint32_t* __
         uint32_t bits = 0u, flag = 0u;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
-          const float sum = c[m][q >> 1][2 * half + (q & 1)];
+          const float sum = ct[m][q >> 1][2 * half + (q & 1)];
           const float a = fabsf(sum);
           bits |= (sum >= 0.f ? 1u : 0u) << q;
           flag |= ((a > pnr[q] * xnr && a <= 3.0e38f) ? 0u : 1u) << q;
