@@ -532,15 +532,26 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
       const int tc = act ? (k < nfront ? fi + k : wf + bi + (k - nfront)) : 0;
       const float4* c4 = reinterpret_cast<const float4*>(s.tile + (size_t)tc * s.ts);
       float dot = 0.f, nn = 0.f;
+      if (base == 0) {  // the entry's norm comes out of the first pass
 #pragma unroll 4
-      for (int q = 0; q < nq; ++q) {
-        const float4 x = c4[q], y = r4[q];
-        dot = __fadd_rn(dot, __fmul_rn(x.x, y.x)); nn = __fadd_rn(nn, __fmul_rn(y.x, y.x));
-        dot = __fadd_rn(dot, __fmul_rn(x.y, y.y)); nn = __fadd_rn(nn, __fmul_rn(y.y, y.y));
-        dot = __fadd_rn(dot, __fmul_rn(x.z, y.z)); nn = __fadd_rn(nn, __fmul_rn(y.z, y.z));
-        dot = __fadd_rn(dot, __fmul_rn(x.w, y.w)); nn = __fadd_rn(nn, __fmul_rn(y.w, y.w));
+        for (int q = 0; q < nq; ++q) {
+          const float4 x = c4[q], y = r4[q];
+          dot = __fadd_rn(dot, __fmul_rn(x.x, y.x)); nn = __fadd_rn(nn, __fmul_rn(y.x, y.x));
+          dot = __fadd_rn(dot, __fmul_rn(x.y, y.y)); nn = __fadd_rn(nn, __fmul_rn(y.y, y.y));
+          dot = __fadd_rn(dot, __fmul_rn(x.z, y.z)); nn = __fadd_rn(nn, __fmul_rn(y.z, y.z));
+          dot = __fadd_rn(dot, __fmul_rn(x.w, y.w)); nn = __fadd_rn(nn, __fmul_rn(y.w, y.w));
+        }
+        rn = __fsqrt_rn(nn);
+      } else {
+#pragma unroll 4
+        for (int q = 0; q < nq; ++q) {
+          const float4 x = c4[q], y = r4[q];
+          dot = __fadd_rn(dot, __fmul_rn(x.x, y.x));
+          dot = __fadd_rn(dot, __fmul_rn(x.y, y.y));
+          dot = __fadd_rn(dot, __fmul_rn(x.z, y.z));
+          dot = __fadd_rn(dot, __fmul_rn(x.w, y.w));
+        }
       }
-      rn = __fsqrt_rn(nn);
       const bool mt = act && cos_match(dot, s.cnorm[tc], rn, A.threshold);
       const uint32_t blo = (mt && tc < 32) ? (1u << tc) : 0u, bhi = (mt && tc >= 32) ? (1u << (tc - 32)) : 0u;
       w0 |= __reduce_or_sync(0xffffffffu, blo);
@@ -622,24 +633,39 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
       // entry with an invalid mask is compared exactly (every lane computes the same comparison)
       bool hit = ((my_dm_lo & tbit_lo) | (my_dm_hi & tbit_hi)) != 0u;
       if (inval != 0u) {
-        // entries with a stale mask: lane e compares the candidate with entry e's current value
+        // entries with a stale mask: lane e compares the candidate with entry e's current value.  Only
+        // the entry modified last (pend) needs a new norm as well: a lane that owns no stale entry
+        // accumulates entry x entry in the same instruction stream, so the warp walks ONE chain of
+        // mul+add per lane instead of two.
         const bool mine = (inval >> lane) & 1u;
-        const int er = mine ? (int)lane : 0;
+        const uint32_t spare = ~inval;
+        const int nl = (pend >= 0 && spare != 0u) ? (__ffs(spare) - 1) : -1;
+        const bool normer = (int)lane == nl;
+        const bool inline_nn = pend >= 0 && nl < 0;  // all 32 entries stale: the owner walks both chains
+        const int er = mine ? (int)lane : (normer ? pend : 0);
         const float4* r4 = reinterpret_cast<const float4*>(s.dvals + (size_t)er * s.ts);
-        const float4* c4 = reinterpret_cast<const float4*>(s.tile + (size_t)t * s.ts);
+        const float4* c4 = normer ? r4 : reinterpret_cast<const float4*>(s.tile + (size_t)t * s.ts);
         float dot = 0.f, nn = 0.f;
 #pragma unroll 4
         for (int q = 0; q < nq; ++q) {
           const float4 x = c4[q], y = r4[q];
-          dot = __fadd_rn(dot, __fmul_rn(x.x, y.x)); nn = __fadd_rn(nn, __fmul_rn(y.x, y.x));
-          dot = __fadd_rn(dot, __fmul_rn(x.y, y.y)); nn = __fadd_rn(nn, __fmul_rn(y.y, y.y));
-          dot = __fadd_rn(dot, __fmul_rn(x.z, y.z)); nn = __fadd_rn(nn, __fmul_rn(y.z, y.z));
-          dot = __fadd_rn(dot, __fmul_rn(x.w, y.w)); nn = __fadd_rn(nn, __fmul_rn(y.w, y.w));
+          dot = __fadd_rn(dot, __fmul_rn(x.x, y.x));
+          dot = __fadd_rn(dot, __fmul_rn(x.y, y.y));
+          dot = __fadd_rn(dot, __fmul_rn(x.z, y.z));
+          dot = __fadd_rn(dot, __fmul_rn(x.w, y.w));
+          if (inline_nn) {
+            nn = __fadd_rn(nn, __fmul_rn(y.x, y.x));
+            nn = __fadd_rn(nn, __fmul_rn(y.y, y.y));
+            nn = __fadd_rn(nn, __fmul_rn(y.z, y.z));
+            nn = __fadd_rn(nn, __fmul_rn(y.w, y.w));
+          }
         }
-        const float rn = __fsqrt_rn(nn);
+        float rn_p = 0.f;
+        if (pend >= 0) rn_p = __shfl_sync(0xffffffffu, __fsqrt_rn(inline_nn ? nn : dot), inline_nn ? pend : nl);
         if (mine) {
+          const float rn = ((int)lane == pend) ? rn_p : s.dnorm[lane];
           hit = cos_match(dot, s.cnorm[t], rn, A.threshold);
-          if ((int)lane == pend) s.dnorm[lane] = rn;
+          if ((int)lane == pend) s.dnorm[lane] = rn_p;
         }
         pend = -1;  // the latest entry's norm is now published
       }
