@@ -8,10 +8,12 @@
 //
 // The work is candidates x representatives x D, strictly sequential in the reference.  Here a
 // TEAM processes a WINDOW of up to 64 upcoming candidates at once:
-//   parallel phase : every thread owns representatives (row held in registers) and compares them
-//                    with all window candidates (shared-memory tile, broadcast reads), recording
-//                    per candidate the first matching representative as of the window start
-//                    (atomicMin), plus the candidate x candidate match bits;
+//   parallel phase : the window (fp16, unit norm, A fragments in registers) is screened against all
+//                    representatives on the tensor cores (mma.sync; the representatives' fp16 copies are
+//                    streamed in fragment order through a cp.async ring); pairs that pass are re-tested
+//                    with the reference's exact fp32 arithmetic, recording per candidate the first
+//                    matching representative as of the window start (atomicMin), plus the candidate x
+//                    candidate match bits;
 //   resolver       : one warp replays the reference's sequential order over the window using
 //                    those results; representatives modified inside the window live in a small
 //                    "dirty" cache and are re-compared exactly with their current values; when a
