@@ -9,7 +9,8 @@
  * owned host buffers, library-owned device memory, `int` status (0 = ok) instead of exit().
  * INTEGRATION.md shows the reference-side shim that routes Cluster() through it.
  *
- * One context = one GPU = one driving host thread (not re-entrant).  The library never prints.
+ * One context = one GPU = one driving host thread (not re-entrant).  The library never prints
+ * (exception: with KLSH_DEBUG=1 in the environment it writes per-kernel diagnostics to stderr).
  * There is no CPU fallback: every entry point fails with KLSH_ERR_CUDA when no sm_100 device is
  * usable.
  */
@@ -93,6 +94,15 @@ int klsh_sign(klsh_ctx* ctx, const float* rows, uint64_t n, int D, const float* 
 int klsh_p_cluster(klsh_ctx* ctx, float threshold);
 /* nestedCluster (function/cluster.cc:89-178) on the context's whole row set. */
 int klsh_nested_cluster(klsh_ctx* ctx, float threshold);
+
+/* Distance::cosine(left, right) (function/distance.cc:27-38) for n pairs of host rows [n][D]:
+ * out[k] = 1 - dot / (sqrtf(|left|^2) * sqrtf(|right|^2)), every sum accumulated in index order. */
+int klsh_cosine_distance(klsh_ctx* ctx, const float* left, const float* right, uint64_t n, int D, float* out);
+/* The values AB::SetConsensus(current, candidate) produces (function/funcAB.cc:49-71) for rows
+ * with n_current and n_candidate member ids: out[i] = current[i]*n_current/all + candidate[i]*n_candidate/all,
+ * counts converted int -> float as the reference's cvtsi2ss does. */
+int klsh_set_consensus(klsh_ctx* ctx, const float* current, int64_t n_current, const float* candidate, int64_t n_candidate,
+                       int D, float* out);
 
 /* ---- rows out -------------------------------------------------------------------------------- */
 int klsh_row_count(klsh_ctx* ctx, uint64_t* n_rows, uint64_t* n_ids);

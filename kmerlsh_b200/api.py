@@ -66,6 +66,8 @@ SYMBOLS = [
     ("klsh_sign", C.c_int, [C.c_void_p, f32p, u64, C.c_int, f32p, C.c_int, u64p]),
     ("klsh_p_cluster", C.c_int, [C.c_void_p, C.c_float]),
     ("klsh_nested_cluster", C.c_int, [C.c_void_p, C.c_float]),
+    ("klsh_cosine_distance", C.c_int, [C.c_void_p, f32p, f32p, u64, C.c_int, f32p]),
+    ("klsh_set_consensus", C.c_int, [C.c_void_p, f32p, i64, f32p, i64, C.c_int, f32p]),
     ("klsh_row_count", C.c_int, [C.c_void_p, u64p, u64p]),
     ("klsh_get_rows", C.c_int, [C.c_void_p, f32p, u64p, u64p]),
     ("klsh_save", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, i64]),
@@ -205,6 +207,24 @@ class Context:
 
     def nested_cluster(self, threshold: float):
         self._ck(self.lib.klsh_nested_cluster(self.h, threshold), "klsh_nested_cluster")
+
+    def cosine_distance(self, left, right):
+        """Distance::cosine for n pairs of rows: 1 - cos, float32 [n]."""
+        left = np.ascontiguousarray(left, dtype=np.float32)
+        right = np.ascontiguousarray(right, dtype=np.float32)
+        n, d = left.shape
+        out = np.empty(n, dtype=np.float32)
+        self._ck(self.lib.klsh_cosine_distance(self.h, _p(left, f32p), _p(right, f32p), n, d, _p(out, f32p)), "klsh_cosine_distance")
+        return out
+
+    def set_consensus(self, current, n_current: int, candidate, n_candidate: int):
+        """The centroid AB::SetConsensus(current, candidate) computes for the given member counts."""
+        current = np.ascontiguousarray(current, dtype=np.float32)
+        candidate = np.ascontiguousarray(candidate, dtype=np.float32)
+        out = np.empty_like(current)
+        self._ck(self.lib.klsh_set_consensus(self.h, _p(current, f32p), n_current, _p(candidate, f32p), n_candidate, current.shape[0],
+                                             _p(out, f32p)), "klsh_set_consensus")
+        return out
 
     # ---- rows out
     def row_count(self, with_ids: bool = True):

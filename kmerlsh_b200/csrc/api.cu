@@ -49,8 +49,12 @@ int dev_reserve(klsh_ctx* ctx, DevBuf& b, size_t bytes) {
   }
   if (b.p) {
     // contents are preserved (grow)
-    cudaMemcpyAsync(p, b.p, b.bytes, cudaMemcpyDeviceToDevice, ctx->stream);
-    cudaStreamSynchronize(ctx->stream);
+    cudaError_t ec = cudaMemcpyAsync(p, b.p, b.bytes, cudaMemcpyDeviceToDevice, ctx->stream);
+    if (ec == cudaSuccess) ec = cudaStreamSynchronize(ctx->stream);
+    if (ec != cudaSuccess) {
+      cudaFree(p);
+      return klsh_fail(ctx, KLSH_ERR_CUDA, "growing a device buffer to %zu bytes failed: %s", want, cudaGetErrorString(ec));
+    }
     cudaFree(b.p);
   }
   b.p = p;
@@ -259,6 +263,11 @@ extern "C" int klsh_set_rows(klsh_ctx* ctx, const float* values, const uint64_t*
   KCUDA(ctx, cudaSetDevice(ctx->device));
   ctx->has_snap = false;
   const uint64_t m = n ? id_offsets[n] : 0;
+  for (uint64_t r = 0; r < n; ++r)
+    if (id_offsets[r + 1] < id_offsets[r] || id_offsets[r + 1] - id_offsets[r] > 0x7FFFFFFFull)
+      return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_set_rows: id_offsets must be non-decreasing with at most 2^31-1 ids per row (row %llu)",
+                       (unsigned long long)r);
+  if (n && id_offsets[0] != 0) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_set_rows: id_offsets[0] must be 0");
   KTRY(reserve_rows(ctx, n, m, D));
   const int ld = ctx->ld;
   // values: pad rows to ld
@@ -493,7 +502,7 @@ extern "C" int klsh_cluster(klsh_ctx* ctx, float min_similarity, int iterations,
   float max_similarity = 0.95f;
   float sim_step = (max_similarity - min_similarity) / iterations;
   float threshold = max_similarity;
-  KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long)));
+  KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long) * 2));
   KCUDA(ctx, cudaMemsetAsync(ctx->eps_counter.p, 0, sizeof(unsigned long long), ctx->stream));
   unsigned long long eps_prev = 0;
   for (int iter = 1; iter <= iterations; ++iter) {
@@ -549,14 +558,20 @@ extern "C" int klsh_sign(klsh_ctx* ctx, const float* rows, uint64_t n, int D, co
     if ((rc = dev_reserve(ctx, dp, sizeof(float) * ((size_t)H * ld + 4)))) break;
     if ((rc = dev_reserve(ctx, dk, sizeof(uint32_t) * n))) break;
     if ((rc = dev_reserve(ctx, dr, sizeof(uint32_t) * n))) break;
-    cudaMemsetAsync(dv.p, 0, sizeof(float) * n * (uint64_t)ld, ctx->stream);
-    cudaMemcpy2DAsync(dv.p, sizeof(float) * ld, rows, sizeof(float) * D, sizeof(float) * D, n, cudaMemcpyHostToDevice,
-                      ctx->stream);
-    if (H) cudaMemcpyAsync(dp.p, padded.data(), sizeof(float) * (size_t)H * ld, cudaMemcpyHostToDevice, ctx->stream);
+    cudaError_t e = cudaMemsetAsync(dv.p, 0, sizeof(float) * n * (uint64_t)ld, ctx->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(dv.p, sizeof(float) * ld, rows, sizeof(float) * D, sizeof(float) * D, n, cudaMemcpyHostToDevice,
+                            ctx->stream);
+    if (e == cudaSuccess && H)
+      e = cudaMemcpyAsync(dp.p, padded.data(), sizeof(float) * (size_t)H * ld, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+      rc = klsh_fail(ctx, KLSH_ERR_CUDA, "klsh_sign: upload failed: %s", cudaGetErrorString(e));
+      break;
+    }
     if ((rc = launch_sign(ctx, dv.as<float>(), D, ld, nullptr, n, dp.as<float>(), H, dk.as<uint32_t>(), dr.as<uint32_t>())))
       break;
-    cudaMemcpyAsync(k32.data(), dk.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
-    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    e = cudaMemcpyAsync(k32.data(), dk.p, sizeof(uint32_t) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
     if (e != cudaSuccess) rc = klsh_fail(ctx, KLSH_ERR_CUDA, "klsh_sign: %s", cudaGetErrorString(e));
   } while (0);
   dev_free(dv); dev_free(dp); dev_free(dk); dev_free(dr);
@@ -596,6 +611,62 @@ extern "C" int klsh_nested_cluster(klsh_ctx* ctx, float threshold) {
   std::swap(ctx->cur.alive, ctx->alive_alt);
   ctx->cur.n_alive = kept;
   return KLSH_OK;
+}
+
+extern "C" int klsh_cosine_distance(klsh_ctx* ctx, const float* left, const float* right, uint64_t n, int D, float* out) {
+  if (!ctx || D <= 0 || (n && (!left || !right || !out))) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_cosine_distance: bad argument");
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  if (!n) return KLSH_OK;
+  const int ld = (D + 3) & ~3;
+  const size_t rb = sizeof(float) * n * (uint64_t)ld;
+  DevBuf dl, dr, dout;
+  int rc = KLSH_OK;
+  do {
+    if ((rc = dev_reserve(ctx, dl, rb))) break;
+    if ((rc = dev_reserve(ctx, dr, rb))) break;
+    if ((rc = dev_reserve(ctx, dout, sizeof(float) * n))) break;
+    cudaError_t e = cudaMemsetAsync(dl.p, 0, rb, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemsetAsync(dr.p, 0, rb, ctx->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(dl.p, sizeof(float) * ld, left, sizeof(float) * D, sizeof(float) * D, n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess)
+      e = cudaMemcpy2DAsync(dr.p, sizeof(float) * ld, right, sizeof(float) * D, sizeof(float) * D, n, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+      rc = klsh_fail(ctx, KLSH_ERR_CUDA, "klsh_cosine_distance: upload failed: %s", cudaGetErrorString(e));
+      break;
+    }
+    if ((rc = launch_cosine_pairs(ctx, dl.as<float>(), dr.as<float>(), n, ld, dout.as<float>()))) break;
+    e = cudaMemcpyAsync(out, dout.p, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = klsh_fail(ctx, KLSH_ERR_CUDA, "klsh_cosine_distance: %s", cudaGetErrorString(e));
+  } while (0);
+  dev_free(dl); dev_free(dr); dev_free(dout);
+  return rc;
+}
+
+extern "C" int klsh_set_consensus(klsh_ctx* ctx, const float* current, int64_t n_current, const float* candidate,
+                                  int64_t n_candidate, int D, float* out) {
+  if (!ctx || D <= 0 || !current || !candidate || !out || n_current < 0 || n_candidate < 0 || n_current + n_candidate > 0x7FFFFFFFll)
+    return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_set_consensus: bad argument (member counts are the reference's `int`)");
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  DevBuf buf;
+  int rc = KLSH_OK;
+  do {
+    if ((rc = dev_reserve(ctx, buf, sizeof(float) * 3 * (size_t)D))) break;
+    float* d = buf.as<float>();
+    cudaError_t e = cudaMemcpyAsync(d, current, sizeof(float) * D, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(d + D, candidate, sizeof(float) * D, cudaMemcpyHostToDevice, ctx->stream);
+    if (e != cudaSuccess) {
+      rc = klsh_fail(ctx, KLSH_ERR_CUDA, "klsh_set_consensus: upload failed: %s", cudaGetErrorString(e));
+      break;
+    }
+    if ((rc = launch_consensus(ctx, d, (int)n_current, d + D, (int)n_candidate, D, d + 2 * D))) break;
+    e = cudaMemcpyAsync(out, d + 2 * D, sizeof(float) * D, cudaMemcpyDeviceToHost, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) rc = klsh_fail(ctx, KLSH_ERR_CUDA, "klsh_set_consensus: %s", cudaGetErrorString(e));
+  } while (0);
+  dev_free(buf);
+  return rc;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -685,20 +756,26 @@ static int export_rows(klsh_ctx* ctx, float* values_out, uint64_t* offs_out, uin
   return KLSH_OK;
 }
 
+// sum of the survivors' member counts, reduced on the device (no row gather, 8 bytes back)
+static int count_ids(klsh_ctx* ctx, uint64_t* n_ids) {
+  *n_ids = 0;
+  const uint64_t n = ctx->cur.n_alive;
+  if (!n) return KLSH_OK;
+  KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long) * 2));
+  unsigned long long* d_total = ctx->eps_counter.as<unsigned long long>() + 1;
+  KTRY(launch_sum_counts(ctx, ctx->cur.alive.as<uint32_t>(), n, d_total));
+  unsigned long long h = 0;
+  KCUDA(ctx, cudaMemcpyAsync(&h, d_total, sizeof h, cudaMemcpyDeviceToHost, ctx->stream));
+  KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *n_ids = h;
+  return KLSH_OK;
+}
+
 extern "C" int klsh_row_count(klsh_ctx* ctx, uint64_t* n_rows, uint64_t* n_ids) {
   if (!ctx) return KLSH_ERR_ARG;
   KCUDA(ctx, cudaSetDevice(ctx->device));
   if (n_rows) *n_rows = ctx->cur.n_alive;
-  if (n_ids) {
-    // sum of the survivors' member counts
-    const uint64_t n = ctx->cur.n_alive;
-    *n_ids = 0;
-    if (n) {
-      std::vector<uint64_t> offs(n + 1);
-      KTRY(export_rows(ctx, nullptr, offs.data(), nullptr));
-      *n_ids = offs[n];
-    }
-  }
+  if (n_ids) KTRY(count_ids(ctx, n_ids));
   return KLSH_OK;
 }
 
@@ -712,10 +789,11 @@ extern "C" int klsh_save(klsh_ctx* ctx, const char* bin_path, int delfile, int64
   if (!ctx || !bin_path) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_save: bad argument");
   KCUDA(ctx, cudaSetDevice(ctx->device));
   const uint64_t n = ctx->cur.n_alive;
+  uint64_t n_ids = 0;
+  KTRY(count_ids(ctx, &n_ids));
   std::vector<uint64_t> offs(n + 1, 0);
-  KTRY(export_rows(ctx, nullptr, offs.data(), nullptr));
   std::vector<float> v(n * (uint64_t)ctx->D + 1);
-  std::vector<uint64_t> idv(offs[n] + 1);
+  std::vector<uint64_t> idv(n_ids + 1);
   KTRY(export_rows(ctx, v.data(), offs.data(), idv.data()));
   int rc = io_save(bin_path, delfile, ignore_small, v.data(), ctx->D, offs.data(), idv.data(), n);
   if (rc != KLSH_OK) return klsh_fail(ctx, rc, "cannot write %s(.clust)", bin_path);

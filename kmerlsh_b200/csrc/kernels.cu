@@ -9,6 +9,7 @@
 #include <cstddef>
 #include <cstring>
 
+#include "exact_math.cuh"
 #include "klsh_internal.cuh"
 
 namespace {
@@ -797,38 +798,10 @@ __global__ void k_classify(uint32_t* bstart, uint64_t n, long long nest_threshol
 // candidate's, and moves the tail position into i (swap-remove).
 // ================================================================================================
 
-// sqrt(sum v_i^2), accumulated in index order (the magnitude_* sums of Distance::cosine)
-__device__ __forceinline__ float row_norm4(const float* v, int nq) {  // zero-padded row walked in quads (+0 terms)
-  const float4* v4 = reinterpret_cast<const float4*>(v);
-  float m = 0.f;
-  for (int q = 0; q < nq; ++q) {
-    const float4 x = v4[q];
-    m = __fadd_rn(m, __fmul_rn(x.x, x.x));
-    m = __fadd_rn(m, __fmul_rn(x.y, x.y));
-    m = __fadd_rn(m, __fmul_rn(x.z, x.z));
-    m = __fadd_rn(m, __fmul_rn(x.w, x.w));
-  }
-  return __fsqrt_rn(m);
-}
-__device__ __forceinline__ float row_norm(const float* v, int D) {
+__device__ __forceinline__ float row_norm(const float* v, int D) {  // unpadded row (fallback kernel)
   float m = 0.f;
   for (int i = 0; i < D; ++i) m = __fadd_rn(m, __fmul_rn(v[i], v[i]));
   return __fsqrt_rn(m);
-}
-
-// similarity test of Distance::cosine + p_cluster's `1 - distance >= threshold`
-__device__ __forceinline__ bool cos_match(float dot, float nl, float nr, float threshold) {
-  float sim = __fdiv_rn(dot, __fmul_rn(nl, nr));
-  float dist = __fsub_rn(1.f, sim);
-  return __fsub_rn(1.f, dist) >= threshold;
-}
-
-// one dimension of AB::SetConsensus: cur*c1/all + cand*c2/all, counts converted like cvtsi2ss
-__device__ __forceinline__ float consensus1(float cur, int c1, float cand, int c2) {
-  const float fa = __int2float_rn(c1 + c2);
-  float a = __fdiv_rn(__fmul_rn(cur, __int2float_rn(c1)), fa);
-  float b = __fdiv_rn(__fmul_rn(cand, __int2float_rn(c2)), fa);
-  return __fadd_rn(a, b);
 }
 
 // ---- small buckets: one warp per bucket, rows resident in shared memory -------------------------
@@ -872,7 +845,7 @@ k_merge_small(float* __restrict__ vals, int D, int ld, int32_t* __restrict__ cnt
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
-    if (lane < (uint32_t)n) my_nrm = row_norm4(tile + lane * stride, nq);
+    if (lane < (uint32_t)n) my_nrm = norm_seq(reinterpret_cast<const float4*>(tile + lane * stride), nq);
     int pos_slot = (int)lane;  // slot held by position `lane`
     int size = n, i = 1;
     while (i < size) {
@@ -924,7 +897,7 @@ k_merge_small(float* __restrict__ vals, int D, int ld, int32_t* __restrict__ cnt
           if (my_tail < 0) my_tail = t1;
         }
         my_cnt = c1 + c2;
-        my_nrm = row_norm4(tile + rs * stride, nq);
+        my_nrm = norm_seq(reinterpret_cast<const float4*>(tile + rs * stride), nq);
         my_dirty = true;
       }
       // position i takes the tail position's slot
@@ -1153,6 +1126,33 @@ __global__ void k_gather_rows(const float* __restrict__ vals, int D, int ld, con
     out_cnt[w] = cnt[r];
     out_head[w] = head[r];
   }
+}
+
+
+// ================================================================================================
+// Function-level entry points (parity tests): Distance::cosine and AB::SetConsensus on their own.
+// ================================================================================================
+// out[k] = Distance::cosine(left[k], right[k]) (function/distance.cc:27-38); rows padded to ld.
+__global__ void k_cosine_pairs(const float* __restrict__ left, const float* __restrict__ right, uint64_t n, int ld, float* out) {
+  const uint64_t k = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const float4* l4 = reinterpret_cast<const float4*>(left + k * (uint64_t)ld);
+  const float4* r4 = reinterpret_cast<const float4*>(right + k * (uint64_t)ld);
+  const int nq = ld >> 2;
+  out[k] = cosine_distance(dot_seq(l4, r4, nq), norm_seq(l4, nq), norm_seq(r4, nq));
+}
+// out[d] = the value AB::SetConsensus gives dimension d (function/funcAB.cc:58-63)
+__global__ void k_consensus(const float* __restrict__ cur, int c1, const float* __restrict__ cand, int c2, int D, float* out) {
+  const int d = blockIdx.x * blockDim.x + threadIdx.x;
+  if (d < D) out[d] = consensus1(cur[d], c1, cand[d], c2);
+}
+// sum of the member counts of the rows in `rows` (export sizing)
+__global__ void k_sum_counts(const int32_t* __restrict__ cnt, const uint32_t* __restrict__ rows, uint64_t n, unsigned long long* total) {
+  unsigned long long acc = 0;
+  for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) acc += (unsigned long long)cnt[rows[i]];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane_id() == 0 && acc) atomicAdd(total, acc);
 }
 
 }  // namespace
@@ -1588,6 +1588,28 @@ int launch_gather_rows(klsh_ctx* ctx, const uint32_t* rows, uint64_t n, float* o
   k_gather_rows<<<cdiv64(n * 32, 256), 256, 0, ctx->stream>>>(ctx->cur.vals.as<float>(), ctx->D, ctx->ld,
                                                              ctx->cur.cnt.as<int32_t>(), ctx->cur.head.as<int32_t>(),
                                                              rows, n, out_vals, out_cnt, out_head);
+  KLAUNCH(ctx);
+  return KLSH_OK;
+}
+
+int launch_cosine_pairs(klsh_ctx* ctx, const float* left, const float* right, uint64_t n, int ld, float* out) {
+  if (!n) return KLSH_OK;
+  k_cosine_pairs<<<cdiv64(n, 128), 128, 0, ctx->stream>>>(left, right, n, ld, out);
+  KLAUNCH(ctx);
+  return KLSH_OK;
+}
+
+int launch_consensus(klsh_ctx* ctx, const float* cur, int c1, const float* cand, int c2, int D, float* out) {
+  k_consensus<<<cdiv64((uint64_t)D, 128), 128, 0, ctx->stream>>>(cur, c1, cand, c2, D, out);
+  KLAUNCH(ctx);
+  return KLSH_OK;
+}
+
+int launch_sum_counts(klsh_ctx* ctx, const uint32_t* rows, uint64_t n, unsigned long long* total_dev) {
+  KCUDA(ctx, cudaMemsetAsync(total_dev, 0, sizeof(unsigned long long), ctx->stream));
+  if (!n) return KLSH_OK;
+  const uint32_t grid = std::min<uint32_t>(cdiv64(n, 256), (uint32_t)ctx->sm_count * 8);
+  k_sum_counts<<<grid, 256, 0, ctx->stream>>>(ctx->cur.cnt.as<int32_t>(), rows, n, total_dev);
   KLAUNCH(ctx);
   return KLSH_OK;
 }

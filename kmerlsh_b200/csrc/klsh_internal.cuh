@@ -182,5 +182,8 @@ int launch_compact(klsh_ctx* ctx, PassScratch& s, const uint32_t* rows_sorted, u
 int launch_iota(klsh_ctx* ctx, uint32_t* out, uint64_t n, uint32_t base);
 int launch_fill_tail(klsh_ctx* ctx, uint32_t* seg, uint64_t from, uint64_t to);
 int launch_init_meta(klsh_ctx* ctx, uint64_t n);
+int launch_cosine_pairs(klsh_ctx* ctx, const float* left, const float* right, uint64_t n, int ld, float* out);
+int launch_consensus(klsh_ctx* ctx, const float* cur, int c1, const float* cand, int c2, int D, float* out);
+int launch_sum_counts(klsh_ctx* ctx, const uint32_t* rows, uint64_t n, unsigned long long* total_dev);
 int launch_gather_rows(klsh_ctx* ctx, const uint32_t* rows, uint64_t n, float* out_vals, int32_t* out_cnt,
                        int32_t* out_head);

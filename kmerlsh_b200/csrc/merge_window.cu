@@ -32,6 +32,7 @@
 #include <chrono>
 #include <cstdio>
 
+#include "exact_math.cuh"
 #include "klsh_internal.cuh"
 
 #ifndef KLSH_CTA_THREADS
@@ -58,33 +59,6 @@ constexpr int kRing = 8;  // representative groups in flight per warp in the scr
 constexpr uint32_t kInf = 0x7fffffffu;
 
 __device__ __forceinline__ uint32_t lane_id() { return threadIdx.x & 31u; }
-
-// ---- exact arithmetic ---------------------------------------------------------------------------------
-// Rows are padded with zeros to a multiple of 4 floats; the padded products are +0 and x + (+0) == x
-// (a running sum that starts at +0 is never -0), so walking quads gives the reference's D-term sums.
-__device__ __forceinline__ float norm_seq(const float4* a, int nq) {  // sqrt(sum v_i^2), Distance::cosine's magnitudes
-  float s = 0.f;
-#pragma unroll 4
-  for (int q = 0; q < nq; ++q) {
-    const float4 x = a[q];
-    s = __fadd_rn(s, __fmul_rn(x.x, x.x));
-    s = __fadd_rn(s, __fmul_rn(x.y, x.y));
-    s = __fadd_rn(s, __fmul_rn(x.z, x.z));
-    s = __fadd_rn(s, __fmul_rn(x.w, x.w));
-  }
-  return __fsqrt_rn(s);
-}
-__device__ __forceinline__ bool cos_match(float dot, float nl, float nr, float threshold) {
-  float sim = __fdiv_rn(dot, __fmul_rn(nl, nr));
-  float dist = __fsub_rn(1.f, sim);
-  return __fsub_rn(1.f, dist) >= threshold;
-}
-__device__ __forceinline__ float consensus1(float cur, int c1, float cand, int c2) {
-  const float fa = __int2float_rn(c1 + c2);
-  float a = __fdiv_rn(__fmul_rn(cur, __int2float_rn(c1)), fa);
-  float b = __fdiv_rn(__fmul_rn(cand, __int2float_rn(c2)), fa);
-  return __fadd_rn(a, b);
-}
 
 // ---- tensor-core prefilter ----------------------------------------------------------------------------
 // The parallel phase is a contraction (window candidates x representatives x D).  Its exact form is

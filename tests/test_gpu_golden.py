@@ -56,11 +56,11 @@ def test_p_cluster_kats(gpu):
 
 
 def test_consensus_counts_beyond_2_24(gpu):
-    """Member counts 2^24 and 2^24+1: int->float conversion rounds like cvtsi2ss."""
+    """Member counts 2^24 and 2^24+1: the int->float conversion must round like
+    cvtsi2ss.  Through p_cluster with that many REAL member ids (the merge kernels' consensus) ..."""
     g = load("scalar_kats.npz")
     for k, (c1, c2) in enumerate(g["cons_counts"]):
-        if max(c1, c2) > 70000:
-            continue  # needs that many real member ids; covered by the small counts + oracle
+        c1, c2 = int(c1), int(c2)
         a, b = g["a"][10 + k], g["b"][10 + k]
         # two rows that certainly merge at threshold -1: current=row1 (c1 ids), candidate=row0 (c2 ids)
         values = np.stack([b, a])
@@ -69,7 +69,26 @@ def test_consensus_counts_beyond_2_24(gpu):
         gpu.p_cluster(-1.0)
         v, o, i = gpu.get_rows()
         assert len(v) == 1 and v[0].tobytes() == g["cons"][k].tobytes(), (c1, c2)
-        assert np.array_equal(i, np.concatenate([np.arange(c2, c1 + c2), np.arange(c2)]).astype(np.uint64))
+        assert len(i) == c1 + c2 and np.array_equal(i[:c1], np.arange(c2, c1 + c2, dtype=np.uint64)), (c1, c2)
+        assert np.array_equal(i[c1:], np.arange(c2, dtype=np.uint64)), (c1, c2)
+
+
+def test_set_consensus_function(gpu):
+    """... and through the function-level entry klsh_set_consensus (AB::SetConsensus, funcAB.cc:49-71)."""
+    g = load("scalar_kats.npz")
+    for k, (c1, c2) in enumerate(g["cons_counts"]):
+        got = gpu.set_consensus(g["a"][10 + k], int(c1), g["b"][10 + k], int(c2))
+        assert got.tobytes() == g["cons"][k].tobytes(), (c1, c2)
+
+
+def test_cosine_distance_function(gpu):
+    """klsh_cosine_distance = Distance::cosine (distance.cc:27-38) on the reference's own outputs for
+    64 adversarial pairs: zero vector (NaN), identical, opposite, 1e-20 and 1e18 magnitudes."""
+    g = load("scalar_kats.npz")
+    got = gpu.cosine_distance(g["a"], g["b"])
+    assert got.view(np.uint32).tolist() == g["dist"].view(np.uint32).tolist() or all(
+        (x == y) or (np.isnan(x) and np.isnan(y)) for x, y in zip(got.tolist(), g["dist"].tolist()))
+    assert np.isnan(got[0]) and got[1] <= 1e-6
 
 
 @pytest.mark.parametrize("tag", ["plain", "nested", "one_iter"])
