@@ -35,6 +35,13 @@ import numpy as np  # noqa: E402
 
 from kmerlsh_b200 import synth  # noqa: E402
 
+# Rows one GPU clusters per step.  C1 and C2 are whole matrices.  C3-C5 do not fit one GPU as one Cluster()
+# call and the reference does not run them that way either: it cuts the matrix into batches of 100 M rows
+# (app/kmerLSH.cc:285) that are clustered independently (:311-345).  The bench line for those shapes is one
+# such batch (D = 64: the reference's 100 M rows; D = 256: 40 M rows, what the windowed merge's scratch
+# leaves room for in 180 GB), phase 1 + the -I iterations on that batch's survivors.
+BENCH_ROWS = {"C1": 1_000_000, "C2": 50_000_000, "C3": 100_000_000, "C4": 100_000_000, "C5": 40_000_000}
+
 METRIC = "kmer_vectors_clustered_per_sec_per_lsh_iteration"
 UNIT = "rows/s"
 REF_BIN = os.path.join(ROOT, "oracle", "_ref", "kmerLSH_ref")
@@ -92,10 +99,10 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": float(np.median(top)), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons)}
 
 
-def make_inputs(workload, rows_override, device):
-    n, sa, sb, seed = synth.CONFIGS[workload]
-    if rows_override:
-        n = rows_override
+def make_inputs(workload, rows_override, device, seed_offset=0):
+    n_full, sa, sb, seed = synth.CONFIGS[workload]
+    n = rows_override if rows_override else min(n_full, BENCH_ROWS[workload])
+    seed += seed_offset
     if n <= 2_000_000:
         counts, cov = synth.synth_counts(n, sa, sb, seed)
         import torch
@@ -184,12 +191,17 @@ def reference_arm(args, rank, world):
 
 
 def workload_config(args, n, sa, sb, world):
+    n_full = synth.CONFIGS[args.workload][0]
+    what = "mode C" if n == n_full else "one phase-1 batch (%d of the shape's %d k-mers; the reference clusters such batches independently) of mode C" % (n, n_full)
     return {
-        "workload": "%s: mode C on synthetic %d k-mers x %d samples (%d A + %d B), phase 1 I=1 + phase 2 I=%d, N=%.2f" % (
-            args.workload, n, sa + sb, sa, sb, args.iters, args.min_similarity),
+        "workload": "%s: %s on synthetic %d k-mers x %d samples (%d A + %d B), phase 1 I=1 + phase 2 I=%d, N=%.2f" % (
+            args.workload, what, n, sa + sb, sa, sb, args.iters, args.min_similarity),
         "rows": n, "dim": sa + sb, "iterations": 1 + args.iters, "min_similarity": args.min_similarity,
-        "parallelism": "1 GPU" if world == 1 else ("%d GPUs: replicated rows, bucket ranges partitioned over ranks, per-iteration NCCL "
-                                                   "all-gather of survivors + modified rows (kmerlsh_b200/distributed.py)" % world),
+        "parallelism": "1 GPU" if world == 1 else (
+            "%d GPUs, one process each: Cluster() sharded inside libklsh (klsh_mg_cluster: rows replicated, bucket ranges partitioned "
+            "over ranks; per iteration one 32-byte ncclAllGather of sizes and one grouped ncclBroadcast per rank carrying survivors + "
+            "modified rows + chain writes over NVLink).  The communication-free decomposition (phase-1 batch per GPU + NCCL all-gather "
+            "of the survivors) is timed separately in phase1_batch_per_gpu" % world),
         "l2_policy": "inputs larger than L2 (row arena %.1f GB per GPU); no flush" % (n * (sa + sb) * 4 / 1e9),
         "state_reset": "untimed device-to-device restore between steps",
     }
@@ -234,7 +246,7 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- inputs: the SAME matrix on every rank (the multi-GPU path replicates the rows and
+    # ---- inputs: the SAME matrix on every rank (the sharded Cluster() replicates the rows and
     # partitions the merge work, so total work is fixed as N grows: strong scaling) ----------------
     n, sa, sb, counts, cov, vk, _keep = make_inputs(args.workload, args.rows, "cuda:%d" % local_rank)
     d = sa + sb
@@ -250,25 +262,22 @@ def main():
     ctx = Context(local_rank, seed=42)
     p1_thr, p2_thr = 100000, 1000000
 
-    class _S:  # the fields of klsh_iter_stats this script reads, for the sharded path
-        def __init__(self, d_):
-            self.rows_in, self.rows_out = d_["rows_in"], d_["rows_out"]
-            self.ms_sign = self.ms_group = self.ms_merge = self.ms_compact = self.ms_total = 0.0
-
     if world > 1:
-        from kmerlsh_b200 import distributed as kd
+        # the NCCL communicator lives inside libklsh; torch.distributed only carries the 128-byte id
+        from kmerlsh_b200 import nccl_unique_id
 
-        backend = kd.TorchBackend(ctx, torch.device("cuda", local_rank))
+        uid = [nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        ctx.mg_init(rank, world, uid[0])
 
     def one_pass():
         if world == 1:
             st = ctx.cluster(args.min_similarity, 1, p1_thr)
             st += ctx.cluster(args.min_similarity, args.iters, p2_thr)
             return st
-        raw = []
-        kd.run_with_torch_distributed(backend, args.min_similarity, 1, p1_thr, raw)
-        kd.run_with_torch_distributed(backend, args.min_similarity, args.iters, p2_thr, raw)
-        return [_S(x) for x in raw]
+        st = ctx.mg_cluster(args.min_similarity, 1, p1_thr)
+        st += ctx.mg_cluster(args.min_similarity, args.iters, p2_thr)
+        return st
 
     # ---- device-resident arm ------------------------------------------------------------------------
     ctx.load_counts(counts, vk, 0)
@@ -319,6 +328,46 @@ def main():
     sampler.join(timeout=2)
     h2d_bytes = counts.nbytes + vk.nbytes
 
+    # ---- the communication-free decomposition (N > 1): phase 1 is one independent Cluster(I=1) per batch in the
+    # reference (app/kmerLSH.cc:311-345), so every GPU clusters ITS OWN batch of this shape concurrently; the
+    # survivors are then all-gathered in batch order over NVLink (klsh_mg_gather_rows) — the working set the
+    # reference gets by appending to and re-reading its spill file.  Reported beside the headline, not in it.
+    p1_block = None
+    if world > 1:
+        nb, _sa, _sb, bcounts, _bcov, bvk, _k2 = make_inputs(args.workload, args.rows, "cuda:%d" % local_rank, seed_offset=1000 * (rank + 1))
+        ctx.load_counts(bcounts, bvk, rank * nb)
+        ctx.snapshot()
+        p1_t, stp = [], None
+        for k in range(1 + max(1, min(args.steps, 3))):
+            ctx.restore()
+            ctx.set_seed(1000 + rank)
+            ctx.sync()
+            barrier()
+            t0 = time.perf_counter()
+            stp = ctx.cluster(args.min_similarity, 1, p1_thr)
+            ctx.sync()
+            barrier()
+            if k:
+                p1_t.append(time.perf_counter() - t0)
+        my_surv = int(stp[0].rows_out)
+        barrier()
+        t0 = time.perf_counter()
+        ctx.mg_gather_rows()
+        ctx.sync()
+        barrier()
+        t_gather = time.perf_counter() - t0
+        gathered = ctx.row_count(False)[0]
+        tt = torch.tensor([float(np.mean(p1_t)), t_gather], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        p1_ms, g_ms = (x * 1e3 for x in tt.tolist())
+        p1_block = {
+            "what": "every GPU clusters its own %d-row batch (phase 1, I=1, threshold 0.95, nested above %d), no communication; then the "
+                    "survivors are all-gathered in batch order with NCCL broadcasts" % (nb, p1_thr),
+            "rows_per_gpu": nb, "value": world * nb / (p1_ms * 1e-3), "unit": UNIT, "ms_per_step": p1_ms, "scaling": "weak",
+            "gather_ms": g_ms, "gathered_rows": int(gathered), "my_survivors": my_surv,
+            "gather_GBps_per_gpu": (gathered * (4.0 * d + 12.0) + 4.0 * world * nb) / (g_ms * 1e-3) / 1e9,
+        }
+
     # ---- aggregate over ranks (max time, sum rows) -----------------------------------------------------
     t_total, rows_total = float(sum(t_steps)), float(sum(rows_steps))
     e_total, erows_total = float(sum(e2e_t)), float(sum(e2e_rows))
@@ -355,6 +404,7 @@ def main():
     dev_total_ms = sum(fam.values())
     if world > 1:  # per-family event times exist only on the single-GPU path; use the step time
         dev_total_ms = t_total * 1e3
+        merge_bytes = 0.0
     sign_bytes = sum(s.rows_in * (4.0 * d + 8.0) for st in all_stats for s in st if s.rows_in)
     sign_achieved = sign_bytes / (fam["sign"] * 1e-3) / 1e9 if fam["sign"] > 0 else 0.0
     # DRAM traffic of the merge family for one step of this workload, from the committed ncu capture
@@ -367,8 +417,26 @@ def main():
         traffic_src = "bytes per step over the family's launches, " + tj["source"]
     achieved = merge_bytes / (fam["merge"] * 1e-3) / 1e9 if fam["merge"] > 0 else 0.0
     job_achieved = job_bytes / (dev_total_ms * 1e-3) / 1e9 if dev_total_ms > 0 else 0.0
+    # The merge is not bound by bytes: its work is candidates x representatives x D compares (screened on the tensor
+    # cores with mma.sync) and a dependent chain of window resolutions.  Counted on the device per window.
+    kw = 32 if d <= 32 else (64 if d <= 64 else (d + 31) // 32 * 32)
+    pairs = sum(getattr(s_, "screen_pairs", 0) for st in all_stats for s_ in st)
+    exact = sum(getattr(s_, "exact_pairs", 0) for st in all_stats for s_ in st)
+    clk = (sampler.summary().get("sm_mhz") or 1965.0) * 1e6
+    mma_peak = 1324.0 * 148 * clk  # MAC/s: mma.sync.m16n8k16 back to back, measured per SM and clock (tools/microbench/mma_bench.cu)
+    compare = None
+    if world == 1 and fam["merge"] > 0:
+        mac_s = pairs * kw / (fam["merge"] * 1e-3)
+        compare = {
+            "pairs_per_step": pairs / args.steps, "exact_pairs_per_step": exact / args.steps, "k_width": kw,
+            "mac_per_s": mac_s, "mma_peak_mac_per_s": mma_peak, "frac_of_mma_peak": mac_s / mma_peak,
+            "sum_largest_bucket_rows_per_step": sum(s_.bucket_max for st in all_stats for s_ in st if s_.rows_in) / args.steps,
+            "note": "pairs = window candidates x representatives screened (fp16 mma.sync, k = k_width) + the window's own 64 x 64 block; "
+                    "exact_pairs = pairs re-tested with the reference's fp32 chain.  The merge time follows the longest sequential "
+                    "chain of windows (the largest bucket of each iteration), not this rate",
+        }
     roofline = {
-        "bound": "hbm", "kernel": "k_merge_* (in-bucket greedy merge, per iteration)", "achieved": achieved, "peak": peak,
+        "bound": "hbm", "kernel": "k_merge_* (in-bucket greedy merge, per iteration)", "compare": compare, "achieved": achieved, "peak": peak,
         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_note": traffic_src,
         "algorithmic_bytes_per_step": merge_bytes / args.steps, "peak_source": peak_src,
         "share_of_step": (fam["merge"] / dev_total_ms if dev_total_ms else None) if world == 1 else None, "dominant_family": dom,
@@ -403,6 +471,8 @@ def main():
         "device_ms_per_step": float(np.mean(dev_ms)) if world == 1 else None,
         "rows_iterations_per_step": rows_total / args.steps,
         "final_clusters": int(all_stats[-1][-1].rows_out),
+        "phase1_ms_per_step": float(np.mean([st[0].ms_total for st in all_stats])) if world == 1 else None,
+        "phase1_batch_per_gpu": p1_block,
     }
     print(json.dumps(out))
     if world > 1:

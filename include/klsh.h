@@ -59,6 +59,18 @@ uint64_t klsh_launch_count(const klsh_ctx* ctx);
  * the reference's generator with its std::random_device replaced by a seeded one. */
 int klsh_set_seed(klsh_ctx* ctx, uint64_t seed);
 int klsh_set_plane_source(klsh_ctx* ctx, klsh_plane_fn fn, void* user);
+/* Position of the built-in source: its seed and the number of hash functions drawn since (every table
+ * of H functions advances it by H).  klsh_plane_seek(seed, drawn) puts any context at that position,
+ * e.g. to give several contexts identical copies of one stream. */
+int klsh_plane_tell(const klsh_ctx* ctx, uint64_t* seed, uint64_t* drawn);
+int klsh_plane_seek(klsh_ctx* ctx, uint64_t seed, uint64_t drawn);
+/* fn(user) is called once per klsh_cluster call, from inside it, as soon as the call has drawn its LAST
+ * hyperplane table (the table of its last iteration and those of that iteration's oversized buckets) —
+ * before that iteration's merge runs.  A driver that serialises several contexts on one generator stream
+ * (the reference draws its tables from one stream, batch after batch: app/kmerLSH.cc:311-345) uses it to
+ * hand the stream to the next context while this one is still merging. */
+typedef void (*klsh_done_fn)(void* user);
+int klsh_set_draws_done_callback(klsh_ctx* ctx, klsh_done_fn fn, void* user);
 /* Draw one table from the current source (advances it), e.g. to replay what a run used. */
 int klsh_draw_table(klsh_ctx* ctx, int H, int D, float* out);
 
@@ -141,6 +153,28 @@ int klsh_mg_apply(klsh_ctx* ctx, const uint32_t* d_mod_rows, const float* d_mod_
                   uint64_t n_modified_rows, const uint32_t* d_chain_slots, const int32_t* d_chain_vals,
                   uint64_t n_chain_writes);
 int klsh_mg_set_alive(klsh_ctx* ctx, const uint32_t* d_alive, uint64_t n);
+
+
+/* ---- multi-GPU, NCCL inside the library (kmerlsh_b200/csrc/multi.cu) ---------------------------
+ * One context per GPU/rank.  klsh_nccl_unique_id (rank 0) makes the 128-byte NCCL id the caller hands
+ * to every rank by its own means (threads of one process: a shared variable; processes: any
+ * broadcast).  klsh_mg_init joins the communicator (collective: every rank calls it concurrently). */
+int klsh_nccl_unique_id(void* out, uint64_t bytes /* >= 128 */);
+int klsh_mg_init(klsh_ctx* ctx, int rank, int world, const void* unique_id, uint64_t bytes);
+int klsh_mg_finalize(klsh_ctx* ctx);
+int klsh_mg_rank(const klsh_ctx* ctx, int* rank, int* world);
+/* = Cluster(...) (function/cluster.cc:181-340) over ALL ranks' GPUs: every rank holds the same row set
+ * and the same hyperplane source and calls this collectively; the loop over the klsh_mg_* building
+ * blocks above and the NCCL exchange (sizes: one ncclAllGather; survivors + modified rows + chain
+ * writes: one grouped ncclBroadcast per rank) run inside the library.  Every rank ends with the
+ * clusters klsh_cluster computes on one GPU, bit for bit. */
+int klsh_mg_cluster(klsh_ctx* ctx, float min_similarity, int iterations, int64_t bucket_size_threshold,
+                    klsh_iter_stats* stats);
+/* All-gather of row sets over NVLink: every rank contributes its working set (the survivors of its
+ * phase-1 batch, app/kmerLSH.cc:311-345) and ends with the concatenation in rank order — the vector
+ * the reference gets by appending batch after batch to tmp/0.bin and reading it back (:326-335, :415).
+ * Rows must come from klsh_load_counts with batch offsets contiguous in rank order. */
+int klsh_mg_gather_rows(klsh_ctx* ctx);
 
 #ifdef __cplusplus
 }

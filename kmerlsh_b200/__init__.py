@@ -12,4 +12,5 @@ from .api import (  # noqa: F401
     Cluster,
     lib_path,
     load_library,
+    nccl_unique_id,
 )

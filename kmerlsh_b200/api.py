@@ -20,6 +20,7 @@ u64p = C.POINTER(C.c_uint64)
 u16p = C.POINTER(C.c_uint16)
 
 PLANE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, f32p)
+DONE_FN = C.CFUNCTYPE(None, C.c_void_p)
 
 
 class KlshError(RuntimeError):
@@ -59,6 +60,9 @@ SYMBOLS = [
     ("klsh_set_seed", C.c_int, [C.c_void_p, u64]),
     ("klsh_set_plane_source", C.c_int, [C.c_void_p, PLANE_FN, C.c_void_p]),
     ("klsh_draw_table", C.c_int, [C.c_void_p, C.c_int, C.c_int, f32p]),
+    ("klsh_plane_tell", C.c_int, [C.c_void_p, u64p, u64p]),
+    ("klsh_plane_seek", C.c_int, [C.c_void_p, u64, u64]),
+    ("klsh_set_draws_done_callback", C.c_int, [C.c_void_p, DONE_FN, C.c_void_p]),
     ("klsh_load_counts", C.c_int, [C.c_void_p, u16p, f32p, C.c_int, u64, u64]),
     ("klsh_set_rows", C.c_int, [C.c_void_p, f32p, u64p, u64p, u64, C.c_int]),
     ("klsh_load_cluster_file", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, u64, u64]),
@@ -81,6 +85,12 @@ SYMBOLS = [
     ("klsh_mg_export", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     ("klsh_mg_apply", C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, u64, C.c_void_p, C.c_void_p, u64]),
     ("klsh_mg_set_alive", C.c_int, [C.c_void_p, C.c_void_p, u64]),
+    ("klsh_nccl_unique_id", C.c_int, [C.c_void_p, u64]),
+    ("klsh_mg_init", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, u64]),
+    ("klsh_mg_finalize", C.c_int, [C.c_void_p]),
+    ("klsh_mg_rank", C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    ("klsh_mg_cluster", C.c_int, [C.c_void_p, C.c_float, C.c_int, i64, C.POINTER(IterStats)]),
+    ("klsh_mg_gather_rows", C.c_int, [C.c_void_p]),
 ]
 
 
@@ -154,6 +164,20 @@ class Context:
 
         self._cb = PLANE_FN(tramp)
         self._ck(self.lib.klsh_set_plane_source(self.h, self._cb, None), "klsh_set_plane_source")
+
+    def plane_tell(self):
+        """(seed, hash functions drawn so far) of the built-in hyperplane stream."""
+        a, b = u64(), u64()
+        self._ck(self.lib.klsh_plane_tell(self.h, C.byref(a), C.byref(b)), "klsh_plane_tell")
+        return a.value, b.value
+
+    def plane_seek(self, seed: int, drawn: int):
+        self._ck(self.lib.klsh_plane_seek(self.h, seed, drawn), "klsh_plane_seek")
+
+    def set_draws_done_callback(self, fn):
+        """fn() is called from inside cluster() once the call has drawn its last hyperplane table."""
+        self._done_cb = DONE_FN(lambda _user: fn()) if fn is not None else C.cast(None, DONE_FN)
+        self._ck(self.lib.klsh_set_draws_done_callback(self.h, self._done_cb, None), "klsh_set_draws_done_callback")
 
     def draw_table(self, H: int, D: int):
         out = np.empty((H, D), dtype=np.float32)
@@ -294,6 +318,32 @@ class Context:
 
     def mg_set_alive(self, d_alive, n: int):
         self._ck(self.lib.klsh_mg_set_alive(self.h, d_alive, n), "klsh_mg_set_alive")
+
+    # ---- multi-GPU with NCCL inside the library
+    def mg_init(self, rank: int, world: int, unique_id: bytes):
+        buf = C.create_string_buffer(bytes(unique_id), 128)
+        self._ck(self.lib.klsh_mg_init(self.h, rank, world, buf, 128), "klsh_mg_init")
+
+    def mg_finalize(self):
+        self._ck(self.lib.klsh_mg_finalize(self.h), "klsh_mg_finalize")
+
+    def mg_cluster(self, min_similarity: float, iterations: int, bucket_size_threshold: int):
+        stats = (IterStats * max(1, iterations))()
+        self._ck(self.lib.klsh_mg_cluster(self.h, min_similarity, iterations, bucket_size_threshold, stats), "klsh_mg_cluster")
+        return list(stats)
+
+    def mg_gather_rows(self):
+        self._ck(self.lib.klsh_mg_gather_rows(self.h), "klsh_mg_gather_rows")
+
+
+def nccl_unique_id() -> bytes:
+    """128-byte NCCL unique id (create on rank 0, hand to every rank)."""
+    lib = load_library()
+    buf = C.create_string_buffer(128)
+    rc = lib.klsh_nccl_unique_id(buf, 128)
+    if rc != 0:
+        raise KlshError("klsh_nccl_unique_id: " + lib.klsh_last_error(None).decode())
+    return buf.raw
 
 
 def Cluster(rows, min_similarity, cluster_iteration, threads_to_use, dim, bucket_size_threshold, verbose=False,

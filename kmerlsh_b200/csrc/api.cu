@@ -71,7 +71,7 @@ static void dev_free(DevBuf& b) {
 static void free_scratch(PassScratch& s) {
   dev_free(s.keys_a); dev_free(s.keys_b); dev_free(s.rows_a); dev_free(s.rows_b);
   dev_free(s.hist); dev_free(s.blkcnt); dev_free(s.bstart);
-  dev_free(s.list_small); dev_free(s.list_large); dev_free(s.list_big); dev_free(s.esc1); dev_free(s.esc2); dev_free(s.esc3); dev_free(s.list_nested);
+  dev_free(s.list_small); dev_free(s.list_large); dev_free(s.list_big); dev_free(s.list_direct); dev_free(s.escb2); dev_free(s.escb3); dev_free(s.esc1); dev_free(s.esc2); dev_free(s.esc3); dev_free(s.list_nested);
   dev_free(s.pos_nrm); dev_free(s.pos_h);
   dev_free(s.planes); dev_free(s.counters);
 }
@@ -116,7 +116,14 @@ int klsh_create(int device, klsh_ctx** out) {
     delete ctx;
     return klsh_fail(nullptr, KLSH_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
   }
+  if ((e = cudaStreamCreateWithFlags(&ctx->stream2, cudaStreamNonBlocking)) != cudaSuccess) {
+    cudaStreamDestroy(ctx->stream);
+    delete ctx;
+    return klsh_fail(nullptr, KLSH_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e));
+  }
   for (auto& ev : ctx->ev) cudaEventCreate(&ev);
+  cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming);
+  cudaEventCreateWithFlags(&ctx->ev_join, cudaEventDisableTiming);
   if ((e = cudaMallocHost(&ctx->h_counters, sizeof(PassCounters) * 2)) != cudaSuccess) {
     delete ctx;
     return klsh_fail(nullptr, KLSH_ERR_NOMEM, "cudaMallocHost: %s", cudaGetErrorString(e));
@@ -125,12 +132,16 @@ int klsh_create(int device, klsh_ctx** out) {
   // development knobs (bucket size classes of the windowed merge)
   if (const char* e = std::getenv("KLSH_DEBUG")) ctx->debug = std::atoi(e) != 0;
   if (const char* e = std::getenv("KLSH_MERGE_V1")) ctx->merge_v1 = std::atoi(e) != 0;
+  if (const char* e = std::getenv("KLSH_NO_SPEC")) ctx->no_spec = std::atoi(e) != 0;
   if (const char* e = std::getenv("KLSH_CTA_MAX")) ctx->cta_max = (uint32_t)std::strtoul(e, nullptr, 10);
   if (const char* e = std::getenv("KLSH_CLUSTER_MAX")) ctx->cluster_max = (uint32_t)std::strtoul(e, nullptr, 10);
   if (const char* e = std::getenv("KLSH_CLUSTER_SIZE")) ctx->cluster_size = std::atoi(e);
   if (const char* e = std::getenv("KLSH_CLUSTER2_MAX")) ctx->cluster2_max = (uint32_t)std::strtoul(e, nullptr, 10);
   if (const char* e = std::getenv("KLSH_CLUSTER2_SIZE")) ctx->cluster2_size = std::atoi(e);
   if (const char* e = std::getenv("KLSH_CLUSTER_CTAS_PER_SM")) ctx->cluster_ctas_per_sm = std::max(1, std::atoi(e));
+  if (const char* e = std::getenv("KLSH_DIRECT_MIN")) ctx->direct_min = (uint32_t)std::strtoul(e, nullptr, 10);
+  if (ctx->direct_min < 2) ctx->direct_min = 2;
+  if (const char* e = std::getenv("KLSH_MAX_DIRECT")) ctx->max_direct = (uint32_t)std::strtoul(e, nullptr, 10);
   if (ctx->cta_max < 1) ctx->cta_max = 1;
   if (ctx->cluster_max < ctx->cta_max) ctx->cluster_max = ctx->cta_max;
   if (ctx->cluster2_max < ctx->cluster_max) ctx->cluster2_max = ctx->cluster_max;
@@ -140,8 +151,10 @@ int klsh_create(int device, klsh_ctx** out) {
 
 void klsh_destroy(klsh_ctx* ctx) {
   if (!ctx) return;
+  klsh_mg_finalize(ctx);
   cudaSetDevice(ctx->device);
   cudaStreamSynchronize(ctx->stream);
+  cudaStreamSynchronize(ctx->stream2);
   free_state(ctx->cur);
   free_state(ctx->snap);
   free_scratch(ctx->top);
@@ -152,6 +165,7 @@ void klsh_destroy(klsh_ctx* ctx) {
   dev_free(ctx->alive_alt);
   dev_free(ctx->nested_out);
   dev_free(ctx->team_ctl);
+  dev_free(ctx->team_ctl_b);
   dev_free(ctx->exp_vals); dev_free(ctx->exp_cnt); dev_free(ctx->exp_head);
   dev_free(ctx->rank_buf); dev_free(ctx->exp_offs); dev_free(ctx->exp_slots);
   if (ctx->h_slots.p) cudaFreeHost(ctx->h_slots.p);
@@ -164,6 +178,9 @@ void klsh_destroy(klsh_ctx* ctx) {
   if (ctx->h_counters) cudaFreeHost(ctx->h_counters);
   for (auto& ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  cudaStreamDestroy(ctx->stream2);
   cudaStreamDestroy(ctx->stream);
   planes_free(ctx->planes);
   delete ctx;
@@ -181,6 +198,25 @@ int klsh_set_seed(klsh_ctx* ctx, uint64_t seed) {
 int klsh_set_plane_source(klsh_ctx* ctx, klsh_plane_fn fn, void* user) {
   if (!ctx || !fn) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_set_plane_source: NULL argument");
   planes_callback(ctx->planes, fn, user);
+  return KLSH_OK;
+}
+
+int klsh_plane_tell(const klsh_ctx* ctx, uint64_t* seed, uint64_t* drawn) {
+  if (!ctx || !seed || !drawn) return KLSH_ERR_ARG;
+  planes_tell(ctx->planes, seed, drawn);
+  return KLSH_OK;
+}
+
+int klsh_plane_seek(klsh_ctx* ctx, uint64_t seed, uint64_t drawn) {
+  if (!ctx) return KLSH_ERR_ARG;
+  planes_seek(ctx->planes, seed, drawn);
+  return KLSH_OK;
+}
+
+int klsh_set_draws_done_callback(klsh_ctx* ctx, klsh_done_fn fn, void* user) {
+  if (!ctx) return KLSH_ERR_ARG;
+  ctx->draws_done_fn = fn;
+  ctx->draws_done_user = user;
   return KLSH_OK;
 }
 
@@ -376,34 +412,35 @@ static int run_pass(klsh_ctx* ctx, PassScratch& s, const uint32_t* rows_in, uint
       nb_h[k]++;
       rows_h[k] += sz;
     }
-    fprintf(stderr, "[klsh] pass n=%llu H=%d buckets=%u small=%u large=%u big=%u nested=%u | size<=2^k: buckets/rows",
-            (unsigned long long)n, H, c.n_buckets, c.n_small, c.n_large, c.n_big, c.n_nested);
+    fprintf(stderr, "[klsh] pass n=%llu H=%d buckets=%u small=%u large=%u big=%u direct=%u nested=%u | size<=2^k: buckets/rows",
+            (unsigned long long)n, H, c.n_buckets, c.n_small, c.n_large, c.n_big, c.n_direct, c.n_nested);
     for (int k = 0; k < 33; ++k)
       if (nb_h[k]) fprintf(stderr, " %d:%llu/%llu", k, (unsigned long long)nb_h[k], (unsigned long long)rows_h[k]);
     fprintf(stderr, "\n");
   }
-  KTRY(launch_merge(ctx, s, rows_sorted, threshold, c));
+  // Oversized buckets (reference nestedCluster): their sizes are known now, so their hash tables are
+  // drawn BEFORE the top-level merge is launched — the host never waits for the merge to learn what to
+  // draw, and a multi-context driver can pass the hyperplane stream on (draws-done callback).
   uint64_t nested_calls = 0;
+  std::vector<uint32_t> nb, bs;
+  std::vector<int> H2;
+  std::vector<float> padded;
+  int Hmax = 0, pb = 0;
+  uint64_t total = 0;
+  bool combined = false;
   if (c.n_nested) {
-    // oversized buckets in ascending key order (= ascending bucket index), like the reference's
-    // serial bucket loop; each consumes one fresh table from the plane source
-    std::vector<uint32_t> nb(c.n_nested);
+    if (&s == &ctx->nested) return klsh_fail(ctx, KLSH_ERR_ARG, "internal: nested pass may not nest");
+    // ascending key order (= ascending bucket index), like the reference's serial bucket loop; each
+    // bucket consumes one fresh table from the plane source
+    nb.resize(c.n_nested);
     KCUDA(ctx, cudaMemcpyAsync(nb.data(), s.list_nested.p, sizeof(uint32_t) * c.n_nested, cudaMemcpyDeviceToHost, st));
     KCUDA(ctx, cudaStreamSynchronize(st));
     std::sort(nb.begin(), nb.end());
-    if (&s == &ctx->nested) return klsh_fail(ctx, KLSH_ERR_ARG, "internal: nested pass may not nest");
-    std::vector<uint32_t> bs(2 * nb.size());
+    bs.resize(2 * nb.size());
     for (size_t k = 0; k < nb.size(); ++k)
       KCUDA(ctx, cudaMemcpyAsync(&bs[2 * k], s.bstart.as<uint32_t>() + nb[k], sizeof(uint32_t) * 2, cudaMemcpyDeviceToHost, st));
     KCUDA(ctx, cudaStreamSynchronize(st));
-    // All oversized buckets go through ONE combined nested pass: bucket k's rows are signed with
-    // bucket k's own fresh table (drawn in bucket order, like the reference's serial loop) and get
-    // the key prefix k, so one sort / bounds / merge handles every sub-bucket of every nested bucket
-    // and their greedy chains run side by side.  The merged, still sentinel-holed, row lists are
-    // copied back over the parent's segments; the parent's compaction drops the sentinels.
-    int Hmax = 0, pb = 0;
-    uint64_t total = 0;
-    std::vector<int> H2(nb.size());
+    H2.resize(nb.size());
     for (size_t k = 0; k < nb.size(); ++k) {
       const uint64_t seg_n = bs[2 * k + 1] - bs[2 * k];
       H2[k] = floor_log2_u64(seg_n);
@@ -411,15 +448,13 @@ static int run_pass(klsh_ctx* ctx, PassScratch& s, const uint32_t* rows_in, uint
       total += seg_n;
     }
     while ((1ull << pb) < nb.size()) ++pb;
-    const bool combined = Hmax + pb <= 32 && total < 0xFFFFFFF0ull;
+    combined = Hmax + pb <= 32 && total < 0xFFFFFFF0ull;
     if (combined) {
-      PassScratch& ns = ctx->nested;
       const int D = ctx->D, ld = ctx->ld;
-      KTRY(reserve_scratch(ctx, ns, total, Hmax));
       size_t plane_floats = 0;
       for (int h : H2) plane_floats += (size_t)h * ld;
-      KTRY(dev_reserve(ctx, ns.planes, sizeof(float) * (plane_floats + 4)));
-      std::vector<float> padded(plane_floats + 1, 0.f), t;
+      padded.assign(plane_floats + 1, 0.f);
+      std::vector<float> t;
       size_t po = 0;
       for (size_t k = 0; k < nb.size(); ++k) {  // hyperplane stream order = bucket order
         t.resize((size_t)H2[k] * D + 1);
@@ -427,12 +462,31 @@ static int run_pass(klsh_ctx* ctx, PassScratch& s, const uint32_t* rows_in, uint
         for (int h = 0; h < H2[k]; ++h) std::memcpy(&padded[po + (size_t)h * ld], &t[(size_t)h * D], sizeof(float) * D);
         po += (size_t)H2[k] * ld;
       }
+    }
+  }
+  if (&s == &ctx->top && ctx->last_iteration && (!c.n_nested || combined) && !ctx->draws_done_fired) {
+    ctx->draws_done_fired = true;  // nothing after this point draws from the plane source
+    if (ctx->draws_done_fn) ctx->draws_done_fn(ctx->draws_done_user);
+  }
+  KTRY(launch_merge(ctx, s, rows_sorted, threshold, c));
+  if (c.n_nested) {
+    // All oversized buckets go through ONE combined nested pass: bucket k's rows are signed with
+    // bucket k's own fresh table and get the key prefix k, so one sort / bounds / merge handles every
+    // sub-bucket of every nested bucket and their greedy chains run side by side.  The merged, still
+    // sentinel-holed, row lists are copied back over the parent's segments; the parent's compaction
+    // drops the sentinels.
+    if (combined) {
+      PassScratch& ns = ctx->nested;
+      const int D = ctx->D, ld = ctx->ld;
+      KTRY(reserve_scratch(ctx, ns, total, Hmax));
+      const size_t plane_floats = padded.size() - 1;
+      KTRY(dev_reserve(ctx, ns.planes, sizeof(float) * (plane_floats + 4)));
       if (plane_floats) {
         KCUDA(ctx, cudaMemcpyAsync(ns.planes.p, padded.data(), sizeof(float) * plane_floats, cudaMemcpyHostToDevice, st));
-        KCUDA(ctx, cudaStreamSynchronize(st));
+        KCUDA(ctx, cudaStreamSynchronize(st));  // `padded` is pageable
       }
       uint64_t off = 0;
-      po = 0;
+      size_t po = 0;
       for (size_t k = 0; k < nb.size(); ++k) {
         const uint64_t seg_n = bs[2 * k + 1] - bs[2 * k];
         KTRY(launch_sign(ctx, ctx->cur.vals.as<float>(), D, ld, rows_sorted + bs[2 * k], seg_n, ns.planes.as<float>() + po, H2[k],
@@ -505,9 +559,19 @@ extern "C" int klsh_cluster(klsh_ctx* ctx, float min_similarity, int iterations,
   KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long) * 2));
   KCUDA(ctx, cudaMemsetAsync(ctx->eps_counter.p, 0, sizeof(unsigned long long), ctx->stream));
   unsigned long long eps_prev = 0;
+  ctx->draws_done_fired = false;
+  struct DoneGuard {  // the callback fires exactly once per call, whatever path the call takes
+    klsh_ctx* c;
+    ~DoneGuard() {
+      if (!c->draws_done_fired && c->draws_done_fn) c->draws_done_fn(c->draws_done_user);
+      c->draws_done_fired = true;
+      c->last_iteration = false;
+    }
+  } done_guard{ctx};
   for (int iter = 1; iter <= iterations; ++iter) {
     const uint64_t n = ctx->cur.n_alive;
     if (n == 0) break;  // the reference takes log2(0) here (undefined); an empty set stays empty
+    ctx->last_iteration = iter == iterations;
     const int H = floor_log2_u64(n);
     PassInfo info;
     uint64_t kept = 0;
@@ -863,7 +927,8 @@ extern "C" int klsh_row_stride(const klsh_ctx* ctx) { return ctx ? ctx->ld : 0; 
 
 extern "C" int klsh_mg_pass_begin(klsh_ctx* ctx, uint64_t* n_rows, int32_t* H_out, uint64_t* n_buckets) {
   if (!ctx || ctx->D <= 0) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_pass_begin: no rows loaded");
-  if (ctx->merge_v1) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_*: not available with KLSH_MERGE_V1");
+  if (launch_merge_uses_fallback(ctx))
+    return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_*: not available with the block-per-bucket fallback merge (KLSH_MERGE_V1 or D > ~280)");
   KCUDA(ctx, cudaSetDevice(ctx->device));
   const uint64_t n = ctx->cur.n_alive;
   ctx->mg_n = n;

@@ -754,14 +754,50 @@ __device__ __forceinline__ void warp_append_item(bool pred, uint32_t* counter, u
   }
 }
 
+// Bucket-size histogram by power-of-two class (only classes that can be "direct" matter): the input of
+// the direct threshold below.
+__global__ void k_size_hist(const uint32_t* __restrict__ bstart, uint64_t n, uint32_t b_lo, uint32_t b_hi, long long nest_threshold,
+                            PassCounters* counters) {
+  const uint32_t nb = counters->n_buckets;
+  for (uint32_t b0 = blockIdx.x * blockDim.x; b0 < nb; b0 += gridDim.x * blockDim.x) {
+    const uint32_t b = b0 + threadIdx.x;
+    uint32_t size = 0;
+    if (b < nb && b >= b_lo && b < b_hi) {
+      const uint32_t e = (b + 1 < nb) ? bstart[b + 1] : (uint32_t)n;
+      size = e - bstart[b];
+      if (nest_threshold >= 0 && (long long)size > nest_threshold) size = 0;  // oversized buckets are not merged here
+    }
+    if (size > KLSH_SMALL_MAX) atomicAdd(&counters->size_hist[31 - __clz(size)], 1u);  // few buckets are this large
+  }
+}
+
+// Buckets with at least direct_threshold() rows start on cluster teams on the second stream.  The
+// threshold is the smallest power of two >= direct_min that leaves at most max_direct such buckets
+// (there are only a few dozen cluster teams: more items than that would queue behind each other
+// while the single-CTA stage runs hundreds of buckets side by side).
+__device__ __forceinline__ uint32_t direct_threshold(const PassCounters* c, uint32_t direct_min, uint32_t max_direct) {
+  uint32_t k = 31u - (uint32_t)__clz(max(direct_min, 2u));
+  if ((1u << k) < direct_min) ++k;  // ceil(log2(direct_min))
+  for (; k < 32u; ++k) {
+    uint32_t above = 0;
+    for (uint32_t j = k; j < 32u; ++j) above += c->size_hist[j];
+    if (above <= max_direct) break;
+  }
+  return k >= 32u ? 0xFFFFFFFFu : max(1u << k, direct_min);
+}
+
 // Only buckets in [b_lo, b_hi) are queued for merging (multi-GPU: each rank owns a contiguous
 // range); oversized buckets are listed regardless of the range because every rank has to draw their
 // hash tables to keep the hyperplane stream in step.
-__global__ void k_classify(uint32_t* bstart, uint64_t n, long long nest_threshold, uint32_t b_lo, uint32_t b_hi,
-                           PassCounters* counters, uint32_t* list_small, uint32_t* list_large, uint32_t* list_big,
-                           uint32_t* list_nested) {
+__global__ void k_classify(uint32_t* bstart, uint64_t n, long long nest_threshold, uint32_t b_lo, uint32_t b_hi, uint32_t direct_min,
+                           uint32_t max_direct, PassCounters* counters, uint32_t* list_small, uint32_t* list_large, uint32_t* list_big,
+                           uint32_t* list_direct, uint32_t* list_nested) {
   const uint32_t nb = counters->n_buckets;
-  if (blockIdx.x == 0 && threadIdx.x == 0) bstart[nb] = (uint32_t)n;
+  const uint32_t dthr = direct_threshold(counters, direct_min, max_direct);
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    bstart[nb] = (uint32_t)n;
+    counters->direct_thr = dthr;
+  }
   uint32_t tmax = 0;
   // grid-stride over the buckets (their number is only known on the device); whole warps iterate together
   for (uint32_t b0 = blockIdx.x * blockDim.x; b0 < nb; b0 += gridDim.x * blockDim.x) {
@@ -775,13 +811,16 @@ __global__ void k_classify(uint32_t* bstart, uint64_t n, long long nest_threshol
     }
     tmax = max(tmax, size);
     const bool nested = nest_threshold >= 0 && (long long)size > nest_threshold && size >= 2;
-    const bool small = mine && !nested && size >= 2 && size <= KLSH_SMALL_MAX;
-    const bool large = mine && !nested && size > KLSH_SMALL_MAX && size < KLSH_BIG;
-    const bool big = mine && !nested && size >= KLSH_BIG;
+    const bool merged = mine && !nested;
+    const bool small = merged && size >= 2 && size <= KLSH_SMALL_MAX;
+    const bool direct = merged && size > KLSH_SMALL_MAX && size >= dthr;
+    const bool large = merged && size > KLSH_SMALL_MAX && size < KLSH_BIG && !direct;
+    const bool big = merged && size >= KLSH_BIG && !direct;
     warp_append(nested, &counters->n_nested, list_nested, b);
     warp_append(small, &counters->n_small, list_small, b);
     warp_append_item(large, &counters->n_large, list_large, b);
     warp_append_item(big, &counters->n_big, list_big, b);
+    warp_append_item(direct, &counters->n_direct, list_direct, b);
   }
   const uint32_t wmax = __reduce_max_sync(0xffffffffu, tmax);
   if (lane_id() == 0 && wmax > 0) atomicMax(&counters->bucket_max, wmax);
@@ -1288,6 +1327,7 @@ int launch_bounds(klsh_ctx* ctx, PassScratch& s, const uint32_t* keys_sorted, ui
   KTRY(dev_reserve(ctx, s.list_small, sizeof(uint32_t) * (n / 2 + 2)));
   KTRY(dev_reserve(ctx, s.list_large, sizeof(uint32_t) * 3 * (n / (KLSH_SMALL_MAX + 1) + 2)));
   KTRY(dev_reserve(ctx, s.list_big, sizeof(uint32_t) * 3 * (n / KLSH_BIG + 2)));
+  KTRY(dev_reserve(ctx, s.list_direct, sizeof(uint32_t) * 3 * ((size_t)ctx->max_direct + 2)));
   KTRY(dev_reserve(ctx, s.list_nested, sizeof(uint32_t) * (n / 2 + 2)));
   KTRY(dev_reserve(ctx, s.pos_nrm, sizeof(float) * (n + 2)));
   KTRY(dev_reserve(ctx, s.pos_h, (size_t)(ctx->ld <= 32 ? 64 : (ctx->ld <= 64 ? 128 : 2 * ((ctx->ld + 31) & ~31))) * (n + 2)));
@@ -1308,9 +1348,16 @@ int launch_classify(klsh_ctx* ctx, PassScratch& s, uint64_t n, int64_t nest_thre
   PassCounters* dc = s.counters.as<PassCounters>();
   KCUDA(ctx, cudaMemsetAsync(&dc->n_small, 0, sizeof(PassCounters) - offsetof(PassCounters, n_small), ctx->stream));
   // bucket count is on the device; launch enough threads for the worst case (n buckets)
-  k_classify<<<std::min<uint32_t>(cdiv64(n, 256), (uint32_t)ctx->sm_count * 8), 256, 0, ctx->stream>>>(s.bstart.as<uint32_t>(), n, (long long)nest_threshold, b_lo, b_hi, dc,
-                                                      s.list_small.as<uint32_t>(), s.list_large.as<uint32_t>(),
-                                                      s.list_big.as<uint32_t>(), s.list_nested.as<uint32_t>());
+  const uint32_t grid = std::min<uint32_t>(cdiv64(n, 256), (uint32_t)ctx->sm_count * 8);
+  const bool fallback = launch_merge_uses_fallback(ctx);
+  if (!fallback) {
+    k_size_hist<<<grid, 256, 0, ctx->stream>>>(s.bstart.as<uint32_t>(), n, b_lo, b_hi, (long long)nest_threshold, dc);
+    KLAUNCH(ctx);
+  }
+  k_classify<<<grid, 256, 0, ctx->stream>>>(s.bstart.as<uint32_t>(), n, (long long)nest_threshold, b_lo, b_hi,
+                                            fallback ? 0xFFFFFFFFu : ctx->direct_min, ctx->max_direct, dc,
+                                            s.list_small.as<uint32_t>(), s.list_large.as<uint32_t>(), s.list_big.as<uint32_t>(),
+                                            s.list_direct.as<uint32_t>(), s.list_nested.as<uint32_t>());
   KLAUNCH(ctx);
   return KLSH_OK;
 }
@@ -1491,6 +1538,32 @@ static int large_smem_config(klsh_ctx* ctx, int ld, int* rep_cap, size_t* smem) 
   return KLSH_OK;
 }
 
+// The windowed merge stages its window in shared memory (about 768 bytes per float of row width): rows
+// wider than that allows (D > ~280) and KLSH_MERGE_V1=1 go to the block-per-bucket kernel, which sizes
+// its representative cache from whatever shared memory there is and is exact for any D (and slow).
+bool launch_merge_uses_fallback(const klsh_ctx* ctx) {
+  return ctx->merge_v1 || merge_window_smem_bytes(ctx->ld) > (size_t)ctx->max_smem_optin;
+}
+
+static int launch_merge_fallback(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, const PassCounters& c) {
+  int rep_cap;
+  size_t smem;
+  KTRY(large_smem_config(ctx, ctx->ld, &rep_cap, &smem));
+  const uint32_t n_large = c.n_large + c.n_big;
+  uint32_t grid = std::min<uint32_t>(n_large, (uint32_t)ctx->sm_count);
+  uint64_t spill_stride = 0;
+  if ((int64_t)c.bucket_max > rep_cap) spill_stride = c.bucket_max - rep_cap;
+  KTRY(dev_reserve(ctx, ctx->io_b, sizeof(float) * (spill_stride * grid + 1)));
+  k_merge_large<<<grid, kLargeThreads, smem, ctx->stream>>>(ctx->cur.vals.as<float>(), ctx->D, ctx->ld, ctx->cur.cnt.as<int32_t>(),
+                                                            ctx->cur.head.as<int32_t>(), ctx->cur.tail.as<int32_t>(),
+                                                            ctx->cur.next.as<int32_t>(), rows_sorted, s.bstart.as<uint32_t>(),
+                                                            s.list_large.as<uint32_t>(), s.list_big.as<uint32_t>(),
+                                                            s.counters.as<PassCounters>(), threshold, rep_cap, ctx->io_b.as<float>(),
+                                                            spill_stride, -1);
+  KLAUNCH(ctx);
+  return KLSH_OK;
+}
+
 int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, const PassCounters& c) {
   const int D = ctx->D, ld = ctx->ld;
   float* vals = ctx->cur.vals.as<float>();
@@ -1499,44 +1572,68 @@ int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float thr
   int32_t* tail = ctx->cur.tail.as<int32_t>();
   int32_t* next = ctx->cur.next.as<int32_t>();
   PassCounters* dc = s.counters.as<PassCounters>();
-  const uint32_t n_small = c.n_small, n_large = c.n_large + c.n_big;
-  if (n_small) {
-    size_t per_warp = sizeof(float) * (size_t)KLSH_SMALL_MAX * (ld + 4);
-    int wpb = 4;
-    while (wpb > 1 && per_warp * wpb > (size_t)ctx->max_smem_optin - 1024) wpb >>= 1;
-    size_t smem = per_warp * wpb;
-    if (smem > (size_t)ctx->max_smem_optin) return klsh_fail(ctx, KLSH_ERR_ARG, "dimension %d too large", D);
-    if (smem > 48 * 1024)  // per device, so not cached process-wide
-      KCUDA(ctx, cudaFuncSetAttribute(k_merge_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    uint32_t grid = std::min<uint32_t>((n_small + wpb - 1) / wpb, (uint32_t)ctx->sm_count * 32);
-    k_merge_small<<<grid, wpb * 32, smem, ctx->stream>>>(vals, D, ld, cnt, head, tail, next, rows_sorted,
-                                                         s.bstart.as<uint32_t>(), s.list_small.as<uint32_t>(), dc,
-                                                         threshold, ctx->mg);
-    KLAUNCH(ctx);
+  const uint32_t n_small = c.n_small, n_large = c.n_large + c.n_big, n_direct = c.n_direct;
+  const bool v1 = launch_merge_uses_fallback(ctx);
+  // The few largest buckets are long sequential window chains: they start right away on cluster
+  // teams on the second stream and run beside the small buckets and the single-CTA stage.
+  bool forked = false;
+  if (n_direct && !v1) {
+    KCUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    KCUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
+    forked = true;
+    int rc = launch_merge_direct(ctx, s, rows_sorted, threshold, n_direct, c.bucket_max);
+    if (rc != KLSH_OK) {
+      cudaStreamSynchronize(ctx->stream2);
+      return rc;
+    }
+    KCUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
   }
-  if (!n_large) return KLSH_OK;
-  if (!ctx->merge_v1) return launch_merge_window(ctx, s, rows_sorted, threshold, n_large, c.bucket_max);
-  // first-generation kernel (KLSH_MERGE_V1=1): one block per bucket, kept for A/B checks
-  int rep_cap;
-  size_t smem;
-  KTRY(large_smem_config(ctx, ld, &rep_cap, &smem));
-  uint32_t grid = std::min<uint32_t>(n_large, (uint32_t)ctx->sm_count);
-  uint64_t spill_stride = 0;
-  if ((int64_t)c.bucket_max > rep_cap) spill_stride = c.bucket_max - rep_cap;
-  KTRY(dev_reserve(ctx, ctx->io_b, sizeof(float) * (spill_stride * grid + 1)));
-  k_merge_large<<<grid, kLargeThreads, smem, ctx->stream>>>(vals, D, ld, cnt, head, tail, next, rows_sorted,
-                                                            s.bstart.as<uint32_t>(), s.list_large.as<uint32_t>(),
-                                                            s.list_big.as<uint32_t>(), dc, threshold, rep_cap,
-                                                            ctx->io_b.as<float>(), spill_stride, -1);
-  KLAUNCH(ctx);
-  return KLSH_OK;
+  int rc = KLSH_OK;
+  do {
+    if (n_small) {
+      size_t per_warp = sizeof(float) * (size_t)KLSH_SMALL_MAX * (ld + 4);
+      int wpb = 4;
+      while (wpb > 1 && per_warp * wpb > (size_t)ctx->max_smem_optin - 1024) wpb >>= 1;
+      size_t smem = per_warp * wpb;
+      if (smem > (size_t)ctx->max_smem_optin) {
+        rc = klsh_fail(ctx, KLSH_ERR_ARG, "dimension %d too large", D);
+        break;
+      }
+      if (smem > 48 * 1024 &&  // per device, so not cached process-wide
+          cudaFuncSetAttribute(k_merge_small, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        rc = klsh_fail(ctx, KLSH_ERR_CUDA, "cudaFuncSetAttribute(k_merge_small) failed");
+        break;
+      }
+      uint32_t grid = std::min<uint32_t>((n_small + wpb - 1) / wpb, (uint32_t)ctx->sm_count * 32);
+      k_merge_small<<<grid, wpb * 32, smem, ctx->stream>>>(vals, D, ld, cnt, head, tail, next, rows_sorted,
+                                                           s.bstart.as<uint32_t>(), s.list_small.as<uint32_t>(), dc,
+                                                           threshold, ctx->mg);
+      ctx->launches++;
+      if (cudaGetLastError() != cudaSuccess) {
+        rc = klsh_fail(ctx, KLSH_ERR_CUDA, "k_merge_small launch failed");
+        break;
+      }
+    }
+    if (!(n_large + (v1 ? n_direct : 0u))) break;
+    if (!v1) {
+      rc = launch_merge_window(ctx, s, rows_sorted, threshold, n_large, c.n_direct ? std::min(c.bucket_max, c.direct_thr - 1u) : c.bucket_max);
+      break;
+    }
+    rc = launch_merge_fallback(ctx, s, rows_sorted, threshold, c);
+  } while (0);
+  if (forked) {
+    cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
+    if (e != cudaSuccess && rc == KLSH_OK) rc = klsh_fail(ctx, KLSH_ERR_CUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e));
+    if (rc != KLSH_OK) cudaStreamSynchronize(ctx->stream2);
+  }
+  return rc;
 }
 
 // klsh_p_cluster: rows_sorted[0..n) is ONE bucket
 int launch_merge_one(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, uint64_t n, float threshold) {
   if (n < 2) return KLSH_OK;
   KTRY(dev_reserve(ctx, s.counters, sizeof(PassCounters)));
-  if (!ctx->merge_v1) {
+  if (!launch_merge_uses_fallback(ctx)) {
     KTRY(dev_reserve(ctx, s.pos_nrm, sizeof(float) * (n + 2)));
     KTRY(dev_reserve(ctx, s.pos_h, (size_t)(ctx->ld <= 32 ? 64 : (ctx->ld <= 64 ? 128 : 2 * ((ctx->ld + 31) & ~31))) * (n + 2)));
     KTRY(dev_reserve(ctx, s.bstart, sizeof(uint32_t) * 4));

@@ -13,6 +13,7 @@
 #define KLSH_BIG 4096      // buckets at least this large are scheduled first
 
 struct PlaneSource;  // planes.cc
+struct MgComm;       // multi.cu
 
 struct HostBuf {  // grow-only pinned host buffer
   void* p = nullptr;
@@ -36,7 +37,9 @@ struct PassScratch {
   DevBuf bstart;                          // bucket start offsets (uint32, nb+1)
   DevBuf list_small, list_nested;   // bucket ids
   DevBuf list_big, list_large;      // windowed-merge work items {bucket, i, size}: >= KLSH_BIG rows / the rest
+  DevBuf list_direct;               // ... buckets of >= direct_min rows: straight to cluster teams on the second stream
   DevBuf esc1, esc2, esc3;          // buckets handed on: CTA -> cluster -> large cluster -> grid
+  DevBuf escb2, escb3;              // the same hand-over lists of the direct pipeline
   DevBuf pos_nrm;   // norm of the representative at each sorted position (merge scratch)
   DevBuf pos_h;     // unit-norm fp16 copy of the representative at each sorted position (merge scratch, D <= 64)
   DevBuf planes;    // H*ld floats
@@ -57,7 +60,13 @@ struct PassCounters {  // lives in device memory, mirrored to pinned host memory
   uint32_t large_cursor;
   uint32_t cluster_cursor;
   uint32_t cluster2_cursor;
-  uint32_t pad[3];
+  // direct pipeline (buckets of >= direct_min rows, second stream): its own lists and cursors
+  uint32_t n_direct;
+  uint32_t nb_esc2, nb_esc3;
+  uint32_t b_cursor1, b_cursor2;
+  uint32_t direct_thr;     // the threshold k_classify chose (rows)
+  uint32_t pad[1];
+  uint32_t size_hist[32];  // buckets to merge by floor(log2(rows)), classes above KLSH_SMALL_MAX
 };
 
 // Multi-GPU update logs (all null in single-GPU runs): rows whose values/metadata changed and the
@@ -77,6 +86,8 @@ struct RowState {  // everything klsh_snapshot copies
 struct klsh_ctx {
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // the direct pipeline of the merge runs here, concurrently with the rest
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   std::string err;
   uint64_t launches = 0;
   int sm_count = 148;
@@ -103,12 +114,13 @@ struct klsh_ctx {
   DevBuf io_a, io_b;  // staging for loads/exports
   DevBuf alive_alt;   // the other half of the alive-list ping-pong
   DevBuf nested_out;  // survivors of one nested pass
-  DevBuf team_ctl;    // per-team control blocks of the windowed merge
+  DevBuf team_ctl, team_ctl_b;  // per-team control blocks of the windowed merge (one set per pipeline)
   DevBuf exp_vals, exp_cnt, exp_head;  // export staging (device)
   DevBuf rank_buf, exp_offs, exp_slots; // chain ranking scratch, offsets and flat slot order (device)
   HostBuf h_slots;                     // flat slot order (pinned host)
   HostBuf h_cnt, h_head;               // export staging (pinned host)
   DevBuf eps_counter; // rows whose key needed the exact re-evaluation of at least one plane (cumulative)
+  MgComm* comm = nullptr;  // NCCL communicator + exchange buffers (klsh_mg_init)
   MgLog mg;           // multi-GPU update logs (null pointers unless a sharded pass is running)
   DevBuf mg_counts, mg_mod_rows, mg_next_slot, mg_next_val, mg_splits, mg_surv;
   uint32_t* mg_keys_sorted = nullptr;  // state of the sharded pass between klsh_mg_* calls
@@ -119,14 +131,22 @@ struct klsh_ctx {
   // escalation of the windowed merge: a bucket leaves its CTA for a cluster once it has more than
   // cta_max representatives, and the cluster for the whole grid above cluster_max
   uint32_t cta_max = 4096, cluster_max = 65536, cluster2_max = 1000000;  // measured on C2 (profiles/README.md)
+  // buckets with at least this many rows skip the single-CTA stage: they start on cluster teams on a
+  // second stream, so the long window chains of the few largest buckets run beside everything else
+  uint32_t direct_min = 8192;
+  uint32_t max_direct = 32;  // at most this many buckets take the direct pipeline per pass (about one per cluster team)
   int cluster_size = 8, cluster2_size = 16;
   int cluster_ctas_per_sm = 2;
   bool debug = false;     // KLSH_DEBUG=1
   DevBuf dbg;
+  bool no_spec = false;   // KLSH_NO_SPEC=1: windows are resolved by the sequential loop only
   bool merge_v1 = false;  // KLSH_MERGE_V1=1: first-generation block-per-bucket kernel (A/B checks)
   PassCounters* h_counters = nullptr;  // pinned
 
   PlaneSource* planes = nullptr;
+  klsh_done_fn draws_done_fn = nullptr;  // see klsh_set_draws_done_callback
+  void* draws_done_user = nullptr;
+  bool last_iteration = false, draws_done_fired = false;  // state of the running klsh_cluster call
   cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -153,6 +173,8 @@ void planes_free(PlaneSource* p);
 void planes_seed(PlaneSource* p, uint64_t seed);
 void planes_callback(PlaneSource* p, klsh_plane_fn fn, void* user);
 void planes_draw(PlaneSource* p, int H, int D, float* out);
+void planes_tell(const PlaneSource* p, uint64_t* seed, uint64_t* drawn);
+void planes_seek(PlaneSource* p, uint64_t seed, uint64_t drawn);
 
 // ---- io.cc -------------------------------------------------------------------------------------
 int io_save(const char* bin_path, int delfile, int64_t ignore_small, const float* values, int D,
@@ -177,6 +199,10 @@ int launch_apply_mod(klsh_ctx* ctx, const uint32_t* rows, uint32_t n, const floa
 int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, const PassCounters& c);
 int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, uint32_t n_items_host,
                         uint32_t bucket_max_host);
+int launch_merge_direct(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, uint32_t n_direct_host,
+                        uint32_t bucket_max_host);
+bool launch_merge_uses_fallback(const klsh_ctx* ctx);
+size_t merge_window_smem_bytes(int ld);
 int launch_merge_one(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, uint64_t n, float threshold);
 int launch_compact(klsh_ctx* ctx, PassScratch& s, const uint32_t* rows_sorted, uint64_t n, uint32_t* out);
 int launch_iota(klsh_ctx* ctx, uint32_t* out, uint64_t n, uint32_t base);

@@ -139,7 +139,8 @@ struct Team<2> {  // the whole cooperative grid
 struct TeamCtl {  // global memory, one per team
   uint32_t f[kW];  // per window candidate: first matching old representative (position), kInf if none
   uint32_t i, size, wb, work;
-  uint32_t pad[4];
+  uint32_t mode;  // 1: the next window is resolved by the sequential loop (after a mispredicted speculative window)
+  uint32_t pad[3];
 };
 
 struct MergeArgs {
@@ -165,7 +166,8 @@ struct MergeArgs {
   uint4* pos_h;
   TeamCtl* ctl;
   MgLog mg;
-  unsigned long long* dbg;  // [16] (8..13: leader cycles in stage/parallel/sync1/prefetch/resolve/sync2) windows, candidates, merges, undecidable, cache_full, back_exhausted, accepted, escalated
+  int no_spec;   // KLSH_NO_SPEC=1: sequential resolution only (A/B checks)
+  unsigned long long* dbg;  // [32] 26: speculative windows, 27: ... cut short; 0..7: windows, candidates, merges, undecidable, cache_full, back_exhausted, accepted, escalated; 8..13: leader cycles in stage/parallel/sync1/prefetch/decide/flush+sync2; 18..21: staging detail
   float threshold;
 };
 
@@ -197,23 +199,45 @@ struct Smem {
   int32_t* ptail;   // [kW]
   int32_t* mprev;   // [kW] merge log: previous candidate merged into the same entry (-1: none)
   int32_t* ment;    // [kW] merge log: dirty entry the candidate was merged into (-1: not merged)
+  // decision warp <-> mask helper warps (seqlock per dirty entry, see resolve_decide / mask_helpers)
+  uint32_t* dver;   // [kKD] version of the entry's value: odd while it is being written
+  uint32_t* mver;   // [kKD] version the published match mask belongs to
+  uint32_t* dmlo;   // [kKD] published match mask, window candidates 0..31
+  uint32_t* dmhi;   // [kKD] ... candidates 32..63
+  int32_t* dlast;   // [kKD] last candidate merged into the entry that carried ids (-1: none)
+  uint32_t* ro;     // [16] what the decision loop hands to the flush (RO_*)
   int ts;
 };
+
+enum { RO_A = 0, RO_ND, RO_I, RO_SIZE, RO_FROM_BACK, RO_BI, RO_MERGES, RO_BACK_EXH, RO_UNDEC, RO_FULL, RO_DONE, RO_EXAMINED, RO_WORDS = 16 };
+
+__device__ __forceinline__ void fence_cta() { asm volatile("fence.acq_rel.cta;" ::: "memory"); }
+__device__ __forceinline__ uint32_t ld_vol(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+__device__ __forceinline__ void st_vol(uint32_t* p, uint32_t v) { *reinterpret_cast<volatile uint32_t*>(p) = v; }
 
 // width (halfs) of the fp16 window copy: the k extent the kernel variant for this ld multiplies over
 __host__ __device__ inline int tc_width(int ld) { return ld <= 32 ? 32 : (ld <= 64 ? 64 : ((ld + 31) & ~31)); }
 
+// floats per staged row in shared memory: rows are zero-padded to the kernel variant's compile-time width
+// (32 or 64) so that the decision warp's chains have compile-time trip counts; adding the padded +0
+// products leaves every reference sum bit-identical
+__host__ __device__ inline int row_width(int ld) { return ld <= 32 ? 32 : (ld <= 64 ? 64 : ld); }
+
+__host__ __device__ inline size_t spec_bytes_for(int ld);
 __host__ __device__ inline size_t ring_bytes_for(int ld, int threads) {
-  return ld <= 64 ? (size_t)(threads / 32) * kRing * 32 * (tc_width(ld) / 32) * 16 : 0;
+  if (ld > 64) return 0;
+  const size_t ring = (size_t)(threads / 32) * kRing * 32 * (tc_width(ld) / 32) * 16;
+  const size_t spec = spec_bytes_for(ld);  // the speculative resolver's scratch lives in the idle ring
+  return ring > spec ? ring : ((spec + 15) & ~(size_t)15);
 }
 __host__ __device__ inline size_t smem_bytes_for(int ld, int threads) {
   const int hs = tc_width(ld) + 8;
-  return sizeof(float) * ((size_t)(2 * kW + kKD) * (ld + 4) + kW + kKD) + sizeof(uint32_t) * (kW * 14 + kKD * 5) + 64 +
+  return sizeof(float) * ((size_t)(2 * kW + kKD) * (row_width(ld) + 4) + kW + kKD) + sizeof(uint32_t) * (kW * 14 + kKD * 10 + RO_WORDS) + 64 +
          sizeof(__half) * (size_t)kW * hs + 16 + sizeof(uint32_t) * (kSurvCap + 1) + ring_bytes_for(ld, threads);
 }
 
 __device__ __forceinline__ void carve(Smem& s, float* base, int ld) {
-  s.ts = ld + 4;
+  s.ts = row_width(ld) + 4;
   s.tile = base;
   s.dvals = s.tile + (size_t)kW * s.ts;
   s.pre = s.dvals + (size_t)kKD * s.ts;
@@ -238,6 +262,12 @@ __device__ __forceinline__ void carve(Smem& s, float* base, int ld) {
   s.ptail = reinterpret_cast<int32_t*>(u); u += kW;
   s.mprev = reinterpret_cast<int32_t*>(u); u += kW;
   s.ment = reinterpret_cast<int32_t*>(u); u += kW;
+  s.dver = u; u += kKD;
+  s.mver = u; u += kKD;
+  s.dmlo = u; u += kKD;
+  s.dmhi = u; u += kKD;
+  s.dlast = reinterpret_cast<int32_t*>(u); u += kKD;
+  s.ro = u; u += RO_WORDS;
   s.hs = tc_width(ld) + 8;  // +8 halfs: rows 16 bytes apart modulo 128 -> conflict-free fragment loads
   s.htile = reinterpret_cast<__half*>(u + 4);
   s.surv = reinterpret_cast<uint32_t*>(s.htile + (size_t)kW * s.hs);  // kW*hs halves: a multiple of 16 bytes
@@ -463,18 +493,60 @@ __device__ __forceinline__ void tc_compare_wide(const MergeArgs& A, const uint32
   }
 }
 
-// ---- the resolver: warp 0 of the team's leader CTA ---------------------------------------------------
-// Lane e owns dirty-cache entry e: its position, member count and a 64-bit mask of the window
-// candidates that match the entry's CURRENT value (recomputed, for all unexamined candidates at once,
-// whenever the entry changes; the new norm comes out of the same pass).  Examining a candidate is
-// then a handful of bit tests; the floating-point work happens once per merge.  Member-chain
-// splices and the swap-remove writes are independent of the decisions, so they are logged and
-// applied in parallel when the window ends.
-template <int TEAM>
-__device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm, uint4* seg_h, int qh, TeamCtl* ctl, Smem& s,
-                               int W, int wf, int wb, bool tail_mode, uint32_t i0, uint32_t size0) {
-  const int D = A.D, ld = A.ld, nq = ld >> 2;
+// ---- window resolution in the team's leader CTA ---------------------------------------------------------
+// Warp 0 replays the reference's sequential order over the window (resolve_decide).  Representatives
+// modified inside the window live in a dirty cache of kKD entries; lane e of the decision warp owns
+// entry e: its position, member count and a 64-bit mask of the window candidates that match the
+// entry's CURRENT value.  A mask goes stale whenever the entry is modified.  Stale masks are NOT
+// rebuilt by the decision warp: the CTA's other warps (mask_helpers) rebuild them concurrently under a
+// per-entry seqlock (dver odd = being written; a mask is valid iff its version equals the entry's),
+// while the decision warp compares each candidate with the stale entries' current values exactly,
+// lane per entry, which costs one mul+add chain per candidate however many entries are stale.  Runs of
+// candidates that cannot merge (no old match, no pair bit, no dirty match) are accepted in one step as
+// soon as every mask is valid again.  Member-chain splices, swap-remove writes and the modified
+// rows are independent of the decisions: they are logged and applied by the whole CTA afterwards
+// (flush_window).
+// Fast pre-test of candidate x entry: dot and |entry|^2 with fused multiply-adds in four independent
+// accumulators.  Against the reference's mul-then-add chains the cosine it yields is off by less than
+// (4D+40)*2^-24 (products and D-1 additions rounded once each on both sides: 2*gamma_D on the dot,
+// gamma_D/2 + u per norm, rsqrt and the final divisions a few u, the reference's 1-(1-sim) at most
+// 2^-23), provided the norms are far from the denormal and overflow ranges.  Outside that band the
+// decision is therefore the reference's; inside it (or with unsafe norms, NaN, inf) the exact chain decides.
+template <int NQ>
+__device__ __forceinline__ void fast_dot_nn(const float4* c4, const float4* r4, int nq, float& dot, float& nn) {
+  float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f, n0 = 0.f, n1 = 0.f, n2 = 0.f, n3 = 0.f;
+  if (NQ > 0) {
+#pragma unroll 4
+    for (int q = 0; q < NQ; ++q) {
+      const float4 x = c4[q], y = r4[q];
+      d0 = __fmaf_rn(x.x, y.x, d0); n0 = __fmaf_rn(y.x, y.x, n0);
+      d1 = __fmaf_rn(x.y, y.y, d1); n1 = __fmaf_rn(y.y, y.y, n1);
+      d2 = __fmaf_rn(x.z, y.z, d2); n2 = __fmaf_rn(y.z, y.z, n2);
+      d3 = __fmaf_rn(x.w, y.w, d3); n3 = __fmaf_rn(y.w, y.w, n3);
+    }
+  } else {
+#pragma unroll 4
+    for (int q = 0; q < nq; ++q) {
+      const float4 x = c4[q], y = r4[q];
+      d0 = __fmaf_rn(x.x, y.x, d0); n0 = __fmaf_rn(y.x, y.x, n0);
+      d1 = __fmaf_rn(x.y, y.y, d1); n1 = __fmaf_rn(y.y, y.y, n1);
+      d2 = __fmaf_rn(x.z, y.z, d2); n2 = __fmaf_rn(y.z, y.z, n2);
+      d3 = __fmaf_rn(x.w, y.w, d3); n3 = __fmaf_rn(y.w, y.w, n3);
+    }
+  }
+  dot = (d0 + d1) + (d2 + d3);
+  nn = (n0 + n1) + (n2 + n3);
+}
+
+template <int TEAM, int DR>
+__device__ void resolve_decide(const MergeArgs& A, Smem& s, int W, int wf, int wb, bool tail_mode, uint32_t i0, uint32_t size0) {
+  constexpr int NQ = DR / 4;  // 0: run-time width
+  const int D = A.D, ld = A.ld, nq = NQ > 0 ? NQ : (ld >> 2);
+  const int ts = NQ > 0 ? DR + 4 : s.ts;
   const uint32_t lane = lane_id();
+  const float thr = A.threshold;
+  const float band = (4.f * (float)D + 40.f) * 5.9604645e-8f;
+  const float thr_hi = thr + band, thr_lo = thr - band;
   int nd = 0, a = 0, fi = 0, bi = 0, merges = 0;
   uint32_t i = i0, size = size0;
   bool from_back = false, back_exhausted = false;
@@ -482,67 +554,12 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
   uint32_t accd_lo = 0, accd_hi = 0;  // accepted-in-window candidates that have since been modified
   uint32_t accm_lo = 0, accm_hi = 0;  // accepted-in-window candidates (tile indices)
   uint32_t my_dpos = kInf, my_dm_lo = 0, my_dm_hi = 0;  // this lane's dirty entry
+  uint32_t my_ver = 0;                                  // version of its value (even)
+  bool my_valid = true;                                 // its mask belongs to that version (lanes without an entry: true)
   int my_dcnt = 0, my_last = -1;                        // its member count; last candidate merged into it
-  // The entry modified by the latest merge keeps an INVALID mask: runs of candidates merging into the
-  // same representative (the common shape of a merge-heavy bucket) then cost one exact comparison
-  // each instead of a whole-window mask rebuild.  The mask is rebuilt when another entry is modified
-  // or a candidate is accepted.
-  uint32_t inval = 0;  // entries whose match mask is stale (modified since it was built)
-  int pend = -1;       // the entry whose norm is stale too (modified by the latest merge)
-  // which unexamined candidates match entry e's current value; its norm falls out of the same pass
-  long long pv = 0, pa = 0, pm = 0;
-  int nval = 0;
   const bool rprof = A.dbg != nullptr;
-  auto validate = [&](int e) {
-    const long long tv0 = rprof ? clock64() : 0;
-    ++nval;
-    const float4* r4 = reinterpret_cast<const float4*>(s.dvals + (size_t)e * s.ts);
-    const int nfront = tail_mode ? max(0, wf - fi - bi) : (wf - fi);
-    const int nback = tail_mode ? 0 : (wb - bi);
-    const int nun = nfront + nback;
-    uint32_t w0 = 0, w1 = 0;
-    float rn = 0.f;
-    for (int base = 0; base < max(nun, 1); base += 32) {
-      const int k = base + (int)lane;
-      const bool act = k < nun;
-      const int tc = act ? (k < nfront ? fi + k : wf + bi + (k - nfront)) : 0;
-      const float4* c4 = reinterpret_cast<const float4*>(s.tile + (size_t)tc * s.ts);
-      float dot = 0.f, nn = 0.f;
-      if (base == 0) {  // the entry's norm comes out of the first pass
-#pragma unroll 4
-        for (int q = 0; q < nq; ++q) {
-          const float4 x = c4[q], y = r4[q];
-          dot = __fadd_rn(dot, __fmul_rn(x.x, y.x)); nn = __fadd_rn(nn, __fmul_rn(y.x, y.x));
-          dot = __fadd_rn(dot, __fmul_rn(x.y, y.y)); nn = __fadd_rn(nn, __fmul_rn(y.y, y.y));
-          dot = __fadd_rn(dot, __fmul_rn(x.z, y.z)); nn = __fadd_rn(nn, __fmul_rn(y.z, y.z));
-          dot = __fadd_rn(dot, __fmul_rn(x.w, y.w)); nn = __fadd_rn(nn, __fmul_rn(y.w, y.w));
-        }
-        rn = __fsqrt_rn(nn);
-      } else {
-#pragma unroll 4
-        for (int q = 0; q < nq; ++q) {
-          const float4 x = c4[q], y = r4[q];
-          dot = __fadd_rn(dot, __fmul_rn(x.x, y.x));
-          dot = __fadd_rn(dot, __fmul_rn(x.y, y.y));
-          dot = __fadd_rn(dot, __fmul_rn(x.z, y.z));
-          dot = __fadd_rn(dot, __fmul_rn(x.w, y.w));
-        }
-      }
-      const bool mt = act && cos_match(dot, s.cnorm[tc], rn, A.threshold);
-      const uint32_t blo = (mt && tc < 32) ? (1u << tc) : 0u, bhi = (mt && tc >= 32) ? (1u << (tc - 32)) : 0u;
-      w0 |= __reduce_or_sync(0xffffffffu, blo);
-      w1 |= __reduce_or_sync(0xffffffffu, bhi);
-    }
-    if ((int)lane == e) {
-      my_dm_lo = w0;
-      my_dm_hi = w1;
-    }
-    if (lane == 0) s.dnorm[e] = rn;
-    if (rprof) pv += clock64() - tv0;
-  };
-  // s.pair is dead once a candidate has been examined; reuse the per-candidate slots s.acc/... no:
-  // the merge log lives in s.pridx (prefetch row index, dead after the entry was allocated) as
-  // "previous candidate merged into the same entry" (kInf: none) and s.pcnt as the entry index.
+  long long p_top = 0, p_cmp = 0, p_bc = 0, p_mrg = 0, tq0 = 0, tq1 = 0;
+  int n_run = 0, n_cmp = 0, n_it = 0, n_exact = 0;
   // Candidates with no old match and no match bit against any other window row ("easy") can only merge
   // into a representative modified in this window; while every dirty mask is valid that is one bit
   // test, so whole runs of them are accepted at once instead of one loop trip each.
@@ -555,6 +572,16 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
     easy_hi = __ballot_sync(0xffffffffu, e1);
   }
   while (i < size) {
+    if (rprof) tq0 = clock64();
+    ++n_it;
+    // masks the helper warps have finished since the last look
+    if (!my_valid && ld_vol(s.mver + lane) == my_ver) {
+      fence_cta();
+      my_dm_lo = ld_vol(s.dmlo + lane);
+      my_dm_hi = ld_vol(s.dmhi + lane);
+      my_valid = true;
+    }
+    const uint32_t inval = __ballot_sync(0xffffffffu, !my_valid);  // entries whose match mask is stale
     if (!from_back && inval == 0u && fi < wf) {
       uint32_t any_lo = 0u, any_hi = 0u;
       if (nd > 0) {
@@ -573,6 +600,8 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
         a += k;
         i += (uint32_t)k;
         fi += k;
+        ++n_run;
+        if (rprof) p_top += clock64() - tq0;
         continue;
       }
     }
@@ -584,68 +613,58 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
       if (!tail_mode && fi >= wf) break;
       t = fi;
     }
+    // everything the trip needs about the candidate, requested together
     const uint32_t fpos = s.s_f[t];
     const uint32_t plo = s.pair[2 * t], phi = s.pair[2 * t + 1];
+    const float cn = s.cnorm[t];
+    const int c1 = s.ccnt[t];
+    const int ct_tail = s.ctail[t];
+    const float4* c4 = reinterpret_cast<const float4*>(s.tile + (size_t)t * ts);
     const uint32_t tbit_lo = (t < 32) ? (1u << t) : 0u, tbit_hi = (t < 32) ? 0u : (1u << (t - 32));
-    if (inval != 0u) {
-      // Stale masks still predict well.  If nothing suggests that t merges, it will be accepted and the
-      // masks would be rebuilt right after its exact comparisons: rebuild them first (t is still in
-      // the unexamined set, so its bits come out of the same pass) and skip those comparisons.
-      const bool stale_hit = ((my_dm_lo & tbit_lo) | (my_dm_hi & tbit_hi)) != 0u;
-      const bool likely = fpos != kInf || ((plo & accm_lo) | (phi & accm_hi)) != 0u || __any_sync(0xffffffffu, stale_hit);
-      if (!likely) {
-        while (inval != 0u) {
-          const int e2 = __ffs(inval) - 1;
-          inval &= inval - 1;
-          validate(e2);
-        }
-        pend = -1;
-      }
-    }
     if (from_back) ++bi; else ++fi;
     uint32_t best = kInf;
+    if (rprof) {
+      tq1 = clock64();
+      p_top += tq1 - tq0;
+    }
     if (nd > 0) {
-      // (a) representatives modified in this window: match bits against their current values; the
-      // entry with an invalid mask is compared exactly (every lane computes the same comparison)
-      bool hit = ((my_dm_lo & tbit_lo) | (my_dm_hi & tbit_hi)) != 0u;
+      // (a) representatives modified in this window: match bits against their current values where the
+      // mask is valid; where it is stale, lane e tests the candidate against entry e's current value
+      bool hit = my_valid && ((my_dm_lo & tbit_lo) | (my_dm_hi & tbit_hi)) != 0u;
       if (inval != 0u) {
-        // entries with a stale mask: lane e compares the candidate with entry e's current value.  Only
-        // the entry modified last (pend) needs a new norm as well: a lane that owns no stale entry
-        // accumulates entry x entry in the same instruction stream, so the warp walks ONE chain of
-        // mul+add per lane instead of two.
-        const bool mine = (inval >> lane) & 1u;
-        const uint32_t spare = ~inval;
-        const int nl = (pend >= 0 && spare != 0u) ? (__ffs(spare) - 1) : -1;
-        const bool normer = (int)lane == nl;
-        const bool inline_nn = pend >= 0 && nl < 0;  // all 32 entries stale: the owner walks both chains
-        const int er = mine ? (int)lane : (normer ? pend : 0);
-        const float4* r4 = reinterpret_cast<const float4*>(s.dvals + (size_t)er * s.ts);
-        const float4* c4 = normer ? r4 : reinterpret_cast<const float4*>(s.tile + (size_t)t * s.ts);
-        float dot = 0.f, nn = 0.f;
-#pragma unroll 4
-        for (int q = 0; q < nq; ++q) {
-          const float4 x = c4[q], y = r4[q];
-          dot = __fadd_rn(dot, __fmul_rn(x.x, y.x));
-          dot = __fadd_rn(dot, __fmul_rn(x.y, y.y));
-          dot = __fadd_rn(dot, __fmul_rn(x.z, y.z));
-          dot = __fadd_rn(dot, __fmul_rn(x.w, y.w));
-          if (inline_nn) {
-            nn = __fadd_rn(nn, __fmul_rn(y.x, y.x));
-            nn = __fadd_rn(nn, __fmul_rn(y.y, y.y));
-            nn = __fadd_rn(nn, __fmul_rn(y.z, y.z));
-            nn = __fadd_rn(nn, __fmul_rn(y.w, y.w));
-          }
-        }
-        float rn_p = 0.f;
-        if (pend >= 0) rn_p = __shfl_sync(0xffffffffu, __fsqrt_rn(inline_nn ? nn : dot), inline_nn ? pend : nl);
+        ++n_cmp;
+        const bool mine = !my_valid;
+        const float4* r4 = reinterpret_cast<const float4*>(s.dvals + (size_t)(mine ? lane : 0u) * ts);
+        float dot, nn;
+        fast_dot_nn<NQ>(c4, r4, nq, dot, nn);
+        const float rn = sqrtf(nn);
+        const float prod = cn * rn;
+        const float sim = __fdividef(dot, prod);
+        const bool safe = prod > 1e-18f && prod < 1e18f;
+        bool amb = false;
         if (mine) {
-          const float rn = ((int)lane == pend) ? rn_p : s.dnorm[lane];
-          hit = cos_match(dot, s.cnorm[t], rn, A.threshold);
-          if ((int)lane == pend) s.dnorm[lane] = rn_p;
+          hit = safe && sim >= thr_hi;
+          amb = !hit && !(safe && sim < thr_lo);
         }
-        pend = -1;  // the latest entry's norm is now published
+        if (__any_sync(0xffffffffu, amb)) {  // inside the error band: the reference's own arithmetic decides
+          ++n_exact;
+          float de = 0.f, ne = 0.f;
+#pragma unroll 4
+          for (int q = 0; q < nq; ++q) {
+            const float4 x = c4[q], y = r4[q];
+            de = __fadd_rn(de, __fmul_rn(x.x, y.x)); ne = __fadd_rn(ne, __fmul_rn(y.x, y.x));
+            de = __fadd_rn(de, __fmul_rn(x.y, y.y)); ne = __fadd_rn(ne, __fmul_rn(y.y, y.y));
+            de = __fadd_rn(de, __fmul_rn(x.z, y.z)); ne = __fadd_rn(ne, __fmul_rn(y.z, y.z));
+            de = __fadd_rn(de, __fmul_rn(x.w, y.w)); ne = __fadd_rn(ne, __fmul_rn(y.w, y.w));
+          }
+          if (amb) hit = cos_match(de, cn, __fsqrt_rn(ne), thr);
+        }
       }
       best = __reduce_min_sync(0xffffffffu, hit ? my_dpos : kInf);
+    }
+    if (rprof) {
+      tq0 = clock64();
+      p_cmp += tq0 - tq1;
     }
     // (b) first matching old representative as of the window start
     if (fpos != kInf) {
@@ -681,175 +700,668 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
     }
     if (best == kInf) {
       // no merge: the candidate becomes representative i (its norm is published with the flush)
-      // an accept usually means more accepts follow: rebuild the stale masks once so that the
-      // following candidates are decided by bit tests alone
-      while (inval != 0u) {
-        const int e2 = __ffs(inval) - 1;
-        inval &= inval - 1;
-        validate(e2);
-      }
-      pend = -1;
       if (lane == 0) s.acc[a] = (uint32_t)t;
       accm_lo |= tbit_lo;
       accm_hi |= tbit_hi;
       ++a;
       ++i;
       from_back = false;
+      if (rprof) p_bc += clock64() - tq0;
       continue;
     }
     // merge the candidate into the representative at position `best`
-    const long long tm0 = rprof ? clock64() : 0;
+    if (rprof) {
+      tq1 = clock64();
+      p_bc += tq1 - tq0;
+    }
     const uint32_t p = best;
-    int e;
+    const uint32_t em = __ballot_sync(0xffffffffu, my_dpos == p);
+    const bool fresh = em == 0u;
+    const int e = fresh ? nd : (__ffs(em) - 1);
+    // seqlock: the entry's version is odd while its value is being written
+    const uint32_t ver_e = __shfl_sync(0xffffffffu, my_ver, e);
+    if (lane == 0) st_vol(s.dver + e, ver_e + 1u);
+    fence_cta();
+    // the representative's value before this merge: its cache entry, or (first modification in this
+    // window) the prefetched row of an old representative / the window row of an accepted candidate
+    const float* src;
+    int c2;
+    if (!fresh) {
+      src = s.dvals + (size_t)e * ts;
+      c2 = __shfl_sync(0xffffffffu, my_dcnt, e);
+    } else if (p < i0) {
+      // an old representative enters the cache only as this candidate's precomputed first match
+      // (any other old position in `best` is already dirty), so its row was prefetched
+      src = s.pre + (size_t)t * ts;
+      c2 = s.pcnt[t];
+      if (lane == 0) {
+        s.dridx[e] = s.pridx[t];
+        s.dhead[e] = s.phead[t];
+        s.dtail[e] = s.ptail[t];
+        s.dpos[e] = p;
+      }
+    } else {
+      __syncwarp();  // s.acc[] is written by lane 0
+      const uint32_t u = s.acc[p - i0];
+      src = s.tile + (size_t)u * ts;
+      c2 = s.ccnt[u];
+      if (lane == 0) {
+        s.dridx[e] = s.ridx[u];
+        s.dhead[e] = s.chead[u];
+        s.dtail[e] = s.ctail[u];
+        s.dpos[e] = p;
+      }
+      if (u < 32) accd_lo |= 1u << u; else accd_hi |= 1u << (u - 32);
+    }
     {
-      const uint32_t m = __ballot_sync(0xffffffffu, my_dpos == p);
-      if (m) {
-        e = __ffs(m) - 1;
-      } else {
-        e = nd++;
-        float* dst = s.dvals + (size_t)e * s.ts;
-        int cnt_e;
-        if (p < i0) {
-          // an old representative enters the cache only as this candidate's precomputed first match
-          // (any other old position in `best` is already dirty), so its row was prefetched
-          const float* src = s.pre + (size_t)t * s.ts;
-          for (int d = lane; d < ld; d += 32) dst[d] = src[d];
-          cnt_e = s.pcnt[t];
-          if (lane == 0) {
-            s.dridx[e] = s.pridx[t];
-            s.dhead[e] = s.phead[t];
-            s.dtail[e] = s.ptail[t];
-          }
-        } else {
-          __syncwarp();
-          const uint32_t u = s.acc[p - i0];
-          const float* src = s.tile + (size_t)u * s.ts;
-          for (int d = lane; d < ld; d += 32) dst[d] = src[d];
-          cnt_e = s.ccnt[u];
-          if (lane == 0) {
-            s.dridx[e] = s.ridx[u];
-            s.dhead[e] = s.chead[u];
-            s.dtail[e] = s.ctail[u];
-          }
-          if (u < 32) accd_lo |= 1u << u; else accd_hi |= 1u << (u - 32);
-        }
-        if (lane == 0) s.dpos[e] = p;
-        if ((int)lane == e) {
-          my_dpos = p;
-          my_dcnt = cnt_e;
-          my_last = -1;
-        }
-        __syncwarp();
+      const float* c = s.tile + (size_t)t * ts;
+      float* r = s.dvals + (size_t)e * ts;
+      for (int d = lane; d < ld; d += 32) {
+        const float v = src[d];
+        r[d] = d < D ? consensus1(c[d], c1, v, c2) : v;
       }
     }
-    const int c1 = s.ccnt[t];
-    const int c2 = __shfl_sync(0xffffffffu, my_dcnt, e);
+    // merge log: which candidate was merged into this entry just before t (applied by the flush)
     {
-      const float* c = s.tile + (size_t)t * s.ts;
-      float* r = s.dvals + (size_t)e * s.ts;
-      for (int d = lane; d < D; d += 32) r[d] = consensus1(c[d], c1, r[d], c2);
-    }
-    // merge log: which candidate was merged into this entry just before t (applied at window end)
-    {
-      const int prev = __shfl_sync(0xffffffffu, my_last, e);
+      const int prev = fresh ? -1 : __shfl_sync(0xffffffffu, my_last, e);
       if (lane == 0) {
         s.mprev[t] = prev;
         s.ment[t] = e;
       }
       if ((int)lane == e) {
+        if (fresh) {
+          my_dpos = p;
+          my_last = -1;
+        }
         my_dcnt = c1 + c2;
-        if (s.ctail[t] >= 0) my_last = t;  // only candidates that carry ids take part in the chain
+        if (ct_tail >= 0) my_last = t;  // only candidates that carry ids take part in the chain
+        my_ver = ver_e + 2u;
+        my_valid = false;
       }
     }
+    fence_cta();
+    __syncwarp();
+    if (lane == 0) {
+      st_vol(s.dver + e, ver_e + 2u);
+      if (fresh) {
+        fence_cta();
+        st_vol(s.ro + RO_ND, (uint32_t)(nd + 1));  // the helpers may look at the entry from now on
+      }
+    }
+    if (fresh) ++nd;
     --size;
     ++merges;
     from_back = true;
-    __syncwarp();
-    inval |= 1u << e;
-    pend = e;
-    if (rprof) pm += clock64() - tm0;
+    if (rprof) p_mrg += clock64() - tq1;
     if (nd == kKD) { dbg_full = 1; break; }  // dirty cache full: flush and start a new window
   }
   __syncwarp();
-  if (pend >= 0) validate(pend);  // publishes the latest entry's norm
+  if (rprof && lane == 0) {
+    atomicAdd(A.dbg + 14, (unsigned long long)p_top);
+    atomicAdd(A.dbg + 15, (unsigned long long)p_cmp);
+    atomicAdd(A.dbg + 16, (unsigned long long)p_bc);
+    atomicAdd(A.dbg + 17, (unsigned long long)p_mrg);
+    atomicAdd(A.dbg + 22, (unsigned long long)n_it);
+    atomicAdd(A.dbg + 23, (unsigned long long)n_run);
+    atomicAdd(A.dbg + 24, (unsigned long long)n_cmp);
+    atomicAdd(A.dbg + 25, (unsigned long long)n_exact);
+  }
+  if ((int)lane < nd) {
+    s.dcnt[lane] = my_dcnt;
+    s.dlast[lane] = my_last;
+  }
+  if (lane == 0) {
+    s.ro[RO_A] = (uint32_t)a;
+    s.ro[RO_I] = i;
+    s.ro[RO_SIZE] = size;
+    s.ro[RO_FROM_BACK] = from_back ? 1u : 0u;
+    s.ro[RO_BI] = (uint32_t)bi;
+    s.ro[RO_MERGES] = (uint32_t)merges;
+    s.ro[RO_BACK_EXH] = back_exhausted ? 1u : 0u;
+    s.ro[RO_UNDEC] = (uint32_t)dbg_undec;
+    s.ro[RO_FULL] = (uint32_t)dbg_full;
+    s.ro[RO_EXAMINED] = (uint32_t)(fi + bi);
+  }
+  fence_cta();
   __syncwarp();
-  const long long ta0 = rprof ? clock64() : 0;
-  // ---- apply the window's effects to global memory, in parallel ----
-  // accepted candidates: positions i0.. in acceptance order (row index + norm)
-  for (int k = lane; k < a; k += 32) {
-    const uint32_t u = s.acc[k];
-    seg[i0 + k] = s.ridx[u];
-    pos_nrm[i0 + k] = s.cnorm[u];
-  }
-  if (qh) {
-    // fp16 copies: accepted candidates take theirs from the window's fp16 tile, modified
-    // representatives are re-scaled from their current value and norm
-    for (int idx = lane; idx < a * qh; idx += 32) {
-      const int k = idx / qh, c = idx - k * qh;
-      seg_h[(size_t)(i0 + k) * qh + c] = h16_chunk_from_htile(s.htile + (size_t)s.acc[k] * s.hs, c);
+  if (lane == 0) st_vol(s.ro + RO_DONE, 1u);
+}
+
+// The CTA's other warps while warp 0 decides: rebuild the match masks of modified entries.  Helper
+// hw looks after entries hw, hw + nh, ...  A mask is computed for ALL window candidates against one
+// version of the entry's value and published only if the version is unchanged afterwards.
+__device__ void mask_helpers(const MergeArgs& A, Smem& s, int W, int hw, int nh) {
+  const int nq = A.ld >> 2;
+  const uint32_t lane = lane_id();
+  for (;;) {
+    bool did = false;
+    const int nd = (int)__shfl_sync(0xffffffffu, ld_vol(s.ro + RO_ND), 0);
+    for (int e = hw; e < nd; e += nh) {
+      const uint32_t v1 = __shfl_sync(0xffffffffu, ld_vol(s.dver + e), 0);
+      const uint32_t mv = __shfl_sync(0xffffffffu, ld_vol(s.mver + e), 0);
+      if ((v1 & 1u) || v1 == mv) continue;
+      fence_cta();
+      const float4* r4 = reinterpret_cast<const float4*>(s.dvals + (size_t)e * s.ts);
+      uint32_t w[2] = {0u, 0u};
+      float rn = 0.f;
+#pragma unroll
+      for (int half = 0; half < 2; ++half) {
+        if (half * 32 >= W) break;
+        const int tc = half * 32 + (int)lane;
+        const float4* c4 = reinterpret_cast<const float4*>(s.tile + (size_t)min(tc, W - 1) * s.ts);
+        float dot = 0.f, nn = 0.f;
+        if (half == 0) {  // the entry's norm comes out of the first pass (every lane walks the same chain)
+#pragma unroll 4
+          for (int q = 0; q < nq; ++q) {
+            const float4 x = c4[q], y = r4[q];
+            dot = __fadd_rn(dot, __fmul_rn(x.x, y.x)); nn = __fadd_rn(nn, __fmul_rn(y.x, y.x));
+            dot = __fadd_rn(dot, __fmul_rn(x.y, y.y)); nn = __fadd_rn(nn, __fmul_rn(y.y, y.y));
+            dot = __fadd_rn(dot, __fmul_rn(x.z, y.z)); nn = __fadd_rn(nn, __fmul_rn(y.z, y.z));
+            dot = __fadd_rn(dot, __fmul_rn(x.w, y.w)); nn = __fadd_rn(nn, __fmul_rn(y.w, y.w));
+          }
+          rn = __fsqrt_rn(nn);
+        } else {
+          dot = dot_seq(c4, r4, nq);
+        }
+        const bool mt = tc < W && cos_match(dot, s.cnorm[min(tc, W - 1)], rn, A.threshold);
+        w[half] = __ballot_sync(0xffffffffu, mt);
+      }
+      fence_cta();
+      const uint32_t v2 = __shfl_sync(0xffffffffu, ld_vol(s.dver + e), 0);
+      if (v2 == v1) {
+        if (lane == 0) {
+          st_vol(s.dmlo + e, w[0]);
+          st_vol(s.dmhi + e, w[1]);
+          fence_cta();
+          st_vol(s.mver + e, v1);
+        }
+        did = true;
+      }
     }
-    __syncwarp();  // an accepted candidate modified later in the window is rewritten below
-    for (int idx = lane; idx < nd * qh; idx += 32) {
-      const int e = idx / qh, c = idx - e * qh;
-      seg_h[(size_t)s.dpos[e] * qh + c] = h16_chunk_from_row(s.dvals + (size_t)e * s.ts, ld, s.dnorm[e], c);
+    if (__shfl_sync(0xffffffffu, ld_vol(s.ro + RO_DONE), 0)) break;
+    if (!did) __nanosleep(64);
+  }
+}
+
+// ---- speculative window resolution -----------------------------------------------------------------------
+// The sequential loop above is bound by the latency of one warp's dependent instructions (about 1.5 k
+// cycles per candidate).  Almost all of that is floating point that rarely changes a decision: a
+// candidate merges into the first representative that matched it at the window start, or into an earlier
+// window candidate it has a pair bit with, or becomes a representative.  So the window is resolved in
+// four parallel-friendly passes and the sequential loop is only the fallback:
+//   scan    (warp 0, integers only) replays the reference's order with PREDICTED decisions: first old
+//           match, else earliest accepted candidate with a pair bit, else accept.  It records, per
+//           examined candidate x, everything the prediction depended on, and per merge a version link;
+//   versions (all warps, one entry's chain per warp) computes the consensus values every predicted merge
+//           produces, with the reference's exact arithmetic;
+//   match   (all warps) tests every examined candidate against the CURRENT version, at its turn, of every
+//           representative modified before it (fast test + exact chain inside its error band);
+//   verify  (warp 0, lane per candidate) derives the TRUE decision each candidate would get if everything
+//           before it went as predicted.  The first candidate whose true decision differs from the
+//           prediction cuts the window: everything before it is exactly what the sequential algorithm
+//           does (by induction over the examine order) and is committed; the rest is re-examined by the
+//           next window, which then runs the sequential loop once (so a hard spot cannot stall progress).
+struct Spec {
+  float* vers;        // [kW][ts] value after predicted merge k
+  unsigned long long* emask;  // [kKD] merges (bit k) that went into the entry, in merge order
+  int32_t* vcnt;      // [kW] member count after merge k
+  uint32_t* xtarget;  // [kW] predicted position (kInf: accept) per examined candidate
+  uint32_t* snap_i;   // [kW+1] i before examine index x
+  uint32_t* snap_size;  // [kW+1]
+  uint32_t* snap_pk;  // [kW+1] fi | bi<<8 | a<<16 | nd<<24
+  uint32_t* snap_pk2; // [kW+1] merges | from_back<<8
+  uint32_t* acc_lo;   // [kW] accepted candidates before x (tile index bits 0..31)
+  uint32_t* acc_hi;   // [kW]
+  uint32_t* accd_lo;  // [kW] ... of those, the ones modified before x
+  uint32_t* accd_hi;  // [kW]
+  uint32_t* dmatch;   // [kW] entries whose current version matches the candidate examined at x
+  uint32_t* dbase;    // [kKD] where the entry's value before its first merge lives: t (prefetched row of t's first match) or 0x100|u (window row u)
+  int32_t* dbcnt;     // [kKD] its member count before the first merge
+  uint8_t* xcand;     // [kW] candidate examined at x
+  uint8_t* xep;       // [kW] merges before x
+  uint8_t* xfe;       // [kW] entry that holds the candidate's first old match if that representative was modified before x, else 0xFF
+  uint8_t* vcand;     // [kW] candidate merged by k
+  int8_t* vlast;      // [kW] last id-carrying candidate merged into the entry up to and including k (-1: none)
+  uint8_t* arank;     // [kW] acceptance rank of a candidate
+  uint8_t* cls;       // [kW] class of a candidate's first old match: the smallest candidate index with the same one
+  uint8_t* dense;     // [2 kW] target id (class, or kW + accepted candidate) -> cache entry, 0xFF: none yet
+  int8_t* elast;      // [kKD] last id-carrying candidate merged into the entry so far
+};
+__host__ __device__ inline size_t spec_bytes_for(int ld) {
+  return sizeof(float) * (size_t)kW * (row_width(ld) + 4) + 8 * (size_t)kKD + 4 * (size_t)(kW * 7 + (kW + 1) * 4 + kKD * 2) + (size_t)kW * 9 + kKD + 16;
+}
+__device__ __forceinline__ void carve_spec(Spec& sp, void* base, int ts) {
+  sp.vers = reinterpret_cast<float*>(base);
+  sp.emask = reinterpret_cast<unsigned long long*>(sp.vers + (size_t)kW * ts);  // kW*ts floats: a multiple of 16 bytes
+  uint32_t* u = reinterpret_cast<uint32_t*>(sp.emask + kKD);
+  sp.vcnt = reinterpret_cast<int32_t*>(u); u += kW;
+  sp.xtarget = u; u += kW;
+  sp.snap_i = u; u += kW + 1;
+  sp.snap_size = u; u += kW + 1;
+  sp.snap_pk = u; u += kW + 1;
+  sp.snap_pk2 = u; u += kW + 1;
+  sp.acc_lo = u; u += kW;
+  sp.acc_hi = u; u += kW;
+  sp.accd_lo = u; u += kW;
+  sp.accd_hi = u; u += kW;
+  sp.dmatch = u; u += kW;
+  sp.dbase = u; u += kKD;
+  sp.dbcnt = reinterpret_cast<int32_t*>(u); u += kKD;
+  uint8_t* b = reinterpret_cast<uint8_t*>(u);
+  sp.xcand = b; b += kW;
+  sp.xep = b; b += kW;
+  sp.xfe = b; b += kW;
+  sp.vcand = b; b += kW;
+  sp.vlast = reinterpret_cast<int8_t*>(b); b += kW;
+  sp.arank = b; b += kW;
+  sp.cls = b; b += kW;
+  sp.dense = b; b += 2 * kW;
+  sp.elast = reinterpret_cast<int8_t*>(b);
+}
+
+// scan: returns the number of examined candidates.  Warp 0 only.  The whole warp prepares the class
+// table; the replay itself is an integer loop on ONE thread (no shuffles, no votes: a warp-synchronous
+// version of this loop cost three times as much per candidate).
+__device__ int spec_scan(Smem& s, Spec& sp, int W, int wf, int wb, bool tail_mode, uint32_t i0, uint32_t size0) {
+  const uint32_t lane = lane_id();
+  // candidates whose first old match is the same representative share a cache entry: class = the
+  // smallest candidate index with that first match
+#pragma unroll
+  for (int half = 0; half < 2; ++half) {
+    const int t = half * 32 + (int)lane;
+    if (t < W) {
+      const uint32_t f = s.s_f[t];
+      int c = t;
+      if (f != kInf)
+        for (int u = 0; u < t; ++u)
+          if (s.s_f[u] == f) {
+            c = u;
+            break;
+          }
+      sp.cls[t] = (uint8_t)c;
+    }
+    sp.dense[half * 32 + lane] = 0xFF;
+    sp.dense[kW + half * 32 + lane] = 0xFF;
+  }
+  sp.emask[lane] = 0ull;
+  unsigned long long easy;
+  {
+    const int t0 = (int)lane, t1 = (int)lane + 32;
+    const bool e0 = t0 < wf && s.s_f[t0] == kInf && (s.pair[2 * t0] | s.pair[2 * t0 + 1]) == 0u;
+    const bool e1 = t1 < wf && s.s_f[t1] == kInf && (s.pair[2 * t1] | s.pair[2 * t1 + 1]) == 0u;
+    easy = ((unsigned long long)__ballot_sync(0xffffffffu, e1) << 32) | (unsigned long long)__ballot_sync(0xffffffffu, e0);
+  }
+  __syncwarp();
+  int x = 0;
+  if (lane == 0) {
+    int nd = 0, a = 0, fi = 0, bi = 0, merges = 0;
+    uint32_t i = i0, size = size0;
+    bool from_back = false, back_exhausted = false, full = false;
+    unsigned long long accm = 0ull, accd = 0ull;
+    while (i < size) {
+      int t;
+      if (from_back) {
+        if (!tail_mode && bi >= wb) { back_exhausted = true; break; }
+        t = tail_mode ? (wf - 1 - bi) : (wf + bi);
+      } else {
+        if (!tail_mode && fi >= wf) break;
+        t = fi;
+      }
+      // the state before this candidate, and what its decision will be checked against
+      sp.xcand[x] = (uint8_t)t;
+      sp.xep[x] = (uint8_t)merges;
+      sp.acc_lo[x] = (uint32_t)accm;
+      sp.acc_hi[x] = (uint32_t)(accm >> 32);
+      sp.accd_lo[x] = (uint32_t)accd;
+      sp.accd_hi[x] = (uint32_t)(accd >> 32);
+      sp.snap_i[x] = i;
+      sp.snap_size[x] = size;
+      sp.snap_pk[x] = (uint32_t)fi | ((uint32_t)bi << 8) | ((uint32_t)a << 16) | ((uint32_t)nd << 24);
+      sp.snap_pk2[x] = (uint32_t)merges | (from_back ? 0x100u : 0u);
+      const unsigned long long tbit = 1ull << t;
+      // predicted decision: first old match, else the earliest accepted candidate with a pair bit, else accept
+      uint32_t P = kInf;
+      int id = -1;
+      uint32_t fpos = kInf;
+      if (!(!from_back && ((easy >> t) & 1ull))) {
+        fpos = s.s_f[t];
+        if (fpos != kInf) {
+          P = fpos;
+          id = sp.cls[t];
+        } else {
+          unsigned long long pm = (((unsigned long long)s.pair[2 * t + 1] << 32) | (unsigned long long)s.pair[2 * t]) & accm;
+          uint32_t rank = 0xFFu;
+          while (pm) {
+            const int u = __ffsll((long long)pm) - 1;
+            pm &= pm - 1ull;
+            rank = min(rank, (uint32_t)sp.arank[u]);
+          }
+          if (rank != 0xFFu) {
+            P = i0 + rank;
+            id = kW + (int)s.acc[rank];
+          }
+        }
+      }
+      if (from_back) ++bi; else ++fi;
+      sp.xtarget[x] = P;
+      if (P == kInf) {
+        s.acc[a] = (uint32_t)t;
+        sp.arank[t] = (uint8_t)a;
+        sp.xfe[x] = 0xFF;
+        accm |= tbit;
+        ++a;
+        ++i;
+        ++x;
+        from_back = false;
+        continue;
+      }
+      int e = sp.dense[id];
+      const bool fresh = e == 0xFF;
+      if (fresh) {
+        e = nd++;
+        sp.dense[id] = (uint8_t)e;
+        sp.elast[e] = -1;
+        s.dpos[e] = P;
+        if (P < i0) {
+          sp.dbase[e] = (uint32_t)t;  // the prefetched row of t's first match
+          sp.dbcnt[e] = s.pcnt[t];
+          s.dridx[e] = s.pridx[t];
+          s.dhead[e] = s.phead[t];
+          s.dtail[e] = s.ptail[t];
+        } else {
+          const uint32_t u = (uint32_t)(id - kW);
+          sp.dbase[e] = 0x100u | u;
+          sp.dbcnt[e] = s.ccnt[u];
+          s.dridx[e] = s.ridx[u];
+          s.dhead[e] = s.chead[u];
+          s.dtail[e] = s.ctail[u];
+          accd |= 1ull << u;
+        }
+      }
+      sp.xfe[x] = (fpos != kInf && !fresh) ? (uint8_t)e : (uint8_t)0xFF;
+      const int prev_last = sp.elast[e];
+      const int new_last = s.ctail[t] >= 0 ? t : prev_last;  // only candidates that carry ids take part in the chain
+      sp.vcand[merges] = (uint8_t)t;
+      sp.vlast[merges] = (int8_t)new_last;
+      sp.elast[e] = (int8_t)new_last;
+      sp.emask[e] |= 1ull << merges;
+      s.mprev[t] = prev_last;
+      s.ment[t] = e;
+      ++merges;
+      --size;
+      ++x;
+      from_back = true;
+      if (nd == kKD) { full = true; break; }
+    }
+    sp.snap_i[x] = i;
+    sp.snap_size[x] = size;
+    sp.snap_pk[x] = (uint32_t)fi | ((uint32_t)bi << 8) | ((uint32_t)a << 16) | ((uint32_t)nd << 24);
+    sp.snap_pk2[x] = (uint32_t)merges | (from_back ? 0x100u : 0u);
+    s.ro[RO_BACK_EXH] = back_exhausted ? 1u : 0u;
+    s.ro[RO_FULL] = full ? 1u : 0u;
+    s.ro[RO_ND] = (uint32_t)nd;       // entries the scan allocated (match pass)
+    s.ro[RO_MERGES] = (uint32_t)merges;
+  }
+  x = __shfl_sync(0xffffffffu, x, 0);
+  return x;
+}
+
+// versions: the consensus value every predicted merge produces.  One entry's chain per warp, the entry's
+// value in registers (lane d holds dimensions d and d + 32), the next candidate's operands requested
+// before the current consensus is computed: the chain costs one multiply-divide-add per merge.
+__device__ void spec_versions(const MergeArgs& A, Smem& s, Spec& sp, int warp, int nwarps) {
+  const int D = A.D, ts = s.ts, rw = s.ts - 4;  // rw: 32 or 64 (speculation is off for wider rows)
+  const uint32_t lane = lane_id();
+  const int nd = (int)s.ro[RO_ND];
+  const bool two = rw > 32;
+  const int d0 = (int)lane, d1 = (int)lane + 32;
+  for (int e = warp; e < nd; e += nwarps) {
+    const uint32_t base = sp.dbase[e];
+    const float* src = (base & 0x100u) ? s.tile + (size_t)(base & 0xFFu) * ts : s.pre + (size_t)base * ts;
+    float r0 = src[d0], r1 = two ? src[d1] : 0.f;
+    int c2 = sp.dbcnt[e];
+    unsigned long long m = sp.emask[e];
+    int k = __ffsll((long long)m) - 1;
+    int t = sp.vcand[k];
+    int c1 = s.ccnt[t];
+    float x0 = s.tile[(size_t)t * ts + d0], x1 = two ? s.tile[(size_t)t * ts + d1] : 0.f;
+    while (m) {
+      m &= m - 1ull;
+      // operands of the next merge of this entry
+      const int kn = m ? (__ffsll((long long)m) - 1) : k;
+      const int tn = sp.vcand[kn];
+      const int c1n = s.ccnt[tn];
+      const float x0n = s.tile[(size_t)tn * ts + d0], x1n = two ? s.tile[(size_t)tn * ts + d1] : 0.f;
+      if (d0 < D) r0 = consensus1(x0, c1, r0, c2);
+      if (two && d1 < D) r1 = consensus1(x1, c1, r1, c2);
+      c2 += c1;
+      float* dst = sp.vers + (size_t)k * ts;
+      dst[d0] = r0;
+      if (two) dst[d1] = r1;
+      if (lane == 0) sp.vcnt[k] = c2;
+      k = kn; t = tn; c1 = c1n; x0 = x0n; x1 = x1n;
     }
   }
-  // a moved tail element waiting at position i (the window ended right after a merge)
-  if (from_back && i < size && lane == 0) {
+}
+
+// match: candidate examined at x against the current version of every entry modified before x.
+template <int DR>
+__device__ void spec_match(const MergeArgs& A, Smem& s, Spec& sp, int n_ex, int warp, int nwarps) {
+  constexpr int NQ = DR / 4;
+  const int D = A.D, ts = s.ts, nq = NQ > 0 ? NQ : (A.ld >> 2);
+  const uint32_t lane = lane_id();
+  const float thr = A.threshold;
+  const float band = (4.f * (float)D + 40.f) * 5.9604645e-8f;
+  const float thr_hi = thr + band, thr_lo = thr - band;
+  const unsigned long long my_mask = sp.emask[lane];  // merges into this lane's entry
+  for (int x = warp; x < n_ex; x += nwarps) {
+    const int ep = sp.xep[x];
+    const unsigned long long before = my_mask & ((1ull << ep) - 1ull);  // ep <= 63: a window has at most kW - 1 merges before a candidate
+    const bool mine = before != 0ull;
+    if (!__any_sync(0xffffffffu, mine)) {  // nothing modified yet
+      if (lane == 0) sp.dmatch[x] = 0u;
+      continue;
+    }
+    const int t = sp.xcand[x];
+    const int k = mine ? (63 - __clzll((long long)before)) : 0;  // the entry's current version at x's turn (row 0 is valid filler)
+    const float4* c4 = reinterpret_cast<const float4*>(s.tile + (size_t)t * ts);
+    const float4* r4 = reinterpret_cast<const float4*>(sp.vers + (size_t)k * ts);
+    const float cn = s.cnorm[t];
+    float dot, nn;
+    fast_dot_nn<NQ>(c4, r4, nq, dot, nn);
+    const float rn = sqrtf(nn);
+    const float prod = cn * rn;
+    const float sim = __fdividef(dot, prod);
+    const bool safe = prod > 1e-18f && prod < 1e18f;
+    bool hit = false, amb = false;
+    if (mine) {
+      hit = safe && sim >= thr_hi;
+      amb = !hit && !(safe && sim < thr_lo);
+    }
+    if (__any_sync(0xffffffffu, amb)) {  // inside the error band: the reference's own arithmetic decides
+      float de = 0.f, ne = 0.f;
+#pragma unroll 4
+      for (int q = 0; q < nq; ++q) {
+        const float4 xx = c4[q], y = r4[q];
+        de = __fadd_rn(de, __fmul_rn(xx.x, y.x)); ne = __fadd_rn(ne, __fmul_rn(y.x, y.x));
+        de = __fadd_rn(de, __fmul_rn(xx.y, y.y)); ne = __fadd_rn(ne, __fmul_rn(y.y, y.y));
+        de = __fadd_rn(de, __fmul_rn(xx.z, y.z)); ne = __fadd_rn(ne, __fmul_rn(y.z, y.z));
+        de = __fadd_rn(de, __fmul_rn(xx.w, y.w)); ne = __fadd_rn(ne, __fmul_rn(y.w, y.w));
+      }
+      if (amb) hit = cos_match(de, cn, __fsqrt_rn(ne), thr);
+    }
+    const uint32_t m = __ballot_sync(0xffffffffu, hit);
+    if (lane == 0) sp.dmatch[x] = m;
+  }
+}
+
+// verify + cut: returns the number of leading examined candidates whose prediction is the true decision.
+__device__ int spec_verify(Smem& s, Spec& sp, int n_ex, uint32_t i0) {
+  const uint32_t lane = lane_id();
+  int cut = n_ex;
+  for (int half = 0; half < 2; ++half) {
+    const int x = half * 32 + (int)lane;
+    bool ok = true;
+    if (x < n_ex) {
+      const int t = sp.xcand[x];
+      const uint32_t P = sp.xtarget[x];
+      uint32_t best = kInf;
+      uint32_t dm = sp.dmatch[x];
+      const uint32_t dm_all = dm;
+      while (dm) {  // modified representatives whose current value matches
+        const int e = __ffs(dm) - 1;
+        dm &= dm - 1;
+        best = min(best, s.dpos[e]);
+      }
+      const uint32_t fpos = s.s_f[t];
+      bool undecidable = false;
+      if (fpos != kInf) {
+        const int fe = sp.xfe[x];
+        if (fe == 0xFF) best = min(best, fpos);  // the first old match is unmodified: it still matches
+        else if (!((dm_all >> fe) & 1u) && best > fpos) undecidable = true;  // a clean match behind it cannot be ruled out
+      }
+      // accepted in this window before x and not modified since: the precomputed pair bits hold
+      uint32_t plo = s.pair[2 * t] & sp.acc_lo[x] & ~sp.accd_lo[x];
+      uint32_t phi = s.pair[2 * t + 1] & sp.acc_hi[x] & ~sp.accd_hi[x];
+      uint32_t rank = 0xFFu;
+      while (plo) {
+        const int u = __ffs(plo) - 1;
+        plo &= plo - 1;
+        rank = min(rank, (uint32_t)sp.arank[u]);
+      }
+      while (phi) {
+        const int u = 32 + __ffs(phi) - 1;
+        phi &= phi - 1;
+        rank = min(rank, (uint32_t)sp.arank[u]);
+      }
+      if (rank != 0xFFu) best = min(best, i0 + rank);
+      ok = !undecidable && best == P;
+    }
+    const uint32_t bad = __ballot_sync(0xffffffffu, !ok);
+    if (bad && cut == n_ex) cut = half * 32 + (__ffs(bad) - 1);
+  }
+  return cut;
+}
+
+// commit the verified prefix [0, cut): the state the sequential loop would have reached there, in the form
+// flush_window expects.  All threads of the CTA.
+template <int TEAM>
+__device__ void spec_commit(const MergeArgs& A, Smem& s, Spec& sp, int n_ex, int cut) {
+  constexpr int kMT = Shape<TEAM>::kMT;
+  const int tid = threadIdx.x, ts = s.ts, ld = A.ld;
+  const uint32_t pk = sp.snap_pk[cut], pk2 = sp.snap_pk2[cut];
+  const int nd = (int)(pk >> 24), merges = (int)(pk2 & 0xFFu), all_merges = (int)s.ro[RO_MERGES];
+  // merges beyond the cut did not happen
+  for (int k = merges + tid; k < all_merges; k += kMT) s.ment[sp.vcand[k]] = -1;
+  // an entry below nd has at least one merge before the cut: its value there is its last version before it
+  const unsigned long long below = merges >= 64 ? ~0ull : ((1ull << merges) - 1ull);
+  if (tid < nd) {
+    const int k = 63 - __clzll((long long)(sp.emask[tid] & below));
+    s.dcnt[tid] = sp.vcnt[k];
+    s.dlast[tid] = (int32_t)sp.vlast[k];
+  }
+  for (int idx = tid; idx < nd * ld; idx += kMT) {
+    const int e = idx / ld, d = idx - e * ld;
+    const int k = 63 - __clzll((long long)(sp.emask[e] & below));
+    s.dvals[(size_t)e * ts + d] = sp.vers[(size_t)k * ts + d];
+  }
+  if (tid == 0) {
+    const bool whole = cut == n_ex;
+    s.ro[RO_A] = (pk >> 16) & 0xFFu;
+    s.ro[RO_ND] = (uint32_t)nd;
+    s.ro[RO_I] = sp.snap_i[cut];
+    s.ro[RO_SIZE] = sp.snap_size[cut];
+    s.ro[RO_FROM_BACK] = (pk2 >> 8) & 1u;
+    s.ro[RO_BI] = (pk >> 8) & 0xFFu;
+    s.ro[RO_MERGES] = (uint32_t)merges;
+    if (!whole) {
+      s.ro[RO_BACK_EXH] = 0u;
+      s.ro[RO_FULL] = 0u;
+    }
+    s.ro[RO_UNDEC] = whole ? 0u : 1u;
+    s.ro[RO_EXAMINED] = (pk & 0xFFu) + ((pk >> 8) & 0xFFu);
+  }
+}
+
+// Apply the window's effects to global memory with the whole CTA.
+template <int TEAM>
+__device__ void flush_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm, uint4* seg_h, int qh, TeamCtl* ctl, Smem& s,
+                             int W, int wf, int wb, bool tail_mode, uint32_t i0, uint32_t size0) {
+  constexpr int kMT = Shape<TEAM>::kMT;
+  const int D = A.D, ld = A.ld, nq = ld >> 2;
+  const int tid = threadIdx.x;
+  const int a = (int)s.ro[RO_A], nd = (int)s.ro[RO_ND], bi = (int)s.ro[RO_BI], merges = (int)s.ro[RO_MERGES];
+  const uint32_t i = s.ro[RO_I], size = s.ro[RO_SIZE];
+  const bool from_back = s.ro[RO_FROM_BACK] != 0u, back_exhausted = s.ro[RO_BACK_EXH] != 0u;
+  // norms of the modified representatives' final values
+  if (tid < nd) s.dnorm[tid] = norm_seq(reinterpret_cast<const float4*>(s.dvals + (size_t)tid * s.ts), nq);
+  // a moved tail element waiting at position i (the window ended right after a merge); its source may
+  // lie in the range the sentinels overwrite below, so it is read before the barrier
+  if (tid == kMT - 1 && from_back && i < size) {
     uint32_t moved;
     if (tail_mode) moved = s.ridx[wf - 1 - bi];
     else if (bi < wb) moved = s.ridx[wf + bi];
     else moved = __ldcg(seg + size);  // the element that was at the old tail position
     seg[i] = moved;
   }
-  __syncwarp();
-  for (uint32_t k = size + lane; k < size0; k += 32) seg[k] = KLSH_SENTINEL;
+  // accepted candidates: positions i0.. in acceptance order (row index + norm + fp16 copy)
+  for (int k = tid; k < a; k += kMT) {
+    const uint32_t u = s.acc[k];
+    seg[i0 + k] = s.ridx[u];
+    pos_nrm[i0 + k] = s.cnorm[u];
+  }
+  if (qh) {
+    for (int idx = tid; idx < a * qh; idx += kMT) {
+      const int k = idx / qh, c = idx - k * qh;
+      seg_h[(size_t)(i0 + k) * qh + c] = h16_chunk_from_htile(s.htile + (size_t)s.acc[k] * s.hs, c);
+    }
+  }
+  __syncthreads();  // an accepted candidate modified later in the window is rewritten below
+  for (uint32_t k = size + (uint32_t)tid; k < size0; k += kMT) seg[k] = KLSH_SENTINEL;
+  if (qh) {
+    // modified representatives are re-scaled from their current value and norm
+    for (int idx = tid; idx < nd * qh; idx += kMT) {
+      const int e = idx / qh, c = idx - e * qh;
+      seg_h[(size_t)s.dpos[e] * qh + c] = h16_chunk_from_row(s.dvals + (size_t)e * s.ts, ld, s.dnorm[e], c);
+    }
+  }
   // member chains: ids(current) ++ ids(candidate) for every logged merge
-  for (int round = 0; round < 2; ++round) {
-    const int t = round * 32 + (int)lane;
-    if (t < W) {
-      const bool examined_merge = s.ment[t] >= 0;
-      if (examined_merge) {
-        const int e = s.ment[t], prev = s.mprev[t];
-        const int t1 = s.ctail[t];
-        if (t1 >= 0) {
-          const int nv = (prev < 0) ? s.dhead[e] : s.chead[prev];
-          A.next[t1] = nv;
-          if (A.mg.counts) {
-            const uint32_t k = atomicAdd(A.mg.counts + 1, 1u);
-            A.mg.next_slot[k] = (uint32_t)t1;
-            A.mg.next_val[k] = nv;
-          }
-        }
+  if (tid < W && s.ment[tid] >= 0) {
+    const int e = s.ment[tid], prev = s.mprev[tid];
+    const int t1 = s.ctail[tid];
+    if (t1 >= 0) {
+      const int nv = (prev < 0) ? s.dhead[e] : s.chead[prev];
+      A.next[t1] = nv;
+      if (A.mg.counts) {
+        const uint32_t k = atomicAdd(A.mg.counts + 1, 1u);
+        A.mg.next_slot[k] = (uint32_t)t1;
+        A.mg.next_val[k] = nv;
       }
     }
   }
-  __syncwarp();
-  // modified representatives: values, count, head, tail, norm
-  {
-    const int e = (int)lane;
-    if (e < nd) {
-      const uint32_t rr = s.dridx[e];
-      if (A.mg.counts) A.mg.mod_rows[atomicAdd(A.mg.counts, 1u)] = rr;
-      A.cnt[rr] = my_dcnt;
-      // each merge prepends the candidate's members: the chain now starts with the LAST merged
-      // candidate that carried ids
-      if (my_last >= 0) A.head[rr] = s.chead[my_last];
-      if (s.dtail[e] < 0 && my_last >= 0) {  // the representative had no ids: its tail is the EARLIEST such candidate's
-        int first_t = my_last;
-        for (int tt = s.mprev[my_last]; tt >= 0; tt = s.mprev[tt]) first_t = tt;
-        A.tail[rr] = s.ctail[first_t];
-      }
-      pos_nrm[my_dpos] = s.dnorm[e];
+  // modified representatives: count, head, tail, norm ...
+  if (tid < nd) {
+    const int e = tid;
+    const uint32_t rr = s.dridx[e];
+    const int last = s.dlast[e];
+    if (A.mg.counts) A.mg.mod_rows[atomicAdd(A.mg.counts, 1u)] = rr;
+    A.cnt[rr] = s.dcnt[e];
+    // each merge prepends the candidate's members: the chain now starts with the LAST merged
+    // candidate that carried ids
+    if (last >= 0) A.head[rr] = s.chead[last];
+    if (s.dtail[e] < 0 && last >= 0) {  // the representative had no ids: its tail is the EARLIEST such candidate's
+      int first_t = last;
+      for (int tt = s.mprev[last]; tt >= 0; tt = s.mprev[tt]) first_t = tt;
+      A.tail[rr] = s.ctail[first_t];
     }
+    pos_nrm[s.dpos[e]] = s.dnorm[e];
   }
-  for (int e = 0; e < nd; ++e) {
-    float* dst = A.vals + (uint64_t)s.dridx[e] * ld;
-    const float* src = s.dvals + (size_t)e * s.ts;
-    for (int d = lane; d < D; d += 32) dst[d] = src[d];
+  // ... and values
+  for (int idx = tid; idx < nd * D; idx += kMT) {
+    const int e = idx / D, d = idx - e * D;
+    A.vals[(uint64_t)s.dridx[e] * ld + d] = s.dvals[(size_t)e * s.ts + d];
   }
-  if (rprof) pa = clock64() - ta0;
-  if (lane == 0) {
+  if (tid == 0) {
     ctl->i = i;
     ctl->size = size;
     // back candidates for the next window: grow fast when they ran out, shrink slowly otherwise (a
@@ -858,19 +1370,14 @@ __device__ void resolve_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm
                              : (uint32_t)min(kWbMax, max(max(2, merges + merges / 2 + 2), wb - (wb + 3) / 4));
     if (A.dbg) {
       atomicAdd(A.dbg + 0, 1ull);
-      atomicAdd(A.dbg + 1, (unsigned long long)(fi + bi));
+      atomicAdd(A.dbg + 1, (unsigned long long)s.ro[RO_EXAMINED]);
       atomicAdd(A.dbg + 2, (unsigned long long)merges);
-      atomicAdd(A.dbg + 3, (unsigned long long)dbg_undec);
-      atomicAdd(A.dbg + 4, (unsigned long long)dbg_full);
+      atomicAdd(A.dbg + 3, (unsigned long long)s.ro[RO_UNDEC]);
+      atomicAdd(A.dbg + 4, (unsigned long long)s.ro[RO_FULL]);
       atomicAdd(A.dbg + 5, (unsigned long long)(back_exhausted ? 1 : 0));
       atomicAdd(A.dbg + 6, (unsigned long long)a);
-      atomicAdd(A.dbg + 14, (unsigned long long)pv);
-      atomicAdd(A.dbg + 15, (unsigned long long)pm);
-      atomicAdd(A.dbg + 16, (unsigned long long)pa);
-      atomicAdd(A.dbg + 17, (unsigned long long)nval);
     }
   }
-  __syncwarp();
 }
 
 // Window staging.  Rows go global -> shared with cp.async (no registers, no wait until the whole
@@ -905,11 +1412,13 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
         ctl->i = 1;
         ctl->size = A.bstart[bucket + 1] - st;
         ctl->wb = 4;
+        ctl->mode = 0u;
       }
     } else if (lane == 0) {
       ctl->i = start_i;
       ctl->size = start_size;
       ctl->wb = 4;
+      ctl->mode = 0u;
     }
     if (TEAM != 0)
       for (int t = lane; t < kW; t += 32) ctl->f[t] = kInf;
@@ -918,6 +1427,7 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
   Team<TEAM>::sync();
   for (;;) {
     const uint32_t i0 = __ldcg(&ctl->i), size0 = __ldcg(&ctl->size);
+    const uint32_t mode0 = __ldcg(&ctl->mode);  // read here by everybody: the leader rewrites it while resolving
     if (i0 >= size0) return false;
     const uint32_t remaining = size0 - i0;
     if (i0 > A.max_reps && A.esc_list) {  // more compare work than this team should carry: hand on
@@ -988,6 +1498,14 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
       s.pair[2 * tid + 1] = 0u;
       s.ment[tid] = -1;
       s.mprev[tid] = -1;
+    }
+    if (tid < kKD) {
+      s.dver[tid] = 0u;
+      s.mver[tid] = 0u;
+    }
+    if (tid == 0) {
+      s.ro[RO_ND] = 0u;
+      s.ro[RO_DONE] = 0u;
     }
     __syncthreads();
     if (prof) ts1 = clock64();
@@ -1105,8 +1623,42 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
       }
       __syncthreads();
       if (prof) tk4 = clock64();
-      if (warp == 0) resolve_window<TEAM>(A, seg, pos_nrm, seg_h, QH, ctl, s, W, wf, wb, tail_mode, i0, size0);
+      const bool sequential = DR == 0 || mode0 != 0u || A.no_spec;
+      if (!sequential) {
+        // speculative resolution (see above); the cp.async ring of the screen is idle now and holds its scratch
+        Spec sp;
+        carve_spec(sp, s.ring, s.ts);
+        if (warp == 0) {
+          const int n = spec_scan(s, sp, W, wf, wb, tail_mode, i0, size0);
+          if (lane == 0) s.ro[RO_EXAMINED] = (uint32_t)n;
+        }
+        __syncthreads();
+        const int n_ex = (int)s.ro[RO_EXAMINED];
+        spec_versions(A, s, sp, (int)warp, kMT / 32);
+        __syncthreads();
+        spec_match<DR>(A, s, sp, n_ex, (int)warp, kMT / 32);
+        __syncthreads();
+        if (warp == 0) {
+          const int cut = spec_verify(s, sp, n_ex, i0);
+          if (lane == 0) {
+            s.ro[RO_DONE] = (uint32_t)cut;
+            if (cut < n_ex) ctl->mode = 1u;  // a misprediction: the next window takes the sequential loop
+            if (A.dbg) {
+              atomicAdd(A.dbg + 26, 1ull);
+              atomicAdd(A.dbg + 27, (unsigned long long)(cut < n_ex ? 1 : 0));
+            }
+          }
+        }
+        __syncthreads();
+        spec_commit<TEAM>(A, s, sp, n_ex, (int)s.ro[RO_DONE]);
+      } else {
+        if (tid == 0) ctl->mode = 0u;
+        if (warp == 0) resolve_decide<TEAM, DR>(A, s, W, wf, wb, tail_mode, i0, size0);
+        else mask_helpers(A, s, W, (int)warp - 1, kMT / 32 - 1);
+      }
+      __syncthreads();
       if (prof) tk5 = clock64();
+      flush_window<TEAM>(A, seg, pos_nrm, seg_h, QH, ctl, s, W, wf, wb, tail_mode, i0, size0);
     }
     __threadfence();
     Team<TEAM>::sync();
@@ -1132,6 +1684,9 @@ __global__ void __launch_bounds__(Shape<TEAM>::kMT, Shape<TEAM>::kCtasPerSm) k_m
   __shared__ uint32_t s_work;
   Smem s;
   carve(s, smem_raw, A.ld);
+  // staged rows are zero beyond the row's own width (row_width): nothing ever writes there
+  for (int v = threadIdx.x; v < (2 * kW + kKD) * s.ts; v += blockDim.x) s.tile[v] = 0.f;
+  __syncthreads();
   TeamCtl* ctl = A.ctl + Team<TEAM>::id();
   const uint32_t na = A.n_a ? *A.n_a : 0u, nb = A.n_b ? *A.n_b : 0u;
   if (TEAM == 2) {  // the grid walks the lists together
@@ -1173,7 +1728,10 @@ const void* kernel_for(int ld) {
 // ================================================================================================
 // Launch: stage 0 (CTA teams) over the classified lists, then the escalation stages.
 // ================================================================================================
-static int launch_stage(klsh_ctx* ctx, int team, int csize, MergeArgs& A, uint32_t host_items /* upper bound, 0 = unknown */) {
+size_t merge_window_smem_bytes(int ld) { return smem_bytes_for(ld, Shape<1>::kMT); }
+
+static int launch_stage(klsh_ctx* ctx, cudaStream_t stream, DevBuf& ctl_buf, int team, int csize, MergeArgs& A,
+                        uint32_t host_items /* upper bound, 0 = unknown */) {
   const int ld = ctx->ld;
   const size_t smem = smem_bytes_for(ld, team == 0 ? Shape<0>::kMT : Shape<1>::kMT);
   if (smem > (size_t)ctx->max_smem_optin)
@@ -1205,14 +1763,14 @@ static int launch_stage(klsh_ctx* ctx, int team, int csize, MergeArgs& A, uint32
     nteams = 1;
     grid = (uint32_t)ctx->sm_count * std::min(per_sm, ctx->cluster_ctas_per_sm);
   }
-  KTRY(dev_reserve(ctx, ctx->team_ctl, sizeof(TeamCtl) * (size_t)std::max<uint32_t>(nteams, 1)));
-  A.ctl = ctx->team_ctl.as<TeamCtl>();
+  KTRY(dev_reserve(ctx, ctl_buf, sizeof(TeamCtl) * (size_t)std::max<uint32_t>(nteams, 1)));
+  A.ctl = ctl_buf.as<TeamCtl>();
 
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kMT);
   cfg.dynamicSmemBytes = smem;
-  cfg.stream = ctx->stream;
+  cfg.stream = stream;
   cudaLaunchAttribute attr[1];
   cfg.attrs = attr;
   cfg.numAttrs = 0;
@@ -1230,7 +1788,8 @@ static int launch_stage(klsh_ctx* ctx, int team, int csize, MergeArgs& A, uint32
   std::chrono::high_resolution_clock::time_point t0;
   if (ctx->debug) {
     cudaStreamSynchronize(ctx->stream);
-    cudaMemset(ctx->dbg.p, 0, sizeof(unsigned long long) * 24);
+    cudaStreamSynchronize(ctx->stream2);
+    cudaMemset(ctx->dbg.p, 0, sizeof(unsigned long long) * 32);
     t0 = std::chrono::high_resolution_clock::now();
   }
   void* args[] = {&A};
@@ -1240,8 +1799,8 @@ static int launch_stage(klsh_ctx* ctx, int team, int csize, MergeArgs& A, uint32
     return klsh_fail(ctx, KLSH_ERR_CUDA, "merge kernel launch (team %d, grid %u, smem %zu) failed: %s", team, grid, smem,
                      cudaGetErrorString(e));
   if (ctx->debug) {  // KLSH_DEBUG=1: per-stage timing and window statistics on stderr
-    unsigned long long h[24];
-    cudaStreamSynchronize(ctx->stream);
+    unsigned long long h[32];
+    cudaStreamSynchronize(stream);
     double ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
     cudaMemcpy(h, ctx->dbg.p, sizeof h, cudaMemcpyDeviceToHost);
     if (h[0])
@@ -1250,31 +1809,21 @@ static int launch_stage(klsh_ctx* ctx, int team, int csize, MergeArgs& A, uint32
               "undecidable %llu cache_full %llu back_exhausted %llu\n",
               team, csize, grid, ms, h[0], h[1], h[2], h[6], h[7], h[3], h[4], h[5]);
     if (h[0])
-      fprintf(stderr, "[klsh]   leader kcycles/window: stage %.1f parallel %.1f sync1 %.1f prefetch %.1f resolve %.1f sync2 %.1f\n",
+      fprintf(stderr, "[klsh]   leader kcycles/window: stage %.1f parallel %.1f sync1 %.1f prefetch %.1f decide %.1f flush+sync2 %.1f\n",
               h[8] / 1e3 / h[0], h[9] / 1e3 / h[0], h[10] / 1e3 / h[0], h[11] / 1e3 / h[0], h[12] / 1e3 / h[0], h[13] / 1e3 / h[0]);
     if (h[0])
       fprintf(stderr, "[klsh]   stage kcycles/window: index+meta %.1f rows %.1f norms %.1f fp16 %.1f\n", h[18] / 1e3 / h[0],
               h[19] / 1e3 / h[0], h[20] / 1e3 / h[0], h[21] / 1e3 / h[0]);
     if (h[0])
-      fprintf(stderr, "[klsh]   resolver kcycles/window: validate %.1f (%.2f calls) merge-step %.1f apply %.1f\n", h[14] / 1e3 / h[0],
-              (double)h[17] / h[0], h[15] / 1e3 / h[0], h[16] / 1e3 / h[0]);
-
+      fprintf(stderr, "[klsh]   decide kcycles/window: select %.1f dirty-compare %.1f old+accepted %.1f merge %.1f | per window: loop trips %.1f runs %.1f dirty tests %.1f\n",
+              h[14] / 1e3 / h[0], h[15] / 1e3 / h[0], h[16] / 1e3 / h[0], h[17] / 1e3 / h[0], (double)h[22] / h[0], (double)h[23] / h[0], (double)h[24] / h[0]);
+    if (h[26]) fprintf(stderr, "[klsh]   speculative windows %llu, cut short by a misprediction %llu\n", h[26], h[27]);
+    if (h[0]) fprintf(stderr, "[klsh]   dirty tests decided by the exact chain (inside the fast test's error band): %.3f per window\n", (double)h[25] / h[0]);
   }
   return KLSH_OK;
 }
 
-// Work items {bucket, 0, 0} come from k_classify (list_big first, then list_large); their counts
-// live in the pass counters on the device.
-int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, uint32_t n_items_host,
-                        uint32_t bucket_max_host) {
-  if (n_items_host == 0) return KLSH_OK;
-  PassCounters* dc = s.counters.as<PassCounters>();
-  // escalation lists: every large bucket can escalate at most once per stage
-  KTRY(dev_reserve(ctx, s.esc1, sizeof(uint32_t) * 3 * ((size_t)n_items_host + 1)));
-  KTRY(dev_reserve(ctx, s.esc2, sizeof(uint32_t) * 3 * ((size_t)n_items_host + 1)));
-  KTRY(dev_reserve(ctx, s.esc3, sizeof(uint32_t) * 3 * ((size_t)n_items_host + 1)));
-  if (ctx->debug) KTRY(dev_reserve(ctx, ctx->dbg, sizeof(unsigned long long) * 24));
-
+static MergeArgs base_args(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold) {
   MergeArgs A;
   A.vals = ctx->cur.vals.as<float>();
   A.D = ctx->D;
@@ -1290,6 +1839,30 @@ int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
   A.dbg = ctx->debug ? ctx->dbg.as<unsigned long long>() : nullptr;
   A.mg = ctx->mg;
   A.threshold = threshold;
+  A.no_spec = ctx->no_spec ? 1 : 0;
+  A.list_a = A.list_b = nullptr;
+  A.n_a = A.n_b = nullptr;
+  A.cursor = nullptr;
+  A.esc_list = nullptr;
+  A.esc_count = nullptr;
+  A.max_reps = 0xFFFFFFFFu;
+  A.ctl = nullptr;
+  return A;
+}
+
+// Work items {bucket, 0, 0} come from k_classify (list_big first, then list_large); their counts
+// live in the pass counters on the device.
+int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, uint32_t n_items_host,
+                        uint32_t bucket_max_host) {
+  if (n_items_host == 0) return KLSH_OK;
+  PassCounters* dc = s.counters.as<PassCounters>();
+  // escalation lists: every large bucket can escalate at most once per stage
+  KTRY(dev_reserve(ctx, s.esc1, sizeof(uint32_t) * 3 * ((size_t)n_items_host + 1)));
+  KTRY(dev_reserve(ctx, s.esc2, sizeof(uint32_t) * 3 * ((size_t)n_items_host + 1)));
+  KTRY(dev_reserve(ctx, s.esc3, sizeof(uint32_t) * 3 * ((size_t)n_items_host + 1)));
+  if (ctx->debug) KTRY(dev_reserve(ctx, ctx->dbg, sizeof(unsigned long long) * 32));
+
+  MergeArgs A = base_args(ctx, s, rows_sorted, threshold);
 
   // stage 0: one CTA per bucket, biggest buckets first
   A.list_a = s.list_big.as<uint32_t>();
@@ -1300,7 +1873,7 @@ int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
   A.esc_list = s.esc1.as<uint32_t>();
   A.esc_count = &dc->n_esc1;
   A.max_reps = ctx->cta_max;
-  KTRY(launch_stage(ctx, 0, 1, A, n_items_host));
+  KTRY(launch_stage(ctx, ctx->stream, ctx->team_ctl, 0, 1, A, n_items_host));
   if (bucket_max_host <= ctx->cta_max) return KLSH_OK;  // nothing can have escalated
 
   // stage 1: one cluster per escalated bucket
@@ -1312,7 +1885,7 @@ int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
   A.esc_list = s.esc2.as<uint32_t>();
   A.esc_count = &dc->n_esc2;
   A.max_reps = ctx->cluster_max;
-  KTRY(launch_stage(ctx, 1, ctx->cluster_size, A, 0));
+  KTRY(launch_stage(ctx, ctx->stream, ctx->team_ctl, 1, ctx->cluster_size, A, 0));
   if (bucket_max_host <= ctx->cluster_max) return KLSH_OK;
 
   // stage 2: one large cluster per bucket
@@ -1322,7 +1895,7 @@ int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
   A.esc_list = s.esc3.as<uint32_t>();
   A.esc_count = &dc->n_esc3;
   A.max_reps = ctx->cluster2_max;
-  KTRY(launch_stage(ctx, 1, ctx->cluster2_size, A, 0));
+  KTRY(launch_stage(ctx, ctx->stream, ctx->team_ctl, 1, ctx->cluster2_size, A, 0));
   if (bucket_max_host <= ctx->cluster2_max) return KLSH_OK;
 
   // stage 3: the whole grid per bucket
@@ -1332,6 +1905,48 @@ int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
   A.esc_list = nullptr;
   A.esc_count = nullptr;
   A.max_reps = 0xFFFFFFFFu;
-  KTRY(launch_stage(ctx, 2, 1, A, 0));
+  KTRY(launch_stage(ctx, ctx->stream, ctx->team_ctl, 2, 1, A, 0));
+  return KLSH_OK;
+}
+
+// The direct pipeline: buckets of at least direct_min rows start on cluster teams (no single-CTA stage)
+// and escalate to large clusters and the grid like the others.  Everything is enqueued on the
+// context's second stream with its own work lists, cursors and team control blocks, so it runs beside
+// the small buckets and the single-CTA stage: the step ends when the longer of the two ends, not their sum.
+int launch_merge_direct(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, uint32_t n_direct_host,
+                        uint32_t bucket_max_host) {
+  if (n_direct_host == 0) return KLSH_OK;
+  PassCounters* dc = s.counters.as<PassCounters>();
+  KTRY(dev_reserve(ctx, s.escb2, sizeof(uint32_t) * 3 * ((size_t)n_direct_host + 1)));
+  KTRY(dev_reserve(ctx, s.escb3, sizeof(uint32_t) * 3 * ((size_t)n_direct_host + 1)));
+  if (ctx->debug) KTRY(dev_reserve(ctx, ctx->dbg, sizeof(unsigned long long) * 32));
+  MergeArgs A = base_args(ctx, s, rows_sorted, threshold);
+  cudaStream_t st = ctx->stream2;
+
+  A.list_a = s.list_direct.as<uint32_t>();
+  A.n_a = &dc->n_direct;
+  A.cursor = &dc->b_cursor1;
+  A.esc_list = s.escb2.as<uint32_t>();
+  A.esc_count = &dc->nb_esc2;
+  A.max_reps = ctx->cluster_max;
+  KTRY(launch_stage(ctx, st, ctx->team_ctl_b, 1, ctx->cluster_size, A, n_direct_host));
+  if (bucket_max_host <= ctx->cluster_max) return KLSH_OK;
+
+  A.list_a = s.escb2.as<uint32_t>();
+  A.n_a = &dc->nb_esc2;
+  A.cursor = &dc->b_cursor2;
+  A.esc_list = s.escb3.as<uint32_t>();
+  A.esc_count = &dc->nb_esc3;
+  A.max_reps = ctx->cluster2_max;
+  KTRY(launch_stage(ctx, st, ctx->team_ctl_b, 1, ctx->cluster2_size, A, 0));
+  if (bucket_max_host <= ctx->cluster2_max) return KLSH_OK;
+
+  A.list_a = s.escb3.as<uint32_t>();
+  A.n_a = &dc->nb_esc3;
+  A.cursor = nullptr;
+  A.esc_list = nullptr;
+  A.esc_count = nullptr;
+  A.max_reps = 0xFFFFFFFFu;
+  KTRY(launch_stage(ctx, st, ctx->team_ctl_b, 2, 1, A, 0));
   return KLSH_OK;
 }

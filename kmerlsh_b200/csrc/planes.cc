@@ -13,6 +13,8 @@
 
 struct PlaneSource {
   std::mt19937_64 master;
+  uint64_t seed = 12345ULL;
+  uint64_t drawn = 0;  // master outputs consumed since the seed (one per hash function)
   klsh_plane_fn fn = nullptr;
   void* user = nullptr;
 };
@@ -25,8 +27,20 @@ PlaneSource* planes_new() {
 void planes_free(PlaneSource* p) { delete p; }
 void planes_seed(PlaneSource* p, uint64_t seed) {
   p->master.seed(seed);
+  p->seed = seed;
+  p->drawn = 0;
   p->fn = nullptr;
   p->user = nullptr;
+}
+// position of the built-in stream: (seed, hash functions drawn so far); seeking replays the seed and discards
+void planes_tell(const PlaneSource* p, uint64_t* seed, uint64_t* drawn) {
+  *seed = p->seed;
+  *drawn = p->drawn;
+}
+void planes_seek(PlaneSource* p, uint64_t seed, uint64_t drawn) {
+  planes_seed(p, seed);
+  p->master.discard(drawn);
+  p->drawn = drawn;
 }
 void planes_callback(PlaneSource* p, klsh_plane_fn fn, void* user) {
   p->fn = fn;
@@ -38,6 +52,7 @@ void planes_draw(PlaneSource* p, int H, int D, float* out) {
     p->fn(p->user, H, D, out);
     return;
   }
+  p->drawn += static_cast<uint64_t>(H);
   for (int h = 0; h < H; ++h) {
     std::mt19937 gen(static_cast<unsigned int>(p->master()));
     std::normal_distribution<> dis(0, 1);

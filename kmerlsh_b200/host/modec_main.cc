@@ -15,14 +15,18 @@
 // Modes K, B and E are outside this tool.
 #include <getopt.h>
 
+#include <atomic>
 #include <chrono>
+#include <condition_variable>
 #include <cstdio>
 #include <cstdlib>
 #include <fstream>
 #include <iostream>
+#include <mutex>
 #include <random>
 #include <sstream>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "klsh.h"
@@ -42,8 +46,10 @@ struct Params {
   bool have_seed = false;
   uint64_t seed = 0;
   int device = 0;
+  int gpus = 1;
   uint64_t batch = 100000000ull;
   bool reload_tmp = false, no_tmp_files = false;
+  std::string stats_json;
 };
 
 int count_lines(const std::string& path) {  // GetInput, reference io/ioHT.cc:3-19
@@ -58,37 +64,92 @@ int count_lines(const std::string& path) {  // GetInput, reference io/ioHT.cc:3-
   return n;
 }
 
-#define CK(ctx, call)                                                        \
-  do {                                                                       \
-    int rc__ = (call);                                                       \
-    if (rc__ != KLSH_OK) {                                                   \
-      std::cerr << #call << " failed: " << klsh_last_error(ctx) << std::endl; \
-      return 1;                                                              \
-    }                                                                        \
-  } while (0)
+// ---- several GPUs, one hyperplane stream ---------------------------------------------------------------
+// The reference draws every hash table of a run from one generator, Cluster() call after Cluster() call
+// (app/kmerLSH.cc:311-345: batch after batch).  With several GPUs the batches run on different contexts,
+// but the tables still come from ONE seeded stream in the reference's order: a context may draw only when
+// it is its call's turn, and hands the stream on as soon as its call has drawn its last table (the
+// draws-done callback) — i.e. while it is still merging.  Phase-1 calls (one iteration each) therefore
+// overlap almost completely; results are byte-identical to --gpus=1 whatever the number of GPUs.
+struct Shared {
+  klsh_ctx* gen = nullptr;  // holds the run's seeded stream; never computes
+  std::mutex mu;
+  std::condition_variable cv;
+  uint64_t draw_turn = 0;   // index of the Cluster() call that may draw
+  uint64_t save_turn = 0;   // index of the batch that may append to the spill file
+  std::atomic<bool> failed{false};
+  std::string error;
+  std::ostringstream json;  // --stats-json: one record per Cluster() iteration
+  void fail(const std::string& msg) {
+    std::lock_guard<std::mutex> lk(mu);
+    if (!failed.exchange(true)) error = msg;
+    cv.notify_all();
+  }
+};
 
-void print_iterations(const std::vector<klsh_iter_stats>& st, int dim) {
+struct Worker {
+  klsh_ctx* ctx = nullptr;
+  Shared* sh = nullptr;
+  int index = 0, device = 0;
+  uint64_t my_call = 0;
+};
+
+void plane_tramp(void* user, int H, int D, float* out) {
+  Worker* w = static_cast<Worker*>(user);
+  std::unique_lock<std::mutex> lk(w->sh->mu);
+  w->sh->cv.wait(lk, [&] { return w->sh->draw_turn == w->my_call || w->sh->failed.load(); });
+  klsh_draw_table(w->sh->gen, H, D, out);
+}
+
+void done_tramp(void* user) {
+  Worker* w = static_cast<Worker*>(user);
+  std::lock_guard<std::mutex> lk(w->sh->mu);
+  if (w->sh->draw_turn == w->my_call) w->sh->draw_turn = w->my_call + 1;
+  w->sh->cv.notify_all();
+}
+
+std::string iteration_lines(const std::vector<klsh_iter_stats>& st, int dim, float secs) {
+  std::ostringstream o;
   for (size_t k = 0; k < st.size(); ++k) {
     if (st[k].rows_in == 0) break;
-    std::cout << "Iteration:\t" << (k + 1) << ", cos sim threshold:\t" << st[k].threshold << " dimension : " << dim << std::endl;
-    std::cout << "Size of profilings : " << st[k].rows_in << std::endl;
-    std::cout << "hashing takes secs:\t" << (st[k].ms_sign + st[k].ms_group) * 1e-3f << std::endl;
-    std::cout << "clustering takes secs:\t" << st[k].ms_merge * 1e-3f << std::endl << std::endl;
-    std::cout << "merging takes secs:\t" << st[k].ms_compact * 1e-3f << std::endl;
-    std::cout << "#k-mers after clustering:\t" << st[k].rows_out << std::endl << std::endl;
+    o << "Iteration:\t" << (k + 1) << ", cos sim threshold:\t" << st[k].threshold << " dimension : " << dim << std::endl;
+    o << "Size of profilings : " << st[k].rows_in << std::endl;
+    o << "hashing takes secs:\t" << (st[k].ms_sign + st[k].ms_group) * 1e-3f << std::endl;
+    o << "clustering takes secs:\t" << st[k].ms_merge * 1e-3f << std::endl << std::endl;
+    o << "merging takes secs:\t" << st[k].ms_compact * 1e-3f << std::endl;
+    o << "#k-mers after clustering:\t" << st[k].rows_out << std::endl << std::endl;
+  }
+  o << "kmerLSH algorithm hash+cluster takes (secs): " << secs << std::endl;
+  return o.str();
+}
+
+void json_records(Shared& sh, const char* phase, uint64_t call, int gpu, const std::vector<klsh_iter_stats>& st) {
+  std::lock_guard<std::mutex> lk(sh.mu);
+  for (size_t k = 0; k < st.size(); ++k) {
+    if (st[k].rows_in == 0) break;
+    sh.json << "{\"phase\": \"" << phase << "\", \"call\": " << call << ", \"gpu\": " << gpu << ", \"iteration\": " << (k + 1)
+            << ", \"rows_in\": " << st[k].rows_in << ", \"rows_out\": " << st[k].rows_out << ", \"H\": " << st[k].H
+            << ", \"threshold\": " << st[k].threshold << ", \"buckets\": " << st[k].buckets << ", \"bucket_max\": " << st[k].bucket_max
+            << ", \"nested_calls\": " << st[k].nested_calls << ", \"eps_margin_rows\": " << st[k].eps_margin_rows
+            << ", \"ms_sign\": " << st[k].ms_sign << ", \"ms_group\": " << st[k].ms_group << ", \"ms_merge\": " << st[k].ms_merge
+            << ", \"ms_compact\": " << st[k].ms_compact << ", \"ms_total\": " << st[k].ms_total << "}\n";
   }
 }
 
-int cluster_logged(klsh_ctx* ctx, float sim, int iters, int64_t thr, int dim, bool verbose) {
+// One Cluster() call on a worker, in stream order `call`.  Returns the reference-style log lines.
+bool cluster_call(Worker& w, const char* phase, uint64_t call, float sim, int iters, int64_t thr, int dim, std::string* log) {
+  w.my_call = call;
   std::vector<klsh_iter_stats> st((size_t)iters);
   auto t0 = std::chrono::high_resolution_clock::now();
-  CK(ctx, klsh_cluster(ctx, sim, iters, thr, st.data()));
-  if (verbose) {
-    print_iterations(st, dim);
-    float secs = std::chrono::duration_cast<std::chrono::duration<float>>(std::chrono::high_resolution_clock::now() - t0).count();
-    std::cout << "kmerLSH algorithm hash+cluster takes (secs): " << secs << std::endl;
+  if (klsh_cluster(w.ctx, sim, iters, thr, st.data()) != KLSH_OK) {
+    w.sh->fail(std::string("klsh_cluster failed: ") + klsh_last_error(w.ctx));
+    done_tramp(&w);
+    return false;
   }
-  return 0;
+  const float secs = std::chrono::duration_cast<std::chrono::duration<float>>(std::chrono::high_resolution_clock::now() - t0).count();
+  if (log) *log = iteration_lines(st, dim, secs);
+  json_records(*w.sh, phase, call, w.index, st);
+  return true;
 }
 
 }  // namespace
@@ -120,6 +181,8 @@ int main(int argc, char** argv) {
                                          {"batch", required_argument, 0, 1002},
                                          {"reload-tmp", no_argument, 0, 1003},
                                          {"no-tmp-files", no_argument, 0, 1004},
+                                         {"gpus", required_argument, 0, 1005},
+                                         {"stats-json", required_argument, 0, 1006},
                                          {0, 0, 0, 0}};
   for (;;) {
     int idx = 0;
@@ -141,6 +204,8 @@ int main(int argc, char** argv) {
       case 1002: p.batch = strtoull(optarg, 0, 10); break;
       case 1003: p.reload_tmp = true; break;
       case 1004: p.no_tmp_files = true; break;
+      case 1005: p.gpus = atoi(optarg); break;
+      case 1006: p.stats_json = optarg; break;
       default: break;  // -H -X -C -K -S -P -V: accepted, meaningless for mode C
     }
   }
@@ -152,6 +217,10 @@ int main(int argc, char** argv) {
   }
   if (p.batch < 1000) {
     std::cerr << "--batch must be at least 1000" << std::endl;
+    return 2;
+  }
+  if (p.gpus < 1 || p.gpus > 63) {
+    std::cerr << "--gpus must be between 1 and 63" << std::endl;
     return 2;
   }
 
@@ -184,8 +253,10 @@ int main(int argc, char** argv) {
     }
   }
 
-  klsh_ctx* ctx = nullptr;
-  if (klsh_create(p.device, &ctx) != KLSH_OK) {
+  // ---- contexts: one worker per requested GPU (workers share physical GPUs when there are fewer), plus
+  // the generator context that holds the run's hyperplane stream
+  Shared sh;
+  if (klsh_create(p.device, &sh.gen) != KLSH_OK) {
     std::cerr << "klsh_create failed: " << klsh_last_error(nullptr) << std::endl;
     return 1;
   }
@@ -193,69 +264,150 @@ int main(int argc, char** argv) {
     std::random_device rd;
     p.seed = ((uint64_t)rd() << 32) | rd();
   }
-  CK(ctx, klsh_set_seed(ctx, p.seed));
+  klsh_set_seed(sh.gen, p.seed);
+  int physical = 1;
+  for (int d = p.device + 1; d < p.device + p.gpus; ++d) {
+    klsh_ctx* probe = nullptr;
+    if (klsh_create(d, &probe) != KLSH_OK) break;
+    klsh_destroy(probe);
+    ++physical;
+  }
+  std::vector<Worker> workers((size_t)p.gpus);
+  for (int g = 0; g < p.gpus; ++g) {
+    Worker& w = workers[(size_t)g];
+    w.sh = &sh;
+    w.index = g;
+    w.device = p.device + g % physical;
+    if (klsh_create(w.device, &w.ctx) != KLSH_OK) {
+      std::cerr << "klsh_create(device " << w.device << ") failed: " << klsh_last_error(nullptr) << std::endl;
+      return 1;
+    }
+    klsh_set_plane_source(w.ctx, plane_tramp, &w);
+    klsh_set_draws_done_callback(w.ctx, done_tramp, &w);
+  }
+  if (p.gpus > 1)
+    std::cout << "kmerLSH_b200: " << p.gpus << " workers on " << physical << " GPU(s); phase-1 batches round-robin, one hyperplane stream"
+              << std::endl;
 
   // ---- init_clustering, reference app/kmerLSH.cc:278-430 -------------------------------------
   const uint64_t batch_thresh = p.batch;
   const int64_t phase1_bucket_thr = (int64_t)(batch_thresh / 1000);
-  std::ifstream inStream("kmer_count.bin", std::ios::binary);
-  if (!inStream.is_open()) {
-    std::cerr << "cannot open kmer_count.bin" << std::endl;
-    return 1;
+  {
+    std::ifstream probe("kmer_count.bin", std::ios::binary);
+    if (!probe.is_open()) {
+      std::cerr << "cannot open kmer_count.bin" << std::endl;
+      return 1;
+    }
   }
-  uint64_t batch_offset = 0, total_size = 0;
-  int tmp = 0, batches_run = 0;
+  uint64_t total_size = 0, next_call = 0;
+  int tmp = 0;
   int iter = (int)(kmap_size / batch_thresh);
   std::cout << "iteration : " << iter << " kmap_size : " << kmap_size << std::endl;
   std::string write_tmp = p.tmp_dir + std::to_string(tmp++) + ".bin";
-  std::vector<uint16_t> counts;
-  for (int i = 0; i < iter + 1; i++) {
-    const uint64_t batch_size = (i == iter) ? kmap_size - batch_offset : batch_thresh;
-    std::cout << "i: " << i << " batch_size : " << batch_size << " batch_offset : " << batch_offset << std::endl;
-    if (batch_size == 0) continue;  // the reference would call Cluster on an empty set here (undefined)
-    counts.resize((size_t)tot_sample * batch_size);
-    for (int j = 0; j < tot_sample; j++) {  // ReadHT, reference io/ioHT.cc:59-81
-      inStream.seekg((std::streamoff)(((uint64_t)j * kmap_size + batch_offset) * sizeof(uint16_t)), std::ios::beg);
-      inStream.read(reinterpret_cast<char*>(&counts[(size_t)j * batch_size]), (std::streamsize)(sizeof(uint16_t) * batch_size));
+
+  // One round of batches (phase 1 from kmer_count.bin, or a re-batch round from the previous spill):
+  // batch i runs on worker i % gpus; tables are drawn in batch order, spills are appended in batch order.
+  struct Batch { uint64_t offset, size, call; int index; };
+  auto run_round = [&](const std::vector<Batch>& batches, bool from_counts, const std::string& read_tmp, float sim, int iters,
+                       bool keep_resident, uint64_t* rows_total) -> bool {
+    sh.save_turn = 0;
+    std::atomic<uint64_t> total{0};
+    auto body = [&](Worker& w) {
+      std::vector<uint16_t> counts;
+      std::ifstream in;
+      if (from_counts) in.open("kmer_count.bin", std::ios::binary);
+      for (size_t bi = (size_t)w.index; bi < batches.size(); bi += (size_t)p.gpus) {
+        const Batch& b = batches[bi];
+        if (sh.failed.load()) return;
+        bool ok = true;
+        if (from_counts) {
+          counts.resize((size_t)tot_sample * b.size);
+          for (int j = 0; j < tot_sample; j++) {  // ReadHT, reference io/ioHT.cc:59-81
+            in.seekg((std::streamoff)(((uint64_t)j * kmap_size + b.offset) * sizeof(uint16_t)), std::ios::beg);
+            in.read(reinterpret_cast<char*>(&counts[(size_t)j * b.size]), (std::streamsize)(sizeof(uint16_t) * b.size));
+          }
+          ok = klsh_load_counts(w.ctx, counts.data(), v_kmers.data(), tot_sample, b.size, b.offset) == KLSH_OK;
+        } else {
+          ok = klsh_load_cluster_file(w.ctx, read_tmp.c_str(), tot_sample, b.offset, b.size) == KLSH_OK;
+        }
+        if (!ok) {
+          sh.fail(std::string("loading a batch failed: ") + klsh_last_error(w.ctx));
+          w.my_call = b.call;
+          done_tramp(&w);
+          return;
+        }
+        std::string log;
+        if (!cluster_call(w, from_counts ? "phase1" : "rebatch", b.call, sim, iters, phase1_bucket_thr, tot_sample, p.verbose ? &log : nullptr)) return;
+        uint64_t rows = 0;
+        klsh_row_count(w.ctx, &rows, nullptr);
+        total += rows;
+        {  // spill and log in batch order
+          std::unique_lock<std::mutex> lk(sh.mu);
+          sh.cv.wait(lk, [&] { return sh.save_turn == (uint64_t)b.index || sh.failed.load(); });
+        }
+        if (sh.failed.load()) return;
+        std::cout << "i: " << b.index << " batch_size : " << b.size << " batch_offset : " << b.offset << std::endl;
+        if (p.verbose) std::cout << log;
+        if (!keep_resident && klsh_save(w.ctx, write_tmp.c_str(), b.index == 0, 0) != KLSH_OK) {
+          sh.fail(std::string("klsh_save failed: ") + klsh_last_error(w.ctx));
+          return;
+        }
+        if (p.verbose) std::cout << "# loaded kmers: " << (b.offset + b.size) << std::endl;
+        {
+          std::lock_guard<std::mutex> lk(sh.mu);
+          sh.save_turn = (uint64_t)b.index + 1;
+          sh.cv.notify_all();
+        }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int g = 1; g < p.gpus; ++g) pool.emplace_back(body, std::ref(workers[(size_t)g]));
+    body(workers[0]);
+    for (auto& t : pool) t.join();
+    *rows_total = total.load();
+    return !sh.failed.load();
+  };
+  auto make_batches = [&](uint64_t rows, int n_iter) {
+    std::vector<Batch> out;
+    uint64_t off = 0;
+    int index = 0;
+    for (int i = 0; i < n_iter + 1; i++) {
+      const uint64_t size = (i == n_iter) ? rows - off : batch_thresh;
+      if (size == 0) {  // the reference would call Cluster on an empty set here (undefined)
+        std::cout << "i: " << i << " batch_size : 0 batch_offset : " << off << std::endl;
+        continue;
+      }
+      out.push_back(Batch{off, size, next_call++, index++});
+      off += size;
     }
-    CK(ctx, klsh_load_counts(ctx, counts.data(), v_kmers.data(), tot_sample, batch_size, batch_offset));
-    if (cluster_logged(ctx, p.min_similarity, 1, phase1_bucket_thr, tot_sample, p.verbose)) return 1;
-    uint64_t rows = 0;
-    CK(ctx, klsh_row_count(ctx, &rows, nullptr));
-    total_size += rows;
-    ++batches_run;
-    // a single batch that needs no re-batching stays on the device; its spill is optional then
-    const bool resident_ok = !p.reload_tmp && iter == 0 && rows <= batch_thresh;
-    if (!(resident_ok && p.no_tmp_files)) CK(ctx, klsh_save(ctx, write_tmp.c_str(), i == 0, 0));
-    batch_offset += batch_size;
-    if (p.verbose) std::cout << "# loaded kmers: " << batch_offset << std::endl;
+    return out;
+  };
+
+  std::vector<Batch> batches = make_batches(kmap_size, iter);
+  // a single batch that needs no re-batching stays on the device (one GPU); its spill is optional then
+  const bool single = batches.size() == 1 && !p.reload_tmp && p.gpus == 1;
+  if (!run_round(batches, true, "", p.min_similarity, 1, single && p.no_tmp_files, &total_size)) {
+    std::cerr << sh.error << std::endl;
+    return 1;
   }
-  const bool resident = !p.reload_tmp && iter == 0 && batches_run == 1 && total_size <= batch_thresh;
-  counts.clear();
-  counts.shrink_to_fit();
-  inStream.close();
+  const bool resident = single && total_size <= batch_thresh;
+  if (single && p.no_tmp_files && !resident) {  // the optional spill turned out to be needed after all
+    if (klsh_save(workers[0].ctx, write_tmp.c_str(), 1, 0) != KLSH_OK) {
+      std::cerr << "klsh_save failed: " << klsh_last_error(workers[0].ctx) << std::endl;
+      return 1;
+    }
+  }
 
   float similarity = p.min_similarity;
   while (total_size > batch_thresh) {
     similarity -= 0.001;
-    batch_offset = 0;
     const std::string read_tmp = write_tmp;
     write_tmp = p.tmp_dir + std::to_string(tmp++) + ".bin";
     iter = (int)(total_size / batch_thresh);
-    const uint64_t kcnt_rem = total_size;
-    total_size = 0;
-    for (int i = 0; i < iter + 1; i++) {
-      const uint64_t batch_size = (i == iter) ? kcnt_rem - batch_offset : batch_thresh;
-      std::cout << "i: " << i << " batch_size : " << batch_size << " batch_offset : " << batch_offset << std::endl;
-      if (batch_size == 0) continue;
-      CK(ctx, klsh_load_cluster_file(ctx, read_tmp.c_str(), tot_sample, batch_offset, batch_size));
-      if (cluster_logged(ctx, similarity, 1 + 4, phase1_bucket_thr, tot_sample, p.verbose)) return 1;
-      uint64_t rows = 0;
-      CK(ctx, klsh_row_count(ctx, &rows, nullptr));
-      total_size += rows;
-      CK(ctx, klsh_save(ctx, write_tmp.c_str(), i == 0, 0));
-      batch_offset += batch_size;
-      if (p.verbose) std::cout << "# loaded kmers: " << batch_offset << std::endl;
+    batches = make_batches(total_size, iter);
+    if (!run_round(batches, false, read_tmp, similarity, 1 + 4, false, &total_size)) {
+      std::cerr << sh.error << std::endl;
+      return 1;
     }
     if (std::remove(read_tmp.c_str()) != 0) perror("The temporary file deletion failed");
     else std::cout << read_tmp << "file are removed" << std::endl;
@@ -263,14 +415,64 @@ int main(int argc, char** argv) {
     if (std::remove(rc.c_str()) != 0) perror("The temporary file deletion failed");
     else std::cout << rc << "file are removed" << std::endl;
   }
-  if (!resident) CK(ctx, klsh_load_cluster_file(ctx, write_tmp.c_str(), tot_sample, 0, 0));
 
   // ---- the -I iterations, reference app/kmerLSH.cc:490 -----------------------------------------
-  if (cluster_logged(ctx, p.min_similarity, p.cluster_iteration, 1000000, tot_sample, p.verbose)) return 1;
+  // With several physical GPUs the single Cluster() call is sharded over them (klsh_mg_cluster: rows
+  // replicated, merge work partitioned, NCCL exchange inside the library); every rank needs the same rows
+  // and an identical copy of the hyperplane stream at its current position.
+  uint64_t seed0 = 0, drawn0 = 0;
+  klsh_plane_tell(sh.gen, &seed0, &drawn0);
+  const bool sharded = p.gpus > 1 && physical >= p.gpus;
+  klsh_ctx* ctx = workers[0].ctx;
+  if (!sharded) {
+    if (!resident && klsh_load_cluster_file(ctx, write_tmp.c_str(), tot_sample, 0, 0) != KLSH_OK) {
+      std::cerr << "klsh_load_cluster_file failed: " << klsh_last_error(ctx) << std::endl;
+      return 1;
+    }
+    std::string log;
+    if (!cluster_call(workers[0], "phase2", next_call++, p.min_similarity, p.cluster_iteration, 1000000, tot_sample, p.verbose ? &log : nullptr)) {
+      std::cerr << sh.error << std::endl;
+      return 1;
+    }
+    if (p.verbose) std::cout << log;
+  } else {
+    unsigned char uid[128];
+    if (klsh_nccl_unique_id(uid, sizeof uid) != KLSH_OK) {
+      std::cerr << "klsh_nccl_unique_id failed: " << klsh_last_error(nullptr) << std::endl;
+      return 1;
+    }
+    std::vector<std::vector<klsh_iter_stats>> st((size_t)p.gpus, std::vector<klsh_iter_stats>((size_t)p.cluster_iteration));
+    auto body = [&](Worker& w) {
+      klsh_set_draws_done_callback(w.ctx, nullptr, nullptr);
+      if (klsh_mg_init(w.ctx, w.index, p.gpus, uid, sizeof uid) != KLSH_OK ||
+          klsh_load_cluster_file(w.ctx, write_tmp.c_str(), tot_sample, 0, 0) != KLSH_OK ||
+          klsh_plane_seek(w.ctx, seed0, drawn0) != KLSH_OK ||
+          klsh_mg_cluster(w.ctx, p.min_similarity, p.cluster_iteration, 1000000, st[(size_t)w.index].data()) != KLSH_OK)
+        sh.fail(std::string("sharded phase 2 failed on worker ") + std::to_string(w.index) + ": " + klsh_last_error(w.ctx));
+    };
+    std::vector<std::thread> pool;
+    for (int g = 1; g < p.gpus; ++g) pool.emplace_back(body, std::ref(workers[(size_t)g]));
+    body(workers[0]);
+    for (auto& t : pool) t.join();
+    if (sh.failed.load()) {
+      std::cerr << sh.error << std::endl;
+      return 1;
+    }
+    if (p.verbose) std::cout << iteration_lines(st[0], tot_sample, 0.f);
+    json_records(sh, "phase2-sharded", next_call++, 0, st[0]);
+  }
 
   // ---- reference app/kmerLSH.cc:498-499 ---------------------------------------------------------
   if (p.verbose) std::cout << "Saving cluster results starts: " << std::endl;
-  CK(ctx, klsh_save(ctx, p.clust_file_name.c_str(), 1, 5));
-  klsh_destroy(ctx);
+  if (klsh_save(ctx, p.clust_file_name.c_str(), 1, 5) != KLSH_OK) {
+    std::cerr << "klsh_save failed: " << klsh_last_error(ctx) << std::endl;
+    return 1;
+  }
+  if (!p.stats_json.empty()) {
+    std::ofstream js(p.stats_json.c_str());
+    js << sh.json.str();
+  }
+  for (auto& w : workers) klsh_destroy(w.ctx);
+  klsh_destroy(sh.gen);
   return 0;
 }

@@ -129,6 +129,31 @@ def test_mode_c_cli_matches_reference_binary(tag, extra, tmp_path):
     assert md5(out + ".clust") == m["clust_md5"]
 
 
+@pytest.mark.parametrize("tag", ["modec_small", "modec_C1"])
+def test_reference_program_with_cluster_shim(tag, tmp_path):
+    """The drop-in proof for function/cluster.h:42: oracle/_ref/kmerLSH_shim is the reference's OWN
+    app/kmerLSH.cc and objects, linked with oracle/cluster_b200.cc in place of
+    function/cluster.o, so every Cluster() call of mode C (app/kmerLSH.cc:323, :490) runs on libklsh
+    with the reference's own LSH::generateHashTable behind the plane callback.  Its output files must be
+    byte-identical to the unmodified reference binary's (the golden md5s)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "kmerLSH_shim")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/kmerLSH_shim not built (needs /root/reference at build time)")
+    m = json.load(open(os.path.join(G, "golden.json")))[tag]
+    work = str(tmp_path)
+    synth.write_mode_c_inputs(work, m["n"], m["sa"], m["sb"], m["gen_seed"])
+    if md5(os.path.join(work, "kmer_count.bin")) != m["kmer_count_bin_md5"]:
+        pytest.skip("numpy generator stream differs from the one the golden run used")
+    env = dict(os.environ, KLSH_SEED=str(m["klsh_seed"]), OMP_THREAD_LIMIT="1")
+    subprocess.run([exe, "-a", "A.txt", "-b", "B.txt", "-o", "oa", "-p", "ob", "-M", "C", "--only", "-I", str(m["iters"]),
+                    "-N", str(m["min_similarity"]), "-K", "23", "-T", "1"], cwd=work, env=env, check=True, stdout=subprocess.DEVNULL)
+    out = os.path.join(work, "clustering_result.txt")
+    assert md5(os.path.join(work, "tmp", "0.bin")) == m["tmp_bin_md5"]
+    assert md5(os.path.join(work, "tmp", "0.bin.clust")) == m["tmp_clust_md5"]
+    assert md5(out) == m["bin_md5"]
+    assert md5(out + ".clust") == m["clust_md5"]
+
+
 def test_mode_c_cli_two_batches(oracle, tmp_path):
     """--batch smaller than the input: independent phase-1 batches appended to tmp/0.bin, the
     re-batch loop (similarity -= 0.001, 5 iterations per batch) while survivors exceed the batch

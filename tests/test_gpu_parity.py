@@ -203,13 +203,18 @@ def test_save_files(gpu, oracle, tmp_path):
     assert_rows_equal(gpu.get_rows(), back.export())
 
 
-@pytest.mark.parametrize("cta_max,cluster_max,cluster2_max,csize", [(8, 64, 200, 8), (1, 1, 1, 8), (2, 1000000, 1000000, 4), (16, 100, 150, 16),
-                                                                  (4, 4, 1000000, 8), (1000000, 1000000, 1000000, 8)])
-def test_merge_team_variants(oracle, monkeypatch, cta_max, cluster_max, cluster2_max, csize):
+@pytest.mark.parametrize("cta_max,cluster_max,cluster2_max,csize,direct_min", [
+    (8, 64, 200, 8, 8192), (1, 1, 1, 8, 8192), (2, 1000000, 1000000, 4, 8192), (16, 100, 150, 16, 8192), (4, 4, 1000000, 8, 8192),
+    (1000000, 1000000, 1000000, 8, 8192),
+    # buckets of >= direct_min rows take the direct pipeline (cluster teams on the second stream, concurrent
+    # with the single-CTA stage), with its own escalation to large clusters and the grid
+    (8, 64, 200, 8, 40), (1000000, 20, 60, 8, 100), (4, 1000000, 1000000, 16, 33), (2, 2, 2, 8, 300)])
+def test_merge_team_variants(oracle, monkeypatch, cta_max, cluster_max, cluster2_max, csize, direct_min):
     """The windowed merge with the escalation thresholds (representatives per team) forced low, so
     that small test buckets travel CTA -> cluster -> large cluster -> cooperative grid, against the oracle."""
     from kmerlsh_b200 import Context
 
+    monkeypatch.setenv("KLSH_DIRECT_MIN", str(direct_min))
     monkeypatch.setenv("KLSH_CTA_MAX", str(cta_max))
     monkeypatch.setenv("KLSH_CLUSTER_MAX", str(cluster_max))
     monkeypatch.setenv("KLSH_CLUSTER2_MAX", str(cluster2_max))
