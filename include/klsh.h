@@ -13,6 +13,9 @@
  * (exception: with KLSH_DEBUG=1 in the environment it writes per-kernel diagnostics to stderr).
  * There is no CPU fallback: every entry point fails with KLSH_ERR_CUDA when no sm_100 device is
  * usable.
+ * Row width: any D up to 768 samples.  Up to D = 280 the in-bucket merge is the windowed tensor-core
+ * kernel; wider rows take a block-per-bucket kernel automatically (exact, much slower).  Beyond 768 the
+ * signing kernel's plane tables no longer fit in shared memory and klsh_cluster returns KLSH_ERR_ARG.
  */
 #ifndef KLSH_H
 #define KLSH_H
@@ -43,6 +46,9 @@ typedef struct {
   uint64_t buckets, bucket_max, nested_calls;
   uint64_t eps_margin_rows; /* rows whose key needed the exact re-evaluation path (0 = exact everywhere) */
   float ms_sign, ms_group, ms_merge, ms_compact, ms_total; /* CUDA-event times on the context's stream */
+  /* compare work of the in-bucket merge: (window candidate, representative) pairs screened on the tensor
+   * cores and the pairs that went on to the reference's exact fp32 test */
+  uint64_t screen_pairs, exact_pairs;
 } klsh_iter_stats;
 
 /* ---- lifetime -------------------------------------------------------------------------------- */

@@ -42,6 +42,8 @@ class IterStats(C.Structure):
         ("ms_merge", C.c_float),
         ("ms_compact", C.c_float),
         ("ms_total", C.c_float),
+        ("screen_pairs", u64),
+        ("exact_pairs", u64),
     ]
 
 

@@ -556,9 +556,9 @@ extern "C" int klsh_cluster(klsh_ctx* ctx, float min_similarity, int iterations,
   float max_similarity = 0.95f;
   float sim_step = (max_similarity - min_similarity) / iterations;
   float threshold = max_similarity;
-  KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long) * 2));
-  KCUDA(ctx, cudaMemsetAsync(ctx->eps_counter.p, 0, sizeof(unsigned long long), ctx->stream));
-  unsigned long long eps_prev = 0;
+  KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long) * 4));
+  KCUDA(ctx, cudaMemsetAsync(ctx->eps_counter.p, 0, sizeof(unsigned long long) * 4, ctx->stream));
+  unsigned long long eps_prev = 0, pairs_prev = 0, exact_prev = 0;
   ctx->draws_done_fired = false;
   struct DoneGuard {  // the callback fires exactly once per call, whatever path the call takes
     klsh_ctx* c;
@@ -590,11 +590,15 @@ extern "C" int klsh_cluster(klsh_ctx* ctx, float min_similarity, int iterations,
       s.buckets = info.buckets;
       s.bucket_max = info.bucket_max;
       s.nested_calls = info.nested_calls;
-      unsigned long long eps_now = 0;
-      KCUDA(ctx, cudaMemcpyAsync(&eps_now, ctx->eps_counter.p, sizeof eps_now, cudaMemcpyDeviceToHost, ctx->stream));
+      unsigned long long cnt_now[4] = {0, 0, 0, 0};
+      KCUDA(ctx, cudaMemcpyAsync(cnt_now, ctx->eps_counter.p, sizeof cnt_now, cudaMemcpyDeviceToHost, ctx->stream));
       KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
-      s.eps_margin_rows = eps_now - eps_prev;  // includes the signing passes of nested buckets
-      eps_prev = eps_now;
+      s.eps_margin_rows = cnt_now[0] - eps_prev;  // includes the signing passes of nested buckets
+      eps_prev = cnt_now[0];
+      s.screen_pairs = cnt_now[2] - pairs_prev;
+      pairs_prev = cnt_now[2];
+      s.exact_pairs = cnt_now[3] - exact_prev;
+      exact_prev = cnt_now[3];
       s.ms_sign = info.ms_sign;
       s.ms_group = info.ms_group;
       s.ms_merge = info.ms_merge;
@@ -825,7 +829,7 @@ static int count_ids(klsh_ctx* ctx, uint64_t* n_ids) {
   *n_ids = 0;
   const uint64_t n = ctx->cur.n_alive;
   if (!n) return KLSH_OK;
-  KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long) * 2));
+  KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long) * 4));
   unsigned long long* d_total = ctx->eps_counter.as<unsigned long long>() + 1;
   KTRY(launch_sum_counts(ctx, ctx->cur.alive.as<uint32_t>(), n, d_total));
   unsigned long long h = 0;

@@ -153,12 +153,13 @@ constexpr int kSignWarps = 4;
 // [rows x D] x [D x H] product, so it goes to the tensor cores as 3xTF32: every operand is split
 // into hi = tf32(v) and lo = tf32(v - hi) and the sum hi*hi + hi*lo + lo*hi is accumulated in fp32
 // (mma.sync.m16n8k8).  Error budget in units of 2^-24 * sum|w_i x_i| (<= 2^-24 * |w| * |x|):
-//   12   the dropped lo*lo products and the split residues (3 * 2^-22 per term);
+//   28   the dropped lo*lo products and the split residues: rows are split by truncation (residue < 2^-20 |x|),
+//        planes by rounding (2^-22 |w|): (2^-21 + 2^-20 + 2^-22) per term;
 //   10   per mma for the tensor core's truncating fp32 accumulation (alignment of the 8 products to the
 //        largest exponent with a few guard bits + the final truncation; a worst-case figure, the
 //        measured behaviour is far better), 3*ceil(D/8) mma per sum;
 //   D    the reference chain's own rounding (its sign is what has to be reproduced).
-// So   eps = (D + 16 + 30*ceil(D/8)) * 2^-24 * |w| * |x|   (D = 32: 168 * 2^-24 = 1.0e-5)
+// So   eps = (D + 32 + 30*ceil(D/8)) * 2^-24 * |w| * |x|   (D = 32: 184 * 2^-24 = 1.1e-5)
 // guarantees that a sum outside it has the sign of the reference's mul-then-add chain; a sum inside it
 // is re-evaluated with the reference's exact arithmetic (and the row counted), so every key bit is
 // the reference's.  A warp owns 32 rows: cp.async gathers them into a double-buffered shared tile
@@ -168,6 +169,14 @@ __device__ __forceinline__ uint32_t tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
   return r;
+}
+// Row operands are split by masking: hi = the top 19 bits (what a tf32 operand keeps; mma ignores the low 13
+// bits of a .tf32 register), lo = x - hi, exact in fp32 and itself truncated by the mma.  One LOP and one
+// FADD per element instead of two cvt.rna and an FADD; the residue is < 2^-20 |x| instead of 2^-22 |x|,
+// which the error budget below accounts for.
+__device__ __forceinline__ void tf32_split(float x, uint32_t& hi, uint32_t& lo) {
+  hi = __float_as_uint(x) & 0xFFFFE000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
   asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -200,7 +209,7 @@ k_sign_tc(const float* __restrict__ vals, int D, int ld, const uint32_t* __restr
   for (int h = threadIdx.x; h < 32; h += blockDim.x) {
     float m = 0.f;
     for (int i = 0; i < D; ++i) m = __fmaf_rn(sp[h * KW + i], sp[h * KW + i], m);
-    pn[h] = sqrtf(m) * (((float)D + 16.f + 30.f * (float)((D + 7) / 8)) * 5.9604645e-8f);
+    pn[h] = sqrtf(m) * (((float)D + 32.f + 30.f * (float)((D + 7) / 8)) * 5.9604645e-8f);
   }
   for (int i = threadIdx.x; i < KS8 * 4 * 32; i += blockDim.x) {
     const int l = i & 31, nt = (i >> 5) & 3, ks = i >> 7;
@@ -286,10 +295,10 @@ k_sign_tc(const float* __restrict__ vals, int D, int ld, const uint32_t* __restr
       for (int m = 0; m < 2; ++m) {
         const float* p0 = tile + (m * 16 + g) * TS + ks * 8 + tg;
         const float a0 = p0[0], a1 = p0[8 * TS], a2 = p0[4], a3 = p0[8 * TS + 4];
-        ahi[m][0] = tf32_rna(a0); alo[m][0] = tf32_rna(a0 - __uint_as_float(ahi[m][0]));
-        ahi[m][1] = tf32_rna(a1); alo[m][1] = tf32_rna(a1 - __uint_as_float(ahi[m][1]));
-        ahi[m][2] = tf32_rna(a2); alo[m][2] = tf32_rna(a2 - __uint_as_float(ahi[m][2]));
-        ahi[m][3] = tf32_rna(a3); alo[m][3] = tf32_rna(a3 - __uint_as_float(ahi[m][3]));
+        tf32_split(a0, ahi[m][0], alo[m][0]);
+        tf32_split(a1, ahi[m][1], alo[m][1]);
+        tf32_split(a2, ahi[m][2], alo[m][2]);
+        tf32_split(a3, ahi[m][3], alo[m][3]);
       }
 #pragma unroll
       for (int nt = 0; nt < 4; ++nt)
@@ -389,7 +398,7 @@ k_sign_tc_wide(const float* __restrict__ vals, int D, int ld, const uint32_t* __
     float m = 0.f;
     if (h < H)
       for (int i = 0; i < D; ++i) m = __fmaf_rn(planes[h * ld + i], planes[h * ld + i], m);
-    pn[h] = sqrtf(m) * (((float)D + 16.f + 240.f + (float)nch) * 5.9604645e-8f);  // 24 mma per 64-column chunk
+    pn[h] = sqrtf(m) * (((float)D + 32.f + 240.f + (float)nch) * 5.9604645e-8f);  // 24 mma per 64-column chunk
   }
   for (int i = threadIdx.x; i < nch * KS8 * 4 * 32; i += blockDim.x) {
     const int l = i & 31, nt = (i >> 5) & 3, ks = i >> 7;  // ks runs over the whole width
@@ -480,10 +489,10 @@ k_sign_tc_wide(const float* __restrict__ vals, int D, int ld, const uint32_t* __
         for (int m = 0; m < 2; ++m) {
           const float* p0 = tile + (m * 16 + g) * TS + ks * 8 + tg;
           const float a0 = p0[0], a1 = p0[8 * TS], a2 = p0[4], a3 = p0[8 * TS + 4];
-          ahi[m][0] = tf32_rna(a0); alo[m][0] = tf32_rna(a0 - __uint_as_float(ahi[m][0]));
-          ahi[m][1] = tf32_rna(a1); alo[m][1] = tf32_rna(a1 - __uint_as_float(ahi[m][1]));
-          ahi[m][2] = tf32_rna(a2); alo[m][2] = tf32_rna(a2 - __uint_as_float(ahi[m][2]));
-          ahi[m][3] = tf32_rna(a3); alo[m][3] = tf32_rna(a3 - __uint_as_float(ahi[m][3]));
+          tf32_split(a0, ahi[m][0], alo[m][0]);
+          tf32_split(a1, ahi[m][1], alo[m][1]);
+          tf32_split(a2, ahi[m][2], alo[m][2]);
+          tf32_split(a3, ahi[m][3], alo[m][3]);
         }
 #pragma unroll
         for (int nt = 0; nt < 4; ++nt)
@@ -1261,7 +1270,7 @@ int launch_transform(klsh_ctx* ctx, const uint16_t* d_counts, const float* d_vk,
 int launch_sign(klsh_ctx* ctx, const float* vals, int D, int ld, const uint32_t* rows, uint64_t n,
                 const float* d_planes, int H, uint32_t* keys_out, uint32_t* rows_out, uint32_t key_or) {
   if (!n) return KLSH_OK;
-  KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long)));
+  KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long) * 4));
   if (ld <= 64) {
     const int ks8 = ld <= 32 ? 4 : 8, kw = ks8 * 8;
     const size_t smem = sizeof(float) * ((size_t)32 * kw + 32) + 16 * (size_t)ks8 * 4 * 32 +

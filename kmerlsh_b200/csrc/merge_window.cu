@@ -166,6 +166,7 @@ struct MergeArgs {
   uint4* pos_h;
   TeamCtl* ctl;
   MgLog mg;
+  unsigned long long* work;  // [2] device counters: pairs screened on the tensor cores, pairs re-tested exactly
   int no_spec;   // KLSH_NO_SPEC=1: sequential resolution only (A/B checks)
   unsigned long long* dbg;  // [32] 26: speculative windows, 27: ... cut short; 0..7: windows, candidates, merges, undecidable, cache_full, back_exhausted, accepted, escalated; 8..13: leader cycles in stage/parallel/sync1/prefetch/decide/flush+sync2; 18..21: staging detail
   float threshold;
@@ -1452,6 +1453,7 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
       wf = kW - wb;
     }
     const int W = wf + wb;
+    if (leader && tid == 0 && A.work) atomicAdd(A.work, (unsigned long long)W * ((unsigned long long)i0 + (unsigned long long)W));
     long long tk0 = 0, tk1 = 0, tk2 = 0, tk3 = 0, tk4 = 0, tk5 = 0;
     const bool prof = A.dbg && leader && tid == 0;
     if (prof) tk0 = clock64();
@@ -1552,6 +1554,7 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
       // exact tests of the pairs the screen parked: all of the CTA's threads at once, so the
       // dependent row fetches of different pairs overlap
       const uint32_t ns = min(s.surv[kSurvCap], (uint32_t)kSurvCap);
+      if (tid == 0 && ns && A.work) atomicAdd(A.work + 1, (unsigned long long)ns);
       for (uint32_t k0 = 0; k0 < ns; k0 += 2 * kMT) {
         uint32_t ent[2], rr2[2];
         bool on[2];
@@ -1840,6 +1843,7 @@ static MergeArgs base_args(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted,
   A.mg = ctx->mg;
   A.threshold = threshold;
   A.no_spec = ctx->no_spec ? 1 : 0;
+  A.work = ctx->eps_counter.p ? ctx->eps_counter.as<unsigned long long>() + 2 : nullptr;
   A.list_a = A.list_b = nullptr;
   A.n_a = A.n_b = nullptr;
   A.cursor = nullptr;
@@ -1929,7 +1933,11 @@ int launch_merge_direct(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
   A.esc_list = s.escb2.as<uint32_t>();
   A.esc_count = &dc->nb_esc2;
   A.max_reps = ctx->cluster_max;
-  KTRY(launch_stage(ctx, st, ctx->team_ctl_b, 1, ctx->cluster_size, A, n_direct_host));
+  // few direct buckets: give each a large (16-CTA) cluster from the start — their screen is spread over twice
+  // the SMs and nobody queues; many: the portable 8-CTA clusters, so that more of them run side by side
+  const int per_sm = std::max(1, ctx->cluster_ctas_per_sm);
+  const int csize1 = ((uint64_t)n_direct_host * (uint64_t)ctx->cluster2_size <= (uint64_t)ctx->sm_count * per_sm) ? ctx->cluster2_size : ctx->cluster_size;
+  KTRY(launch_stage(ctx, st, ctx->team_ctl_b, 1, csize1, A, n_direct_host));
   if (bucket_max_host <= ctx->cluster_max) return KLSH_OK;
 
   A.list_a = s.escb2.as<uint32_t>();

@@ -170,3 +170,28 @@ def test_mode_c_cli_two_batches(oracle, tmp_path):
     res = os.path.join(work, "clustering_result.txt")
     assert md5(res) == md5(out)
     assert md5(res + ".clust") == md5(out + ".clust")
+
+
+@pytest.mark.parametrize("gpus", [2, 3])
+def test_mode_c_cli_several_workers(oracle, tmp_path, gpus):
+    """--gpus=N: phase-1 batches and re-batch rounds run round-robin on N worker contexts (sharing the
+    physical GPUs when there are fewer), the hash tables still come from ONE seeded stream in the
+    reference's call order (a context draws only at its call's turn and hands the stream on through the
+    draws-done callback), spills are appended in batch order.  The output must be byte-identical to the
+    oracle's sequential mode C, i.e. to --gpus=1."""
+    work = str(tmp_path)
+    synth.write_mode_c_inputs(work, 60000, 3, 3, 123)
+    out = os.path.join(work, "oracle_result.txt")
+    os.makedirs(os.path.join(work, "otmp"))
+    oracle.mode_c(work, 6, 0.85, 4, out, 29, batch_thresh=9000, tmp_dir=os.path.join(work, "otmp") + "/")
+    exe = os.path.join(ROOT, "kmerlsh_b200", "kmerLSH_b200")
+    stats = os.path.join(work, "stats.json")
+    subprocess.run([exe, "-a", "A.txt", "-b", "B.txt", "-o", "oa", "-p", "ob", "-M", "C", "--only", "-I", "4", "-N", "0.85",
+                    "-T", "1", "--seed=29", "--batch=9000", "--gpus=%d" % gpus, "--stats-json=" + stats], cwd=work, check=True,
+                   stdout=subprocess.DEVNULL)
+    res = os.path.join(work, "clustering_result.txt")
+    assert md5(res) == md5(out)
+    assert md5(res + ".clust") == md5(out + ".clust")
+    recs = [json.loads(ln) for ln in open(stats)]
+    assert {r["phase"] for r in recs} >= {"phase1"} and all(r["rows_out"] <= r["rows_in"] for r in recs)
+    assert len({r["gpu"] for r in recs if r["phase"] == "phase1"}) == gpus

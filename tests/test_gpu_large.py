@@ -55,7 +55,7 @@ def test_sign_adversarial_cancellation(gpu, oracle, D, H, n):
     rng = np.random.default_rng(1000 + D)
     table = oracle.planes(77).table(H, D)
     rows = np.empty((n, D), np.float32)
-    c_eps = (D + 16 + 30 * ((D + 7) // 8)) * 2.0 ** -24
+    c_eps = (D + 32 + 30 * ((D + 7) // 8)) * 2.0 ** -24
     for r0 in range(0, n, 20000):
         m = min(20000, n - r0)
         p = (np.arange(r0, r0 + m) % H)

@@ -136,6 +136,20 @@ def test_cluster_wide_rows(gpu, oracle):
     assert_rows_equal(gpu.get_rows(), rows.export())
 
 
+def test_cluster_rows_beyond_the_windowed_merge(gpu, oracle):
+    """D = 300: the windowed merge's shared-memory window no longer fits (about 768 bytes per float of row
+    width), so the library falls back to the block-per-bucket merge kernel on its own — same results."""
+    rng = np.random.default_rng(31)
+    base = rng.standard_normal((40, 300)).astype(np.float32)
+    values = (base[rng.integers(0, 40, size=2500)] + np.float32(0.25) * rng.standard_normal((2500, 300))).astype(np.float32)
+    rows = oracle.rows(values)
+    rows.cluster(0.8, 3, 100000, oracle.planes(8))
+    gpu.set_seed(8)
+    gpu.set_rows(values)
+    gpu.cluster(0.8, 3, 100000)
+    assert_rows_equal(gpu.get_rows(), rows.export())
+
+
 def test_nested_cluster(gpu, oracle):
     _, _, values, ids = synth_rows(oracle, 20000, 4, 4, 21)
     rows = oracle.rows(values)
@@ -347,4 +361,30 @@ def test_eps_margin_rows_are_reported(gpu, oracle):
     gpu.set_seed(0)
     assert st[0].eps_margin_rows >= 100   # most of the 200 constructed rows
     assert st[0].eps_margin_rows < 2000
+    assert_rows_equal(gpu.get_rows(), rows.export())
+
+
+def test_plane_stream_tell_seek_and_done_callback(gpu, oracle):
+    """klsh_plane_tell / klsh_plane_seek position the seeded hyperplane stream; the draws-done callback fires
+    once per cluster() call, after the call's last table has been drawn."""
+    _, _, values, ids = synth_rows(oracle, 20000, 4, 4, 15)
+    gpu.set_seed(77)
+    t1 = gpu.draw_table(9, 8)
+    seed, drawn = gpu.plane_tell()
+    assert (seed, drawn) == (77, 9)
+    t2 = gpu.draw_table(5, 8)
+    gpu.plane_seek(77, 9)
+    assert gpu.draw_table(5, 8).tobytes() == t2.tobytes()
+    gpu.plane_seek(77, 0)
+    assert gpu.draw_table(9, 8).tobytes() == t1.tobytes()
+    fired = []
+    gpu.set_draws_done_callback(lambda: fired.append(gpu.plane_tell()[1]))
+    gpu.set_seed(5)
+    gpu.set_rows(values)
+    st = gpu.cluster(0.85, 3, 60)      # nested buckets draw tables too
+    end = gpu.plane_tell()[1]
+    gpu.set_draws_done_callback(None)
+    assert len(fired) == 1 and fired[0] == end and end >= sum(s.H for s in st)
+    rows = oracle.rows(values)
+    rows.cluster(0.85, 3, 60, oracle.planes(5))
     assert_rows_equal(gpu.get_rows(), rows.export())
