@@ -239,6 +239,7 @@ def main():
         raise SystemExit("bench.py needs a B200; there is no CPU path")
     torch.cuda.set_device(local_rank)
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")  # stdout carries the one JSON line only
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     def barrier():
@@ -447,6 +448,16 @@ def main():
                 "peak_all_gpus": peak * world},
     }
 
+    if world > 1:
+        # per-family event times exist only on the single-GPU path: the block describes the whole sharded step
+        roofline = {
+            "bound": "hbm", "kernel": "whole step: sign + group on every rank, merge of the rank's bucket range, NCCL exchange",
+            "achieved": job_achieved, "peak": peak * world, "unit": "GB/s", "frac": job_achieved / (peak * world), "traffic": None,
+            "algorithmic_bytes_per_step": job_bytes / args.steps, "peak_source": peak_src, "bytes_per_row_iter": "8D+32+s(4D+12)",
+            "note": "achieved = algorithmic bytes of the job / step time (max over ranks), peak = measured HBM copy peak x GPUs.  Every rank "
+                    "signs and sorts all rows (replicated) and the step follows the longest bucket's sequential window chain, which is why "
+                    "more GPUs shorten it so little; see roofline.compare of the 1-GPU line for the merge itself",
+        }
     cpu = None
     if not args.no_cpu_baseline and os.path.exists(REF_BIN):
         cores = os.cpu_count() or 1

@@ -77,7 +77,7 @@ static void free_scratch(PassScratch& s) {
 }
 
 static void free_state(RowState& r) {
-  dev_free(r.vals); dev_free(r.cnt); dev_free(r.head); dev_free(r.tail); dev_free(r.next); dev_free(r.alive);
+  dev_free(r.vals); dev_free(r.meta); dev_free(r.next); dev_free(r.alive);
   r.n_alive = 0;
 }
 
@@ -245,9 +245,7 @@ static int reserve_rows(klsh_ctx* ctx, uint64_t n_rows, uint64_t n_slots, int D)
   ctx->D = D;
   ctx->ld = (D + 3) & ~3;
   KTRY(dev_reserve(ctx, ctx->cur.vals, sizeof(float) * (n_rows * (uint64_t)ctx->ld + 4)));
-  KTRY(dev_reserve(ctx, ctx->cur.cnt, sizeof(int32_t) * (n_rows + 1)));
-  KTRY(dev_reserve(ctx, ctx->cur.head, sizeof(int32_t) * (n_rows + 1)));
-  KTRY(dev_reserve(ctx, ctx->cur.tail, sizeof(int32_t) * (n_rows + 1)));
+  KTRY(dev_reserve(ctx, ctx->cur.meta, sizeof(int32_t) * 4 * (n_rows + 1)));
   KTRY(dev_reserve(ctx, ctx->cur.next, sizeof(int32_t) * (n_slots + 1)));
   KTRY(dev_reserve(ctx, ctx->cur.alive, sizeof(uint32_t) * (n_rows + 1)));
   return KLSH_OK;
@@ -316,19 +314,16 @@ extern "C" int klsh_set_rows(klsh_ctx* ctx, const float* values, const uint64_t*
                                    cudaMemcpyHostToDevice, ctx->stream));
     }
   }
-  std::vector<int32_t> cnt(n), head(n), tail(n), next(m);
+  std::vector<int32_t> meta(4 * n), next(m);  // records {cnt, head, tail, 0}
   for (uint64_t r = 0; r < n; ++r) {
     uint64_t b = id_offsets[r], e = id_offsets[r + 1];
-    cnt[r] = (int32_t)(e - b);
-    head[r] = e > b ? (int32_t)b : -1;
-    tail[r] = e > b ? (int32_t)(e - 1) : -1;
+    meta[4 * r] = (int32_t)(e - b);
+    meta[4 * r + 1] = e > b ? (int32_t)b : -1;
+    meta[4 * r + 2] = e > b ? (int32_t)(e - 1) : -1;
+    meta[4 * r + 3] = 0;
     for (uint64_t s = b; s < e; ++s) next[s] = (s + 1 < e) ? (int32_t)(s + 1) : -1;
   }
-  if (n) {
-    KCUDA(ctx, cudaMemcpyAsync(ctx->cur.cnt.p, cnt.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
-    KCUDA(ctx, cudaMemcpyAsync(ctx->cur.head.p, head.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
-    KCUDA(ctx, cudaMemcpyAsync(ctx->cur.tail.p, tail.data(), sizeof(int32_t) * n, cudaMemcpyHostToDevice, ctx->stream));
-  }
+  if (n) KCUDA(ctx, cudaMemcpyAsync(ctx->cur.meta.p, meta.data(), sizeof(int32_t) * 4 * n, cudaMemcpyHostToDevice, ctx->stream));
   if (m) KCUDA(ctx, cudaMemcpyAsync(ctx->cur.next.p, next.data(), sizeof(int32_t) * m, cudaMemcpyHostToDevice, ctx->stream));
   ctx->ids.assign(ids, ids + m);
   ctx->ids_implicit = false;
@@ -874,16 +869,12 @@ extern "C" int klsh_save(klsh_ctx* ctx, const char* bin_path, int delfile, int64
 static int copy_state(klsh_ctx* ctx, RowState& dst, const RowState& src, uint64_t n_born, uint64_t n_slots) {
   const size_t vb = sizeof(float) * (n_born * (uint64_t)ctx->ld + 4);
   KTRY(dev_reserve(ctx, dst.vals, vb));
-  KTRY(dev_reserve(ctx, dst.cnt, sizeof(int32_t) * (n_born + 1)));
-  KTRY(dev_reserve(ctx, dst.head, sizeof(int32_t) * (n_born + 1)));
-  KTRY(dev_reserve(ctx, dst.tail, sizeof(int32_t) * (n_born + 1)));
+  KTRY(dev_reserve(ctx, dst.meta, sizeof(int32_t) * 4 * (n_born + 1)));
   KTRY(dev_reserve(ctx, dst.next, sizeof(int32_t) * (n_slots + 1)));
   KTRY(dev_reserve(ctx, dst.alive, sizeof(uint32_t) * (n_born + 1)));
   cudaStream_t st = ctx->stream;
   KCUDA(ctx, cudaMemcpyAsync(dst.vals.p, src.vals.p, sizeof(float) * n_born * (uint64_t)ctx->ld, cudaMemcpyDeviceToDevice, st));
-  KCUDA(ctx, cudaMemcpyAsync(dst.cnt.p, src.cnt.p, sizeof(int32_t) * n_born, cudaMemcpyDeviceToDevice, st));
-  KCUDA(ctx, cudaMemcpyAsync(dst.head.p, src.head.p, sizeof(int32_t) * n_born, cudaMemcpyDeviceToDevice, st));
-  KCUDA(ctx, cudaMemcpyAsync(dst.tail.p, src.tail.p, sizeof(int32_t) * n_born, cudaMemcpyDeviceToDevice, st));
+  KCUDA(ctx, cudaMemcpyAsync(dst.meta.p, src.meta.p, sizeof(int32_t) * 4 * n_born, cudaMemcpyDeviceToDevice, st));
   KCUDA(ctx, cudaMemcpyAsync(dst.next.p, src.next.p, sizeof(int32_t) * n_slots, cudaMemcpyDeviceToDevice, st));
   KCUDA(ctx, cudaMemcpyAsync(dst.alive.p, src.alive.p, sizeof(uint32_t) * src.n_alive, cudaMemcpyDeviceToDevice, st));
   dst.n_alive = src.n_alive;
@@ -937,6 +928,7 @@ extern "C" int klsh_mg_pass_begin(klsh_ctx* ctx, uint64_t* n_rows, int32_t* H_ou
   const uint64_t n = ctx->cur.n_alive;
   ctx->mg_n = n;
   ctx->mg_nb = 0;
+  ctx->mg_stage = 1;
   if (n_rows) *n_rows = n;
   if (n == 0) {
     if (H_out) *H_out = 0;
@@ -962,6 +954,7 @@ extern "C" int klsh_mg_pass_begin(klsh_ctx* ctx, uint64_t* n_rows, int32_t* H_ou
 
 extern "C" int klsh_mg_plan(klsh_ctx* ctx, int world, uint32_t* splits_out) {
   if (!ctx || world < 1 || world > 63 || !splits_out) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_plan: bad argument");
+  if (ctx->mg_stage < 1) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_plan: call klsh_mg_pass_begin first");
   KCUDA(ctx, cudaSetDevice(ctx->device));
   if (ctx->mg_n == 0) {
     for (int r = 0; r <= world; ++r) splits_out[r] = 0;
@@ -978,6 +971,10 @@ extern "C" int klsh_mg_plan(klsh_ctx* ctx, int world, uint32_t* splits_out) {
 extern "C" int klsh_mg_merge(klsh_ctx* ctx, uint32_t b_lo, uint32_t b_hi, float threshold, int64_t bucket_size_threshold,
                              uint64_t* n_surv, uint64_t* n_mod, uint64_t* n_next) {
   if (!ctx || b_lo > b_hi) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_merge: bad argument");
+  if (ctx->mg_stage != 1) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_merge: call klsh_mg_pass_begin first (once per pass)");
+  if (ctx->mg_n && b_hi > ctx->mg_nb)
+    return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_merge: bucket range [%u, %u) exceeds the pass's %u buckets", b_lo, b_hi, ctx->mg_nb);
+  ctx->mg_stage = 2;
   KCUDA(ctx, cudaSetDevice(ctx->device));
   const uint64_t n = ctx->mg_n;
   if (n_surv) *n_surv = 0;
@@ -1067,9 +1064,12 @@ extern "C" int klsh_mg_merge(klsh_ctx* ctx, uint32_t b_lo, uint32_t b_hi, float 
 extern "C" int klsh_mg_export(klsh_ctx* ctx, uint32_t* d_surv, uint32_t* d_mod_rows, float* d_mod_vals, int32_t* d_mod_meta,
                               uint32_t* d_next_slot, int32_t* d_next_val) {
   if (!ctx) return KLSH_ERR_ARG;
+  if (ctx->mg_stage != 2) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_export: call klsh_mg_merge first");
   KCUDA(ctx, cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const uint32_t surv = ctx->h_counters[1].n_out, nmod = ctx->h_counters[1].n_small, nnext = ctx->h_counters[1].n_large;
+  if ((surv && !d_surv) || (nmod && (!d_mod_rows || !d_mod_vals || !d_mod_meta)) || (nnext && (!d_next_slot || !d_next_val)))
+    return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_export: NULL output buffer for a non-empty log");
   if (surv) KCUDA(ctx, cudaMemcpyAsync(d_surv, ctx->mg_surv.p, sizeof(uint32_t) * surv, cudaMemcpyDeviceToDevice, st));
   if (nmod) {
     KCUDA(ctx, cudaMemcpyAsync(d_mod_rows, ctx->mg_mod_rows.p, sizeof(uint32_t) * nmod, cudaMemcpyDeviceToDevice, st));
@@ -1086,6 +1086,11 @@ extern "C" int klsh_mg_export(klsh_ctx* ctx, uint32_t* d_surv, uint32_t* d_mod_r
 extern "C" int klsh_mg_apply(klsh_ctx* ctx, const uint32_t* d_mod_rows, const float* d_mod_vals, const int32_t* d_mod_meta,
                              uint64_t n_mod, const uint32_t* d_next_slot, const int32_t* d_next_val, uint64_t n_next) {
   if (!ctx) return KLSH_ERR_ARG;
+  if (ctx->mg_stage < 1) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_apply: no sharded pass is running");
+  if (n_mod > ctx->n_born || n_next > ctx->n_slots || (n_mod && (!d_mod_rows || !d_mod_vals || !d_mod_meta)) ||
+      (n_next && (!d_next_slot || !d_next_val)))
+    return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_apply: log sizes (%llu rows, %llu chain writes) do not fit the row set, or NULL buffers",
+                     (unsigned long long)n_mod, (unsigned long long)n_next);
   KCUDA(ctx, cudaSetDevice(ctx->device));
   KTRY(launch_apply_mod(ctx, d_mod_rows, (uint32_t)n_mod, d_mod_vals, d_mod_meta, d_next_slot, d_next_val, (uint32_t)n_next));
   KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1093,7 +1098,8 @@ extern "C" int klsh_mg_apply(klsh_ctx* ctx, const uint32_t* d_mod_rows, const fl
 }
 
 extern "C" int klsh_mg_set_alive(klsh_ctx* ctx, const uint32_t* d_alive, uint64_t n) {
-  if (!ctx || n > ctx->n_born) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_set_alive: bad argument");
+  if (!ctx || n > ctx->n_born || (n && !d_alive)) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_mg_set_alive: bad argument");
+  ctx->mg_stage = 0;
   KCUDA(ctx, cudaSetDevice(ctx->device));
   KTRY(dev_reserve(ctx, ctx->cur.alive, sizeof(uint32_t) * (n + 1)));
   if (n) KCUDA(ctx, cudaMemcpyAsync(ctx->cur.alive.p, d_alive, sizeof(uint32_t) * n, cudaMemcpyDeviceToDevice, ctx->stream));

@@ -106,8 +106,8 @@ __global__ void k_transform_count(const uint16_t* __restrict__ counts, uint64_t 
 
 __global__ void k_transform_write(const uint16_t* __restrict__ counts, const float* __restrict__ lut,
                                   const float* __restrict__ vk, uint64_t batch, int D, int ld,
-                                  const uint32_t* __restrict__ blkoff, float* vals, int32_t* cnt, int32_t* head,
-                                  int32_t* tail, uint64_t row_base) {
+                                  const uint32_t* __restrict__ blkoff, float* vals, MetaCol cnt, MetaCol head,
+                                  MetaCol tail, uint64_t row_base) {
   __shared__ uint32_t ws[33];
   uint64_t base = (uint64_t)blockIdx.x * kScanTile;
   uint32_t run = blkoff[blockIdx.x];
@@ -854,8 +854,8 @@ __device__ __forceinline__ float row_norm(const float* v, int D) {  // unpadded 
 
 // ---- small buckets: one warp per bucket, rows resident in shared memory -------------------------
 __global__ void __launch_bounds__(128)
-k_merge_small(float* __restrict__ vals, int D, int ld, int32_t* __restrict__ cnt, int32_t* __restrict__ head,
-              int32_t* __restrict__ tail, int32_t* __restrict__ next, uint32_t* __restrict__ rows_sorted,
+k_merge_small(float* __restrict__ vals, int D, int ld, MetaCol cnt, MetaCol head,
+              MetaCol tail, int32_t* __restrict__ next, uint32_t* __restrict__ rows_sorted,
               const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ list, const PassCounters* counters,
               float threshold, MgLog mg) {
   extern __shared__ __align__(16) float smem[];
@@ -887,9 +887,10 @@ k_merge_small(float* __restrict__ vals, int D, int ld, int32_t* __restrict__ cnt
     float my_nrm = 0.f;
     bool my_dirty = false;
     if (lane < (uint32_t)n) {
-      my_cnt = cnt[ridx];
-      my_head = head[ridx];
-      my_tail = tail[ridx];
+      const int4 m = __ldcg(reinterpret_cast<const int4*>(cnt.p) + ridx);  // one 16-byte record {cnt, head, tail, 0}
+      my_cnt = m.x;
+      my_head = m.y;
+      my_tail = m.z;
     }
     asm volatile("cp.async.wait_all;" ::: "memory");
     __syncwarp();
@@ -961,9 +962,7 @@ k_merge_small(float* __restrict__ vals, int D, int ld, int32_t* __restrict__ cnt
     }
     const uint32_t dirty = __ballot_sync(0xffffffffu, my_dirty);
     if (my_dirty) {
-      cnt[ridx] = my_cnt;
-      head[ridx] = my_head;
-      tail[ridx] = my_tail;
+      *(reinterpret_cast<int4*>(cnt.p) + ridx) = make_int4(my_cnt, my_head, my_tail, 0);
       if (mg.counts) mg.mod_rows[atomicAdd(mg.counts, 1u)] = ridx;
     }
     uint32_t dm = dirty;
@@ -990,7 +989,7 @@ struct LargeShared {
 };
 
 // merges ONE bucket [s, e) with the whole block; rep_cap = representatives that fit in smem
-__device__ void merge_large_bucket(float* vals, int D, int ld, int32_t* cnt, int32_t* head, int32_t* tail,
+__device__ void merge_large_bucket(float* vals, int D, int ld, MetaCol cnt, MetaCol head, MetaCol tail,
                                    int32_t* next, uint32_t* seg, uint32_t n, float threshold, float* cand,
                                    float* rep_nrm, float* rep_rows, int rep_cap, float* nrm_spill, LargeShared* sh) {
   const int stride = ld + 1;
@@ -1094,7 +1093,7 @@ __device__ void merge_large_bucket(float* vals, int D, int ld, int32_t* cnt, int
 }
 
 __global__ void __launch_bounds__(kLargeThreads)
-k_merge_large(float* vals, int D, int ld, int32_t* cnt, int32_t* head, int32_t* tail, int32_t* next,
+k_merge_large(float* vals, int D, int ld, MetaCol cnt, MetaCol head, MetaCol tail, int32_t* next,
               uint32_t* rows_sorted, const uint32_t* __restrict__ bstart, const uint32_t* __restrict__ list,
               const uint32_t* __restrict__ list_big, PassCounters* counters, float threshold, int rep_cap,
               float* nrm_spill_all, uint64_t spill_stride, int single_bucket_n) {
@@ -1160,8 +1159,8 @@ __global__ void k_alive_write(const uint32_t* __restrict__ rows, uint64_t n, con
 // ================================================================================================
 // Export: gather surviving rows densely.
 // ================================================================================================
-__global__ void k_gather_rows(const float* __restrict__ vals, int D, int ld, const int32_t* __restrict__ cnt,
-                              const int32_t* __restrict__ head, const uint32_t* __restrict__ rows, uint64_t n,
+__global__ void k_gather_rows(const float* __restrict__ vals, int D, int ld, const MetaCol cnt,
+                              const MetaCol head, const uint32_t* __restrict__ rows, uint64_t n,
                               float* out_vals, int32_t* out_cnt, int32_t* out_head) {
   const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = lane_id();
@@ -1195,7 +1194,7 @@ __global__ void k_consensus(const float* __restrict__ cur, int c1, const float* 
   if (d < D) out[d] = consensus1(cur[d], c1, cand[d], c2);
 }
 // sum of the member counts of the rows in `rows` (export sizing)
-__global__ void k_sum_counts(const int32_t* __restrict__ cnt, const uint32_t* __restrict__ rows, uint64_t n, unsigned long long* total) {
+__global__ void k_sum_counts(const MetaCol cnt, const uint32_t* __restrict__ rows, uint64_t n, unsigned long long* total) {
   unsigned long long acc = 0;
   for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) acc += (unsigned long long)cnt[rows[i]];
 #pragma unroll
@@ -1258,8 +1257,8 @@ int launch_transform(klsh_ctx* ctx, const uint16_t* d_counts, const float* d_vk,
   KLAUNCH(ctx);
   KTRY(scan_blkcnt(ctx, blk, nblk, &dc->n_out));
   k_transform_write<<<nblk, 256, 0, ctx->stream>>>(d_counts, ctx->lut.as<float>(), d_vk, batch, ctx->D, ctx->ld, blk,
-                                                   ctx->cur.vals.as<float>(), ctx->cur.cnt.as<int32_t>(),
-                                                   ctx->cur.head.as<int32_t>(), ctx->cur.tail.as<int32_t>(), 0);
+                                                   ctx->cur.vals.as<float>(), ctx->cur.cnt(),
+                                                   ctx->cur.head(), ctx->cur.tail(), 0);
   KLAUNCH(ctx);
   KCUDA(ctx, cudaMemcpyAsync(&ctx->h_counters->n_out, &dc->n_out, sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
   KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1388,8 +1387,8 @@ __global__ void k_find_splits(const uint32_t* __restrict__ bstart, uint32_t nb, 
   }
   splits[r] = lo;
 }
-__global__ void k_gather_mod(const float* __restrict__ vals, int ld, const int32_t* __restrict__ cnt,
-                             const int32_t* __restrict__ head, const int32_t* __restrict__ tail,
+__global__ void k_gather_mod(const float* __restrict__ vals, int ld, const MetaCol cnt,
+                             const MetaCol head, const MetaCol tail,
                              const uint32_t* __restrict__ rows, uint32_t n, float* out_vals, int32_t* out_meta) {
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
   if (w >= n) return;
@@ -1401,7 +1400,7 @@ __global__ void k_gather_mod(const float* __restrict__ vals, int ld, const int32
     out_meta[3 * (uint64_t)w + 2] = tail[r];
   }
 }
-__global__ void k_apply_mod(float* vals, int ld, int32_t* cnt, int32_t* head, int32_t* tail, const uint32_t* __restrict__ rows,
+__global__ void k_apply_mod(float* vals, int ld, MetaCol cnt, MetaCol head, MetaCol tail, const uint32_t* __restrict__ rows,
                             uint32_t n, const float* __restrict__ in_vals, const int32_t* __restrict__ in_meta) {
   const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = lane_id();
   if (w >= n) return;
@@ -1451,7 +1450,7 @@ __global__ void k_rank_step(const int32_t* __restrict__ succ_in, const uint32_t*
     succ_out[s] = -1;
   }
 }
-__global__ void k_rank_owner(const int32_t* __restrict__ tail, const uint32_t* __restrict__ alive, uint32_t n, int32_t* owner) {
+__global__ void k_rank_owner(const MetaCol tail, const uint32_t* __restrict__ alive, uint32_t n, int32_t* owner) {
   const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
   if (r >= n) return;
   const int32_t t = tail[alive[r]];
@@ -1486,7 +1485,7 @@ int launch_rank_chains(klsh_ctx* ctx, uint64_t n, const uint32_t* d_offs, uint32
   k_rank_init<<<grid, 256, 0, ctx->stream>>>(ctx->cur.next.as<int32_t>(), m, succ[0], dist[0], tl[0]);
   KLAUNCH(ctx);
   KCUDA(ctx, cudaMemsetAsync(owner, 0xFF, sizeof(int32_t) * m, ctx->stream));
-  k_rank_owner<<<cdiv64(n, 256), 256, 0, ctx->stream>>>(ctx->cur.tail.as<int32_t>(), ctx->cur.alive.as<uint32_t>(), (uint32_t)n, owner);
+  k_rank_owner<<<cdiv64(n, 256), 256, 0, ctx->stream>>>(ctx->cur.tail(), ctx->cur.alive.as<uint32_t>(), (uint32_t)n, owner);
   KLAUNCH(ctx);
   int cur = 0;
   for (int round = 0; round < 34; ++round) {
@@ -1513,8 +1512,8 @@ int launch_find_splits(klsh_ctx* ctx, PassScratch& s, uint32_t nb, uint64_t n, i
 }
 int launch_gather_mod(klsh_ctx* ctx, const uint32_t* rows, uint32_t n, float* out_vals, int32_t* out_meta) {
   if (!n) return KLSH_OK;
-  k_gather_mod<<<cdiv64((uint64_t)n * 32, 256), 256, 0, ctx->stream>>>(ctx->cur.vals.as<float>(), ctx->ld, ctx->cur.cnt.as<int32_t>(),
-                                                                     ctx->cur.head.as<int32_t>(), ctx->cur.tail.as<int32_t>(), rows, n,
+  k_gather_mod<<<cdiv64((uint64_t)n * 32, 256), 256, 0, ctx->stream>>>(ctx->cur.vals.as<float>(), ctx->ld, ctx->cur.cnt(),
+                                                                     ctx->cur.head(), ctx->cur.tail(), rows, n,
                                                                      out_vals, out_meta);
   KLAUNCH(ctx);
   return KLSH_OK;
@@ -1522,8 +1521,8 @@ int launch_gather_mod(klsh_ctx* ctx, const uint32_t* rows, uint32_t n, float* ou
 int launch_apply_mod(klsh_ctx* ctx, const uint32_t* rows, uint32_t n, const float* in_vals, const int32_t* in_meta,
                      const uint32_t* slots, const int32_t* nvals, uint32_t n_next) {
   if (n) {
-    k_apply_mod<<<cdiv64((uint64_t)n * 32, 256), 256, 0, ctx->stream>>>(ctx->cur.vals.as<float>(), ctx->ld, ctx->cur.cnt.as<int32_t>(),
-                                                                      ctx->cur.head.as<int32_t>(), ctx->cur.tail.as<int32_t>(), rows, n,
+    k_apply_mod<<<cdiv64((uint64_t)n * 32, 256), 256, 0, ctx->stream>>>(ctx->cur.vals.as<float>(), ctx->ld, ctx->cur.cnt(),
+                                                                      ctx->cur.head(), ctx->cur.tail(), rows, n,
                                                                       in_vals, in_meta);
     KLAUNCH(ctx);
   }
@@ -1563,8 +1562,8 @@ static int launch_merge_fallback(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_s
   uint64_t spill_stride = 0;
   if ((int64_t)c.bucket_max > rep_cap) spill_stride = c.bucket_max - rep_cap;
   KTRY(dev_reserve(ctx, ctx->io_b, sizeof(float) * (spill_stride * grid + 1)));
-  k_merge_large<<<grid, kLargeThreads, smem, ctx->stream>>>(ctx->cur.vals.as<float>(), ctx->D, ctx->ld, ctx->cur.cnt.as<int32_t>(),
-                                                            ctx->cur.head.as<int32_t>(), ctx->cur.tail.as<int32_t>(),
+  k_merge_large<<<grid, kLargeThreads, smem, ctx->stream>>>(ctx->cur.vals.as<float>(), ctx->D, ctx->ld, ctx->cur.cnt(),
+                                                            ctx->cur.head(), ctx->cur.tail(),
                                                             ctx->cur.next.as<int32_t>(), rows_sorted, s.bstart.as<uint32_t>(),
                                                             s.list_large.as<uint32_t>(), s.list_big.as<uint32_t>(),
                                                             s.counters.as<PassCounters>(), threshold, rep_cap, ctx->io_b.as<float>(),
@@ -1576,9 +1575,7 @@ static int launch_merge_fallback(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_s
 int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, const PassCounters& c) {
   const int D = ctx->D, ld = ctx->ld;
   float* vals = ctx->cur.vals.as<float>();
-  int32_t* cnt = ctx->cur.cnt.as<int32_t>();
-  int32_t* head = ctx->cur.head.as<int32_t>();
-  int32_t* tail = ctx->cur.tail.as<int32_t>();
+  const MetaCol cnt = ctx->cur.cnt(), head = ctx->cur.head(), tail = ctx->cur.tail();
   int32_t* next = ctx->cur.next.as<int32_t>();
   PassCounters* dc = s.counters.as<PassCounters>();
   const uint32_t n_small = c.n_small, n_large = c.n_large + c.n_big, n_direct = c.n_direct;
@@ -1667,8 +1664,8 @@ int launch_merge_one(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, uint6
   uint64_t spill = (n > (uint64_t)rep_cap) ? n - rep_cap : 0;
   KTRY(dev_reserve(ctx, ctx->io_b, sizeof(float) * (spill + 1)));
   k_merge_large<<<1, kLargeThreads, smem, ctx->stream>>>(
-      ctx->cur.vals.as<float>(), ctx->D, ctx->ld, ctx->cur.cnt.as<int32_t>(), ctx->cur.head.as<int32_t>(),
-      ctx->cur.tail.as<int32_t>(), ctx->cur.next.as<int32_t>(), rows_sorted, nullptr, nullptr, nullptr,
+      ctx->cur.vals.as<float>(), ctx->D, ctx->ld, ctx->cur.cnt(), ctx->cur.head(),
+      ctx->cur.tail(), ctx->cur.next.as<int32_t>(), rows_sorted, nullptr, nullptr, nullptr,
       s.counters.as<PassCounters>(), threshold, rep_cap, ctx->io_b.as<float>(), spill, (int)n);
   KLAUNCH(ctx);
   return KLSH_OK;
@@ -1692,7 +1689,7 @@ int launch_gather_rows(klsh_ctx* ctx, const uint32_t* rows, uint64_t n, float* o
                        int32_t* out_head) {
   if (!n) return KLSH_OK;
   k_gather_rows<<<cdiv64(n * 32, 256), 256, 0, ctx->stream>>>(ctx->cur.vals.as<float>(), ctx->D, ctx->ld,
-                                                             ctx->cur.cnt.as<int32_t>(), ctx->cur.head.as<int32_t>(),
+                                                             ctx->cur.cnt(), ctx->cur.head(),
                                                              rows, n, out_vals, out_cnt, out_head);
   KLAUNCH(ctx);
   return KLSH_OK;
@@ -1715,7 +1712,7 @@ int launch_sum_counts(klsh_ctx* ctx, const uint32_t* rows, uint64_t n, unsigned 
   KCUDA(ctx, cudaMemsetAsync(total_dev, 0, sizeof(unsigned long long), ctx->stream));
   if (!n) return KLSH_OK;
   const uint32_t grid = std::min<uint32_t>(cdiv64(n, 256), (uint32_t)ctx->sm_count * 8);
-  k_sum_counts<<<grid, 256, 0, ctx->stream>>>(ctx->cur.cnt.as<int32_t>(), rows, n, total_dev);
+  k_sum_counts<<<grid, 256, 0, ctx->stream>>>(ctx->cur.cnt(), rows, n, total_dev);
   KLAUNCH(ctx);
   return KLSH_OK;
 }

@@ -78,9 +78,20 @@ struct MgLog {
   int32_t* next_val = nullptr;
 };
 
+// One column of the per-row member metadata.  Count, head and tail of a row share ONE 16-byte record
+// {cnt, head, tail, 0}, so a gathered row touches one 32-byte sector of metadata instead of three.
+struct MetaCol {
+  int32_t* p;
+  __host__ __device__ __forceinline__ int32_t& operator[](size_t i) const { return p[4 * i]; }
+  __host__ __device__ __forceinline__ MetaCol operator+(size_t rows) const { return MetaCol{p + 4 * rows}; }
+};
+
 struct RowState {  // everything klsh_snapshot copies
-  DevBuf vals, cnt, head, tail, next, alive;
+  DevBuf vals, meta, next, alive;  // meta: [n_born] records {cnt, head, tail, 0}
   uint64_t n_alive = 0;
+  MetaCol cnt() const { return MetaCol{meta.as<int32_t>()}; }       // member count of the row (cluster size)
+  MetaCol head() const { return MetaCol{meta.as<int32_t>() + 1}; }  // first member slot of its id chain
+  MetaCol tail() const { return MetaCol{meta.as<int32_t>() + 2}; }  // last member slot
 };
 
 struct klsh_ctx {
@@ -128,6 +139,7 @@ struct klsh_ctx {
   uint64_t mg_n = 0;
   uint32_t mg_nb = 0;
   int mg_H = 0;
+  int mg_stage = 0;  // 0: no sharded pass running, 1: after klsh_mg_pass_begin, 2: after klsh_mg_merge
   // escalation of the windowed merge: a bucket leaves its CTA for a cluster once it has more than
   // cta_max representatives, and the cluster for the whole grid above cluster_max
   uint32_t cta_max = 4096, cluster_max = 65536, cluster2_max = 1000000;  // measured on C2 (profiles/README.md)

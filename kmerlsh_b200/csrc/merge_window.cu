@@ -146,7 +146,8 @@ struct TeamCtl {  // global memory, one per team
 struct MergeArgs {
   float* vals;
   int D, ld;
-  int32_t *cnt, *head, *tail, *next;
+  MetaCol cnt, head, tail;
+  int32_t* next;
   uint32_t* rows_sorted;
   const uint32_t* bstart;
   // work items are triples {bucket, i, size}; i == 0 means "not started".  Two lists, walked in order.
@@ -907,10 +908,6 @@ struct Spec {
   unsigned long long* emask;  // [kKD] merges (bit k) that went into the entry, in merge order
   int32_t* vcnt;      // [kW] member count after merge k
   uint32_t* xtarget;  // [kW] predicted position (kInf: accept) per examined candidate
-  uint32_t* snap_i;   // [kW+1] i before examine index x
-  uint32_t* snap_size;  // [kW+1]
-  uint32_t* snap_pk;  // [kW+1] fi | bi<<8 | a<<16 | nd<<24
-  uint32_t* snap_pk2; // [kW+1] merges | from_back<<8
   uint32_t* acc_lo;   // [kW] accepted candidates before x (tile index bits 0..31)
   uint32_t* acc_hi;   // [kW]
   uint32_t* accd_lo;  // [kW] ... of those, the ones modified before x
@@ -919,7 +916,8 @@ struct Spec {
   uint32_t* dbase;    // [kKD] where the entry's value before its first merge lives: t (prefetched row of t's first match) or 0x100|u (window row u)
   int32_t* dbcnt;     // [kKD] its member count before the first merge
   uint8_t* xcand;     // [kW] candidate examined at x
-  uint8_t* xep;       // [kW] merges before x
+  uint8_t* xep;       // [kW+1] merges before x (the state before x follows from it: a = x - merges, i = i0 + a, size = size0 - merges)
+  uint8_t* xfi;       // [kW+1] front candidates examined before x (back candidates: x - xfi)
   uint8_t* xfe;       // [kW] entry that holds the candidate's first old match if that representative was modified before x, else 0xFF
   uint8_t* vcand;     // [kW] candidate merged by k
   int8_t* vlast;      // [kW] last id-carrying candidate merged into the entry up to and including k (-1: none)
@@ -929,7 +927,7 @@ struct Spec {
   int8_t* elast;      // [kKD] last id-carrying candidate merged into the entry so far
 };
 __host__ __device__ inline size_t spec_bytes_for(int ld) {
-  return sizeof(float) * (size_t)kW * (row_width(ld) + 4) + 8 * (size_t)kKD + 4 * (size_t)(kW * 7 + (kW + 1) * 4 + kKD * 2) + (size_t)kW * 9 + kKD + 16;
+  return sizeof(float) * (size_t)kW * (row_width(ld) + 4) + 8 * (size_t)kKD + 4 * (size_t)(kW * 7 + kKD * 2) + (size_t)kW * 10 + 2 + kKD + 16;
 }
 __device__ __forceinline__ void carve_spec(Spec& sp, void* base, int ts) {
   sp.vers = reinterpret_cast<float*>(base);
@@ -937,10 +935,6 @@ __device__ __forceinline__ void carve_spec(Spec& sp, void* base, int ts) {
   uint32_t* u = reinterpret_cast<uint32_t*>(sp.emask + kKD);
   sp.vcnt = reinterpret_cast<int32_t*>(u); u += kW;
   sp.xtarget = u; u += kW;
-  sp.snap_i = u; u += kW + 1;
-  sp.snap_size = u; u += kW + 1;
-  sp.snap_pk = u; u += kW + 1;
-  sp.snap_pk2 = u; u += kW + 1;
   sp.acc_lo = u; u += kW;
   sp.acc_hi = u; u += kW;
   sp.accd_lo = u; u += kW;
@@ -950,7 +944,8 @@ __device__ __forceinline__ void carve_spec(Spec& sp, void* base, int ts) {
   sp.dbcnt = reinterpret_cast<int32_t*>(u); u += kKD;
   uint8_t* b = reinterpret_cast<uint8_t*>(u);
   sp.xcand = b; b += kW;
-  sp.xep = b; b += kW;
+  sp.xep = b; b += kW + 1;
+  sp.xfi = b; b += kW + 1;
   sp.xfe = b; b += kW;
   sp.vcand = b; b += kW;
   sp.vlast = reinterpret_cast<int8_t*>(b); b += kW;
@@ -960,9 +955,10 @@ __device__ __forceinline__ void carve_spec(Spec& sp, void* base, int ts) {
   sp.elast = reinterpret_cast<int8_t*>(b);
 }
 
-// scan: returns the number of examined candidates.  Warp 0 only.  The whole warp prepares the class
-// table; the replay itself is an integer loop on ONE thread (no shuffles, no votes: a warp-synchronous
-// version of this loop cost three times as much per candidate).
+// scan: returns the number of examined candidates.  Warp 0 only.  The replay is scalar integer code on lane 0
+// (measured: the same loop run warp-synchronously with shuffles and votes, or uniformly on all lanes, costs
+// up to three times as much per candidate); only runs of candidates that are accepted for sure (no old
+// match, no pair bit) are spread over the lanes, one candidate each.
 __device__ int spec_scan(Smem& s, Spec& sp, int W, int wf, int wb, bool tail_mode, uint32_t i0, uint32_t size0) {
   const uint32_t lane = lane_id();
   // candidates whose first old match is the same representative share a cache entry: class = the
@@ -993,39 +989,42 @@ __device__ int spec_scan(Smem& s, Spec& sp, int W, int wf, int wb, bool tail_mod
     easy = ((unsigned long long)__ballot_sync(0xffffffffu, e1) << 32) | (unsigned long long)__ballot_sync(0xffffffffu, e0);
   }
   __syncwarp();
-  int x = 0;
-  if (lane == 0) {
-    int nd = 0, a = 0, fi = 0, bi = 0, merges = 0;
-    uint32_t i = i0, size = size0;
-    bool from_back = false, back_exhausted = false, full = false;
-    unsigned long long accm = 0ull, accd = 0ull;
-    while (i < size) {
-      int t;
-      if (from_back) {
-        if (!tail_mode && bi >= wb) { back_exhausted = true; break; }
-        t = tail_mode ? (wf - 1 - bi) : (wf + bi);
-      } else {
-        if (!tail_mode && fi >= wf) break;
-        t = fi;
-      }
-      // the state before this candidate, and what its decision will be checked against
-      sp.xcand[x] = (uint8_t)t;
-      sp.xep[x] = (uint8_t)merges;
-      sp.acc_lo[x] = (uint32_t)accm;
-      sp.acc_hi[x] = (uint32_t)(accm >> 32);
-      sp.accd_lo[x] = (uint32_t)accd;
-      sp.accd_hi[x] = (uint32_t)(accd >> 32);
-      sp.snap_i[x] = i;
-      sp.snap_size[x] = size;
-      sp.snap_pk[x] = (uint32_t)fi | ((uint32_t)bi << 8) | ((uint32_t)a << 16) | ((uint32_t)nd << 24);
-      sp.snap_pk2[x] = (uint32_t)merges | (from_back ? 0x100u : 0u);
-      const unsigned long long tbit = 1ull << t;
-      // predicted decision: first old match, else the earliest accepted candidate with a pair bit, else accept
-      uint32_t P = kInf;
-      int id = -1;
-      uint32_t fpos = kInf;
-      if (!(!from_back && ((easy >> t) & 1ull))) {
-        fpos = s.s_f[t];
+  // Lane 0 replays the order candidate by candidate (scalar integer code; its registers hold the state).  When
+  // it reaches a run of front candidates that are accepted for sure, the state is broadcast and the run is
+  // recorded by all lanes, one candidate each.
+  int nd = 0, a = 0, fi = 0, merges = 0, x = 0;
+  uint32_t i = i0, size = size0;
+  bool from_back = false, back_exhausted = false, full = false;
+  unsigned long long accm = 0ull, accd = 0ull;
+  for (;;) {
+    int mode = 2;  // 1: an easy run starts at fi, 2: the window is over
+    if (lane == 0) {
+      while (i < size) {
+        if (!from_back && fi < wf && ((easy >> fi) & 1ull)) {
+          mode = 1;
+          break;
+        }
+        const int bi = x - fi;
+        int t;
+        if (from_back) {
+          if (!tail_mode && bi >= wb) { back_exhausted = true; break; }
+          t = tail_mode ? (wf - 1 - bi) : (wf + bi);
+        } else {
+          if (!tail_mode && fi >= wf) break;
+          t = fi;
+        }
+        // what this candidate's decision will be checked against
+        sp.xcand[x] = (uint8_t)t;
+        sp.xep[x] = (uint8_t)merges;
+        sp.xfi[x] = (uint8_t)fi;
+        sp.acc_lo[x] = (uint32_t)accm;
+        sp.acc_hi[x] = (uint32_t)(accm >> 32);
+        sp.accd_lo[x] = (uint32_t)accd;
+        sp.accd_hi[x] = (uint32_t)(accd >> 32);
+        // predicted decision: first old match, else the earliest accepted candidate with a pair bit, else accept
+        uint32_t P = kInf;
+        int id = -1;
+        const uint32_t fpos = s.s_f[t];
         if (fpos != kInf) {
           P = fpos;
           id = sp.cls[t];
@@ -1042,68 +1041,99 @@ __device__ int spec_scan(Smem& s, Spec& sp, int W, int wf, int wb, bool tail_mod
             id = kW + (int)s.acc[rank];
           }
         }
-      }
-      if (from_back) ++bi; else ++fi;
-      sp.xtarget[x] = P;
-      if (P == kInf) {
-        s.acc[a] = (uint32_t)t;
-        sp.arank[t] = (uint8_t)a;
-        sp.xfe[x] = 0xFF;
-        accm |= tbit;
-        ++a;
-        ++i;
-        ++x;
-        from_back = false;
-        continue;
-      }
-      int e = sp.dense[id];
-      const bool fresh = e == 0xFF;
-      if (fresh) {
-        e = nd++;
-        sp.dense[id] = (uint8_t)e;
-        sp.elast[e] = -1;
-        s.dpos[e] = P;
-        if (P < i0) {
-          sp.dbase[e] = (uint32_t)t;  // the prefetched row of t's first match
-          sp.dbcnt[e] = s.pcnt[t];
-          s.dridx[e] = s.pridx[t];
-          s.dhead[e] = s.phead[t];
-          s.dtail[e] = s.ptail[t];
-        } else {
-          const uint32_t u = (uint32_t)(id - kW);
-          sp.dbase[e] = 0x100u | u;
-          sp.dbcnt[e] = s.ccnt[u];
-          s.dridx[e] = s.ridx[u];
-          s.dhead[e] = s.chead[u];
-          s.dtail[e] = s.ctail[u];
-          accd |= 1ull << u;
+        if (!from_back) ++fi;
+        sp.xtarget[x] = P;
+        if (P == kInf) {
+          s.acc[a] = (uint32_t)t;
+          sp.arank[t] = (uint8_t)a;
+          sp.xfe[x] = 0xFF;
+          accm |= 1ull << t;
+          ++a;
+          ++i;
+          ++x;
+          from_back = false;
+          continue;
         }
+        int e = sp.dense[id];
+        const bool fresh = e == 0xFF;
+        int prev_last = -1;
+        unsigned long long em = 1ull << merges;
+        if (fresh) {
+          e = nd++;
+          sp.dense[id] = (uint8_t)e;
+          s.dpos[e] = P;
+          if (P < i0) {
+            sp.dbase[e] = (uint32_t)t;  // the prefetched row of t's first match
+            sp.dbcnt[e] = s.pcnt[t];
+            s.dridx[e] = s.pridx[t];
+            s.dhead[e] = s.phead[t];
+            s.dtail[e] = s.ptail[t];
+          } else {
+            const uint32_t u = (uint32_t)(id - kW);
+            sp.dbase[e] = 0x100u | u;
+            sp.dbcnt[e] = s.ccnt[u];
+            s.dridx[e] = s.ridx[u];
+            s.dhead[e] = s.chead[u];
+            s.dtail[e] = s.ctail[u];
+            accd |= 1ull << u;
+          }
+        } else {
+          prev_last = (int)sp.elast[e];
+          em |= sp.emask[e];
+        }
+        const int new_last = s.ctail[t] >= 0 ? t : prev_last;  // only candidates that carry ids take part in the chain
+        sp.xfe[x] = (fpos != kInf && !fresh) ? (uint8_t)e : (uint8_t)0xFF;
+        sp.vcand[merges] = (uint8_t)t;
+        sp.vlast[merges] = (int8_t)new_last;
+        sp.elast[e] = (int8_t)new_last;
+        sp.emask[e] = em;
+        s.mprev[t] = prev_last;
+        s.ment[t] = e;
+        ++merges;
+        --size;
+        ++x;
+        from_back = true;
+        if (nd == kKD) { full = true; break; }
       }
-      sp.xfe[x] = (fpos != kInf && !fresh) ? (uint8_t)e : (uint8_t)0xFF;
-      const int prev_last = sp.elast[e];
-      const int new_last = s.ctail[t] >= 0 ? t : prev_last;  // only candidates that carry ids take part in the chain
-      sp.vcand[merges] = (uint8_t)t;
-      sp.vlast[merges] = (int8_t)new_last;
-      sp.elast[e] = (int8_t)new_last;
-      sp.emask[e] |= 1ull << merges;
-      s.mprev[t] = prev_last;
-      s.ment[t] = e;
-      ++merges;
-      --size;
-      ++x;
-      from_back = true;
-      if (nd == kKD) { full = true; break; }
     }
-    sp.snap_i[x] = i;
-    sp.snap_size[x] = size;
-    sp.snap_pk[x] = (uint32_t)fi | ((uint32_t)bi << 8) | ((uint32_t)a << 16) | ((uint32_t)nd << 24);
-    sp.snap_pk2[x] = (uint32_t)merges | (from_back ? 0x100u : 0u);
+    __syncwarp();
+    mode = __shfl_sync(0xffffffffu, mode, 0);
+    x = __shfl_sync(0xffffffffu, x, 0);
+    if (mode == 2) break;
+    fi = __shfl_sync(0xffffffffu, fi, 0);
+    a = __shfl_sync(0xffffffffu, a, 0);
+    merges = __shfl_sync(0xffffffffu, merges, 0);
+    i = __shfl_sync(0xffffffffu, i, 0);
+    size = __shfl_sync(0xffffffffu, size, 0);
+    // the run: front candidates fi .. fi + k - 1, one lane per candidate
+    const unsigned long long stop = ~(easy >> fi);
+    int k = stop ? (__ffsll((long long)stop) - 1) : 64;
+    k = min(k, min(wf - fi, (int)(size - i)));
+    for (int j = (int)lane; j < k; j += 32) {
+      const int t = fi + j, xx = x + j;
+      s.acc[a + j] = (uint32_t)t;
+      sp.arank[t] = (uint8_t)(a + j);
+      sp.xcand[xx] = (uint8_t)t;
+      sp.xep[xx] = (uint8_t)merges;
+      sp.xfi[xx] = (uint8_t)t;
+      sp.xfe[xx] = 0xFF;
+      sp.xtarget[xx] = kInf;
+    }
+    accm |= ((k >= 64) ? ~0ull : ((1ull << k) - 1ull)) << fi;  // lane 0's copy is the one that is used
+    a += k;
+    i += (uint32_t)k;
+    fi += k;
+    x += k;
+    __syncwarp();
+  }
+  if (lane == 0) {
+    sp.xep[x] = (uint8_t)merges;
+    sp.xfi[x] = (uint8_t)fi;
     s.ro[RO_BACK_EXH] = back_exhausted ? 1u : 0u;
     s.ro[RO_FULL] = full ? 1u : 0u;
     s.ro[RO_ND] = (uint32_t)nd;       // entries the scan allocated (match pass)
     s.ro[RO_MERGES] = (uint32_t)merges;
   }
-  x = __shfl_sync(0xffffffffu, x, 0);
   return x;
 }
 
@@ -1247,17 +1277,21 @@ __device__ int spec_verify(Smem& s, Spec& sp, int n_ex, uint32_t i0) {
 // commit the verified prefix [0, cut): the state the sequential loop would have reached there, in the form
 // flush_window expects.  All threads of the CTA.
 template <int TEAM>
-__device__ void spec_commit(const MergeArgs& A, Smem& s, Spec& sp, int n_ex, int cut) {
+__device__ void spec_commit(const MergeArgs& A, Smem& s, Spec& sp, int n_ex, int cut, uint32_t i0, uint32_t size0) {
   constexpr int kMT = Shape<TEAM>::kMT;
   const int tid = threadIdx.x, ts = s.ts, ld = A.ld;
-  const uint32_t pk = sp.snap_pk[cut], pk2 = sp.snap_pk2[cut];
-  const int nd = (int)(pk >> 24), merges = (int)(pk2 & 0xFFu), all_merges = (int)s.ro[RO_MERGES];
+  // the state before examine index `cut`: merges and front candidates so far say everything
+  const int merges = (int)sp.xep[cut], fi = (int)sp.xfi[cut], all_merges = (int)s.ro[RO_MERGES], nd_all = (int)s.ro[RO_ND];
+  const int a = cut - merges, bi = cut - fi;
+  const bool from_back = cut > 0 && sp.xtarget[cut - 1] != kInf;
+  const unsigned long long below = merges >= 64 ? ~0ull : ((1ull << merges) - 1ull);
+  // entries are allocated in the order of their first merge: those with a merge before the cut exist
+  int nd = 0;
+  for (int e = 0; e < nd_all; ++e) nd += (sp.emask[e] & below) != 0ull ? 1 : 0;
   // merges beyond the cut did not happen
   for (int k = merges + tid; k < all_merges; k += kMT) s.ment[sp.vcand[k]] = -1;
-  // an entry below nd has at least one merge before the cut: its value there is its last version before it
-  const unsigned long long below = merges >= 64 ? ~0ull : ((1ull << merges) - 1ull);
   if (tid < nd) {
-    const int k = 63 - __clzll((long long)(sp.emask[tid] & below));
+    const int k = 63 - __clzll((long long)(sp.emask[tid] & below));  // the entry's last version before the cut
     s.dcnt[tid] = sp.vcnt[k];
     s.dlast[tid] = (int32_t)sp.vlast[k];
   }
@@ -1266,21 +1300,22 @@ __device__ void spec_commit(const MergeArgs& A, Smem& s, Spec& sp, int n_ex, int
     const int k = 63 - __clzll((long long)(sp.emask[e] & below));
     s.dvals[(size_t)e * ts + d] = sp.vers[(size_t)k * ts + d];
   }
+  __syncthreads();  // everybody has read RO_ND / RO_MERGES before they are rewritten
   if (tid == 0) {
     const bool whole = cut == n_ex;
-    s.ro[RO_A] = (pk >> 16) & 0xFFu;
+    s.ro[RO_A] = (uint32_t)a;
     s.ro[RO_ND] = (uint32_t)nd;
-    s.ro[RO_I] = sp.snap_i[cut];
-    s.ro[RO_SIZE] = sp.snap_size[cut];
-    s.ro[RO_FROM_BACK] = (pk2 >> 8) & 1u;
-    s.ro[RO_BI] = (pk >> 8) & 0xFFu;
+    s.ro[RO_I] = i0 + (uint32_t)a;
+    s.ro[RO_SIZE] = size0 - (uint32_t)merges;
+    s.ro[RO_FROM_BACK] = from_back ? 1u : 0u;
+    s.ro[RO_BI] = (uint32_t)bi;
     s.ro[RO_MERGES] = (uint32_t)merges;
     if (!whole) {
       s.ro[RO_BACK_EXH] = 0u;
       s.ro[RO_FULL] = 0u;
     }
     s.ro[RO_UNDEC] = whole ? 0u : 1u;
-    s.ro[RO_EXAMINED] = (pk & 0xFFu) + ((pk >> 8) & 0xFFu);
+    s.ro[RO_EXAMINED] = (uint32_t)cut;
   }
 }
 
@@ -1486,9 +1521,10 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
       if (tid < W) {
         s.ridx[tid] = mr;
         if (leader) {
-          s.ccnt[tid] = A.cnt[mr];
-          s.chead[tid] = A.head[mr];
-          s.ctail[tid] = A.tail[mr];
+          const int4 m = __ldcg(reinterpret_cast<const int4*>(A.cnt.p) + mr);  // one 16-byte record {cnt, head, tail, 0}
+          s.ccnt[tid] = m.x;
+          s.chead[tid] = m.y;
+          s.ctail[tid] = m.z;
         }
       }
       cp_async_wait_all();
@@ -1618,9 +1654,10 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
         }
         if (has) {
           s.pridx[tid] = mr;
-          s.pcnt[tid] = A.cnt[mr];
-          s.phead[tid] = A.head[mr];
-          s.ptail[tid] = A.tail[mr];
+          const int4 m = __ldcg(reinterpret_cast<const int4*>(A.cnt.p) + mr);
+          s.pcnt[tid] = m.x;
+          s.phead[tid] = m.y;
+          s.ptail[tid] = m.z;
         }
         cp_async_wait_all();
       }
@@ -1631,16 +1668,21 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
         // speculative resolution (see above); the cp.async ring of the screen is idle now and holds its scratch
         Spec sp;
         carve_spec(sp, s.ring, s.ts);
+        long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0;
+        if (prof) tp0 = clock64();
         if (warp == 0) {
           const int n = spec_scan(s, sp, W, wf, wb, tail_mode, i0, size0);
           if (lane == 0) s.ro[RO_EXAMINED] = (uint32_t)n;
         }
         __syncthreads();
+        if (prof) tp1 = clock64();
         const int n_ex = (int)s.ro[RO_EXAMINED];
         spec_versions(A, s, sp, (int)warp, kMT / 32);
         __syncthreads();
+        if (prof) tp2 = clock64();
         spec_match<DR>(A, s, sp, n_ex, (int)warp, kMT / 32);
         __syncthreads();
+        if (prof) tp3 = clock64();
         if (warp == 0) {
           const int cut = spec_verify(s, sp, n_ex, i0);
           if (lane == 0) {
@@ -1653,7 +1695,14 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
           }
         }
         __syncthreads();
-        spec_commit<TEAM>(A, s, sp, n_ex, (int)s.ro[RO_DONE]);
+        if (prof) tp4 = clock64();
+        spec_commit<TEAM>(A, s, sp, n_ex, (int)s.ro[RO_DONE], i0, size0);
+        if (prof) {
+          atomicAdd(A.dbg + 28, (unsigned long long)(tp1 - tp0));
+          atomicAdd(A.dbg + 29, (unsigned long long)(tp2 - tp1));
+          atomicAdd(A.dbg + 30, (unsigned long long)(tp3 - tp2));
+          atomicAdd(A.dbg + 31, (unsigned long long)(tp4 - tp3));
+        }
       } else {
         if (tid == 0) ctl->mode = 0u;
         if (warp == 0) resolve_decide<TEAM, DR>(A, s, W, wf, wb, tail_mode, i0, size0);
@@ -1820,7 +1869,9 @@ static int launch_stage(klsh_ctx* ctx, cudaStream_t stream, DevBuf& ctl_buf, int
     if (h[0])
       fprintf(stderr, "[klsh]   decide kcycles/window: select %.1f dirty-compare %.1f old+accepted %.1f merge %.1f | per window: loop trips %.1f runs %.1f dirty tests %.1f\n",
               h[14] / 1e3 / h[0], h[15] / 1e3 / h[0], h[16] / 1e3 / h[0], h[17] / 1e3 / h[0], (double)h[22] / h[0], (double)h[23] / h[0], (double)h[24] / h[0]);
-    if (h[26]) fprintf(stderr, "[klsh]   speculative windows %llu, cut short by a misprediction %llu\n", h[26], h[27]);
+    if (h[26])
+      fprintf(stderr, "[klsh]   speculative windows %llu, cut short by a misprediction %llu; kcycles per speculative window: scan %.1f versions %.1f match %.1f verify %.1f\n",
+              h[26], h[27], h[28] / 1e3 / h[26], h[29] / 1e3 / h[26], h[30] / 1e3 / h[26], h[31] / 1e3 / h[26]);
     if (h[0]) fprintf(stderr, "[klsh]   dirty tests decided by the exact chain (inside the fast test's error band): %.3f per window\n", (double)h[25] / h[0]);
   }
   return KLSH_OK;
@@ -1831,9 +1882,9 @@ static MergeArgs base_args(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted,
   A.vals = ctx->cur.vals.as<float>();
   A.D = ctx->D;
   A.ld = ctx->ld;
-  A.cnt = ctx->cur.cnt.as<int32_t>();
-  A.head = ctx->cur.head.as<int32_t>();
-  A.tail = ctx->cur.tail.as<int32_t>();
+  A.cnt = ctx->cur.cnt();
+  A.head = ctx->cur.head();
+  A.tail = ctx->cur.tail();
   A.next = ctx->cur.next.as<int32_t>();
   A.rows_sorted = rows_sorted;
   A.bstart = s.bstart.as<uint32_t>();

@@ -266,9 +266,9 @@ extern "C" int klsh_mg_cluster(klsh_ctx* ctx, float min_similarity, int iteratio
 // klsh_load_counts) with contiguous batch offsets in rank order, so that ids stay implicit.
 // ------------------------------------------------------------------------------------------------
 namespace {
-__global__ void k_pack_rows(const float* __restrict__ vals, int ld, const int32_t* __restrict__ cnt, const int32_t* __restrict__ head,
-                            const int32_t* __restrict__ tail, const uint32_t* __restrict__ alive, uint64_t n, int32_t slot_base,
-                            float* out_vals, int32_t* out_cnt, int32_t* out_head, int32_t* out_tail) {
+__global__ void k_pack_rows(const float* __restrict__ vals, int ld, const MetaCol cnt, const MetaCol head,
+                            const MetaCol tail, const uint32_t* __restrict__ alive, uint64_t n, int32_t slot_base,
+                            float* out_vals, MetaCol out_cnt, MetaCol out_head, MetaCol out_tail) {
   const uint64_t w = ((uint64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
   if (w >= n) return;
@@ -279,6 +279,7 @@ __global__ void k_pack_rows(const float* __restrict__ vals, int ld, const int32_
     out_cnt[w] = cnt[r];
     out_head[w] = h < 0 ? h : h + slot_base;
     out_tail[w] = t < 0 ? t : t + slot_base;
+    out_cnt.p[4 * w + 3] = 0;
   }
 }
 __global__ void k_shift_next(const int32_t* __restrict__ next, uint64_t n, int32_t slot_base, int32_t* out) {
@@ -323,17 +324,15 @@ extern "C" int klsh_mg_gather_rows(klsh_ctx* ctx) {
   int rc = KLSH_OK;
   do {
     if ((rc = dev_reserve(ctx, g.vals, sizeof(float) * (rows * (uint64_t)ld + 4)))) break;
-    if ((rc = dev_reserve(ctx, g.cnt, sizeof(int32_t) * (rows + 1)))) break;
-    if ((rc = dev_reserve(ctx, g.head, sizeof(int32_t) * (rows + 1)))) break;
-    if ((rc = dev_reserve(ctx, g.tail, sizeof(int32_t) * (rows + 1)))) break;
+    if ((rc = dev_reserve(ctx, g.meta, sizeof(int32_t) * 4 * (rows + 1)))) break;
     if ((rc = dev_reserve(ctx, g.next, sizeof(int32_t) * (slots + 1)))) break;
     if ((rc = dev_reserve(ctx, g.alive, sizeof(uint32_t) * (rows + 1)))) break;
     const uint64_t n = ctx->cur.n_alive, m = ctx->n_slots;
     if (n) {
       k_pack_rows<<<(uint32_t)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(
-          ctx->cur.vals.as<float>(), ld, ctx->cur.cnt.as<int32_t>(), ctx->cur.head.as<int32_t>(), ctx->cur.tail.as<int32_t>(),
+          ctx->cur.vals.as<float>(), ld, ctx->cur.cnt(), ctx->cur.head(), ctx->cur.tail(),
           ctx->cur.alive.as<uint32_t>(), n, (int32_t)slot0[rank], g.vals.as<float>() + row0[rank] * (uint64_t)ld,
-          g.cnt.as<int32_t>() + row0[rank], g.head.as<int32_t>() + row0[rank], g.tail.as<int32_t>() + row0[rank]);
+          g.cnt() + row0[rank], g.head() + row0[rank], g.tail() + row0[rank]);
       ctx->launches++;
     }
     if (m) {
@@ -351,12 +350,8 @@ extern "C" int klsh_mg_gather_rows(klsh_ctx* ctx) {
       if (nr_rows) {
         float* v = g.vals.as<float>() + row0[r] * (uint64_t)ld;
         nr = api->Broadcast(v, v, (size_t)(nr_rows * (uint64_t)ld), ncclFloat32, r, c->comm, ctx->stream);
-        int32_t* pc = g.cnt.as<int32_t>() + row0[r];
-        if (nr == ncclSuccess) nr = api->Broadcast(pc, pc, (size_t)nr_rows, ncclInt32, r, c->comm, ctx->stream);
-        int32_t* ph = g.head.as<int32_t>() + row0[r];
-        if (nr == ncclSuccess) nr = api->Broadcast(ph, ph, (size_t)nr_rows, ncclInt32, r, c->comm, ctx->stream);
-        int32_t* pt = g.tail.as<int32_t>() + row0[r];
-        if (nr == ncclSuccess) nr = api->Broadcast(pt, pt, (size_t)nr_rows, ncclInt32, r, c->comm, ctx->stream);
+        int32_t* pm = g.meta.as<int32_t>() + 4 * row0[r];  // {cnt, head, tail, 0} records
+        if (nr == ncclSuccess) nr = api->Broadcast(pm, pm, (size_t)(4 * nr_rows), ncclInt32, r, c->comm, ctx->stream);
       }
       if (nr_slots && nr == ncclSuccess) {
         int32_t* pn = g.next.as<int32_t>() + slot0[r];
@@ -373,21 +368,19 @@ extern "C" int klsh_mg_gather_rows(klsh_ctx* ctx) {
     if (e != cudaSuccess) rc = klsh_fail(ctx, KLSH_ERR_CUDA, "klsh_mg_gather_rows: %s", cudaGetErrorString(e));
   } while (0);
   if (rc != KLSH_OK) {
-    for (DevBuf* b : {&g.vals, &g.cnt, &g.head, &g.tail, &g.next, &g.alive})
+    for (DevBuf* b : {&g.vals, &g.meta, &g.next, &g.alive})
       if (b->p) cudaFree(b->p);
     return rc;
   }
   // swap the gathered state in
-  for (DevBuf* b : {&ctx->cur.vals, &ctx->cur.cnt, &ctx->cur.head, &ctx->cur.tail, &ctx->cur.next, &ctx->cur.alive})
+  for (DevBuf* b : {&ctx->cur.vals, &ctx->cur.meta, &ctx->cur.next, &ctx->cur.alive})
     if (b->p) {
       cudaFree(b->p);
       b->p = nullptr;
       b->bytes = 0;
     }
   ctx->cur.vals = g.vals;
-  ctx->cur.cnt = g.cnt;
-  ctx->cur.head = g.head;
-  ctx->cur.tail = g.tail;
+  ctx->cur.meta = g.meta;
   ctx->cur.next = g.next;
   ctx->cur.alive = g.alive;
   ctx->cur.n_alive = rows;
