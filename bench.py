@@ -410,7 +410,7 @@ def main():
     sign_achieved = sign_bytes / (fam["sign"] * 1e-3) / 1e9 if fam["sign"] > 0 else 0.0
     # DRAM traffic of the merge family for one step of this workload, from the committed ncu capture
     traffic, traffic_src = None, None
-    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r01c_dram_traffic_C2.json")
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_dram_traffic_C2.json")
     if args.workload == "C2" and not args.rows and world == 1 and os.path.exists(tpath):
         with open(tpath) as fh:
             tj = json.load(fh)

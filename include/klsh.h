@@ -136,6 +136,17 @@ int klsh_restore(klsh_ctx* ctx);
 /* Block until all work queued on the context's stream is done. */
 int klsh_sync(klsh_ctx* ctx);
 
+/* ---- survivors of several batches, resident on the device ----------------------------------------
+ * The reference appends every phase-1 batch's survivors to tmp/0.bin(.clust) and reads the files back
+ * (app/kmerLSH.cc:326-335, :415).  klsh_stash_rows appends the context's current working set to a
+ * device-resident stash instead (call it after each batch's klsh_cluster); klsh_unstash_rows makes the stash —
+ * all batches in append order — the current row set.  Same rows, same order, same member lists as the
+ * file round trip.  Member ids stay implicit when the batches came from klsh_load_counts with contiguous
+ * offsets. */
+int klsh_stash_rows(klsh_ctx* ctx);
+int klsh_stash_count(const klsh_ctx* ctx, uint64_t* n_rows);
+int klsh_unstash_rows(klsh_ctx* ctx);
+
 /* ---- multi-GPU building blocks ------------------------------------------------------------------
  * No reference counterpart (the reference is one process).  One context per rank; every rank holds
  * the same row set (load it identically on all ranks) and the same hyperplane source.  Per LSH

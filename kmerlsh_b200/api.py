@@ -77,6 +77,9 @@ SYMBOLS = [
     ("klsh_row_count", C.c_int, [C.c_void_p, u64p, u64p]),
     ("klsh_get_rows", C.c_int, [C.c_void_p, f32p, u64p, u64p]),
     ("klsh_save", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, i64]),
+    ("klsh_stash_rows", C.c_int, [C.c_void_p]),
+    ("klsh_stash_count", C.c_int, [C.c_void_p, u64p]),
+    ("klsh_unstash_rows", C.c_int, [C.c_void_p]),
     ("klsh_snapshot", C.c_int, [C.c_void_p]),
     ("klsh_restore", C.c_int, [C.c_void_p]),
     ("klsh_sync", C.c_int, [C.c_void_p]),
@@ -278,6 +281,18 @@ class Context:
 
     def save(self, path: str, delfile: bool = True, ignore_small: int = 0):
         self._ck(self.lib.klsh_save(self.h, path.encode(), int(delfile), ignore_small), "klsh_save")
+
+    # ---- survivors of several batches, resident on the device
+    def stash_rows(self):
+        self._ck(self.lib.klsh_stash_rows(self.h), "klsh_stash_rows")
+
+    def stash_count(self) -> int:
+        n = u64()
+        self._ck(self.lib.klsh_stash_count(self.h, C.byref(n)), "klsh_stash_count")
+        return n.value
+
+    def unstash_rows(self):
+        self._ck(self.lib.klsh_unstash_rows(self.h), "klsh_unstash_rows")
 
     # ---- state
     def snapshot(self):

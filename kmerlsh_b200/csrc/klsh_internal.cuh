@@ -108,7 +108,11 @@ struct klsh_ctx {
   int D = 0, ld = 0;       // ld = D rounded up to a multiple of 4 floats
   uint64_t n_born = 0;     // rows in the arena
   uint64_t n_slots = 0;    // member slots (id list nodes)
-  RowState cur, snap;
+  RowState cur, snap, stash;  // stash: survivors of earlier batches, appended on the device (klsh_stash_rows)
+  uint64_t stash_rows = 0, stash_slots = 0, stash_id_base = 0;
+  bool stash_implicit = true;
+  int stash_D = 0;
+  std::vector<uint64_t> stash_ids;  // explicit member ids of the stash (when not implicit)
   bool has_snap = false;
   uint64_t snap_born = 0, snap_slots = 0;
   // id payload of member slots: explicit (ids.size()==n_slots) or implicit id = id_base + slot
@@ -151,6 +155,7 @@ struct klsh_ctx {
   int cluster_ctas_per_sm = 2;
   bool debug = false;     // KLSH_DEBUG=1
   DevBuf dbg;
+  bool no_par_scan = false;  // KLSH_NO_PAR_SCAN=1
   bool no_spec = false;   // KLSH_NO_SPEC=1: windows are resolved by the sequential loop only
   bool merge_v1 = false;  // KLSH_MERGE_V1=1: first-generation block-per-bucket kernel (A/B checks)
   PassCounters* h_counters = nullptr;  // pinned

@@ -168,6 +168,7 @@ struct MergeArgs {
   TeamCtl* ctl;
   MgLog mg;
   unsigned long long* work;  // [2] device counters: pairs screened on the tensor cores, pairs re-tested exactly
+  int no_par_scan;  // KLSH_NO_PAR_SCAN=1: speculative windows use the scalar scan only (A/B checks)
   int no_spec;   // KLSH_NO_SPEC=1: sequential resolution only (A/B checks)
   unsigned long long* dbg;  // [32] 26: speculative windows, 27: ... cut short; 0..7: windows, candidates, merges, undecidable, cache_full, back_exhausted, accepted, escalated; 8..13: leader cycles in stage/parallel/sync1/prefetch/decide/flush+sync2; 18..21: staging detail
   float threshold;
@@ -925,9 +926,12 @@ struct Spec {
   uint8_t* cls;       // [kW] class of a candidate's first old match: the smallest candidate index with the same one
   uint8_t* dense;     // [2 kW] target id (class, or kW + accepted candidate) -> cache entry, 0xFF: none yet
   int8_t* elast;      // [kKD] last id-carrying candidate merged into the entry so far
+  uint8_t* sx;        // [kW] examine index of a candidate (0xFF: not examined) — parallel scan
+  uint8_t* xcls;      // [kW] target id of the candidate examined at x (0xFF: accept) — parallel scan
+  uint32_t* cfirst;   // [2 kW] examine index of the first merge into a target id (0xFF: none) — parallel scan
 };
 __host__ __device__ inline size_t spec_bytes_for(int ld) {
-  return sizeof(float) * (size_t)kW * (row_width(ld) + 4) + 8 * (size_t)kKD + 4 * (size_t)(kW * 7 + kKD * 2) + (size_t)kW * 10 + 2 + kKD + 16;
+  return sizeof(float) * (size_t)kW * (row_width(ld) + 4) + 8 * (size_t)kKD + 4 * (size_t)(kW * 9 + kKD * 2) + (size_t)kW * 12 + 2 + kKD + 16;
 }
 __device__ __forceinline__ void carve_spec(Spec& sp, void* base, int ts) {
   sp.vers = reinterpret_cast<float*>(base);
@@ -942,6 +946,7 @@ __device__ __forceinline__ void carve_spec(Spec& sp, void* base, int ts) {
   sp.dmatch = u; u += kW;
   sp.dbase = u; u += kKD;
   sp.dbcnt = reinterpret_cast<int32_t*>(u); u += kKD;
+  sp.cfirst = u; u += 2 * kW;
   uint8_t* b = reinterpret_cast<uint8_t*>(u);
   sp.xcand = b; b += kW;
   sp.xep = b; b += kW + 1;
@@ -952,7 +957,9 @@ __device__ __forceinline__ void carve_spec(Spec& sp, void* base, int ts) {
   sp.arank = b; b += kW;
   sp.cls = b; b += kW;
   sp.dense = b; b += 2 * kW;
-  sp.elast = reinterpret_cast<int8_t*>(b);
+  sp.elast = reinterpret_cast<int8_t*>(b); b += kKD;
+  sp.sx = b; b += kW;
+  sp.xcls = b;
 }
 
 // scan: returns the number of examined candidates.  Warp 0 only.  The replay is scalar integer code on lane 0
@@ -1135,6 +1142,287 @@ __device__ int spec_scan(Smem& s, Spec& sp, int W, int wf, int wb, bool tail_mod
     s.ro[RO_MERGES] = (uint32_t)merges;
   }
   return x;
+}
+
+// ---- the scan as a prefix computation ---------------------------------------------------------------------
+// The predicted outcome of almost every candidate is known before the replay: a candidate with an old match
+// merges, a candidate with no old match and no pair bit is accepted; only a candidate whose possible matches
+// are window candidates ("unsure") depends on what was accepted before it.  Given the outcomes, the examine
+// order is closed form: front candidates are examined in order, and every merging front candidate pulls one
+// BURST of back candidates — consecutive back candidates up to and including the first accepted one.  So
+//   front j  is examined at  j + (back candidates in the bursts of the merging fronts before j),
+//   back  k  is examined at  (index of the merging front that owns k's burst) + 1 + k,
+// both popcounts and n-th-set-bit selections on two 64-bit masks, one lane per candidate.  Unsure candidates
+// start as accepts and are corrected by iterating (each round fixes at least the first wrong one); windows
+// that do not settle in a few rounds, and tail windows (one stream eaten from both ends), use the scalar scan.
+__device__ __forceinline__ int sel64(unsigned long long m, int n) {  // index of the n-th (0-based) set bit; 64: none
+  const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
+  const int pl = __popc(lo);
+  if (n < pl) return (int)__fns(lo, 0u, n + 1);
+  n -= pl;
+  if (n < __popc(hi)) return 32 + (int)__fns(hi, 0u, n + 1);
+  return 64;
+}
+__device__ __forceinline__ unsigned long long below64(int x) { return x >= 64 ? ~0ull : ((1ull << x) - 1ull); }
+__device__ __forceinline__ unsigned long long ballot64(bool p0, bool p1) {
+  return ((unsigned long long)__ballot_sync(0xffffffffu, p1) << 32) | (unsigned long long)__ballot_sync(0xffffffffu, p0);
+}
+
+// Returns the number of examined candidates, or -1 if the window has to take the scalar scan.
+__device__ int spec_scan_par(Smem& s, Spec& sp, int W, int wf, int wb, uint32_t i0) {
+  const uint32_t lane = lane_id();
+  const int INF = 255;
+  // per-candidate facts (two candidates per lane: t = lane and lane + 32)
+  bool valid[2], hasf[2], unsure[2];
+  uint32_t fpos[2], plo[2], phi[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int t = h * 32 + (int)lane;
+    valid[h] = t < W;
+    fpos[h] = valid[h] ? s.s_f[t] : kInf;
+    plo[h] = valid[h] ? s.pair[2 * t] : 0u;
+    phi[h] = valid[h] ? s.pair[2 * t + 1] : 0u;
+    hasf[h] = fpos[h] != kInf;
+    unsure[h] = valid[h] && !hasf[h] && (plo[h] | phi[h]) != 0u;
+    // target ids: candidates whose first old match is the same representative share one (the smallest
+    // candidate index with that first match)
+    if (valid[h]) {
+      int c = t;
+      if (hasf[h])
+        for (int u = 0; u < t; ++u)
+          if (s.s_f[u] == fpos[h]) {
+            c = u;
+            break;
+          }
+      sp.cls[t] = (uint8_t)c;
+    }
+    sp.cfirst[h * 32 + lane] = 0xFFu;
+    sp.cfirst[kW + h * 32 + lane] = 0xFFu;
+  }
+  sp.emask[lane] = 0ull;
+  const unsigned long long fm = below64(wf), bm = below64(wb);
+  unsigned long long OM = ballot64(hasf[0], hasf[1]);  // predicted merges, by candidate index
+  int xs[2] = {INF, INF}, ustar[2] = {-1, -1}, n_ex = 0;
+  bool back_exhausted = false;
+  int round = 0;
+  for (;; ++round) {
+    if (round == 6) return -1;
+    const unsigned long long MF = OM & fm;            // merging fronts, by front index
+    const unsigned long long AB = (~OM >> wf) & bm;   // accepted backs, by back index
+    const int popMF = __popcll(MF), popAB = __popcll(AB);
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int t = h * 32 + (int)lane;
+      int x = INF;
+      if (valid[h]) {
+        if (t < wf) {
+          const int m = __popcll(MF & below64(t));  // bursts before this front
+          if (m == 0) x = t;
+          else if (m - 1 < popAB) x = t + sel64(AB, m - 1) + 1;
+        } else {
+          const int k = t - wf;
+          const int g = __popcll(AB & below64(k));   // the burst this back belongs to
+          if (g < popMF) x = sel64(MF, g) + 1 + k;
+        }
+      }
+      xs[h] = x;
+    }
+    // where the window ends: the next front or back the replay would need does not exist
+    int t1 = INF, t2 = INF;
+    if (popMF == 0) t1 = wf;
+    else if (popMF - 1 < popAB) t1 = wf + sel64(AB, popMF - 1) + 1;
+    if (popAB < popMF) t2 = sel64(MF, popAB) + 1 + wb;
+    n_ex = min(t1, t2);
+    back_exhausted = t2 < t1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (valid[h]) sp.sx[h * 32 + lane] = (uint8_t)(xs[h] < n_ex ? xs[h] : 0xFF);
+    __syncwarp();
+    // unsure candidates: merge iff a pair-bit mate was accepted before their turn
+    bool changed = false, newm[2] = {false, false};
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      if (unsure[h] && xs[h] < n_ex) {
+        unsigned long long pm = ((unsigned long long)phi[h] << 32) | (unsigned long long)plo[h];
+        pm &= ~OM;  // accepted mates only
+        int best = INF, bu = -1;
+        while (pm) {
+          const int u = __ffsll((long long)pm) - 1;
+          pm &= pm - 1ull;
+          const int xu = sp.sx[u];
+          if (xu < xs[h] && xu < best) {
+            best = xu;
+            bu = u;
+          }
+        }
+        newm[h] = bu >= 0;
+        ustar[h] = bu;
+      }
+      const int t = h * 32 + (int)lane;
+      if (unsure[h] && newm[h] != (((OM >> t) & 1ull) != 0ull)) changed = true;
+    }
+    __syncwarp();
+    if (!__any_sync(0xffffffffu, changed)) break;
+    const unsigned long long U = ballot64(unsure[0], unsure[1]);
+    OM = (OM & ~U) | ballot64(unsure[0] && newm[0], unsure[1] && newm[1]);
+  }
+  // ---- records in examine order ----
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+    if (valid[h] && xs[h] < n_ex) sp.xcand[xs[h]] = (uint8_t)(h * 32 + lane);
+  __syncwarp();
+  // lanes now stand for examine indices x = lane and lane + 32
+  int tx[2];
+  bool ism[2], on[2];
+  int cid[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int x = h * 32 + (int)lane;
+    on[h] = x < n_ex;
+    tx[h] = on[h] ? sp.xcand[x] : 0;
+    ism[h] = on[h] && ((OM >> tx[h]) & 1ull) != 0ull;
+    cid[h] = 0xFF;
+  }
+  // target ids (unsure merges: 64 + the earliest accepted mate), first merge of every target id
+  {
+    // ustar lives with the lane that owns the candidate: publish it through sx's neighbour array
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (valid[h]) sp.xcls[h * 32 + lane] = (uint8_t)(ustar[h] >= 0 && xs[h] < n_ex && ((OM >> (h * 32 + lane)) & 1ull) ? ustar[h] : 0xFF);
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (ism[h]) {
+        const int t = tx[h];
+        const int us = sp.xcls[t];
+        cid[h] = (s.s_f[t] != kInf) ? (int)sp.cls[t] : (kW + us);
+        atomicMin(&sp.cfirst[cid[h]], (uint32_t)(h * 32 + lane));
+      }
+    __syncwarp();
+  }
+  bool first[2];
+#pragma unroll
+  for (int h = 0; h < 2; ++h) first[h] = ism[h] && sp.cfirst[cid[h]] == (uint32_t)(h * 32 + lane);
+  unsigned long long FX = ballot64(first[0], first[1]);
+  bool full = false;
+  if (__popcll(FX) >= kKD) {  // the dirty cache fills up: the window ends right after the merge that takes its last entry
+    n_ex = sel64(FX, kKD - 1) + 1;
+    full = true;
+    back_exhausted = false;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int x = h * 32 + (int)lane;
+      on[h] = x < n_ex;
+      ism[h] = ism[h] && on[h];
+      first[h] = first[h] && on[h];
+    }
+    FX &= below64(n_ex);
+  }
+  const unsigned long long MX = ballot64(ism[0], ism[1]);                    // merges, by examine index
+  const unsigned long long AX = ballot64(on[0] && !ism[0], on[1] && !ism[1]);  // accepts
+  const unsigned long long FRX = ballot64(on[0] && tx[0] < wf, on[1] && tx[1] < wf);
+  const int nd = __popcll(FX), merges = __popcll(MX);
+  __syncwarp();
+  // class bookkeeping in examine order: xcls[x] = target id (0xFF: accept)
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int x = h * 32 + (int)lane;
+    if (on[h]) sp.xcls[x] = (uint8_t)(ism[h] ? cid[h] : 0xFF);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int x = h * 32 + (int)lane;
+    if (!on[h]) continue;
+    const int t = tx[h];
+    const unsigned long long bx = below64(x);
+    const int k = __popcll(MX & bx);
+    sp.xep[x] = (uint8_t)k;
+    sp.xfi[x] = (uint8_t)__popcll(FRX & bx);
+    // accepted mates before x (and which of them were modified before x): only pair bits matter to the verify pass
+    {
+      unsigned long long pm = (((unsigned long long)s.pair[2 * t + 1] << 32) | (unsigned long long)s.pair[2 * t]) & ~OM;
+      unsigned long long am = 0ull, dm = 0ull;
+      while (pm) {
+        const int u = __ffsll((long long)pm) - 1;
+        pm &= pm - 1ull;
+        if ((int)sp.sx[u] < x) {
+          am |= 1ull << u;
+          if (sp.cfirst[kW + u] < (uint32_t)x) dm |= 1ull << u;
+        }
+      }
+      sp.acc_lo[x] = (uint32_t)am;
+      sp.acc_hi[x] = (uint32_t)(am >> 32);
+      sp.accd_lo[x] = (uint32_t)dm;
+      sp.accd_hi[x] = (uint32_t)(dm >> 32);
+    }
+    if (!ism[h]) {
+      const int r = __popcll(AX & bx);
+      s.acc[r] = (uint32_t)t;
+      sp.arank[t] = (uint8_t)r;
+      sp.xtarget[x] = kInf;
+      sp.xfe[x] = 0xFF;
+      continue;
+    }
+    const int xf = (int)sp.cfirst[cid[h]];
+    const int e = __popcll(FX & below64(xf));
+    const bool hf = s.s_f[t] != kInf;
+    sp.xfe[x] = (hf && xf != x) ? (uint8_t)e : (uint8_t)0xFF;
+    sp.vcand[k] = (uint8_t)t;
+    s.ment[t] = e;
+    atomicOr(&sp.emask[e], 1ull << k);
+    // the previous id-carrying member of the same target in examine order
+    int prev_last = -1;
+    for (int xp = x - 1; xp >= xf; --xp)
+      if (sp.xcls[xp] == (uint8_t)cid[h] && s.ctail[sp.xcand[xp]] >= 0) {
+        prev_last = sp.xcand[xp];
+        break;
+      }
+    s.mprev[t] = prev_last;
+    sp.vlast[k] = (int8_t)(s.ctail[t] >= 0 ? t : prev_last);
+    if (first[h]) {  // the entry's value before its first merge
+      s.dridx[e] = hf ? s.pridx[t] : 0u;  // (window targets: filled below, their rank is not known to this lane yet)
+      if (hf) {
+        s.dpos[e] = s.s_f[t];
+        sp.dbase[e] = (uint32_t)t;
+        sp.dbcnt[e] = s.pcnt[t];
+        s.dhead[e] = s.phead[t];
+        s.dtail[e] = s.ptail[t];
+      } else {
+        const uint32_t u = (uint32_t)(cid[h] - kW);
+        sp.dbase[e] = 0x100u | u;
+        sp.dbcnt[e] = s.ccnt[u];
+        s.dridx[e] = s.ridx[u];
+        s.dhead[e] = s.chead[u];
+        s.dtail[e] = s.ctail[u];
+      }
+    }
+  }
+  __syncwarp();
+  // targets that are window candidates: position = i0 + acceptance rank of the mate (known now)
+#pragma unroll
+  for (int h = 0; h < 2; ++h) {
+    const int x = h * 32 + (int)lane;
+    if (!on[h] || !ism[h]) continue;
+    const int t = tx[h];
+    if (s.s_f[t] != kInf) {
+      sp.xtarget[x] = s.s_f[t];
+    } else {
+      const uint32_t P = i0 + (uint32_t)sp.arank[cid[h] - kW];
+      sp.xtarget[x] = P;
+      if (first[h]) s.dpos[__popcll(FX & below64(x))] = P;
+    }
+  }
+  if (lane == 0) {
+    sp.xep[n_ex] = (uint8_t)merges;
+    sp.xfi[n_ex] = (uint8_t)__popcll(FRX & below64(n_ex));
+    s.ro[RO_BACK_EXH] = back_exhausted ? 1u : 0u;
+    s.ro[RO_FULL] = full ? 1u : 0u;
+    s.ro[RO_ND] = (uint32_t)nd;
+    s.ro[RO_MERGES] = (uint32_t)merges;
+  }
+  __syncwarp();
+  return n_ex;
 }
 
 // versions: the consensus value every predicted merge produces.  One entry's chain per warp, the entry's
@@ -1671,7 +1959,9 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
         long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0;
         if (prof) tp0 = clock64();
         if (warp == 0) {
-          const int n = spec_scan(s, sp, W, wf, wb, tail_mode, i0, size0);
+          int n = (tail_mode || A.no_par_scan) ? -1 : spec_scan_par(s, sp, W, wf, wb, i0);
+          if (n < 0) n = spec_scan(s, sp, W, wf, wb, tail_mode, i0, size0);
+          else if (A.dbg && lane == 0) atomicAdd(A.dbg + 32, 1ull);
           if (lane == 0) s.ro[RO_EXAMINED] = (uint32_t)n;
         }
         __syncthreads();
@@ -1841,7 +2131,7 @@ static int launch_stage(klsh_ctx* ctx, cudaStream_t stream, DevBuf& ctl_buf, int
   if (ctx->debug) {
     cudaStreamSynchronize(ctx->stream);
     cudaStreamSynchronize(ctx->stream2);
-    cudaMemset(ctx->dbg.p, 0, sizeof(unsigned long long) * 32);
+    cudaMemset(ctx->dbg.p, 0, sizeof(unsigned long long) * 40);
     t0 = std::chrono::high_resolution_clock::now();
   }
   void* args[] = {&A};
@@ -1851,7 +2141,7 @@ static int launch_stage(klsh_ctx* ctx, cudaStream_t stream, DevBuf& ctl_buf, int
     return klsh_fail(ctx, KLSH_ERR_CUDA, "merge kernel launch (team %d, grid %u, smem %zu) failed: %s", team, grid, smem,
                      cudaGetErrorString(e));
   if (ctx->debug) {  // KLSH_DEBUG=1: per-stage timing and window statistics on stderr
-    unsigned long long h[32];
+    unsigned long long h[40];
     cudaStreamSynchronize(stream);
     double ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
     cudaMemcpy(h, ctx->dbg.p, sizeof h, cudaMemcpyDeviceToHost);
@@ -1870,8 +2160,8 @@ static int launch_stage(klsh_ctx* ctx, cudaStream_t stream, DevBuf& ctl_buf, int
       fprintf(stderr, "[klsh]   decide kcycles/window: select %.1f dirty-compare %.1f old+accepted %.1f merge %.1f | per window: loop trips %.1f runs %.1f dirty tests %.1f\n",
               h[14] / 1e3 / h[0], h[15] / 1e3 / h[0], h[16] / 1e3 / h[0], h[17] / 1e3 / h[0], (double)h[22] / h[0], (double)h[23] / h[0], (double)h[24] / h[0]);
     if (h[26])
-      fprintf(stderr, "[klsh]   speculative windows %llu, cut short by a misprediction %llu; kcycles per speculative window: scan %.1f versions %.1f match %.1f verify %.1f\n",
-              h[26], h[27], h[28] / 1e3 / h[26], h[29] / 1e3 / h[26], h[30] / 1e3 / h[26], h[31] / 1e3 / h[26]);
+      fprintf(stderr, "[klsh]   speculative windows %llu (parallel scan %llu), cut short by a misprediction %llu; kcycles per speculative window: scan %.1f versions %.1f match %.1f verify %.1f\n",
+              h[26], h[32], h[27], h[28] / 1e3 / h[26], h[29] / 1e3 / h[26], h[30] / 1e3 / h[26], h[31] / 1e3 / h[26]);
     if (h[0]) fprintf(stderr, "[klsh]   dirty tests decided by the exact chain (inside the fast test's error band): %.3f per window\n", (double)h[25] / h[0]);
   }
   return KLSH_OK;
@@ -1894,6 +2184,7 @@ static MergeArgs base_args(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted,
   A.mg = ctx->mg;
   A.threshold = threshold;
   A.no_spec = ctx->no_spec ? 1 : 0;
+  A.no_par_scan = ctx->no_par_scan ? 1 : 0;
   A.work = ctx->eps_counter.p ? ctx->eps_counter.as<unsigned long long>() + 2 : nullptr;
   A.list_a = A.list_b = nullptr;
   A.n_a = A.n_b = nullptr;
@@ -1915,7 +2206,7 @@ int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
   KTRY(dev_reserve(ctx, s.esc1, sizeof(uint32_t) * 3 * ((size_t)n_items_host + 1)));
   KTRY(dev_reserve(ctx, s.esc2, sizeof(uint32_t) * 3 * ((size_t)n_items_host + 1)));
   KTRY(dev_reserve(ctx, s.esc3, sizeof(uint32_t) * 3 * ((size_t)n_items_host + 1)));
-  if (ctx->debug) KTRY(dev_reserve(ctx, ctx->dbg, sizeof(unsigned long long) * 32));
+  if (ctx->debug) KTRY(dev_reserve(ctx, ctx->dbg, sizeof(unsigned long long) * 40));
 
   MergeArgs A = base_args(ctx, s, rows_sorted, threshold);
 
@@ -1974,7 +2265,7 @@ int launch_merge_direct(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
   PassCounters* dc = s.counters.as<PassCounters>();
   KTRY(dev_reserve(ctx, s.escb2, sizeof(uint32_t) * 3 * ((size_t)n_direct_host + 1)));
   KTRY(dev_reserve(ctx, s.escb3, sizeof(uint32_t) * 3 * ((size_t)n_direct_host + 1)));
-  if (ctx->debug) KTRY(dev_reserve(ctx, ctx->dbg, sizeof(unsigned long long) * 32));
+  if (ctx->debug) KTRY(dev_reserve(ctx, ctx->dbg, sizeof(unsigned long long) * 40));
   MergeArgs A = base_args(ctx, s, rows_sorted, threshold);
   cudaStream_t st = ctx->stream2;
 

@@ -389,3 +389,90 @@ extern "C" int klsh_mg_gather_rows(klsh_ctx* ctx) {
   ctx->id_base = all[2];
   return KLSH_OK;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Multi-batch phase 1 without file round trips: the survivors of each batch
+// are appended to a device-resident stash; klsh_unstash_rows makes the stash — all batches, in append
+// order — the current row set, the vector the reference rebuilds by appending to tmp/0.bin(.clust) and
+// reading it back (app/kmerLSH.cc:326-335, :415).  Member ids stay implicit (id = base + slot) when the
+// batches were loaded by klsh_load_counts with contiguous offsets; otherwise they are kept explicitly.
+// ------------------------------------------------------------------------------------------------
+extern "C" int klsh_stash_rows(klsh_ctx* ctx) {
+  if (!ctx || ctx->D <= 0) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_stash_rows: no rows loaded");
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  const int ld = ctx->ld;
+  const uint64_t n = ctx->cur.n_alive, m = ctx->n_slots;
+  const uint64_t r0 = ctx->stash_rows, s0 = ctx->stash_slots;
+  if (r0 && ctx->stash_D != ctx->D)
+    return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_stash_rows: the stash holds rows of dimension %d, the current rows have %d", ctx->stash_D, ctx->D);
+  ctx->stash_D = ctx->D;
+  if (r0 + n >= 0xFFFFFFF0ull || s0 + m >= 0x7FFFFFF0ull)
+    return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_stash_rows: the stash would exceed one GPU context (%llu rows, %llu ids)",
+                     (unsigned long long)(r0 + n), (unsigned long long)(s0 + m));
+  // member ids: implicit while every appended batch continues the id range of the previous one
+  const bool cont = ctx->ids_implicit && ctx->stash_implicit && (r0 == 0 || ctx->id_base == ctx->stash_id_base + s0);
+  if (!cont) {
+    if (ctx->stash_implicit) {  // materialise what is stashed so far
+      ctx->stash_ids.resize(s0);
+      for (uint64_t k = 0; k < s0; ++k) ctx->stash_ids[k] = ctx->stash_id_base + k;
+      ctx->stash_implicit = false;
+    }
+    ctx->stash_ids.resize(s0 + m);
+    for (uint64_t k = 0; k < m; ++k) ctx->stash_ids[s0 + k] = ctx->ids_implicit ? ctx->id_base + k : ctx->ids[k];
+  } else if (r0 == 0) {
+    ctx->stash_id_base = ctx->id_base;
+  }
+  RowState& g = ctx->stash;
+  KTRY(dev_reserve(ctx, g.vals, sizeof(float) * ((r0 + n) * (uint64_t)ld + 4)));
+  KTRY(dev_reserve(ctx, g.meta, sizeof(int32_t) * 4 * (r0 + n + 1)));
+  KTRY(dev_reserve(ctx, g.next, sizeof(int32_t) * (s0 + m + 1)));
+  if (n) {
+    k_pack_rows<<<(uint32_t)((n * 32 + 255) / 256), 256, 0, ctx->stream>>>(
+        ctx->cur.vals.as<float>(), ld, ctx->cur.cnt(), ctx->cur.head(), ctx->cur.tail(), ctx->cur.alive.as<uint32_t>(), n, (int32_t)s0,
+        g.vals.as<float>() + r0 * (uint64_t)ld, g.cnt() + r0, g.head() + r0, g.tail() + r0);
+    ctx->launches++;
+  }
+  if (m) {
+    k_shift_next<<<(uint32_t)((m + 255) / 256), 256, 0, ctx->stream>>>(ctx->cur.next.as<int32_t>(), m, (int32_t)s0, g.next.as<int32_t>() + s0);
+    ctx->launches++;
+  }
+  KCUDA(ctx, cudaGetLastError());
+  KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stash_rows = r0 + n;
+  ctx->stash_slots = s0 + m;
+  return KLSH_OK;
+}
+
+extern "C" int klsh_stash_count(const klsh_ctx* ctx, uint64_t* n_rows) {
+  if (!ctx || !n_rows) return KLSH_ERR_ARG;
+  *n_rows = ctx->stash_rows;
+  return KLSH_OK;
+}
+
+extern "C" int klsh_unstash_rows(klsh_ctx* ctx) {
+  if (!ctx || ctx->stash_D <= 0) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_unstash_rows: nothing was stashed");
+  ctx->D = ctx->stash_D;
+  ctx->ld = (ctx->D + 3) & ~3;
+  KCUDA(ctx, cudaSetDevice(ctx->device));
+  KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->has_snap = false;
+  const uint64_t rows = ctx->stash_rows, slots = ctx->stash_slots;
+  // the stash becomes the current state (buffers swapped, nothing copied); the old state's buffers become the
+  // empty stash and are reused by the next run
+  std::swap(ctx->cur.vals, ctx->stash.vals);
+  std::swap(ctx->cur.meta, ctx->stash.meta);
+  std::swap(ctx->cur.next, ctx->stash.next);
+  KTRY(dev_reserve(ctx, ctx->cur.alive, sizeof(uint32_t) * (rows + 1)));
+  KTRY(launch_iota(ctx, ctx->cur.alive.as<uint32_t>(), rows, 0));
+  KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->cur.n_alive = rows;
+  ctx->n_born = rows;
+  ctx->n_slots = slots;
+  ctx->ids_implicit = ctx->stash_implicit;
+  ctx->id_base = ctx->stash_id_base;
+  ctx->ids.swap(ctx->stash_ids);
+  ctx->stash_ids.clear();
+  ctx->stash_rows = ctx->stash_slots = ctx->stash_id_base = 0;
+  ctx->stash_implicit = true;
+  return KLSH_OK;
+}

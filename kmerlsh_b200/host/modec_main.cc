@@ -11,7 +11,9 @@
 // iterations instead of being re-read from the spill files (the rows, their order and their member
 // lists are the same either way, so the results are too — SURVEY.md section 8f item 3); the spill
 // files are still written for compatibility.  --reload-tmp forces the reference's file round trip,
-// --no-tmp-files skips writing the spill when it is not needed.
+// --no-tmp-files skips writing the spill when it is not needed.  --resident does the same for an input of
+// SEVERAL batches on one GPU: every batch's survivors are appended to a device-resident stash.
+// --gpus=N runs the batches on N GPUs (see below), --stats-json=FILE writes one record per LSH iteration.
 // Modes K, B and E are outside this tool.
 #include <getopt.h>
 
@@ -48,7 +50,7 @@ struct Params {
   int device = 0;
   int gpus = 1;
   uint64_t batch = 100000000ull;
-  bool reload_tmp = false, no_tmp_files = false;
+  bool reload_tmp = false, no_tmp_files = false, resident = false;
   std::string stats_json;
 };
 
@@ -183,6 +185,7 @@ int main(int argc, char** argv) {
                                          {"no-tmp-files", no_argument, 0, 1004},
                                          {"gpus", required_argument, 0, 1005},
                                          {"stats-json", required_argument, 0, 1006},
+                                         {"resident", no_argument, 0, 1007},
                                          {0, 0, 0, 0}};
   for (;;) {
     int idx = 0;
@@ -206,6 +209,7 @@ int main(int argc, char** argv) {
       case 1004: p.no_tmp_files = true; break;
       case 1005: p.gpus = atoi(optarg); break;
       case 1006: p.stats_json = optarg; break;
+      case 1007: p.resident = true; break;
       default: break;  // -H -X -C -K -S -P -V: accepted, meaningless for mode C
     }
   }
@@ -309,7 +313,7 @@ int main(int argc, char** argv) {
   // batch i runs on worker i % gpus; tables are drawn in batch order, spills are appended in batch order.
   struct Batch { uint64_t offset, size, call; int index; };
   auto run_round = [&](const std::vector<Batch>& batches, bool from_counts, const std::string& read_tmp, float sim, int iters,
-                       bool keep_resident, uint64_t* rows_total) -> bool {
+                       bool keep_resident, bool stash, uint64_t* rows_total) -> bool {
     sh.save_turn = 0;
     std::atomic<uint64_t> total{0};
     auto body = [&](Worker& w) {
@@ -341,6 +345,10 @@ int main(int argc, char** argv) {
         uint64_t rows = 0;
         klsh_row_count(w.ctx, &rows, nullptr);
         total += rows;
+        if (stash && klsh_stash_rows(w.ctx) != KLSH_OK) {  // one worker: batches arrive in order
+          sh.fail(std::string("klsh_stash_rows failed: ") + klsh_last_error(w.ctx));
+          return;
+        }
         {  // spill and log in batch order
           std::unique_lock<std::mutex> lk(sh.mu);
           sh.cv.wait(lk, [&] { return sh.save_turn == (uint64_t)b.index || sh.failed.load(); });
@@ -386,12 +394,22 @@ int main(int argc, char** argv) {
   std::vector<Batch> batches = make_batches(kmap_size, iter);
   // a single batch that needs no re-batching stays on the device (one GPU); its spill is optional then
   const bool single = batches.size() == 1 && !p.reload_tmp && p.gpus == 1;
-  if (!run_round(batches, true, "", p.min_similarity, 1, single && p.no_tmp_files, &total_size)) {
+  // --resident: several batches on one GPU — the survivors of every batch are appended to a device-resident
+  // stash (klsh_stash_rows) instead of being re-read from the spill files afterwards
+  const bool stashing = p.resident && !single && !p.reload_tmp && p.gpus == 1;
+  if (!run_round(batches, true, "", p.min_similarity, 1, (single || stashing) && p.no_tmp_files, stashing, &total_size)) {
     std::cerr << sh.error << std::endl;
     return 1;
   }
-  const bool resident = single && total_size <= batch_thresh;
-  if (single && p.no_tmp_files && !resident) {  // the optional spill turned out to be needed after all
+  bool resident = single && total_size <= batch_thresh;
+  if (stashing) {
+    if (klsh_unstash_rows(workers[0].ctx) != KLSH_OK) {
+      std::cerr << "klsh_unstash_rows failed: " << klsh_last_error(workers[0].ctx) << std::endl;
+      return 1;
+    }
+    resident = total_size <= batch_thresh;
+  }
+  if ((single || stashing) && p.no_tmp_files && !resident) {  // the optional spill turned out to be needed after all
     if (klsh_save(workers[0].ctx, write_tmp.c_str(), 1, 0) != KLSH_OK) {
       std::cerr << "klsh_save failed: " << klsh_last_error(workers[0].ctx) << std::endl;
       return 1;
@@ -405,7 +423,7 @@ int main(int argc, char** argv) {
     write_tmp = p.tmp_dir + std::to_string(tmp++) + ".bin";
     iter = (int)(total_size / batch_thresh);
     batches = make_batches(total_size, iter);
-    if (!run_round(batches, false, read_tmp, similarity, 1 + 4, false, &total_size)) {
+    if (!run_round(batches, false, read_tmp, similarity, 1 + 4, false, false, &total_size)) {
       std::cerr << sh.error << std::endl;
       return 1;
     }

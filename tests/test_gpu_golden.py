@@ -154,11 +154,14 @@ def test_reference_program_with_cluster_shim(tag, tmp_path):
     assert md5(out + ".clust") == m["clust_md5"]
 
 
-def test_mode_c_cli_two_batches(oracle, tmp_path):
+@pytest.mark.parametrize("extra", [[], ["--resident"], ["--resident", "--no-tmp-files"]])
+def test_mode_c_cli_two_batches(oracle, tmp_path, extra):
     """--batch smaller than the input: independent phase-1 batches appended to tmp/0.bin, the
     re-batch loop (similarity -= 0.001, 5 iterations per batch) while survivors exceed the batch
     size, then the -I iterations — byte-identical to the oracle's mode C with the same batch size
-    (the reference hard-codes 100 M rows per batch, app/kmerLSH.cc:285)."""
+    (the reference hard-codes 100 M rows per batch, app/kmerLSH.cc:285).  With --resident the survivors
+    of every batch are appended to a device-resident stash (klsh_stash_rows) instead of being re-read from
+    the spill files; with --no-tmp-files the spill is only written if a re-batch round needs it."""
     work = str(tmp_path)
     synth.write_mode_c_inputs(work, 30000, 3, 3, 99)
     out = os.path.join(work, "oracle_result.txt")
@@ -166,10 +169,26 @@ def test_mode_c_cli_two_batches(oracle, tmp_path):
     oracle.mode_c(work, 6, 0.85, 4, out, 17, batch_thresh=8000, tmp_dir=os.path.join(work, "otmp") + "/")
     exe = os.path.join(ROOT, "kmerlsh_b200", "kmerLSH_b200")
     subprocess.run([exe, "-a", "A.txt", "-b", "B.txt", "-o", "oa", "-p", "ob", "-M", "C", "--only", "-I", "4", "-N", "0.85",
-                    "-T", "1", "--seed=17", "--batch=8000"], cwd=work, check=True, stdout=subprocess.DEVNULL)
+                    "-T", "1", "--seed=17", "--batch=8000"] + extra, cwd=work, check=True, stdout=subprocess.DEVNULL)
     res = os.path.join(work, "clustering_result.txt")
     assert md5(res) == md5(out)
     assert md5(res + ".clust") == md5(out + ".clust")
+
+
+def test_mode_c_cli_resident_batches_without_rebatch(oracle, tmp_path):
+    """Several phase-1 batches whose survivors fit one batch: with --resident --no-tmp-files no spill file is
+    ever written and the -I iterations start from the device-resident stash — same output as the oracle."""
+    work = str(tmp_path)
+    synth.write_mode_c_inputs(work, 20000, 3, 3, 5)
+    out = os.path.join(work, "oracle_result.txt")
+    os.makedirs(os.path.join(work, "otmp"))
+    oracle.mode_c(work, 6, 0.85, 4, out, 23, batch_thresh=14000, tmp_dir=os.path.join(work, "otmp") + "/")
+    exe = os.path.join(ROOT, "kmerlsh_b200", "kmerLSH_b200")
+    subprocess.run([exe, "-a", "A.txt", "-b", "B.txt", "-o", "oa", "-p", "ob", "-M", "C", "--only", "-I", "4", "-N", "0.85",
+                    "-T", "1", "--seed=23", "--batch=14000", "--resident", "--no-tmp-files"], cwd=work, check=True, stdout=subprocess.DEVNULL)
+    res = os.path.join(work, "clustering_result.txt")
+    assert md5(res) == md5(out) and md5(res + ".clust") == md5(out + ".clust")
+    assert not os.path.exists(os.path.join(work, "tmp", "0.bin"))
 
 
 @pytest.mark.parametrize("gpus", [2, 3])

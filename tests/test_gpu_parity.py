@@ -388,3 +388,32 @@ def test_plane_stream_tell_seek_and_done_callback(gpu, oracle):
     rows = oracle.rows(values)
     rows.cluster(0.85, 3, 60, oracle.planes(5))
     assert_rows_equal(gpu.get_rows(), rows.export())
+
+
+def test_stash_rows_equals_file_round_trip(gpu, oracle, tmp_path):
+    """klsh_stash_rows / klsh_unstash_rows: survivors of two batches concatenated on the device — same rows, order
+    and member lists as appending both to a spill file and reading it back (klsh_save + klsh_load_cluster_file),
+    with implicit ids (contiguous klsh_load_counts batches) and with explicit ids (klsh_set_rows batches)."""
+    counts, vk, values, ids = synth_rows(oracle, 40000, 4, 4, 12)
+    spill = str(tmp_path / "spill.bin")
+    for explicit in (False, True):
+        for b, (lo, hi) in enumerate(((0, 25000), (25000, 40000))):
+            gpu.set_seed(100 + b)
+            if explicit:
+                sel = (ids >= lo) & (ids < hi)
+                gpu.set_rows(values[sel], np.arange(sel.sum() + 1, dtype=np.uint64), ids[sel] * 3 + 7)
+            else:
+                gpu.load_counts(np.ascontiguousarray(counts[:, lo:hi]), vk, lo)
+            gpu.cluster(0.8, 1, 40)
+            gpu.save(spill, b == 0, 0)
+            gpu.stash_rows()
+        assert gpu.stash_count() > 0
+        gpu.unstash_rows()
+        assert gpu.stash_count() == 0
+        got = gpu.get_rows()
+        gpu.load_cluster_file(spill, 8)
+        assert_rows_equal(got, gpu.get_rows(), "explicit ids" if explicit else "implicit ids")
+        gpu.set_seed(9)
+        gpu.cluster(0.8, 3, 1000)      # and the stash is a working row set
+        a = gpu.get_rows()
+        assert len(a[1]) - 1 < len(got[1]) - 1

@@ -2,7 +2,10 @@
 dram__bytes_write.sum --clock-control none --csv --log-file X ...`) into a per-kernel table (markdown) and
 a per-family DRAM-traffic JSON (what bench.py reports as roofline.traffic).
 
-  python tools/ncu_summary.py launches.csv[.gz] out_summary.md out_traffic.json "<command that was profiled>"
+  python tools/ncu_summary.py launches.csv[.gz] out_summary.md out_traffic.json "<command that was profiled>" [passes]
+
+`passes` (optional): keep only the launches up to and including the merge of the passes-th `k_classify` launch,
+i.e. exactly one benchmark step (C2: 101 iterations + 1 nested pass = 102) when the capture ran on into the next.
 """
 import csv
 import gzip
@@ -27,6 +30,7 @@ def short(name):
 def main():
     src, out_md, out_json = sys.argv[1], sys.argv[2], sys.argv[3]
     cmd = sys.argv[4] if len(sys.argv) > 4 else ""
+    passes = int(sys.argv[5]) if len(sys.argv) > 5 else 0
     raw = gzip.open(src, "rt").read() if src.endswith(".gz") else open(src).read()
     lines = [ln for ln in raw.splitlines() if ln.startswith('"')]
     rows = list(csv.DictReader(io.StringIO("\n".join(lines))))
@@ -39,6 +43,19 @@ def main():
         else:
             v *= {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
         per_launch[(r["ID"], r["Kernel Name"])][r["Metric Name"]] = v
+    if passes:  # cut the capture after one step: launch ids are chronological
+        ids = sorted(per_launch, key=lambda k: int(k[0]))
+        seen, cut = 0, None
+        for k in ids:
+            if "k_classify" in k[1]:
+                seen += 1
+                if seen == passes + 1:
+                    cut = int(k[0])
+                    break
+        if cut is not None:
+            # the (passes+1)-th classify belongs to the next step, and so do its sign/sort launches just before it
+            last_merge = max(int(k[0]) for k in ids if int(k[0]) < cut and "k_merge" in k[1])
+            per_launch = {k: v for k, v in per_launch.items() if int(k[0]) <= last_merge + 2}
     kern = defaultdict(lambda: [0, 0.0, 0.0, 0.0])
     for (_id, name), m in per_launch.items():
         k = kern[short(name)]
