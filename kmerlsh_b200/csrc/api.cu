@@ -133,7 +133,7 @@ int klsh_create(int device, klsh_ctx** out) {
   if (const char* e = std::getenv("KLSH_DEBUG")) ctx->debug = std::atoi(e) != 0;
   if (const char* e = std::getenv("KLSH_MERGE_V1")) ctx->merge_v1 = std::atoi(e) != 0;
   if (const char* e = std::getenv("KLSH_NO_SPEC")) ctx->no_spec = std::atoi(e) != 0;
-  if (const char* e = std::getenv("KLSH_NO_PAR_SCAN")) ctx->no_par_scan = std::atoi(e) != 0;
+  if (const char* e = std::getenv("KLSH_PAR_SCAN")) ctx->no_par_scan = std::atoi(e) == 0;
   if (const char* e = std::getenv("KLSH_CTA_MAX")) ctx->cta_max = (uint32_t)std::strtoul(e, nullptr, 10);
   if (const char* e = std::getenv("KLSH_CLUSTER_MAX")) ctx->cluster_max = (uint32_t)std::strtoul(e, nullptr, 10);
   if (const char* e = std::getenv("KLSH_CLUSTER_SIZE")) ctx->cluster_size = std::atoi(e);

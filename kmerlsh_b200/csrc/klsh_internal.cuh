@@ -155,7 +155,10 @@ struct klsh_ctx {
   int cluster_ctas_per_sm = 2;
   bool debug = false;     // KLSH_DEBUG=1
   DevBuf dbg;
-  bool no_par_scan = false;  // KLSH_NO_PAR_SCAN=1
+  // The speculative resolver's scan as a warp-parallel prefix computation (spec_scan_par): exact and tested, but
+  // measured no faster than the scalar scan on C2 (10-20 k cycles per window against 12-37 k, and slower on the
+  // single-CTA stage), so it is opt-in: KLSH_PAR_SCAN=1
+  bool no_par_scan = true;
   bool no_spec = false;   // KLSH_NO_SPEC=1: windows are resolved by the sequential loop only
   bool merge_v1 = false;  // KLSH_MERGE_V1=1: first-generation block-per-bucket kernel (A/B checks)
   PassCounters* h_counters = nullptr;  // pinned

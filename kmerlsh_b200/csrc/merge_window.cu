@@ -168,7 +168,7 @@ struct MergeArgs {
   TeamCtl* ctl;
   MgLog mg;
   unsigned long long* work;  // [2] device counters: pairs screened on the tensor cores, pairs re-tested exactly
-  int no_par_scan;  // KLSH_NO_PAR_SCAN=1: speculative windows use the scalar scan only (A/B checks)
+  int no_par_scan;  // default; KLSH_PAR_SCAN=1 selects the warp-parallel scan (spec_scan_par)
   int no_spec;   // KLSH_NO_SPEC=1: sequential resolution only (A/B checks)
   unsigned long long* dbg;  // [32] 26: speculative windows, 27: ... cut short; 0..7: windows, candidates, merges, undecidable, cache_full, back_exhausted, accepted, escalated; 8..13: leader cycles in stage/parallel/sync1/prefetch/decide/flush+sync2; 18..21: staging detail
   float threshold;

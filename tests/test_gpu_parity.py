@@ -225,9 +225,11 @@ def test_save_files(gpu, oracle, tmp_path):
     (8, 64, 200, 8, 40), (1000000, 20, 60, 8, 100), (4, 1000000, 1000000, 16, 33), (2, 2, 2, 8, 300)])
 def test_merge_team_variants(oracle, monkeypatch, cta_max, cluster_max, cluster2_max, csize, direct_min):
     """The windowed merge with the escalation thresholds (representatives per team) forced low, so
-    that small test buckets travel CTA -> cluster -> large cluster -> cooperative grid, against the oracle."""
+    that small test buckets travel CTA -> cluster -> large cluster -> cooperative grid, against the oracle.
+    Variants with an odd cta_max also switch the speculative resolver to its warp-parallel scan."""
     from kmerlsh_b200 import Context
 
+    monkeypatch.setenv("KLSH_PAR_SCAN", "1" if cta_max % 2 else "0")
     monkeypatch.setenv("KLSH_DIRECT_MIN", str(direct_min))
     monkeypatch.setenv("KLSH_CTA_MAX", str(cta_max))
     monkeypatch.setenv("KLSH_CLUSTER_MAX", str(cluster_max))
@@ -417,3 +419,23 @@ def test_stash_rows_equals_file_round_trip(gpu, oracle, tmp_path):
         gpu.cluster(0.8, 3, 1000)      # and the stash is a working row set
         a = gpu.get_rows()
         assert len(a[1]) - 1 < len(got[1]) - 1
+
+
+@pytest.mark.parametrize("env", [{"KLSH_NO_SPEC": "1"}, {"KLSH_PAR_SCAN": "1"}, {}])
+def test_window_resolution_modes(oracle, monkeypatch, env):
+    """The three ways a window is resolved — sequential loop only, speculative with the scalar scan (default),
+    speculative with the warp-parallel scan — give the oracle's clusters bit for bit."""
+    from kmerlsh_b200 import Context
+
+    for k, v in env.items():
+        monkeypatch.setenv(k, v)
+    cases = [(150000, 8, 8, 5, 0.85, 100000, 3), (60000, 16, 16, 4, 0.9, 100000, 5), (90000, 4, 4, 6, 0.8, 60, 7)]
+    with Context(0) as ctx:
+        for n, sa, sb, iters, minsim, thr, seed in cases:
+            _, _, values, ids = synth_rows(oracle, n, sa, sb, 80 + seed)
+            rows = oracle.rows(values)
+            rows.cluster(minsim, iters, thr, oracle.planes(seed))
+            ctx.set_seed(seed)
+            ctx.set_rows(values)
+            ctx.cluster(minsim, iters, thr)
+            assert_rows_equal(ctx.get_rows(), rows.export(), "n=%d D=%d %r" % (n, sa + sb, env))
