@@ -907,6 +907,7 @@ __device__ void mask_helpers(const MergeArgs& A, Smem& s, int W, int hw, int nh)
 struct Spec {
   float* vers;        // [kW][ts] value after predicted merge k
   unsigned long long* emask;  // [kKD] merges (bit k) that went into the entry, in merge order
+  unsigned long long* cmask;  // [2 kW] per target id: examine indices of its id-carrying merged candidates — parallel scan
   int32_t* vcnt;      // [kW] member count after merge k
   uint32_t* xtarget;  // [kW] predicted position (kInf: accept) per examined candidate
   uint32_t* acc_lo;   // [kW] accepted candidates before x (tile index bits 0..31)
@@ -931,12 +932,13 @@ struct Spec {
   uint32_t* cfirst;   // [2 kW] examine index of the first merge into a target id (0xFF: none) — parallel scan
 };
 __host__ __device__ inline size_t spec_bytes_for(int ld) {
-  return sizeof(float) * (size_t)kW * (row_width(ld) + 4) + 8 * (size_t)kKD + 4 * (size_t)(kW * 9 + kKD * 2) + (size_t)kW * 12 + 2 + kKD + 16;
+  return sizeof(float) * (size_t)kW * (row_width(ld) + 4) + 8 * (size_t)(kKD + 2 * kW) + 4 * (size_t)(kW * 9 + kKD * 2) + (size_t)kW * 12 + 2 + kKD + 16;
 }
 __device__ __forceinline__ void carve_spec(Spec& sp, void* base, int ts) {
   sp.vers = reinterpret_cast<float*>(base);
   sp.emask = reinterpret_cast<unsigned long long*>(sp.vers + (size_t)kW * ts);  // kW*ts floats: a multiple of 16 bytes
-  uint32_t* u = reinterpret_cast<uint32_t*>(sp.emask + kKD);
+  sp.cmask = sp.emask + kKD;
+  uint32_t* u = reinterpret_cast<uint32_t*>(sp.cmask + 2 * kW);
   sp.vcnt = reinterpret_cast<int32_t*>(u); u += kW;
   sp.xtarget = u; u += kW;
   sp.acc_lo = u; u += kW;
@@ -1155,12 +1157,25 @@ __device__ int spec_scan(Smem& s, Spec& sp, int W, int wf, int wb, bool tail_mod
 // both popcounts and n-th-set-bit selections on two 64-bit masks, one lane per candidate.  Unsure candidates
 // start as accepts and are corrected by iterating (each round fixes at least the first wrong one); windows
 // that do not settle in a few rounds, and tail windows (one stream eaten from both ends), use the scalar scan.
+__device__ __forceinline__ int sel32(uint32_t m, int n) {  // index of the n-th (0-based) set bit; n < popc(m)
+  int pos = 0;
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const int c = __popc(m & ((1u << w) - 1u));
+    if (n >= c) {
+      n -= c;
+      m >>= w;
+      pos += w;
+    }
+  }
+  return pos;
+}
 __device__ __forceinline__ int sel64(unsigned long long m, int n) {  // index of the n-th (0-based) set bit; 64: none
   const uint32_t lo = (uint32_t)m, hi = (uint32_t)(m >> 32);
   const int pl = __popc(lo);
-  if (n < pl) return (int)__fns(lo, 0u, n + 1);
+  if (n < pl) return sel32(lo, n);
   n -= pl;
-  if (n < __popc(hi)) return 32 + (int)__fns(hi, 0u, n + 1);
+  if (n < __popc(hi)) return 32 + sel32(hi, n);
   return 64;
 }
 __device__ __forceinline__ unsigned long long below64(int x) { return x >= 64 ? ~0ull : ((1ull << x) - 1ull); }
@@ -1168,10 +1183,13 @@ __device__ __forceinline__ unsigned long long ballot64(bool p0, bool p1) {
   return ((unsigned long long)__ballot_sync(0xffffffffu, p1) << 32) | (unsigned long long)__ballot_sync(0xffffffffu, p0);
 }
 
-// Returns the number of examined candidates, or -1 if the window has to take the scalar scan.
-__device__ int spec_scan_par(Smem& s, Spec& sp, int W, int wf, int wb, uint32_t i0) {
+// Returns the number of examined candidates, or -1 if the window has to take the scalar scan.  Tail windows (one
+// stream of W candidates eaten from both ends: back index k is candidate W-1-k) follow the same formulas with both
+// masks over the same candidates; a candidate is examined by whichever end reaches it first, all W are examined.
+__device__ int spec_scan_par(Smem& s, Spec& sp, int W, int wf, int wb, bool tail_mode, uint32_t i0) {
   const uint32_t lane = lane_id();
   const int INF = 255;
+  if (tail_mode) wb = wf;
   // per-candidate facts (two candidates per lane: t = lane and lane + 32)
   bool valid[2], hasf[2], unsure[2];
   uint32_t fpos[2], plo[2], phi[2];
@@ -1184,56 +1202,73 @@ __device__ int spec_scan_par(Smem& s, Spec& sp, int W, int wf, int wb, uint32_t 
     phi[h] = valid[h] ? s.pair[2 * t + 1] : 0u;
     hasf[h] = fpos[h] != kInf;
     unsure[h] = valid[h] && !hasf[h] && (plo[h] | phi[h]) != 0u;
-    // target ids: candidates whose first old match is the same representative share one (the smallest
-    // candidate index with that first match)
-    if (valid[h]) {
-      int c = t;
-      if (hasf[h])
-        for (int u = 0; u < t; ++u)
-          if (s.s_f[u] == fpos[h]) {
-            c = u;
-            break;
-          }
-      sp.cls[t] = (uint8_t)c;
-    }
     sp.cfirst[h * 32 + lane] = 0xFFu;
     sp.cfirst[kW + h * 32 + lane] = 0xFFu;
+    sp.cmask[h * 32 + lane] = 0ull;
+    sp.cmask[kW + h * 32 + lane] = 0ull;
   }
   sp.emask[lane] = 0ull;
+  // target ids: candidates whose first old match is the same representative share one — the smallest candidate
+  // index with that first match (match within each half, then the second half looks its value up in the first)
+  {
+    const uint32_t m0 = __match_any_sync(0xffffffffu, fpos[0]);
+    const uint32_t m1 = __match_any_sync(0xffffffffu, fpos[1]);
+    const int c0 = __ffs(m0) - 1;
+    int c1 = 32 + __ffs(m1) - 1;
+    if (hasf[1] && (int)lane == __ffs(m1) - 1) {  // one lane per distinct value of the second half
+      for (int u = 0; u < 32 && u < W; ++u)
+        if (s.s_f[u] == fpos[1]) {
+          c1 = u;
+          break;
+        }
+    }
+    c1 = __shfl_sync(0xffffffffu, c1, __ffs(m1) - 1);
+    if (valid[0]) sp.cls[lane] = (uint8_t)(hasf[0] ? c0 : (int)lane);
+    if (valid[1]) sp.cls[32 + lane] = (uint8_t)(hasf[1] ? c1 : 32 + (int)lane);
+  }
   const unsigned long long fm = below64(wf), bm = below64(wb);
   unsigned long long OM = ballot64(hasf[0], hasf[1]);  // predicted merges, by candidate index
   int xs[2] = {INF, INF}, ustar[2] = {-1, -1}, n_ex = 0;
+  bool asfront[2] = {true, true};
   bool back_exhausted = false;
   int round = 0;
   for (;; ++round) {
     if (round == 6) return -1;
-    const unsigned long long MF = OM & fm;            // merging fronts, by front index
-    const unsigned long long AB = (~OM >> wf) & bm;   // accepted backs, by back index
+    const unsigned long long MF = OM & fm;  // merging fronts, by front index
+    // accepted backs, by back index
+    const unsigned long long AB = tail_mode ? ((__brevll(~OM) >> (64 - W)) & bm) : ((~OM >> wf) & bm);
     const int popMF = __popcll(MF), popAB = __popcll(AB);
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int t = h * 32 + (int)lane;
-      int x = INF;
+      int xf = INF, xb = INF;
       if (valid[h]) {
         if (t < wf) {
           const int m = __popcll(MF & below64(t));  // bursts before this front
-          if (m == 0) x = t;
-          else if (m - 1 < popAB) x = t + sel64(AB, m - 1) + 1;
-        } else {
-          const int k = t - wf;
+          if (m == 0) xf = t;
+          else if (m - 1 < popAB) xf = t + sel64(AB, m - 1) + 1;
+        }
+        if (tail_mode || t >= wf) {
+          const int k = tail_mode ? (W - 1 - t) : (t - wf);
           const int g = __popcll(AB & below64(k));   // the burst this back belongs to
-          if (g < popMF) x = sel64(MF, g) + 1 + k;
+          if (g < popMF) xb = sel64(MF, g) + 1 + k;
         }
       }
-      xs[h] = x;
+      xs[h] = min(xf, xb);
+      asfront[h] = xf <= xb;
     }
     // where the window ends: the next front or back the replay would need does not exist
-    int t1 = INF, t2 = INF;
-    if (popMF == 0) t1 = wf;
-    else if (popMF - 1 < popAB) t1 = wf + sel64(AB, popMF - 1) + 1;
-    if (popAB < popMF) t2 = sel64(MF, popAB) + 1 + wb;
-    n_ex = min(t1, t2);
-    back_exhausted = t2 < t1;
+    if (tail_mode) {
+      n_ex = W;
+      back_exhausted = false;
+    } else {
+      int t1 = INF, t2 = INF;
+      if (popMF == 0) t1 = wf;
+      else if (popMF - 1 < popAB) t1 = wf + sel64(AB, popMF - 1) + 1;
+      if (popAB < popMF) t2 = sel64(MF, popAB) + 1 + wb;
+      n_ex = min(t1, t2);
+      back_exhausted = t2 < t1;
+    }
 #pragma unroll
     for (int h = 0; h < 2; ++h)
       if (valid[h]) sp.sx[h * 32 + lane] = (uint8_t)(xs[h] < n_ex ? xs[h] : 0xFF);
@@ -1269,37 +1304,32 @@ __device__ int spec_scan_par(Smem& s, Spec& sp, int W, int wf, int wb, uint32_t 
   // ---- records in examine order ----
 #pragma unroll
   for (int h = 0; h < 2; ++h)
-    if (valid[h] && xs[h] < n_ex) sp.xcand[xs[h]] = (uint8_t)(h * 32 + lane);
+    if (valid[h]) {
+      const int t = h * 32 + (int)lane;
+      if (xs[h] < n_ex) sp.xcand[xs[h]] = (uint8_t)t;
+      sp.dense[t] = asfront[h] ? 1 : 0;  // (the scalar scan's table, free here) examined as a front candidate
+      // the earliest accepted mate of an unsure merge, for the lanes that stand for examine indices below
+      sp.xcls[t] = (uint8_t)(ustar[h] >= 0 && xs[h] < n_ex && ((OM >> t) & 1ull) ? ustar[h] : 0xFF);
+    }
   __syncwarp();
   // lanes now stand for examine indices x = lane and lane + 32
-  int tx[2];
-  bool ism[2], on[2];
-  int cid[2];
+  int tx[2], cid[2];
+  bool ism[2], on[2], fr[2], idc[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
     const int x = h * 32 + (int)lane;
     on[h] = x < n_ex;
     tx[h] = on[h] ? sp.xcand[x] : 0;
     ism[h] = on[h] && ((OM >> tx[h]) & 1ull) != 0ull;
+    fr[h] = on[h] && sp.dense[tx[h]] != 0;
+    idc[h] = on[h] && s.ctail[tx[h]] >= 0;
     cid[h] = 0xFF;
+    if (ism[h]) {
+      cid[h] = (s.s_f[tx[h]] != kInf) ? (int)sp.cls[tx[h]] : (kW + (int)sp.xcls[tx[h]]);
+      atomicMin(&sp.cfirst[cid[h]], (uint32_t)x);
+    }
   }
-  // target ids (unsure merges: 64 + the earliest accepted mate), first merge of every target id
-  {
-    // ustar lives with the lane that owns the candidate: publish it through sx's neighbour array
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-      if (valid[h]) sp.xcls[h * 32 + lane] = (uint8_t)(ustar[h] >= 0 && xs[h] < n_ex && ((OM >> (h * 32 + lane)) & 1ull) ? ustar[h] : 0xFF);
-    __syncwarp();
-#pragma unroll
-    for (int h = 0; h < 2; ++h)
-      if (ism[h]) {
-        const int t = tx[h];
-        const int us = sp.xcls[t];
-        cid[h] = (s.s_f[t] != kInf) ? (int)sp.cls[t] : (kW + us);
-        atomicMin(&sp.cfirst[cid[h]], (uint32_t)(h * 32 + lane));
-      }
-    __syncwarp();
-  }
+  __syncwarp();
   bool first[2];
 #pragma unroll
   for (int h = 0; h < 2; ++h) first[h] = ism[h] && sp.cfirst[cid[h]] == (uint32_t)(h * 32 + lane);
@@ -1315,20 +1345,18 @@ __device__ int spec_scan_par(Smem& s, Spec& sp, int W, int wf, int wb, uint32_t 
       on[h] = x < n_ex;
       ism[h] = ism[h] && on[h];
       first[h] = first[h] && on[h];
+      fr[h] = fr[h] && on[h];
     }
     FX &= below64(n_ex);
   }
-  const unsigned long long MX = ballot64(ism[0], ism[1]);                    // merges, by examine index
+  const unsigned long long MX = ballot64(ism[0], ism[1]);                      // merges, by examine index
   const unsigned long long AX = ballot64(on[0] && !ism[0], on[1] && !ism[1]);  // accepts
-  const unsigned long long FRX = ballot64(on[0] && tx[0] < wf, on[1] && tx[1] < wf);
+  const unsigned long long FRX = ballot64(fr[0], fr[1]);
   const int nd = __popcll(FX), merges = __popcll(MX);
-  __syncwarp();
-  // class bookkeeping in examine order: xcls[x] = target id (0xFF: accept)
+  // id-carrying merged candidates per target, by examine index (for the member-chain log)
 #pragma unroll
-  for (int h = 0; h < 2; ++h) {
-    const int x = h * 32 + (int)lane;
-    if (on[h]) sp.xcls[x] = (uint8_t)(ism[h] ? cid[h] : 0xFF);
-  }
+  for (int h = 0; h < 2; ++h)
+    if (ism[h] && idc[h]) atomicOr(&sp.cmask[cid[h]], 1ull << (h * 32 + lane));
   __syncwarp();
 #pragma unroll
   for (int h = 0; h < 2; ++h) {
@@ -1372,20 +1400,16 @@ __device__ int spec_scan_par(Smem& s, Spec& sp, int W, int wf, int wb, uint32_t 
     s.ment[t] = e;
     atomicOr(&sp.emask[e], 1ull << k);
     // the previous id-carrying member of the same target in examine order
-    int prev_last = -1;
-    for (int xp = x - 1; xp >= xf; --xp)
-      if (sp.xcls[xp] == (uint8_t)cid[h] && s.ctail[sp.xcand[xp]] >= 0) {
-        prev_last = sp.xcand[xp];
-        break;
-      }
+    const unsigned long long pmask = sp.cmask[cid[h]] & bx;
+    const int prev_last = pmask ? (int)sp.xcand[63 - __clzll((long long)pmask)] : -1;
     s.mprev[t] = prev_last;
-    sp.vlast[k] = (int8_t)(s.ctail[t] >= 0 ? t : prev_last);
+    sp.vlast[k] = (int8_t)(idc[h] ? t : prev_last);
     if (first[h]) {  // the entry's value before its first merge
-      s.dridx[e] = hf ? s.pridx[t] : 0u;  // (window targets: filled below, their rank is not known to this lane yet)
       if (hf) {
         s.dpos[e] = s.s_f[t];
         sp.dbase[e] = (uint32_t)t;
         sp.dbcnt[e] = s.pcnt[t];
+        s.dridx[e] = s.pridx[t];
         s.dhead[e] = s.phead[t];
         s.dtail[e] = s.ptail[t];
       } else {
@@ -1959,7 +1983,7 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
         long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0;
         if (prof) tp0 = clock64();
         if (warp == 0) {
-          int n = (tail_mode || A.no_par_scan) ? -1 : spec_scan_par(s, sp, W, wf, wb, i0);
+          int n = A.no_par_scan ? -1 : spec_scan_par(s, sp, W, wf, wb, tail_mode, i0);
           if (n < 0) n = spec_scan(s, sp, W, wf, wb, tail_mode, i0, size0);
           else if (A.dbg && lane == 0) atomicAdd(A.dbg + 32, 1ull);
           if (lane == 0) s.ro[RO_EXAMINED] = (uint32_t)n;
