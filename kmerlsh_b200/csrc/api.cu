@@ -131,9 +131,17 @@ int klsh_create(int device, klsh_ctx** out) {
   ctx->planes = planes_new();
   // development knobs (bucket size classes of the windowed merge)
   if (const char* e = std::getenv("KLSH_DEBUG")) ctx->debug = std::atoi(e) != 0;
+  if (const char* e = std::getenv("KLSH_TIMELINE")) ctx->timeline = std::atoi(e) != 0;
+  if (const char* e = std::getenv("KLSH_POOL")) ctx->pool = std::atoi(e) != 0;
+  if (const char* e = std::getenv("KLSH_CPOOL")) ctx->cpool = std::atoi(e) != 0;
+  if (const char* e = std::getenv("KLSH_CPOOL_MIN")) ctx->cpool_min = (uint32_t)std::max(64, std::atoi(e));
+  if (const char* e = std::getenv("KLSH_CPOOL_HELPERS")) ctx->cpool_helper_ctas = (uint32_t)std::max(0, std::atoi(e));
+  if (const char* e = std::getenv("KLSH_CPOOL_GRID")) ctx->cpool_helper_grid = (uint32_t)std::max(0, std::atoi(e));
+  if (const char* e = std::getenv("KLSH_POOL_MIN")) ctx->pool_min = (uint32_t)std::max(64, std::atoi(e));
   if (const char* e = std::getenv("KLSH_MERGE_V1")) ctx->merge_v1 = std::atoi(e) != 0;
   if (const char* e = std::getenv("KLSH_NO_SPEC")) ctx->no_spec = std::atoi(e) != 0;
-  if (const char* e = std::getenv("KLSH_PAR_SCAN")) ctx->no_par_scan = std::atoi(e) == 0;
+  if (const char* e = std::getenv("KLSH_PAR_SCAN")) ctx->scan_mode = std::atoi(e) != 0 ? 1 : 0;
+  if (const char* e = std::getenv("KLSH_SCAN")) ctx->scan_mode = std::max(0, std::min(3, std::atoi(e)));
   if (const char* e = std::getenv("KLSH_CTA_MAX")) ctx->cta_max = (uint32_t)std::strtoul(e, nullptr, 10);
   if (const char* e = std::getenv("KLSH_CLUSTER_MAX")) ctx->cluster_max = (uint32_t)std::strtoul(e, nullptr, 10);
   if (const char* e = std::getenv("KLSH_CLUSTER_SIZE")) ctx->cluster_size = std::atoi(e);
@@ -168,6 +176,8 @@ void klsh_destroy(klsh_ctx* ctx) {
   dev_free(ctx->nested_out);
   dev_free(ctx->team_ctl);
   dev_free(ctx->team_ctl_b);
+  dev_free(ctx->pool_ctl); dev_free(ctx->pool_pub);
+  dev_free(ctx->pool_ctl_b); dev_free(ctx->pool_pub_b);
   dev_free(ctx->exp_vals); dev_free(ctx->exp_cnt); dev_free(ctx->exp_head);
   dev_free(ctx->rank_buf); dev_free(ctx->exp_offs); dev_free(ctx->exp_slots);
   if (ctx->h_slots.p) cudaFreeHost(ctx->h_slots.p);

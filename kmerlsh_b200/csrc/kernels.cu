@@ -835,6 +835,24 @@ __global__ void k_classify(uint32_t* bstart, uint64_t n, long long nest_threshol
   if (lane_id() == 0 && wmax > 0) atomicMax(&counters->bucket_max, wmax);
 }
 
+// The direct list in order of decreasing bucket size: its buckets are the pass's longest window chains, and
+// a long chain picked up late by a team that first worked through a shorter one ends the pass late.
+__global__ void k_order_direct(const uint32_t* __restrict__ bstart, const PassCounters* counters, uint32_t* list_direct) {
+  __shared__ uint32_t sb[1024], ss[1024];
+  const uint32_t n = min(counters->n_direct, 1024u);  // a longer list keeps its tail as it is
+  const uint32_t i = threadIdx.x;
+  if (i < n) {
+    sb[i] = list_direct[3 * i];
+    ss[i] = bstart[sb[i] + 1] - bstart[sb[i]];
+  }
+  __syncthreads();
+  if (i < n) {
+    uint32_t rank = 0;
+    for (uint32_t j = 0; j < n; ++j) rank += (ss[j] > ss[i] || (ss[j] == ss[i] && sb[j] < sb[i])) ? 1u : 0u;
+    list_direct[3 * rank] = sb[i];
+  }
+}
+
 // ================================================================================================
 // Greedy in-bucket merge (reference p_cluster, function/cluster.cc:56-87) with
 //   Distance::cosine   (function/distance.cc:27-38)
@@ -1367,6 +1385,10 @@ int launch_classify(klsh_ctx* ctx, PassScratch& s, uint64_t n, int64_t nest_thre
                                             s.list_small.as<uint32_t>(), s.list_large.as<uint32_t>(), s.list_big.as<uint32_t>(),
                                             s.list_direct.as<uint32_t>(), s.list_nested.as<uint32_t>());
   KLAUNCH(ctx);
+  if (!fallback) {
+    k_order_direct<<<1, 1024, 0, ctx->stream>>>(s.bstart.as<uint32_t>(), dc, s.list_direct.as<uint32_t>());
+    KLAUNCH(ctx);
+  }
   return KLSH_OK;
 }
 
@@ -1580,10 +1602,18 @@ int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float thr
   PassCounters* dc = s.counters.as<PassCounters>();
   const uint32_t n_small = c.n_small, n_large = c.n_large + c.n_big, n_direct = c.n_direct;
   const bool v1 = launch_merge_uses_fallback(ctx);
+  const bool pool = launch_merge_uses_pool(ctx);
   // The few largest buckets are long sequential window chains: they start right away on cluster
   // teams on the second stream and run beside the small buckets and the single-CTA stage.
   bool forked = false;
-  if (n_direct && !v1) {
+  static thread_local cudaEvent_t tl[3] = {nullptr, nullptr, nullptr};  // KLSH_TIMELINE: start, end of the main pipeline, end of the direct one
+  if (ctx->timeline) {
+    for (auto& e : tl)
+      if (!e) cudaEventCreate(&e);
+    cudaEventRecord(tl[0], ctx->stream);
+  }
+  if (n_direct && !v1 && !pool) {
+    KTRY(launch_pool_reset(ctx));
     KCUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
     KCUDA(ctx, cudaStreamWaitEvent(ctx->stream2, ctx->ev_fork, 0));
     forked = true;
@@ -1593,6 +1623,7 @@ int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float thr
       return rc;
     }
     KCUDA(ctx, cudaEventRecord(ctx->ev_join, ctx->stream2));
+    if (ctx->timeline) cudaEventRecord(tl[2], ctx->stream2);
   }
   int rc = KLSH_OK;
   do {
@@ -1620,17 +1651,31 @@ int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float thr
         break;
       }
     }
-    if (!(n_large + (v1 ? n_direct : 0u))) break;
+    if (!(n_large + ((v1 || pool) ? n_direct : 0u))) break;
+    if (pool) {
+      rc = launch_merge_pool(ctx, s, rows_sorted, threshold);
+      break;
+    }
     if (!v1) {
       rc = launch_merge_window(ctx, s, rows_sorted, threshold, n_large, c.n_direct ? std::min(c.bucket_max, c.direct_thr - 1u) : c.bucket_max);
       break;
     }
     rc = launch_merge_fallback(ctx, s, rows_sorted, threshold, c);
   } while (0);
+  if (ctx->timeline) cudaEventRecord(tl[1], ctx->stream);
+  if (forked && rc == KLSH_OK) rc = launch_pool_helper(ctx, s, rows_sorted, threshold);
   if (forked) {
     cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
     if (e != cudaSuccess && rc == KLSH_OK) rc = klsh_fail(ctx, KLSH_ERR_CUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e));
     if (rc != KLSH_OK) cudaStreamSynchronize(ctx->stream2);
+  }
+  if (ctx->timeline && rc == KLSH_OK) {
+    cudaStreamSynchronize(ctx->stream);
+    float a = 0.f, b = 0.f;
+    cudaEventElapsedTime(&a, tl[0], tl[1]);
+    if (forked) cudaEventElapsedTime(&b, tl[0], tl[2]);
+    fprintf(stderr, "[klsh] timeline: main pipeline (small + single-CTA + escalations) ended at %.3f ms, direct pipeline (%u buckets) at %.3f ms; largest bucket %u rows\n",
+            a, n_direct, b, c.bucket_max);
   }
   return rc;
 }

@@ -130,6 +130,8 @@ struct klsh_ctx {
   DevBuf alive_alt;   // the other half of the alive-list ping-pong
   DevBuf nested_out;  // survivors of one nested pass
   DevBuf team_ctl, team_ctl_b;  // per-team control blocks of the windowed merge (one set per pipeline)
+  DevBuf pool_ctl, pool_pub;  // screen pool of the single-CTA teams: control word + board, per-leader blocks
+  DevBuf pool_ctl_b, pool_pub_b;  // ... of the direct pipeline's cluster teams
   DevBuf exp_vals, exp_cnt, exp_head;  // export staging (device)
   DevBuf rank_buf, exp_offs, exp_slots; // chain ranking scratch, offsets and flat slot order (device)
   HostBuf h_slots;                     // flat slot order (pinned host)
@@ -154,11 +156,18 @@ struct klsh_ctx {
   int cluster_size = 8, cluster2_size = 16;
   int cluster_ctas_per_sm = 2;
   bool debug = false;     // KLSH_DEBUG=1
+  bool cpool = true;      // KLSH_CPOOL=0: the direct pipeline's cluster teams screen their windows alone (no helpers)
+  uint32_t cpool_min = 65536;       // KLSH_CPOOL_MIN: representatives from which a cluster team opens its screen to helpers
+  uint32_t cpool_helper_ctas = 0;   // KLSH_CPOOL_HELPERS: CTAs (in whole teams) of the direct pipeline that stay resident as helpers once they run out of buckets
+  uint32_t cpool_helper_grid = 148; // KLSH_CPOOL_GRID: CTAs of the helper kernel that follows the main pipeline (0: none)
+  bool pool = false;      // KLSH_POOL=1: single-CTA teams with a screen pool for every bucket instead of the escalation stages and the direct pipeline (measured slower)
+  uint32_t pool_min = 4096;  // KLSH_POOL_MIN: representatives from which a window's screen goes to the pool
+  bool timeline = false;  // KLSH_TIMELINE=1: per pass, when each of the two merge pipelines ended (stderr)
   DevBuf dbg;
   // The speculative resolver's scan as a warp-parallel prefix computation (spec_scan_par): exact and tested, but
   // measured no faster than the scalar scan on C2 (10-20 k cycles per window against 12-37 k, and slower on the
   // single-CTA stage), so it is opt-in: KLSH_PAR_SCAN=1
-  bool no_par_scan = true;
+  int scan_mode = 3;  // KLSH_SCAN: the speculative resolver's scan: 0 scalar replay, 1 closed-form order (KLSH_PAR_SCAN=1), 2 lean replay + parallel records, 3 = 0 on single-CTA teams, 2 on cluster teams (measured best on C2)
   bool no_spec = false;   // KLSH_NO_SPEC=1: windows are resolved by the sequential loop only
   bool merge_v1 = false;  // KLSH_MERGE_V1=1: first-generation block-per-bucket kernel (A/B checks)
   PassCounters* h_counters = nullptr;  // pinned
@@ -222,6 +231,10 @@ int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
 int launch_merge_direct(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold, uint32_t n_direct_host,
                         uint32_t bucket_max_host);
 bool launch_merge_uses_fallback(const klsh_ctx* ctx);
+bool launch_merge_uses_pool(const klsh_ctx* ctx);
+int launch_merge_pool(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold);
+int launch_pool_reset(klsh_ctx* ctx);
+int launch_pool_helper(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold);
 size_t merge_window_smem_bytes(int ld);
 int launch_merge_one(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, uint64_t n, float threshold);
 int launch_compact(klsh_ctx* ctx, PassScratch& s, const uint32_t* rows_sorted, uint64_t n, uint32_t* out);

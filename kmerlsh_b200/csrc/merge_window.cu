@@ -140,7 +140,40 @@ struct TeamCtl {  // global memory, one per team
   uint32_t f[kW];  // per window candidate: first matching old representative (position), kInf if none
   uint32_t i, size, wb, work;
   uint32_t mode;  // 1: the next window is resolved by the sequential loop (after a mispredicted speculative window)
+  uint32_t big;   // cluster pool: this team's bucket is counted in PoolCtl::big_active
+  uint32_t pad[2];
+};
+
+// ---- screen pool (single-CTA teams) -------------------------------------------------------------------
+// A bucket's windows are a sequential chain led by ONE CTA, but the screen of a window against the bucket's
+// representatives is independent work.  With the pool a leader whose bucket has passed pool_min representatives
+// publishes its window (fp16 A fragments, row indices, norms) and opens its screen as CHUNKS of kPoolChunk
+// representatives.  A chunk is claimed with one atomicAdd on the leader's own counter — by the leader itself
+// (which screens it from its shared-memory copy) or by any CTA of the launch with nothing better to do: leaders
+// waiting for their last chunks and CTAs that ran out of buckets.  Helpers find open windows on a board of one
+// word per leader.  A helper's result is the per-candidate first exact match in its chunk, folded into the
+// leader's block with atomicMin; the leader continues when its done counter reaches the number of chunks.
+// Nothing ever waits for a helper to show up: the leader claims chunks until none is left, so the board is a hint.
+constexpr int kPoolChunk = 2048;
+constexpr uint32_t kPoolCountBits = 20;  // claim word = window epoch << 20 | chunks claimed so far
+struct PoolCtl {
+  uint32_t open;       // leaders with unclaimed chunks (hint: helpers scan the board only when it is non-zero)
+  uint32_t finished;   // teams of this launch that ran out of buckets
+  uint32_t helpers;    // cluster teams that stayed on as helpers after running out of buckets
+  uint32_t big_active; // cluster teams whose current bucket is on its way to pooled windows (pool_min / 4 representatives)
+  uint32_t stop;       // set when the direct pipeline has finished: the helper kernel leaves
   uint32_t pad[3];
+};
+struct PoolPub {  // one per leader CTA
+  uint4 af[kW * 8];      // the window's fp16 copy in A-fragment order: [(row tile * KS16 + k step) * 32 + lane]
+  uint32_t ridx[kW];
+  float cnorm[kW];
+  uint32_t f[kW];        // first exact match per candidate over the chunks helpers have served
+  uint32_t W, st, i0;
+  uint32_t meta;         // window epoch << 20 | number of chunks: ONE word, so a helper validates its claim against a snapshot
+  uint32_t next;         // claim word: window epoch << 20 | chunks claimed so far
+  uint32_t done;         // chunks helpers have finished
+  uint32_t pad[2];
 };
 
 struct MergeArgs {
@@ -166,9 +199,19 @@ struct MergeArgs {
   // row index -> row and converting on the fly
   uint4* pos_h;
   TeamCtl* ctl;
+  // screen pool (nullptr: off)
+  PoolCtl* pool;
+  uint32_t* pool_board;  // [grid] window epoch + 1 while the leader has unclaimed chunks, else 0 (hint)
+  PoolPub* pool_pub;
+  uint32_t pool_min;
+  uint32_t pool_n;        // board entries = teams of the launch
+  uint32_t pool_helpers;  // cluster teams: how many idle teams stay resident as helpers (the others exit and free their SMs)
+  // a third work list, walked before list_a (the pass's largest buckets when the pool is on)
+  const uint32_t* list_0;
+  const uint32_t* n_0;
   MgLog mg;
   unsigned long long* work;  // [2] device counters: pairs screened on the tensor cores, pairs re-tested exactly
-  int no_par_scan;  // default; KLSH_PAR_SCAN=1 selects the warp-parallel scan (spec_scan_par)
+  int scan_mode;  // speculative scan, KLSH_SCAN: 0 scalar replay with records, 1 closed-form order, 2 lean replay + parallel records, 3 (default) 0 on single-CTA teams and 2 on cluster teams
   int no_spec;   // KLSH_NO_SPEC=1: sequential resolution only (A/B checks)
   unsigned long long* dbg;  // [32] 26: speculative windows, 27: ... cut short; 0..7: windows, candidates, merges, undecidable, cache_full, back_exhausted, accepted, escalated; 8..13: leader cycles in stage/parallel/sync1/prefetch/decide/flush+sync2; 18..21: staging detail
   float threshold;
@@ -209,6 +252,8 @@ struct Smem {
   uint32_t* dmhi;   // [kKD] ... candidates 32..63
   int32_t* dlast;   // [kKD] last candidate merged into the entry that carried ids (-1: none)
   uint32_t* ro;     // [16] what the decision loop hands to the flush (RO_*)
+  uint32_t* w_f;    // [kW] pool: first exact match per candidate of the task being served
+  uint32_t* ptask;  // [8] pool: broadcast slots {claimed?, leader, chunk, board value / scan result, own claim, done, epoch}
   int ts;
 };
 
@@ -235,7 +280,7 @@ __host__ __device__ inline size_t ring_bytes_for(int ld, int threads) {
 }
 __host__ __device__ inline size_t smem_bytes_for(int ld, int threads) {
   const int hs = tc_width(ld) + 8;
-  return sizeof(float) * ((size_t)(2 * kW + kKD) * (row_width(ld) + 4) + kW + kKD) + sizeof(uint32_t) * (kW * 14 + kKD * 10 + RO_WORDS) + 64 +
+  return sizeof(float) * ((size_t)(2 * kW + kKD) * (row_width(ld) + 4) + kW + kKD) + sizeof(uint32_t) * (kW * 15 + kKD * 10 + RO_WORDS + 8) + 64 +
          sizeof(__half) * (size_t)kW * hs + 16 + sizeof(uint32_t) * (kSurvCap + 1) + ring_bytes_for(ld, threads);
 }
 
@@ -271,6 +316,8 @@ __device__ __forceinline__ void carve(Smem& s, float* base, int ld) {
   s.dmhi = u; u += kKD;
   s.dlast = reinterpret_cast<int32_t*>(u); u += kKD;
   s.ro = u; u += RO_WORDS;
+  s.w_f = u; u += kW;
+  s.ptask = u; u += 8;
   s.hs = tc_width(ld) + 8;  // +8 halfs: rows 16 bytes apart modulo 128 -> conflict-free fragment loads
   s.htile = reinterpret_cast<__half*>(u + 4);
   s.surv = reinterpret_cast<uint32_t*>(s.htile + (size_t)kW * s.hs);  // kW*hs halves: a multiple of 16 bytes
@@ -293,15 +340,36 @@ __device__ __forceinline__ bool exact_pair(const Smem& s, int t, const float* ro
   return cos_match(dx, s.cnorm[t], rn, threshold);
 }
 
+// The same test served for another CTA's window (pool): the candidate's row and norm come from global memory
+// (the leader staged its tile from exactly these rows; nothing writes them until its flush, which waits for us).
+__device__ __forceinline__ bool exact_pair_remote(const MergeArgs& A, const PoolPub* pub, int t, const float* rowp, float rn, int nq) {
+  const float4* c4 = reinterpret_cast<const float4*>(A.vals + (uint64_t)__ldcg(&pub->ridx[t]) * A.ld);
+  float dx = 0.f;
+  for (int q = 0; q < nq; ++q) {
+    const float4 x = __ldcg(c4 + q);
+    const float4 y = __ldcg(reinterpret_cast<const float4*>(rowp) + q);
+    dx = __fadd_rn(dx, __fmul_rn(x.x, y.x));
+    dx = __fadd_rn(dx, __fmul_rn(x.y, y.y));
+    dx = __fadd_rn(dx, __fmul_rn(x.z, y.z));
+    dx = __fadd_rn(dx, __fmul_rn(x.w, y.w));
+  }
+  return cos_match(dx, __ldcg(&pub->cnorm[t]), rn, A.threshold);
+}
+
 // Tensor-core screened comparison of the window with representatives [j_begin, j_end) (SELF == false)
 // or with the window's own rows (SELF == true: candidate x candidate bits).  One warp handles 8
 // representatives per step; KS16 = number of 16-wide k steps (rows are zero-padded to 16*KS16).
 // Representatives come from the fragment-order fp16 copy seg_h (KS16/2 16-byte chunks per lane and
 // step, coalesced), fetched several steps ahead so that the tensor pipe, not L2 latency, paces the loop.
-template <int KS16, bool SELF>
+// MODE 0: this CTA's window against representatives, 1: against the window's own rows (SELF), 2: ANOTHER CTA's
+// window (pub) against representatives — the pool's worker side: fragments come from the leader's published copy,
+// verified matches go to s.w_f, exact tests read the candidate from global memory.
+template <int KS16, int MODE>
 __device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* seg, const float* pos_nrm, const uint4* seg_h,
                                            Smem& s, int W, uint32_t j_begin, uint32_t j_end, uint32_t warp_rank,
-                                           uint32_t n_warps, int nq) {
+                                           uint32_t n_warps, int nq, const PoolPub* pub = nullptr) {
+  constexpr bool SELF = MODE == 1;
+  uint32_t* const filt = MODE == 2 ? s.w_f : s.s_f;
   const uint32_t lane = lane_id(), g = lane >> 2, tg = lane & 3;
   const float thr_tc = A.threshold - 2e-3f;
   const int ld = A.ld;
@@ -313,12 +381,20 @@ __device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* s
   for (int mt = 0; mt < 4; ++mt)
 #pragma unroll
     for (int ks = 0; ks < KS16; ++ks) {
-      const __half* r0 = s.htile + (size_t)(mt * 16 + g) * s.hs + ks * 16 + tg * 2;
-      const __half* r1 = r0 + 8 * s.hs;
-      af[mt][ks][0] = *reinterpret_cast<const uint32_t*>(r0);
-      af[mt][ks][1] = *reinterpret_cast<const uint32_t*>(r1);
-      af[mt][ks][2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
-      af[mt][ks][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
+      if (MODE == 2) {
+        const uint4 x = __ldcg(pub->af + (mt * KS16 + ks) * 32 + lane);
+        af[mt][ks][0] = x.x;
+        af[mt][ks][1] = x.y;
+        af[mt][ks][2] = x.z;
+        af[mt][ks][3] = x.w;
+      } else {
+        const __half* r0 = s.htile + (size_t)(mt * 16 + g) * s.hs + ks * 16 + tg * 2;
+        const __half* r1 = r0 + 8 * s.hs;
+        af[mt][ks][0] = *reinterpret_cast<const uint32_t*>(r0);
+        af[mt][ks][1] = *reinterpret_cast<const uint32_t*>(r1);
+        af[mt][ks][2] = *reinterpret_cast<const uint32_t*>(r0 + 8);
+        af[mt][ks][3] = *reinterpret_cast<const uint32_t*>(r1 + 8);
+      }
     }
   // screen all 64 x 8 pairs of one step, then every lane works through its own survivors: the exact
   // evaluations of different lanes run side by side instead of one (row tile, element) slot after the other
@@ -345,7 +421,7 @@ __device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* s
           if (SELF) {
             if ((int)jj != t && exact_pair<true>(s, t, s.tile + (size_t)jj * s.ts, s.cnorm[jj], nq, A.threshold))
               atomicOr(&s.pair[2 * t + (jj >> 5)], 1u << (jj & 31));
-          } else if (!(s.s_f[t] < jj)) {  // skip when an earlier match is already recorded
+          } else if (!(filt[t] < jj)) {  // skip when an earlier match is already recorded
             // The exact test needs the representative's fp32 row (two dependent global round trips):
             // park the pair and test all parked pairs of the CTA together after the streaming loop.
             uint32_t k = kSurvCap;
@@ -354,8 +430,10 @@ __device__ __forceinline__ void tc_compare(const MergeArgs& A, const uint32_t* s
               s.surv[k] = (jj << 6) | (uint32_t)t;
             } else {
               const uint32_t rr2 = __ldcg(seg + jj);
-              if (exact_pair<false>(s, t, A.vals + (uint64_t)rr2 * ld, __ldcg(pos_nrm + jj), nq, A.threshold))
-                atomicMin(&s.s_f[t], jj);
+              const float* rowp = A.vals + (uint64_t)rr2 * ld;
+              const float rn = __ldcg(pos_nrm + jj);
+              if (MODE == 2 ? exact_pair_remote(A, pub, t, rowp, rn, nq) : exact_pair<false>(s, t, rowp, rn, nq, A.threshold))
+                atomicMin(&filt[t], jj);
             }
           }
         }
@@ -1186,9 +1264,16 @@ __device__ __forceinline__ unsigned long long ballot64(bool p0, bool p1) {
 // Returns the number of examined candidates, or -1 if the window has to take the scalar scan.  Tail windows (one
 // stream of W candidates eaten from both ends: back index k is candidate W-1-k) follow the same formulas with both
 // masks over the same candidates; a candidate is examined by whichever end reaches it first, all W are examined.
-__device__ int spec_scan_par(Smem& s, Spec& sp, int W, int wf, int wb, bool tail_mode, uint32_t i0) {
+// LEAN: the examine order and the outcomes come from a replay on lane 0 that carries nothing but the order
+// (two counters, the accepted mask in a register, one shared-memory load per candidate); every record is then
+// built by the lanes in parallel exactly as for the closed form.
+template <bool LEAN>
+__device__ int spec_scan_par(const MergeArgs& A, Smem& s, Spec& sp, int W, int wf, int wb, bool tail_mode, uint32_t i0) {
   const uint32_t lane = lane_id();
   const int INF = 255;
+  const int wb_in = wb;
+  long long tq0 = 0, tq1 = 0;
+  if (A.dbg && lane == 0) tq0 = clock64();
   if (tail_mode) wb = wf;
   // per-candidate facts (two candidates per lane: t = lane and lane + 32)
   bool valid[2], hasf[2], unsure[2];
@@ -1231,8 +1316,74 @@ __device__ int spec_scan_par(Smem& s, Spec& sp, int W, int wf, int wb, bool tail
   int xs[2] = {INF, INF}, ustar[2] = {-1, -1}, n_ex = 0;
   bool asfront[2] = {true, true};
   bool back_exhausted = false;
+  if (LEAN) {
+#pragma unroll
+    for (int h = 0; h < 2; ++h)
+      if (valid[h]) sp.sx[h * 32 + lane] = 0xFF;
+    __syncwarp();
+    const unsigned long long HF = OM;
+    unsigned long long om = 0ull, fr = 0ull;
+    int x = 0;
+    if (lane == 0) {
+      unsigned long long accm = 0ull;
+      int fi = 0, bi = 0;
+      bool from_back = false;
+      const uint2* pairs = reinterpret_cast<const uint2*>(s.pair);
+      while (x < W) {
+        int t;
+        if (from_back) {
+          if (!tail_mode && bi >= wb_in) {
+            back_exhausted = true;
+            break;
+          }
+          t = tail_mode ? (wf - 1 - bi) : (wf + bi);
+          ++bi;
+        } else {
+          if (!tail_mode && fi >= wf) break;
+          t = fi;
+          fr |= 1ull << t;
+          ++fi;
+        }
+        const uint2 pr = pairs[t];
+        const unsigned long long pm = ((unsigned long long)pr.y << 32) | (unsigned long long)pr.x;
+        const bool merge = ((HF >> t) & 1ull) != 0ull || (pm & accm) != 0ull;
+        sp.sx[t] = (uint8_t)x;
+        if (merge) om |= 1ull << t;
+        else accm |= 1ull << t;
+        from_back = merge;
+        ++x;
+      }
+    }
+    OM = __shfl_sync(0xffffffffu, om, 0);
+    fr = __shfl_sync(0xffffffffu, fr, 0);
+    n_ex = __shfl_sync(0xffffffffu, x, 0);
+    back_exhausted = __shfl_sync(0xffffffffu, back_exhausted ? 1 : 0, 0) != 0;
+    __syncwarp();
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      const int t = h * 32 + (int)lane;
+      xs[h] = valid[h] ? (int)sp.sx[t] : INF;
+      if (xs[h] == 0xFF) xs[h] = INF;
+      asfront[h] = ((fr >> t) & 1ull) != 0ull;
+      // the earliest accepted mate of an unsure candidate that merges
+      if (unsure[h] && xs[h] < n_ex && ((OM >> t) & 1ull)) {
+        unsigned long long pm = (((unsigned long long)phi[h] << 32) | (unsigned long long)plo[h]) & ~OM;
+        int best = INF, bu = -1;
+        while (pm) {
+          const int u = __ffsll((long long)pm) - 1;
+          pm &= pm - 1ull;
+          const int xu = sp.sx[u];
+          if (xu < xs[h] && xu < best) {
+            best = xu;
+            bu = u;
+          }
+        }
+        ustar[h] = bu;
+      }
+    }
+  }
   int round = 0;
-  for (;; ++round) {
+  for (; !LEAN; ++round) {
     if (round == 6) return -1;
     const unsigned long long MF = OM & fm;  // merging fronts, by front index
     // accepted backs, by back index
@@ -1301,6 +1452,7 @@ __device__ int spec_scan_par(Smem& s, Spec& sp, int W, int wf, int wb, bool tail
     const unsigned long long U = ballot64(unsure[0], unsure[1]);
     OM = (OM & ~U) | ballot64(unsure[0] && newm[0], unsure[1] && newm[1]);
   }
+  if (A.dbg && lane == 0) tq1 = clock64();
   // ---- records in examine order ----
 #pragma unroll
   for (int h = 0; h < 2; ++h)
@@ -1444,6 +1596,10 @@ __device__ int spec_scan_par(Smem& s, Spec& sp, int W, int wf, int wb, bool tail
     s.ro[RO_FULL] = full ? 1u : 0u;
     s.ro[RO_ND] = (uint32_t)nd;
     s.ro[RO_MERGES] = (uint32_t)merges;
+    if (A.dbg) {
+      atomicAdd(A.dbg + 36, (unsigned long long)(tq1 - tq0));
+      atomicAdd(A.dbg + 37, (unsigned long long)(clock64() - tq1));
+    }
   }
   __syncwarp();
   return n_ex;
@@ -1732,6 +1888,136 @@ __device__ void flush_window(const MergeArgs& A, uint32_t* seg, float* pos_nrm, 
 // batch is in flight), so a stage costs two dependent round trips (row index -> row / metadata)
 // however many rows a thread moves.
 
+// ---- screen pool: worker side ----------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t ld_acquire(const uint32_t* p) {
+  uint32_t v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release(uint32_t* p, uint32_t v) {
+  asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t atom_add_acq_rel(uint32_t* p, uint32_t v) {
+  uint32_t old;
+  asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+  return old;
+}
+// the board entry is taken down by whoever sees the last chunk go (or a stale window): only the value that was seen
+__device__ __forceinline__ void pool_close(const MergeArgs& A, uint32_t leader, uint32_t board_val) {
+  if (atomicCAS(A.pool_board + leader, board_val, 0u) == board_val) atomicSub(&A.pool->open, 1u);
+}
+
+// Exact tests of the pairs a screen parked in s.surv: all of the CTA's threads at once, so the dependent row
+// fetches of different pairs overlap.  REMOTE: the window belongs to another CTA (pub), results go to s.w_f.
+template <int KMT, bool REMOTE>
+__device__ __forceinline__ void exact_parked(const MergeArgs& A, Smem& s, const uint32_t* seg, const float* pos_nrm, int nq,
+                                             const PoolPub* pub) {
+  const int tid = threadIdx.x, ld = A.ld;
+  uint32_t* const filt = REMOTE ? s.w_f : s.s_f;
+  const uint32_t ns = min(s.surv[kSurvCap], (uint32_t)kSurvCap);
+  if (tid == 0 && ns && A.work) atomicAdd(A.work + 1, (unsigned long long)ns);
+  for (uint32_t k0 = 0; k0 < ns; k0 += 2 * KMT) {
+    uint32_t ent[2], rr2[2];
+    bool on[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const uint32_t k = k0 + u * KMT + tid;
+      on[u] = k < ns;
+      ent[u] = on[u] ? s.surv[k] : 0u;
+      on[u] = on[u] && !(filt[ent[u] & 63u] < (ent[u] >> 6));
+      rr2[u] = on[u] ? __ldcg(seg + (ent[u] >> 6)) : 0u;
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+      if (on[u]) {
+        const uint32_t jj = ent[u] >> 6;
+        const int t = (int)(ent[u] & 63u);
+        const float* rowp = A.vals + (uint64_t)rr2[u] * ld;
+        const float rn = __ldcg(pos_nrm + jj);
+        if (REMOTE ? exact_pair_remote(A, pub, t, rowp, rn, nq) : exact_pair<false>(s, t, rowp, rn, nq, A.threshold))
+          atomicMin(&filt[t], jj);
+      }
+  }
+  if (ns) __syncthreads();
+}
+
+// Serve one chunk of another leader's window.  All threads.
+template <int KMT, int DR>
+__device__ void pool_serve(const MergeArgs& A, Smem& s, uint32_t leader, uint32_t chunk) {
+  constexpr int KS16 = DR / 16, QH = DR / 8;
+  const int tid = threadIdx.x, nq = A.ld >> 2;
+  PoolPub* pub = A.pool_pub + leader;
+  const int W = (int)__ldcg(&pub->W);
+  const uint32_t st = __ldcg(&pub->st), i0 = __ldcg(&pub->i0);
+  const uint32_t j_begin = chunk * kPoolChunk, j_end = min(i0, (chunk + 1u) * kPoolChunk);
+  const uint32_t* seg = A.rows_sorted + st;
+  const float* pos_nrm = A.pos_nrm + st;
+  const uint4* seg_h = A.pos_h + (size_t)st * QH;
+  if (tid < kW) s.w_f[tid] = kInf;
+  if (tid == 0) s.surv[kSurvCap] = 0u;
+  __syncthreads();
+  tc_compare<KS16, 2>(A, seg, pos_nrm, seg_h, s, W, j_begin, j_end, (uint32_t)(tid >> 5), KMT / 32, nq, pub);
+  __syncthreads();
+  exact_parked<KMT, true>(A, s, seg, pos_nrm, nq, pub);
+  if (tid < W && s.w_f[tid] != kInf) atomicMin(&pub->f[tid], s.w_f[tid]);
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) {
+    atom_add_acq_rel(&pub->done, 1u);
+    if (A.dbg) atomicAdd(A.dbg + 34, 1ull);
+  }
+}
+
+// One step of a CTA that has nothing of its own to do: find an open window on the board, claim a chunk, serve it.
+// Returns false when there was nothing to serve.  All threads; s.ptask holds the broadcast slots.
+template <int KMT, int DR>
+__device__ __forceinline__ bool pool_help(const MergeArgs& A, Smem& s, uint32_t self) {
+  const int tid = threadIdx.x;
+  if (tid == 0) {
+    s.ptask[0] = 0u;
+    s.ptask[3] = ld_acquire(&A.pool->open) ? 0xFFFFFFFFu : 0xFFFFFFFEu;  // FFFFFFFE: nothing open, do not scan
+  }
+  __syncthreads();
+  if (s.ptask[3] == 0xFFFFFFFEu) {
+    __syncthreads();
+    return false;
+  }
+  // scan the board from a CTA-specific offset so that helpers spread over the open windows
+  const uint32_t grid = A.pool_n, off = (blockIdx.x * 37u) % grid;
+  for (uint32_t k = (uint32_t)tid; k < grid; k += KMT) {
+    uint32_t l = k + off;
+    if (l >= grid) l -= grid;
+    if (l != self && __ldcg(A.pool_board + l) != 0u) atomicMin(&s.ptask[3], k);
+  }
+  __syncthreads();
+  if (tid == 0 && s.ptask[3] < grid) {
+    uint32_t l = s.ptask[3] + off;
+    if (l >= grid) l -= grid;
+    PoolPub* pub = A.pool_pub + l;
+    const uint32_t bv = ld_acquire(A.pool_board + l);
+    if (bv != 0u) {
+      const uint32_t v = atom_add_acq_rel(&pub->next, 1u);
+      const uint32_t e = v >> kPoolCountBits, k = v & ((1u << kPoolCountBits) - 1u);
+      const uint32_t meta = ld_acquire(&pub->meta);
+      const uint32_t nt = meta & ((1u << kPoolCountBits) - 1u);
+      // a claim counts only in the window it was made in; then the leader is waiting for it and the block is stable
+      const bool mine = (meta >> kPoolCountBits) == e && k < nt;
+      if (!mine || k + 1u >= nt) pool_close(A, l, bv);
+      if (mine) {
+        s.ptask[0] = 1u;
+        s.ptask[1] = l;
+        s.ptask[2] = k;
+      }
+    }
+  }
+  __syncthreads();
+  const uint32_t got = s.ptask[0], leader = s.ptask[1], chunk = s.ptask[2];
+  __syncthreads();
+  if (!got) return false;
+  pool_serve<KMT, DR>(A, s, leader, chunk);
+  return true;
+}
+
 // ---- one bucket, one team.  Returns true if the bucket was handed on to the next team. -----------------
 template <int TEAM, int DR>
 __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i, uint32_t start_size, TeamCtl* ctl, Smem& s) {
@@ -1761,12 +2047,14 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
         ctl->size = A.bstart[bucket + 1] - st;
         ctl->wb = 4;
         ctl->mode = 0u;
+        ctl->big = 0u;
       }
     } else if (lane == 0) {
       ctl->i = start_i;
       ctl->size = start_size;
       ctl->wb = 4;
       ctl->mode = 0u;
+      ctl->big = 0u;
     }
     if (TEAM != 0)
       for (int t = lane; t < kW; t += 32) ctl->f[t] = kInf;
@@ -1776,6 +2064,19 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
   for (;;) {
     const uint32_t i0 = __ldcg(&ctl->i), size0 = __ldcg(&ctl->size);
     const uint32_t mode0 = __ldcg(&ctl->mode);  // read here by everybody: the leader rewrites it while resolving
+    if constexpr (TEAM == 1 && DR > 0) {
+      // helpers are worth keeping resident only for buckets that collect many representatives: announce early
+      if (A.pool && leader && tid == 0) {
+        const bool over = i0 >= size0 || (i0 > A.max_reps && A.esc_list);
+        if (over && ctl->big) {
+          atomicSub(&A.pool->big_active, 1u);
+          ctl->big = 0u;
+        } else if (!over && !ctl->big && i0 >= A.pool_min / 4u) {
+          atomicAdd(&A.pool->big_active, 1u);
+          ctl->big = 1u;
+        }
+      }
+    }
     if (i0 >= size0) return false;
     const uint32_t remaining = size0 - i0;
     if (i0 > A.max_reps && A.esc_list) {  // more compare work than this team should carry: hand on
@@ -1886,11 +2187,154 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
     }
     if (prof) tk1 = clock64();
     // ---- parallel phase: old representatives [0, i0) across the team, then candidate x candidate bits ----
-    if constexpr (DR > 0) {
+    bool pooled = false;
+    if constexpr (DR > 0 && TEAM == 0) pooled = A.pool != nullptr && i0 >= A.pool_min;
+    if constexpr (DR > 0 && TEAM == 0) {
+      if (pooled) {
+        // publish the window and open its screen; then the candidate x candidate bits, this window's chunks as
+        // long as there are unclaimed ones, and other windows' chunks until all of this window's are done
+        constexpr int KS16 = DR / 16;
+        PoolPub* pub = A.pool_pub + blockIdx.x;
+        const uint32_t ntask = (i0 + kPoolChunk - 1) / kPoolChunk;
+        for (int idx = tid; idx < 4 * KS16 * 32; idx += kMT) {
+          const int l = idx & 31, ks = (idx >> 5) % KS16, mt = (idx >> 5) / KS16;
+          const __half* r0 = s.htile + (size_t)(mt * 16 + (l >> 2)) * s.hs + ks * 16 + (l & 3) * 2;
+          const __half* r1 = r0 + 8 * s.hs;
+          pub->af[idx] = make_uint4(*reinterpret_cast<const uint32_t*>(r0), *reinterpret_cast<const uint32_t*>(r1),
+                                    *reinterpret_cast<const uint32_t*>(r0 + 8), *reinterpret_cast<const uint32_t*>(r1 + 8));
+        }
+        if (tid < kW) {
+          pub->ridx[tid] = tid < W ? s.ridx[tid] : 0u;
+          pub->cnorm[tid] = tid < W ? s.cnorm[tid] : 1.f;
+          pub->f[tid] = kInf;
+        }
+        if (tid == 0) {
+          pub->W = (uint32_t)W;
+          pub->st = st;
+          pub->i0 = i0;
+          pub->done = 0u;
+        }
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) {
+          const uint32_t epoch = (s.ptask[6] + 1u) & 0xFFFu;
+          s.ptask[6] = epoch;
+          st_release(&pub->meta, (epoch << kPoolCountBits) | ntask);
+          st_release(&pub->next, epoch << kPoolCountBits);
+          if (ntask > 1u) {
+            st_release(A.pool_board + blockIdx.x, epoch + 1u);
+            atomicAdd(&A.pool->open, 1u);
+          }
+          if (A.dbg) atomicAdd(A.dbg + 35, (unsigned long long)ntask);
+        }
+        tc_compare<KS16, 1>(A, seg, pos_nrm, seg_h, s, W, 0u, (uint32_t)W, warp, kMT / 32, nq);
+        __syncthreads();
+        uint32_t own = 0;
+        for (;;) {  // own chunks, screened from shared memory
+          if (tid == 0) s.ptask[4] = atom_add_acq_rel(&pub->next, 1u) & ((1u << kPoolCountBits) - 1u);
+          __syncthreads();
+          const uint32_t k = s.ptask[4];
+          __syncthreads();
+          if (k + 1u >= ntask && ntask > 1u && tid == 0) pool_close(A, blockIdx.x, s.ptask[6] + 1u);
+          if (k >= ntask) break;
+          tc_compare<KS16, 0>(A, seg, pos_nrm, seg_h, s, W, k * kPoolChunk, min(i0, (k + 1u) * kPoolChunk), warp, kMT / 32, nq);
+          ++own;
+        }
+        __syncthreads();
+        exact_parked<kMT, false>(A, s, seg, pos_nrm, nq, nullptr);
+        __syncthreads();
+        for (;;) {
+          if (tid == 0) s.ptask[5] = ld_acquire(&pub->done);
+          __syncthreads();
+          const bool all_done = s.ptask[5] + own == ntask;
+          __syncthreads();
+          if (all_done) break;
+          if (!pool_help<kMT, DR>(A, s, blockIdx.x)) __nanosleep(60);
+        }
+        if (tid < W) s.s_f[tid] = min(s.s_f[tid], __ldcg(&pub->f[tid]));
+        if (tid == 0) s.surv[kSurvCap] = 0u;
+      }
+    }
+    uint32_t pool_ntask = 0u;
+    if constexpr (DR > 0 && TEAM == 1) {
+      pooled = A.pool != nullptr && i0 >= A.pool_min;
+      if (pooled) {
+        // The cluster's CTAs claim chunks of the screen like everybody else; idle teams of the launch that stayed
+        // on as helpers take the rest.  Every CTA of the cluster counts the pooled windows itself (s.ptask[6]).
+        constexpr int KS16 = DR / 16;
+        PoolPub* pub = A.pool_pub + Team<TEAM>::id();
+        const uint32_t ntask = (i0 + kPoolChunk - 1) / kPoolChunk;
+        pool_ntask = ntask;
+        const uint32_t epoch = (s.ptask[6] + 1u) & 0xFFFu;
+        __syncthreads();
+        if (tid == 0) s.ptask[6] = epoch;
+        if (leader) {
+          for (int idx = tid; idx < 4 * KS16 * 32; idx += kMT) {
+            const int l = idx & 31, ks = (idx >> 5) % KS16, mt = (idx >> 5) / KS16;
+            const __half* r0 = s.htile + (size_t)(mt * 16 + (l >> 2)) * s.hs + ks * 16 + (l & 3) * 2;
+            const __half* r1 = r0 + 8 * s.hs;
+            pub->af[idx] = make_uint4(*reinterpret_cast<const uint32_t*>(r0), *reinterpret_cast<const uint32_t*>(r1),
+                                      *reinterpret_cast<const uint32_t*>(r0 + 8), *reinterpret_cast<const uint32_t*>(r1 + 8));
+          }
+          if (tid < kW) {
+            pub->ridx[tid] = tid < W ? s.ridx[tid] : 0u;
+            pub->cnorm[tid] = tid < W ? s.cnorm[tid] : 1.f;
+            pub->f[tid] = kInf;
+          }
+          if (tid == 0) {
+            pub->W = (uint32_t)W;
+            pub->st = st;
+            pub->i0 = i0;
+            pub->done = 0u;
+          }
+          __threadfence();
+          __syncthreads();
+          if (tid == 0) {
+            st_release(&pub->meta, (epoch << kPoolCountBits) | ntask);
+            st_release(&pub->next, epoch << kPoolCountBits);
+            st_release(A.pool_board + Team<TEAM>::id(), epoch + 1u);
+            atomicAdd(&A.pool->open, 1u);
+            if (A.dbg) atomicAdd(A.dbg + 35, (unsigned long long)ntask);
+          }
+          tc_compare<KS16, 1>(A, seg, pos_nrm, seg_h, s, W, 0u, (uint32_t)W, warp, kMT / 32, nq);
+          __syncthreads();
+        } else {
+          if (tid == 0)
+            while ((ld_acquire(&pub->meta) >> kPoolCountBits) != epoch) __nanosleep(20);
+          __syncthreads();
+        }
+        uint32_t own = 0;
+        for (;;) {
+          if (tid == 0) {
+            uint32_t v = atom_add_acq_rel(&pub->next, 1u);
+            while ((v >> kPoolCountBits) != epoch) {  // the leader has published the window but not yet reset the claim word
+              __nanosleep(20);
+              v = atom_add_acq_rel(&pub->next, 1u);
+            }
+            s.ptask[4] = v & ((1u << kPoolCountBits) - 1u);
+          }
+          __syncthreads();
+          const uint32_t k = s.ptask[4];
+          __syncthreads();
+          if (k + 1u >= ntask && tid == 0) pool_close(A, Team<TEAM>::id(), epoch + 1u);
+          if (k >= ntask) break;
+          tc_compare<KS16, 0>(A, seg, pos_nrm, seg_h, s, W, k * kPoolChunk, min(i0, (k + 1u) * kPoolChunk), warp, kMT / 32, nq);
+          ++own;
+        }
+        if (own) {
+          __threadfence();
+          if (tid == 0) s.ptask[5] = own;
+        } else if (tid == 0) {
+          s.ptask[5] = 0u;
+        }
+      }
+    }
+    if (pooled) {
+    } else if constexpr (DR > 0) {
       constexpr int KS16 = DR / 16;
-      tc_compare<KS16, false>(A, seg, pos_nrm, seg_h, s, W, 0u, i0, Team<TEAM>::rank() * (kMT / 32) + warp,
+      tc_compare<KS16, 0>(A, seg, pos_nrm, seg_h, s, W, 0u, i0, Team<TEAM>::rank() * (kMT / 32) + warp,
                               Team<TEAM>::ncta() * (kMT / 32), nq);
-      if (leader) tc_compare<KS16, true>(A, seg, pos_nrm, seg_h, s, W, 0u, (uint32_t)W, warp, kMT / 32, nq);
+      if (leader) tc_compare<KS16, 1>(A, seg, pos_nrm, seg_h, s, W, 0u, (uint32_t)W, warp, kMT / 32, nq);
     } else {
       const int ks16 = (s.hs - 8) >> 4;
       tc_compare_wide<false>(A, seg, pos_nrm, seg_h, s, W, 0u, i0, Team<TEAM>::rank() * (kMT / 32) + warp,
@@ -1898,42 +2342,32 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
       if (leader) tc_compare_wide<true>(A, seg, pos_nrm, seg_h, s, W, 0u, (uint32_t)W, warp, kMT / 32, nq, ks16);
     }
     __syncthreads();
-    {
-      // exact tests of the pairs the screen parked: all of the CTA's threads at once, so the
-      // dependent row fetches of different pairs overlap
-      const uint32_t ns = min(s.surv[kSurvCap], (uint32_t)kSurvCap);
-      if (tid == 0 && ns && A.work) atomicAdd(A.work + 1, (unsigned long long)ns);
-      for (uint32_t k0 = 0; k0 < ns; k0 += 2 * kMT) {
-        uint32_t ent[2], rr2[2];
-        bool on[2];
-#pragma unroll
-        for (int u = 0; u < 2; ++u) {
-          const uint32_t k = k0 + u * kMT + tid;
-          on[u] = k < ns;
-          ent[u] = on[u] ? s.surv[k] : 0u;
-          on[u] = on[u] && !(s.s_f[ent[u] & 63u] < (ent[u] >> 6));
-          rr2[u] = on[u] ? __ldcg(seg + (ent[u] >> 6)) : 0u;
-        }
-#pragma unroll
-        for (int u = 0; u < 2; ++u)
-          if (on[u]) {
-            const uint32_t jj = ent[u] >> 6;
-            const int t = (int)(ent[u] & 63u);
-            if (exact_pair<false>(s, t, A.vals + (uint64_t)rr2[u] * ld, __ldcg(pos_nrm + jj), nq, A.threshold))
-              atomicMin(&s.s_f[t], jj);
-          }
-      }
-      if (ns) __syncthreads();
-    }
+    exact_parked<kMT, false>(A, s, seg, pos_nrm, nq, nullptr);
     if (prof) tk2 = clock64();
     if (TEAM != 0) {
       if (tid < W && s.s_f[tid] != kInf) atomicMin(&ctl->f[tid], s.s_f[tid]);
       __threadfence();
+      if constexpr (DR > 0 && TEAM == 1) {
+        if (pooled) {  // this CTA's chunks are finished (their matches are in ctl->f above)
+          __syncthreads();
+          if (tid == 0 && s.ptask[5]) atom_add_acq_rel(&(A.pool_pub + Team<TEAM>::id())->done, s.ptask[5]);
+        }
+      }
       Team<TEAM>::sync();
     }
     if (prof) tk3 = clock64();
     if (leader) {
       if (TEAM != 0) {
+        if constexpr (DR > 0 && TEAM == 1) {
+          if (pooled) {  // chunks taken by helpers outside the cluster
+            const PoolPub* pub = A.pool_pub + Team<TEAM>::id();
+            if (tid == 0)
+              while (ld_acquire(&pub->done) != pool_ntask) __nanosleep(40);
+            __syncthreads();
+            if (tid < W) atomicMin(&ctl->f[tid], __ldcg(&pub->f[tid]));
+            __syncthreads();
+          }
+        }
         if (tid < W) {
           s.s_f[tid] = __ldcg(&ctl->f[tid]);
           ctl->f[tid] = kInf;
@@ -1983,7 +2417,10 @@ __device__ bool merge_team(const MergeArgs& A, uint32_t bucket, uint32_t start_i
         long long tp0 = 0, tp1 = 0, tp2 = 0, tp3 = 0, tp4 = 0;
         if (prof) tp0 = clock64();
         if (warp == 0) {
-          int n = A.no_par_scan ? -1 : spec_scan_par(s, sp, W, wf, wb, tail_mode, i0);
+          int n = -1;
+          const int sm = A.scan_mode == 3 ? (TEAM == 0 ? 0 : 2) : A.scan_mode;
+          if (sm == 2) n = spec_scan_par<true>(A, s, sp, W, wf, wb, tail_mode, i0);
+          else if (sm == 1) n = spec_scan_par<false>(A, s, sp, W, wf, wb, tail_mode, i0);
           if (n < 0) n = spec_scan(s, sp, W, wf, wb, tail_mode, i0, size0);
           else if (A.dbg && lane == 0) atomicAdd(A.dbg + 32, 1ull);
           if (lane == 0) s.ro[RO_EXAMINED] = (uint32_t)n;
@@ -2050,14 +2487,18 @@ __global__ void __launch_bounds__(Shape<TEAM>::kMT, Shape<TEAM>::kCtasPerSm) k_m
   __shared__ uint32_t s_work;
   Smem s;
   carve(s, smem_raw, A.ld);
+  if (threadIdx.x == 0) s.ptask[6] = 0u;  // pool: this leader's window epoch
   // staged rows are zero beyond the row's own width (row_width): nothing ever writes there
   for (int v = threadIdx.x; v < (2 * kW + kKD) * s.ts; v += blockDim.x) s.tile[v] = 0.f;
   __syncthreads();
   TeamCtl* ctl = A.ctl + Team<TEAM>::id();
-  const uint32_t na = A.n_a ? *A.n_a : 0u, nb = A.n_b ? *A.n_b : 0u;
+  const uint32_t n0 = A.n_0 ? *A.n_0 : 0u, na = A.n_a ? *A.n_a : 0u, nb = A.n_b ? *A.n_b : 0u;
+  auto item = [&](uint32_t w) {
+    return (w < n0) ? (A.list_0 + 3 * (size_t)w) : (w - n0 < na) ? (A.list_a + 3 * (size_t)(w - n0)) : (A.list_b + 3 * (size_t)(w - n0 - na));
+  };
   if (TEAM == 2) {  // the grid walks the lists together
-    for (uint32_t w = 0; w < na + nb; ++w) {
-      const uint32_t* it = (w < na) ? (A.list_a + 3 * (size_t)w) : (A.list_b + 3 * (size_t)(w - na));
+    for (uint32_t w = 0; w < n0 + na + nb; ++w) {
+      const uint32_t* it = item(w);
       merge_team<TEAM, DR>(A, it[0], it[1], it[2], ctl, s);
     }
     return;
@@ -2076,11 +2517,68 @@ __global__ void __launch_bounds__(Shape<TEAM>::kMT, Shape<TEAM>::kCtasPerSm) k_m
       w = __ldcg(&ctl->work);
       Team<TEAM>::sync();
     }
-    if (w >= na + nb) break;
-    const uint32_t* it = (w < na) ? (A.list_a + 3 * (size_t)w) : (A.list_b + 3 * (size_t)(w - na));
+    if (w >= n0 + na + nb) break;
+    const uint32_t* it = item(w);
     merge_team<TEAM, DR>(A, it[0], it[1], it[2], ctl, s);
   }
+  if constexpr (TEAM == 1 && DR > 0) {
+    if (A.pool) {
+      // out of buckets: the first pool_helpers teams to get here stay on and serve chunks (each CTA on its own)
+      // until every team of the launch is out of buckets; the others leave and free their SMs
+      if (Team<TEAM>::rank() == 0 && threadIdx.x == 0) {
+        atomicAdd(&A.pool->finished, 1u);
+        ctl->work = atomicAdd(&A.pool->helpers, 1u);
+      }
+      __threadfence();
+      Team<TEAM>::sync();
+      const bool stay = __ldcg(&ctl->work) < A.pool_helpers;
+      while (stay) {
+        if (pool_help<Shape<TEAM>::kMT, DR>(A, s, 0xFFFFFFFFu)) continue;
+        if (threadIdx.x == 0) s.ptask[5] = (ld_acquire(&A.pool->finished) >= A.pool_n || ld_acquire(&A.pool->big_active) == 0u) ? A.pool_n : 0u;
+        __syncthreads();
+        const bool fin = s.ptask[5] >= A.pool_n;
+        __syncthreads();
+        if (fin) break;
+        __nanosleep(200);
+      }
+    }
+  }
+  if constexpr (TEAM == 0 && DR > 0) {
+    if (A.pool) {  // out of buckets: serve screen tasks until every CTA of the launch is out of buckets
+      __syncthreads();
+      if (threadIdx.x == 0) atomicAdd(&A.pool->finished, 1u);
+      for (;;) {
+        if (pool_help<Shape<TEAM>::kMT, DR>(A, s, blockIdx.x)) continue;
+        if (threadIdx.x == 0) s.ptask[5] = ld_acquire(&A.pool->finished);
+        __syncthreads();
+        const bool fin = s.ptask[5] >= A.pool_n;
+        __syncthreads();
+        if (fin) break;
+        __nanosleep(400);
+      }
+    }
+  }
 }
+
+// Helper kernel of the direct pipeline's screen pool: launched on the MAIN stream behind the main pipeline's
+// kernels, so it occupies SMs only once they have nothing else to do, and serves chunks of the cluster teams'
+// windows until the direct pipeline raises the stop word.
+template <int DR>
+__global__ void __launch_bounds__(Shape<1>::kMT, 1) k_pool_helper(MergeArgs A) {
+  extern __shared__ __align__(16) float smem_raw[];
+  Smem s;
+  carve(s, smem_raw, A.ld);
+  for (;;) {
+    if (pool_help<Shape<1>::kMT, DR>(A, s, 0xFFFFFFFFu)) continue;
+    if (threadIdx.x == 0) s.ptask[5] = ld_acquire(&A.pool->stop);
+    __syncthreads();
+    const bool fin = s.ptask[5] != 0u;
+    __syncthreads();
+    if (fin) break;
+    __nanosleep(300);
+  }
+}
+__global__ void k_pool_stop(PoolCtl* pc) { st_release(&pc->stop, 1u); }
 
 template <int TEAM>
 const void* kernel_for(int ld) {
@@ -2158,6 +2656,10 @@ static int launch_stage(klsh_ctx* ctx, cudaStream_t stream, DevBuf& ctl_buf, int
     cudaMemset(ctx->dbg.p, 0, sizeof(unsigned long long) * 40);
     t0 = std::chrono::high_resolution_clock::now();
   }
+  if (A.pool) {
+    A.pool_n = nteams;
+    KCUDA(ctx, cudaMemsetAsync(&A.pool->finished, 0, 3 * sizeof(uint32_t), stream));  // finished, helpers, big_active
+  }
   void* args[] = {&A};
   cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
   ctx->launches++;
@@ -2184,8 +2686,9 @@ static int launch_stage(klsh_ctx* ctx, cudaStream_t stream, DevBuf& ctl_buf, int
       fprintf(stderr, "[klsh]   decide kcycles/window: select %.1f dirty-compare %.1f old+accepted %.1f merge %.1f | per window: loop trips %.1f runs %.1f dirty tests %.1f\n",
               h[14] / 1e3 / h[0], h[15] / 1e3 / h[0], h[16] / 1e3 / h[0], h[17] / 1e3 / h[0], (double)h[22] / h[0], (double)h[23] / h[0], (double)h[24] / h[0]);
     if (h[26])
-      fprintf(stderr, "[klsh]   speculative windows %llu (parallel scan %llu), cut short by a misprediction %llu; kcycles per speculative window: scan %.1f versions %.1f match %.1f verify %.1f\n",
-              h[26], h[32], h[27], h[28] / 1e3 / h[26], h[29] / 1e3 / h[26], h[30] / 1e3 / h[26], h[31] / 1e3 / h[26]);
+      fprintf(stderr, "[klsh]   speculative windows %llu (parallel scan %llu), cut short by a misprediction %llu; kcycles per speculative window: scan %.1f (order %.1f records %.1f) versions %.1f match %.1f verify %.1f\n",
+              h[26], h[32], h[27], h[28] / 1e3 / h[26], h[36] / 1e3 / h[26], h[37] / 1e3 / h[26], h[29] / 1e3 / h[26], h[30] / 1e3 / h[26], h[31] / 1e3 / h[26]);
+    if (h[35]) fprintf(stderr, "[klsh]   screen pool: %llu tasks posted, %llu served\n", h[35], h[34]);
     if (h[0]) fprintf(stderr, "[klsh]   dirty tests decided by the exact chain (inside the fast test's error band): %.3f per window\n", (double)h[25] / h[0]);
   }
   return KLSH_OK;
@@ -2208,10 +2711,16 @@ static MergeArgs base_args(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted,
   A.mg = ctx->mg;
   A.threshold = threshold;
   A.no_spec = ctx->no_spec ? 1 : 0;
-  A.no_par_scan = ctx->no_par_scan ? 1 : 0;
+  A.scan_mode = ctx->scan_mode;
   A.work = ctx->eps_counter.p ? ctx->eps_counter.as<unsigned long long>() + 2 : nullptr;
-  A.list_a = A.list_b = nullptr;
-  A.n_a = A.n_b = nullptr;
+  A.list_a = A.list_b = A.list_0 = nullptr;
+  A.n_a = A.n_b = A.n_0 = nullptr;
+  A.pool = nullptr;
+  A.pool_board = nullptr;
+  A.pool_pub = nullptr;
+  A.pool_min = 0xFFFFFFFFu;
+  A.pool_n = 0u;
+  A.pool_helpers = 0u;
   A.cursor = nullptr;
   A.esc_list = nullptr;
   A.esc_count = nullptr;
@@ -2279,6 +2788,77 @@ int launch_merge_window(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
   return KLSH_OK;
 }
 
+// ---- screen pool launch ---------------------------------------------------------------------------------------
+bool launch_merge_uses_pool(const klsh_ctx* ctx) { return ctx->pool && ctx->ld <= 64 && !launch_merge_uses_fallback(ctx); }
+
+// One launch of single-CTA teams over every bucket of more than KLSH_SMALL_MAX rows, the pass's largest first
+// (list_direct, then list_big, then list_large); screens of buckets past pool_min representatives go through the pool.
+int launch_merge_pool(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold) {
+  PassCounters* dc = s.counters.as<PassCounters>();
+  if (ctx->debug) KTRY(dev_reserve(ctx, ctx->dbg, sizeof(unsigned long long) * 40));
+  const uint32_t grid_max = (uint32_t)ctx->sm_count * (uint32_t)Shape<0>::kCtasPerSm;
+  if (!ctx->pool_ctl.p) {  // control word and board start as zeros and every launch leaves them that way
+    KTRY(dev_reserve(ctx, ctx->pool_ctl, sizeof(PoolCtl) + sizeof(uint32_t) * (size_t)grid_max));
+    KCUDA(ctx, cudaMemsetAsync(ctx->pool_ctl.p, 0, ctx->pool_ctl.bytes, ctx->stream));
+    KTRY(dev_reserve(ctx, ctx->pool_pub, sizeof(PoolPub) * (size_t)grid_max));
+    KCUDA(ctx, cudaMemsetAsync(ctx->pool_pub.p, 0, ctx->pool_pub.bytes, ctx->stream));
+  }
+  MergeArgs A = base_args(ctx, s, rows_sorted, threshold);
+  A.list_0 = s.list_direct.as<uint32_t>();
+  A.n_0 = &dc->n_direct;
+  A.list_a = s.list_big.as<uint32_t>();
+  A.n_a = &dc->n_big;
+  A.list_b = s.list_large.as<uint32_t>();
+  A.n_b = &dc->n_large;
+  A.cursor = &dc->large_cursor;
+  A.pool = ctx->pool_ctl.as<PoolCtl>();
+  A.pool_board = reinterpret_cast<uint32_t*>(ctx->pool_ctl.as<PoolCtl>() + 1);
+  A.pool_pub = ctx->pool_pub.as<PoolPub>();
+  A.pool_min = ctx->pool_min;
+  return launch_stage(ctx, ctx->stream, ctx->team_ctl, 0, 1, A, 0);
+}
+
+static bool cluster_pool_on(const klsh_ctx* ctx) { return ctx->cpool && ctx->ld <= 64; }
+
+// Called once per pass BEFORE the fork: the stop word must be down before the direct pipeline starts.
+int launch_pool_reset(klsh_ctx* ctx) {
+  if (!cluster_pool_on(ctx)) return KLSH_OK;
+  const uint32_t teams_max = (uint32_t)ctx->sm_count * 2u;
+  if (!ctx->pool_ctl_b.p) {  // control block + board and the per-team blocks start as zeros and every pass leaves them that way
+    KTRY(dev_reserve(ctx, ctx->pool_ctl_b, sizeof(PoolCtl) + sizeof(uint32_t) * (size_t)teams_max));
+    KCUDA(ctx, cudaMemsetAsync(ctx->pool_ctl_b.p, 0, ctx->pool_ctl_b.bytes, ctx->stream));
+    KTRY(dev_reserve(ctx, ctx->pool_pub_b, sizeof(PoolPub) * (size_t)teams_max));
+    KCUDA(ctx, cudaMemsetAsync(ctx->pool_pub_b.p, 0, ctx->pool_pub_b.bytes, ctx->stream));
+  }
+  KCUDA(ctx, cudaMemsetAsync(&ctx->pool_ctl_b.as<PoolCtl>()->stop, 0, sizeof(uint32_t), ctx->stream));
+  return KLSH_OK;
+}
+
+// Called after the main pipeline's kernels are enqueued (the direct pipeline is already enqueued on stream2).
+int launch_pool_helper(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold) {
+  if (!cluster_pool_on(ctx) || ctx->cpool_helper_grid == 0) return KLSH_OK;
+  const int ld = ctx->ld;
+  MergeArgs A = base_args(ctx, s, rows_sorted, threshold);
+  A.dbg = nullptr;
+  A.pool = ctx->pool_ctl_b.as<PoolCtl>();
+  A.pool_board = reinterpret_cast<uint32_t*>(ctx->pool_ctl_b.as<PoolCtl>() + 1);
+  A.pool_pub = ctx->pool_pub_b.as<PoolPub>();
+  A.pool_n = (uint32_t)ctx->sm_count * 2u;
+  const size_t smem = smem_bytes_for(ld, Shape<1>::kMT);
+  const void* fn = ld <= 32 ? (const void*)k_pool_helper<32> : (const void*)k_pool_helper<64>;
+  KCUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(std::min<uint32_t>(ctx->cpool_helper_grid, (uint32_t)ctx->sm_count));
+  cfg.blockDim = dim3(Shape<1>::kMT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = ctx->stream;
+  void* args[] = {&A};
+  cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
+  ctx->launches++;
+  if (e != cudaSuccess) return klsh_fail(ctx, KLSH_ERR_CUDA, "pool helper launch failed: %s", cudaGetErrorString(e));
+  return KLSH_OK;
+}
+
 // The direct pipeline: buckets of at least direct_min rows start on cluster teams (no single-CTA stage)
 // and escalate to large clusters and the grid like the others.  Everything is enqueued on the
 // context's second stream with its own work lists, cursors and team control blocks, so it runs beside
@@ -2303,8 +2883,25 @@ int launch_merge_direct(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
   // the SMs and nobody queues; many: the portable 8-CTA clusters, so that more of them run side by side
   const int per_sm = std::max(1, ctx->cluster_ctas_per_sm);
   const int csize1 = ((uint64_t)n_direct_host * (uint64_t)ctx->cluster2_size <= (uint64_t)ctx->sm_count * per_sm) ? ctx->cluster2_size : ctx->cluster_size;
+  const bool cpool = cluster_pool_on(ctx);
+  auto stop_helpers = [&]() -> int {
+    if (!cpool) return KLSH_OK;
+    k_pool_stop<<<1, 1, 0, st>>>(ctx->pool_ctl_b.as<PoolCtl>());
+    ctx->launches++;
+    KCUDA(ctx, cudaGetLastError());
+    return KLSH_OK;
+  };
+  if (cpool) {
+    // screen pool of the cluster teams: their windows' screens are open to the helper kernel that follows the
+    // main pipeline on the other stream (and to teams of this launch told to stay on, none by default)
+    A.pool = ctx->pool_ctl_b.as<PoolCtl>();
+    A.pool_board = reinterpret_cast<uint32_t*>(ctx->pool_ctl_b.as<PoolCtl>() + 1);
+    A.pool_pub = ctx->pool_pub_b.as<PoolPub>();
+    A.pool_min = ctx->cpool_min;
+    A.pool_helpers = ctx->cpool_helper_ctas / (uint32_t)csize1;
+  }
   KTRY(launch_stage(ctx, st, ctx->team_ctl_b, 1, csize1, A, n_direct_host));
-  if (bucket_max_host <= ctx->cluster_max) return KLSH_OK;
+  if (bucket_max_host <= ctx->cluster_max) return stop_helpers();
 
   A.list_a = s.escb2.as<uint32_t>();
   A.n_a = &dc->nb_esc2;
@@ -2312,9 +2909,18 @@ int launch_merge_direct(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
   A.esc_list = s.escb3.as<uint32_t>();
   A.esc_count = &dc->nb_esc3;
   A.max_reps = ctx->cluster2_max;
+  if (cpool) {
+    A.pool_helpers = ctx->cpool_helper_ctas / (uint32_t)ctx->cluster2_size;
+    // with helpers the large clusters carry any bucket: no grid stage (a cooperative launch could not become
+    // resident beside the helper kernel)
+    A.esc_list = nullptr;
+    A.esc_count = nullptr;
+    A.max_reps = 0xFFFFFFFFu;
+  }
   KTRY(launch_stage(ctx, st, ctx->team_ctl_b, 1, ctx->cluster2_size, A, 0));
-  if (bucket_max_host <= ctx->cluster2_max) return KLSH_OK;
+  if (cpool || bucket_max_host <= ctx->cluster2_max) return stop_helpers();
 
+  A.pool = nullptr;
   A.list_a = s.escb3.as<uint32_t>();
   A.n_a = &dc->nb_esc3;
   A.cursor = nullptr;
