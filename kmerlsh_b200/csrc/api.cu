@@ -129,6 +129,7 @@ int klsh_create(int device, klsh_ctx** out) {
     return klsh_fail(nullptr, KLSH_ERR_NOMEM, "cudaMallocHost: %s", cudaGetErrorString(e));
   }
   ctx->planes = planes_new();
+  merge_window_preload();
   // development knobs (bucket size classes of the windowed merge)
   if (const char* e = std::getenv("KLSH_DEBUG")) ctx->debug = std::atoi(e) != 0;
   if (const char* e = std::getenv("KLSH_TIMELINE")) ctx->timeline = std::atoi(e) != 0;

@@ -159,7 +159,9 @@ constexpr int kSignWarps = 4;
 //        largest exponent with a few guard bits + the final truncation; a worst-case figure, the
 //        measured behaviour is far better), 3*ceil(D/8) mma per sum;
 //   D    the reference chain's own rounding (its sign is what has to be reproduced).
-// So   eps = (D + 32 + 30*ceil(D/8)) * 2^-24 * |w| * |x|   (D = 32: 184 * 2^-24 = 1.1e-5)
+//    2   the planes are multiplied as unit vectors w/|w| (a positive factor keeps the sign; the scaling rounds each
+//        element once, and |w/|w|| <= 1 + 2^-22), which makes the margin the same for every plane of a row.
+// So   eps = (D + 34 + 30*ceil(D/8)) * 2^-24 * |x|   (D = 32: 186 * 2^-24 = 1.1e-5) on the sum with the unit plane
 // guarantees that a sum outside it has the sign of the reference's mul-then-add chain; a sum inside it
 // is re-evaluated with the reference's exact arithmetic (and the row counted), so every key bit is
 // the reference's.  A warp owns 32 rows: cp.async gathers them into a double-buffered shared tile
@@ -196,25 +198,34 @@ k_sign_tc(const float* __restrict__ vals, int D, int ld, const uint32_t* __restr
   constexpr int KW = KS8 * 8;     // padded row width
   constexpr int TS = KW + 4;      // tile row stride: fragment loads and per-row float4 walks are conflict-free
   extern __shared__ __align__(16) float smem[];
-  float* sp = smem;                                          // planes [32][KW] fp32, zero padded (exact path)
-  float* pn = sp + 32 * KW;                                  // eps factor per plane [32]
-  uint4* bfrag = reinterpret_cast<uint4*>(pn + 32);          // [KS8][4][32] {hi b0, hi b1, lo b0, lo b1}
+  float* pinv = smem;                                        // 1 / |w_h| per plane [32] (0: the plane is always decided exactly)
+  uint4* bfrag = reinterpret_cast<uint4*>(pinv + 32);        // [KS8][4][32] {hi b0, hi b1, lo b0, lo b1} of the UNIT planes
   float* tiles = reinterpret_cast<float*>(bfrag + KS8 * 4 * 32);  // [kSignWarps][2][32][TS]
-  for (int i = threadIdx.x; i < 32 * KW; i += blockDim.x) {
-    const int h = i / KW, c = i - h * KW;
-    sp[i] = (h < H && c < ld) ? planes[h * ld + c] : 0.f;
-  }
   for (int i = threadIdx.x; i < kSignWarps * 2 * 32 * TS; i += blockDim.x) tiles[i] = 0.f;  // padding columns stay zero
-  __syncthreads();
   for (int h = threadIdx.x; h < 32; h += blockDim.x) {
     float m = 0.f;
-    for (int i = 0; i < D; ++i) m = __fmaf_rn(sp[h * KW + i], sp[h * KW + i], m);
-    pn[h] = sqrtf(m) * (((float)D + 32.f + 30.f * (float)((D + 7) / 8)) * 5.9604645e-8f);
+    if (h < H)
+      for (int i = 0; i < D; ++i) {
+        const float w = __ldg(planes + h * ld + i);
+        m = __fmaf_rn(w, w, m);
+      }
+    const float nrm = sqrtf(m);
+    pinv[h] = (nrm > 1e-30f && nrm < 1e30f) ? 1.f / nrm : 0.f;  // also false for NaN
   }
+  __syncthreads();
+  // The fast path multiplies with the planes scaled to unit length (a positive factor per plane: the sign of the
+  // sum is the same), so that ONE margin per row, c * |x|, covers all planes.  Planes past H in the last tile of
+  // eight repeat plane 0: their sums can never be the only ones inside the margin, and their bits are masked out.
   for (int i = threadIdx.x; i < KS8 * 4 * 32; i += blockDim.x) {
     const int l = i & 31, nt = (i >> 5) & 3, ks = i >> 7;
-    const int h = nt * 8 + (l >> 2), k0 = ks * 8 + (l & 3);
-    const float w0 = sp[h * KW + k0], w1 = sp[h * KW + k0 + 4];
+    int h = nt * 8 + (l >> 2);
+    if (h >= H) h = 0;
+    const int k0 = ks * 8 + (l & 3);
+    const float inv = H > 0 ? pinv[h] : 0.f;
+    float w0 = (H > 0 && k0 < ld) ? __ldg(planes + h * ld + k0) : 0.f;
+    float w1 = (H > 0 && k0 + 4 < ld) ? __ldg(planes + h * ld + k0 + 4) : 0.f;
+    w0 = inv != 0.f ? w0 * inv : 0.f;
+    w1 = inv != 0.f ? w1 * inv : 0.f;
     const uint32_t h0 = tf32_rna(w0), h1 = tf32_rna(w1);
     bfrag[i] = make_uint4(h0, h1, tf32_rna(w0 - __uint_as_float(h0)), tf32_rna(w1 - __uint_as_float(h1)));
   }
@@ -226,13 +237,12 @@ k_sign_tc(const float* __restrict__ vals, int D, int ld, const uint32_t* __restr
   const int rr_lane = (int)lane / vec_per_row, cc_lane = (int)lane - rr_lane * vec_per_row;
   const int rr_step = 32 / vec_per_row, cc_step = 32 - rr_step * vec_per_row;
   uint32_t my_eps = 0;
-  // this lane's 8 planes (nt*8 + 2*tg + e): eps factors and which of them exist
-  float pnr[8];
+  const float kc = ((float)D + 34.f + 30.f * (float)((D + 7) / 8)) * 5.9604645e-8f;
+  // which of this lane's 8 planes (nt*8 + 2*tg + e) exist
   uint32_t vmask = 0u;
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     const int h = (q >> 1) * 8 + 2 * (int)tg + (q & 1);
-    pnr[q] = pn[h];
     if (h < H) vmask |= 1u << q;
   }
   // gather the 32 rows of the tile starting at t0 into buffer b; returns this lane's row index
@@ -312,8 +322,8 @@ k_sign_tc(const float* __restrict__ vals, int D, int ld, const uint32_t* __restr
           }
         }
     }
-    // c[m][nt][2*half + e]: row m*16 + half*8 + g, plane nt*8 + 2*tg + e.  Branch-free: sign bits and
-    // "inside the margin" flags for the lane's 4 rows x 8 planes, then one rare pass over the flagged.
+    // c[m][nt][2*half + e]: row m*16 + half*8 + g, plane nt*8 + 2*tg + e.  Sign bits of the lane's 4 rows x 8
+    // planes; the smallest |sum| of a row against the row's margin decides whether anything needs a second look.
     uint32_t part[4];
     uint32_t slow = 0u;
 #pragma unroll
@@ -321,25 +331,33 @@ k_sign_tc(const float* __restrict__ vals, int D, int ld, const uint32_t* __restr
 #pragma unroll
       for (int half = 0; half < 2; ++half) {
         const int row = m * 16 + half * 8 + (int)g;
-        const float xnr = __shfl_sync(0xffffffffu, xn, row);
-        uint32_t bits = 0u, flag = 0u;
+        const float thr = kc * __shfl_sync(0xffffffffu, xn, row);
+        uint32_t bits = 0u;
+        float mn = 3.4e38f;
 #pragma unroll
         for (int q = 0; q < 8; ++q) {
           const float sum = c[m][q >> 1][2 * half + (q & 1)];
-          const float a = fabsf(sum);
           bits |= (sum >= 0.f ? 1u : 0u) << q;
-          flag |= ((a > pnr[q] * xnr && a <= 3.0e38f) ? 0u : 1u) << q;
+          if ((q >> 1) * 8 < H) mn = fminf(mn, fabsf(sum));  // warp-uniform: tiles of eight planes past H were not multiplied
         }
-        flag &= vmask;
-        while (flag) {  // reference arithmetic: sum = fl(sum + fl(w_i * x_i)), i ascending (hash/lshash.cc:44-51)
-          const int q = __ffs(flag) - 1;
-          flag &= flag - 1;
-          const float* w = sp + ((q >> 1) * 8 + 2 * (int)tg + (q & 1)) * KW;
-          const float* x = tile + row * TS;
-          float sum = 0.f;
-          for (int j = 0; j < D; ++j) sum = __fadd_rn(sum, __fmul_rn(w[j], x[j]));
-          bits = (bits & ~(1u << q)) | ((sum >= 0.f ? 1u : 0u) << q);
-          slow |= 1u << (m * 2 + half);
+        if (!(mn > thr && thr <= 3.0e38f)) {  // rare; also taken for NaN or infinite |x|
+          uint32_t flag = 0u;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float a = fabsf(c[m][q >> 1][2 * half + (q & 1)]);
+            flag |= ((a > thr && a <= 3.0e38f) ? 0u : 1u) << q;
+          }
+          flag &= vmask;
+          while (flag) {  // reference arithmetic: sum = fl(sum + fl(w_i * x_i)), i ascending (hash/lshash.cc:44-51)
+            const int q = __ffs(flag) - 1;
+            flag &= flag - 1;
+            const float* w = planes + ((q >> 1) * 8 + 2 * (int)tg + (q & 1)) * ld;
+            const float* x = tile + row * TS;
+            float sum = 0.f;
+            for (int j = 0; j < D; ++j) sum = __fadd_rn(sum, __fmul_rn(__ldg(w + j), x[j]));
+            bits = (bits & ~(1u << q)) | ((sum >= 0.f ? 1u : 0u) << q);
+            slow |= 1u << (m * 2 + half);
+          }
         }
         bits &= vmask;
         // bit q = (nt, e) -> plane h = nt*8 + 2*tg + e -> key bit H-1-h (plane 0 is the most significant)
@@ -1290,8 +1308,7 @@ int launch_sign(klsh_ctx* ctx, const float* vals, int D, int ld, const uint32_t*
   KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long) * 4));
   if (ld <= 64) {
     const int ks8 = ld <= 32 ? 4 : 8, kw = ks8 * 8;
-    const size_t smem = sizeof(float) * ((size_t)32 * kw + 32) + 16 * (size_t)ks8 * 4 * 32 +
-                        sizeof(float) * (size_t)kSignWarps * 2 * 32 * (kw + 4);
+    const size_t smem = sizeof(float) * 32 + 16 * (size_t)ks8 * 4 * 32 + sizeof(float) * (size_t)kSignWarps * 2 * 32 * (kw + 4);
     auto fn = ld <= 32 ? k_sign_tc<4> : k_sign_tc<8>;
     KCUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 1;

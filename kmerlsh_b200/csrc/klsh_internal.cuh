@@ -159,7 +159,7 @@ struct klsh_ctx {
   bool cpool = true;      // KLSH_CPOOL=0: the direct pipeline's cluster teams screen their windows alone (no helpers)
   uint32_t cpool_min = 65536;       // KLSH_CPOOL_MIN: representatives from which a cluster team opens its screen to helpers
   uint32_t cpool_helper_ctas = 0;   // KLSH_CPOOL_HELPERS: CTAs (in whole teams) of the direct pipeline that stay resident as helpers once they run out of buckets
-  uint32_t cpool_helper_grid = 148; // KLSH_CPOOL_GRID: CTAs of the helper kernel that follows the main pipeline (0: none)
+  uint32_t cpool_helper_grid = 74;  // KLSH_CPOOL_GRID: CTAs of the helper kernel that follows the main pipeline (0: none; at most one per two SMs)
   bool pool = false;      // KLSH_POOL=1: single-CTA teams with a screen pool for every bucket instead of the escalation stages and the direct pipeline (measured slower)
   uint32_t pool_min = 4096;  // KLSH_POOL_MIN: representatives from which a window's screen goes to the pool
   bool timeline = false;  // KLSH_TIMELINE=1: per pass, when each of the two merge pipelines ended (stderr)
@@ -236,6 +236,7 @@ int launch_merge_pool(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, floa
 int launch_pool_reset(klsh_ctx* ctx);
 int launch_pool_helper(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold);
 size_t merge_window_smem_bytes(int ld);
+void merge_window_preload();
 int launch_merge_one(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, uint64_t n, float threshold);
 int launch_compact(klsh_ctx* ctx, PassScratch& s, const uint32_t* rows_sorted, uint64_t n, uint32_t* out);
 int launch_iota(klsh_ctx* ctx, uint32_t* out, uint64_t n, uint32_t base);

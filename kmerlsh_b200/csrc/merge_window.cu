@@ -2487,7 +2487,14 @@ __global__ void __launch_bounds__(Shape<TEAM>::kMT, Shape<TEAM>::kCtasPerSm) k_m
   __shared__ uint32_t s_work;
   Smem s;
   carve(s, smem_raw, A.ld);
-  if (threadIdx.x == 0) s.ptask[6] = 0u;  // pool: this leader's window epoch
+  // pool: window epochs of this team continue where the team slot's previous user (an earlier launch) stopped —
+  // the per-team blocks persist, and a CTA of the team must never take a leftover block for the window it waits for
+  if (threadIdx.x == 0) {
+    uint32_t e0 = 0u;
+    if constexpr (DR > 0 && TEAM != 2)
+      if (A.pool) e0 = ld_acquire(&(A.pool_pub + Team<TEAM>::id())->meta) >> kPoolCountBits;
+    s.ptask[6] = e0;
+  }
   // staged rows are zero beyond the row's own width (row_width): nothing ever writes there
   for (int v = threadIdx.x; v < (2 * kW + kKD) * s.ts; v += blockDim.x) s.tile[v] = 0.f;
   __syncthreads();
@@ -2563,11 +2570,29 @@ __global__ void __launch_bounds__(Shape<TEAM>::kMT, Shape<TEAM>::kCtasPerSm) k_m
 // Helper kernel of the direct pipeline's screen pool: launched on the MAIN stream behind the main pipeline's
 // kernels, so it occupies SMs only once they have nothing else to do, and serves chunks of the cluster teams'
 // windows until the direct pipeline raises the stop word.
+// A helper CTA must never keep a kernel of the direct pipeline from becoming resident (that kernel is what ends
+// the helpers): it holds at most half of an SM's registers (256 threads x <= 128) and only the shared memory the
+// worker side needs (the cp.async ring, the parked pairs, two small arrays: 37 KB for rows of up to 32 floats,
+// 69 KB up to 64), and the launch has at most one helper CTA per two SMs — however they are placed, most SMs stay
+// entirely free.
+__host__ __device__ inline size_t helper_smem_bytes(int ld) {
+  return sizeof(uint32_t) * (8 + kW + kSurvCap + 1) + (size_t)(Shape<1>::kMT / 32) * kRing * 32 * (tc_width(ld) / 32) * 16 + 16;
+}
 template <int DR>
-__global__ void __launch_bounds__(Shape<1>::kMT, 1) k_pool_helper(MergeArgs A) {
+__global__ void __launch_bounds__(Shape<1>::kMT, 2) k_pool_helper(MergeArgs A) {
   extern __shared__ __align__(16) float smem_raw[];
   Smem s;
-  carve(s, smem_raw, A.ld);
+  {
+    uint32_t* u = reinterpret_cast<uint32_t*>(smem_raw);
+    s.ring = reinterpret_cast<uint4*>(u);
+    u += (size_t)(Shape<1>::kMT / 32) * kRing * 32 * (DR / 32) * 4;
+    s.surv = u; u += kSurvCap + 1;
+    s.w_f = u; u += kW;
+    s.ptask = u;
+    s.s_f = s.w_f;
+    s.ts = DR + 4;
+    s.hs = DR + 8;
+  }
   for (;;) {
     if (pool_help<Shape<1>::kMT, DR>(A, s, 0xFFFFFFFFu)) continue;
     if (threadIdx.x == 0) s.ptask[5] = ld_acquire(&A.pool->stop);
@@ -2593,6 +2618,16 @@ const void* kernel_for(int ld) {
 // Launch: stage 0 (CTA teams) over the classified lists, then the escalation stages.
 // ================================================================================================
 size_t merge_window_smem_bytes(int ld) { return smem_bytes_for(ld, Shape<1>::kMT); }
+
+// The merge kernels are large; with CUDA's lazy module loading the first launch of each pays its load while the
+// GPU waits between the launches of the first pass.  Touch them once when the context is created instead.
+void merge_window_preload() {
+  cudaFuncAttributes fa;
+  const void* fns[] = {kernel_for<0>(32), kernel_for<0>(64), kernel_for<0>(128), kernel_for<1>(32), kernel_for<1>(64), kernel_for<1>(128),
+                       kernel_for<2>(32), kernel_for<2>(64), kernel_for<2>(128), (const void*)k_pool_helper<32>, (const void*)k_pool_helper<64>};
+  for (const void* f : fns)
+    if (cudaFuncGetAttributes(&fa, f) != cudaSuccess) (void)cudaGetLastError();
+}
 
 static int launch_stage(klsh_ctx* ctx, cudaStream_t stream, DevBuf& ctl_buf, int team, int csize, MergeArgs& A,
                         uint32_t host_items /* upper bound, 0 = unknown */) {
@@ -2844,11 +2879,11 @@ int launch_pool_helper(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, flo
   A.pool_board = reinterpret_cast<uint32_t*>(ctx->pool_ctl_b.as<PoolCtl>() + 1);
   A.pool_pub = ctx->pool_pub_b.as<PoolPub>();
   A.pool_n = (uint32_t)ctx->sm_count * 2u;
-  const size_t smem = smem_bytes_for(ld, Shape<1>::kMT);
+  const size_t smem = helper_smem_bytes(ld);
   const void* fn = ld <= 32 ? (const void*)k_pool_helper<32> : (const void*)k_pool_helper<64>;
   KCUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(std::min<uint32_t>(ctx->cpool_helper_grid, (uint32_t)ctx->sm_count));
+  cfg.gridDim = dim3(std::min<uint32_t>(ctx->cpool_helper_grid, (uint32_t)ctx->sm_count / 2u));
   cfg.blockDim = dim3(Shape<1>::kMT);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = ctx->stream;

@@ -242,7 +242,7 @@ def test_merge_team_variants(oracle, monkeypatch, cta_max, cluster_max, cluster2
     monkeypatch.setenv("KLSH_CLUSTER2_MAX", str(cluster2_max))
     monkeypatch.setenv("KLSH_CLUSTER_SIZE", str(csize))
     cases = [(40000, 4, 4, 6, 0.85, 100000, 7), (120000, 10, 10, 4, 0.80, 1000, 4), (30000, 16, 16, 5, 0.9, 100000, 5),
-             (8000, 40, 40, 3, 0.8, 100000, 9)]
+             (8000, 40, 40, 3, 0.8, 100000, 9), (20000, 24, 24, 4, 0.85, 100000, 13)]
     with Context(0) as ctx:
         for n, sa, sb, iters, minsim, thr, seed in cases:
             _, _, values, ids = synth_rows(oracle, n, sa, sb, 60 + seed)
@@ -442,7 +442,8 @@ def test_window_resolution_modes(oracle, monkeypatch, env):
 
     for k, v in env.items():
         monkeypatch.setenv(k, v)
-    cases = [(150000, 8, 8, 5, 0.85, 100000, 3), (60000, 16, 16, 4, 0.9, 100000, 5), (90000, 4, 4, 6, 0.8, 60, 7)]
+    cases = [(150000, 8, 8, 5, 0.85, 100000, 3), (60000, 16, 16, 4, 0.9, 100000, 5), (90000, 4, 4, 6, 0.8, 60, 7),
+             (50000, 24, 24, 4, 0.85, 100000, 11)]
     with Context(0) as ctx:
         for n, sa, sb, iters, minsim, thr, seed in cases:
             _, _, values, ids = synth_rows(oracle, n, sa, sb, 80 + seed)
