@@ -129,6 +129,36 @@ int klsh_get_rows(klsh_ctx* ctx, float* values, uint64_t* id_offsets, uint64_t* 
  * delfile, ignore_small) (io/ioMatrix.cc:265-294, :322-351). */
 int klsh_save(klsh_ctx* ctx, const char* bin_path, int delfile, int64_t ignore_small);
 
+/* ---- mode E statistics on the clusters -------------------------------------
+ * = the loop of app/kmerLSH.cc:541-545 over the clustering result: AB::WRS (function/funcAB.cc:73-109) per
+ * cluster of the context's current row set (after klsh_cluster, or klsh_load_cluster_file for a result on disk).
+ * A cluster with more than size_thresh member ids is tested with alglib::studentttest2 on values[0 .. num_sample1)
+ * against values[num_sample1 .. num_sample1+num_sample2) (widened to double); row_group[r] = 2 when
+ * lefttail <= pvalue_thresh (its ids join the group-B set, :100-101), else 1 when righttail <= pvalue_thresh (group-A
+ * set, :102-103), else 0.  lefttail/righttail (optional, [rows]) receive the two probabilities, -1 for untested rows.
+ * The test statistic is bit-identical to ALGLIB's; the tail probabilities agree to a relative 1e-9 (ALGLIB's Cephes
+ * incomplete beta is replaced by a continued fraction, see csrc/stats.cu) and `margin` counts the clusters whose
+ * decision lies inside that tolerance of the threshold. */
+typedef struct {
+  uint64_t rows, tested;     /* clusters in the row set / clusters above size_thresh */
+  uint64_t rows_a, rows_b;   /* clusters filed under group A (row_group 1) / group B (row_group 2) */
+  uint64_t ids_a, ids_b;     /* their member ids */
+  uint64_t margin;           /* tested clusters with a tail probability within 1e-9 (relative) of pvalue_thresh */
+} klsh_ttest_stats;
+int klsh_ttest(klsh_ctx* ctx, int num_sample1, int num_sample2, float pvalue_thresh, int size_thresh,
+               uint8_t* row_group /* [rows] or NULL */, double* lefttail /* [rows] or NULL */,
+               double* righttail /* [rows] or NULL */, klsh_ttest_stats* stats /* or NULL */);
+/* The two id sets g_kmer_id1 / g_kmer_id2 the same loop fills (app/kmerLSH.cc:543-545), as one label per k-mer id
+ * below n_kmers (= kmap_size): 1 = in the group-A set, 2 = in the group-B set only, 0 = in neither — the
+ * precedence of the join at :571-576.  Runs the test itself (same arguments as klsh_ttest). */
+int klsh_differential_ids(klsh_ctx* ctx, int num_sample1, int num_sample2, float pvalue_thresh, int size_thresh,
+                          uint64_t n_kmers, uint8_t* id_label /* [n_kmers] */, klsh_ttest_stats* stats /* or NULL */);
+/* = the join over kmer_set.hex (app/kmerLSH.cc:565-579): records[n_kmers][record_bytes] are the k-mers in id order
+ * (record_bytes = Kmer::MAX_K/4 = 8 in the reference build, kmer/Kmer.h:68-78); out_a / out_b (room for n_kmers
+ * records each) receive the records labelled 1 / 2 in id order — the contents of g_kmer1 / g_kmer2. */
+int klsh_select_kmers(klsh_ctx* ctx, const uint8_t* records, uint64_t n_kmers, int record_bytes, const uint8_t* id_label,
+                      uint8_t* out_a, uint64_t* n_a, uint8_t* out_b, uint64_t* n_b);
+
 /* ---- device-resident state control (benchmarks; multi-batch phase 1) --------------------------- */
 /* Remember / restore the current row set on the device (no host traffic). */
 int klsh_snapshot(klsh_ctx* ctx);

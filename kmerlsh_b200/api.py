@@ -18,6 +18,8 @@ i64 = C.c_int64
 f32p = C.POINTER(C.c_float)
 u64p = C.POINTER(C.c_uint64)
 u16p = C.POINTER(C.c_uint16)
+u8p = C.POINTER(C.c_uint8)
+f64p = C.POINTER(C.c_double)
 
 PLANE_FN = C.CFUNCTYPE(None, C.c_void_p, C.c_int, C.c_int, f32p)
 DONE_FN = C.CFUNCTYPE(None, C.c_void_p)
@@ -45,6 +47,11 @@ class IterStats(C.Structure):
         ("screen_pairs", u64),
         ("exact_pairs", u64),
     ]
+
+
+class TtestStats(C.Structure):
+    _fields_ = [("rows", u64), ("tested", u64), ("rows_a", u64), ("rows_b", u64), ("ids_a", u64), ("ids_b", u64),
+                ("margin", u64)]
 
 
 def lib_path() -> str:
@@ -77,6 +84,9 @@ SYMBOLS = [
     ("klsh_row_count", C.c_int, [C.c_void_p, u64p, u64p]),
     ("klsh_get_rows", C.c_int, [C.c_void_p, f32p, u64p, u64p]),
     ("klsh_save", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, i64]),
+    ("klsh_ttest", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, u8p, f64p, f64p, C.POINTER(TtestStats)]),
+    ("klsh_differential_ids", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, u64, u8p, C.POINTER(TtestStats)]),
+    ("klsh_select_kmers", C.c_int, [C.c_void_p, u8p, u64, C.c_int, u8p, u8p, u64p, u8p, u64p]),
     ("klsh_stash_rows", C.c_int, [C.c_void_p]),
     ("klsh_stash_count", C.c_int, [C.c_void_p, u64p]),
     ("klsh_unstash_rows", C.c_int, [C.c_void_p]),
@@ -281,6 +291,41 @@ class Context:
 
     def save(self, path: str, delfile: bool = True, ignore_small: int = 0):
         self._ck(self.lib.klsh_save(self.h, path.encode(), int(delfile), ignore_small), "klsh_save")
+
+    # ---- mode E statistics (reference app/kmerLSH.cc:541-585, function/funcAB.cc:73-109)
+    def ttest(self, num_sample1: int, num_sample2: int, pvalue_thresh: float, size_thresh: int, tails: bool = True):
+        """AB::WRS on every cluster of the row set: (row_group, lefttail, righttail, stats)."""
+        n, _ = self.row_count(False)
+        group = np.zeros(max(n, 1), dtype=np.uint8)
+        left = np.empty(max(n, 1), dtype=np.float64) if tails else None
+        right = np.empty(max(n, 1), dtype=np.float64) if tails else None
+        st = TtestStats()
+        self._ck(self.lib.klsh_ttest(self.h, num_sample1, num_sample2, pvalue_thresh, size_thresh, _p(group, u8p),
+                                     _p(left, f64p) if tails else None, _p(right, f64p) if tails else None, C.byref(st)),
+                 "klsh_ttest")
+        return group[:n], (left[:n] if tails else None), (right[:n] if tails else None), st
+
+    def differential_ids(self, num_sample1: int, num_sample2: int, pvalue_thresh: float, size_thresh: int, n_kmers: int):
+        """One label per k-mer id < n_kmers: 1 = group-A set, 2 = group-B set, 0 = neither; plus the stats."""
+        label = np.zeros(max(n_kmers, 1), dtype=np.uint8)
+        st = TtestStats()
+        self._ck(self.lib.klsh_differential_ids(self.h, num_sample1, num_sample2, pvalue_thresh, size_thresh, n_kmers,
+                                                _p(label, u8p), C.byref(st)), "klsh_differential_ids")
+        return label[:n_kmers], st
+
+    def select_kmers(self, records, id_label):
+        """The join over kmer_set.hex: (records labelled 1, records labelled 2), each in id order."""
+        records = np.ascontiguousarray(records, dtype=np.uint8)
+        n, rb = records.shape
+        id_label = np.ascontiguousarray(id_label, dtype=np.uint8)
+        if id_label.shape[0] != n:
+            raise KlshError("select_kmers: %d records but %d labels" % (n, id_label.shape[0]))
+        a = np.empty((max(n, 1), rb), dtype=np.uint8)
+        b = np.empty((max(n, 1), rb), dtype=np.uint8)
+        na, nb = u64(), u64()
+        self._ck(self.lib.klsh_select_kmers(self.h, _p(records, u8p), n, rb, _p(id_label, u8p), _p(a, u8p), C.byref(na),
+                                            _p(b, u8p), C.byref(nb)), "klsh_select_kmers")
+        return a[: na.value].copy(), b[: nb.value].copy()
 
     # ---- survivors of several batches, resident on the device
     def stash_rows(self):

@@ -137,7 +137,6 @@ int klsh_create(int device, klsh_ctx** out) {
   if (const char* e = std::getenv("KLSH_CPOOL")) ctx->cpool = std::atoi(e) != 0;
   if (const char* e = std::getenv("KLSH_CPOOL_MIN")) ctx->cpool_min = (uint32_t)std::max(64, std::atoi(e));
   if (const char* e = std::getenv("KLSH_CPOOL_HELPERS")) ctx->cpool_helper_ctas = (uint32_t)std::max(0, std::atoi(e));
-  if (const char* e = std::getenv("KLSH_CPOOL_GRID")) ctx->cpool_helper_grid = (uint32_t)std::max(0, std::atoi(e));
   if (const char* e = std::getenv("KLSH_POOL_MIN")) ctx->pool_min = (uint32_t)std::max(64, std::atoi(e));
   if (const char* e = std::getenv("KLSH_MERGE_V1")) ctx->merge_v1 = std::atoi(e) != 0;
   if (const char* e = std::getenv("KLSH_NO_SPEC")) ctx->no_spec = std::atoi(e) != 0;
@@ -185,6 +184,9 @@ void klsh_destroy(klsh_ctx* ctx) {
   if (ctx->h_cnt.p) cudaFreeHost(ctx->h_cnt.p);
   if (ctx->h_head.p) cudaFreeHost(ctx->h_head.p);
   dev_free(ctx->eps_counter);
+  dev_free(ctx->st_group); dev_free(ctx->st_left); dev_free(ctx->st_right); dev_free(ctx->st_counts); dev_free(ctx->st_label);
+  dev_free(ctx->st_ids); dev_free(ctx->st_slot_row); dev_free(ctx->st_rec); dev_free(ctx->st_lab); dev_free(ctx->st_out_a);
+  dev_free(ctx->st_out_b); dev_free(ctx->st_blk);
   dev_free(ctx->dbg);
   dev_free(ctx->mg_counts); dev_free(ctx->mg_mod_rows); dev_free(ctx->mg_next_slot); dev_free(ctx->mg_next_val);
   dev_free(ctx->mg_splits); dev_free(ctx->mg_surv);

@@ -1506,11 +1506,17 @@ __global__ void k_rank_emit(const uint32_t* __restrict__ dist, const uint32_t* _
   const uint32_t d = dist[s];
   if (d <= end - offs[r]) slot_out[end - d] = s;
 }
+__global__ void k_rank_slot_row(const uint32_t* __restrict__ tailof, const int32_t* __restrict__ owner, uint32_t m, int32_t* slot_row) {
+  const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < m) slot_row[s] = owner[tailof[s]];
+}
 }  // namespace
 
 // slot_out[0 .. total_ids): member slots in output order (cluster after cluster, chain order inside).
 // d_offs: exclusive prefix of the survivors' member counts (n+1 entries, uint32) on the device.
-int launch_rank_chains(klsh_ctx* ctx, uint64_t n, const uint32_t* d_offs, uint32_t* slot_out) {
+// With slot_row_out instead (d_offs, slot_out NULL): slot_row_out[s] = position in the working set of the row
+// whose member chain holds slot s, -1 for slots of rows that are not in the set.
+int launch_rank_chains(klsh_ctx* ctx, uint64_t n, const uint32_t* d_offs, uint32_t* slot_out, int32_t* slot_row_out) {
   const uint32_t m = (uint32_t)ctx->n_slots;
   if (!m || !n) return KLSH_OK;
   KTRY(dev_reserve(ctx, ctx->rank_buf, sizeof(uint32_t) * ((size_t)m * 7 + 64)));
@@ -1538,6 +1544,11 @@ int launch_rank_chains(klsh_ctx* ctx, uint64_t n, const uint32_t* d_offs, uint32
       KCUDA(ctx, cudaStreamSynchronize(ctx->stream));
       if (!h) break;
     }
+  }
+  if (slot_row_out) {
+    k_rank_slot_row<<<grid, 256, 0, ctx->stream>>>(tl[cur], owner, m, slot_row_out);
+    KLAUNCH(ctx);
+    return KLSH_OK;
   }
   k_rank_emit<<<grid, 256, 0, ctx->stream>>>(dist[cur], tl[cur], owner, d_offs, m, slot_out);
   KLAUNCH(ctx);
@@ -1680,7 +1691,6 @@ int launch_merge(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float thr
     rc = launch_merge_fallback(ctx, s, rows_sorted, threshold, c);
   } while (0);
   if (ctx->timeline) cudaEventRecord(tl[1], ctx->stream);
-  if (forked && rc == KLSH_OK) rc = launch_pool_helper(ctx, s, rows_sorted, threshold);
   if (forked) {
     cudaError_t e = cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
     if (e != cudaSuccess && rc == KLSH_OK) rc = klsh_fail(ctx, KLSH_ERR_CUDA, "cudaStreamWaitEvent: %s", cudaGetErrorString(e));

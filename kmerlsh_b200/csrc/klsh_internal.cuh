@@ -136,6 +136,8 @@ struct klsh_ctx {
   DevBuf rank_buf, exp_offs, exp_slots; // chain ranking scratch, offsets and flat slot order (device)
   HostBuf h_slots;                     // flat slot order (pinned host)
   HostBuf h_cnt, h_head;               // export staging (pinned host)
+  DevBuf st_group, st_left, st_right, st_counts, st_label, st_ids, st_slot_row;  // mode E statistics (stats.cu)
+  DevBuf st_rec, st_lab, st_out_a, st_out_b, st_blk;
   DevBuf eps_counter; // rows whose key needed the exact re-evaluation of at least one plane (cumulative)
   MgComm* comm = nullptr;  // NCCL communicator + exchange buffers (klsh_mg_init)
   MgLog mg;           // multi-GPU update logs (null pointers unless a sharded pass is running)
@@ -156,10 +158,9 @@ struct klsh_ctx {
   int cluster_size = 8, cluster2_size = 16;
   int cluster_ctas_per_sm = 2;
   bool debug = false;     // KLSH_DEBUG=1
-  bool cpool = true;      // KLSH_CPOOL=0: the direct pipeline's cluster teams screen their windows alone (no helpers)
+  bool cpool = false;     // KLSH_CPOOL=1: the direct pipeline's cluster teams split the screen of a window into chunks claimed by their CTAs (and by idle teams, KLSH_CPOOL_HELPERS); measured slower than the static split on C2
   uint32_t cpool_min = 65536;       // KLSH_CPOOL_MIN: representatives from which a cluster team opens its screen to helpers
   uint32_t cpool_helper_ctas = 0;   // KLSH_CPOOL_HELPERS: CTAs (in whole teams) of the direct pipeline that stay resident as helpers once they run out of buckets
-  uint32_t cpool_helper_grid = 74;  // KLSH_CPOOL_GRID: CTAs of the helper kernel that follows the main pipeline (0: none; at most one per two SMs)
   bool pool = false;      // KLSH_POOL=1: single-CTA teams with a screen pool for every bucket instead of the escalation stages and the direct pipeline (measured slower)
   uint32_t pool_min = 4096;  // KLSH_POOL_MIN: representatives from which a window's screen goes to the pool
   bool timeline = false;  // KLSH_TIMELINE=1: per pass, when each of the two merge pipelines ended (stderr)
@@ -220,7 +221,7 @@ int launch_sort_pairs(klsh_ctx* ctx, PassScratch& s, uint64_t n, int bits, uint3
                       uint32_t** rows_sorted);
 int launch_bounds(klsh_ctx* ctx, PassScratch& s, const uint32_t* keys_sorted, uint64_t n);
 int launch_classify(klsh_ctx* ctx, PassScratch& s, uint64_t n, int64_t nest_threshold, uint32_t b_lo, uint32_t b_hi);
-int launch_rank_chains(klsh_ctx* ctx, uint64_t n, const uint32_t* d_offs, uint32_t* slot_out);
+int launch_rank_chains(klsh_ctx* ctx, uint64_t n, const uint32_t* d_offs, uint32_t* slot_out, int32_t* slot_row_out = nullptr);
 int launch_find_splits(klsh_ctx* ctx, PassScratch& s, uint32_t nb, uint64_t n, int world, uint32_t* d_splits);
 int launch_gather_mod(klsh_ctx* ctx, const uint32_t* rows, uint32_t n, float* out_vals, int32_t* out_meta);
 int launch_apply_mod(klsh_ctx* ctx, const uint32_t* rows, uint32_t n, const float* in_vals, const int32_t* in_meta,
@@ -234,7 +235,6 @@ bool launch_merge_uses_fallback(const klsh_ctx* ctx);
 bool launch_merge_uses_pool(const klsh_ctx* ctx);
 int launch_merge_pool(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold);
 int launch_pool_reset(klsh_ctx* ctx);
-int launch_pool_helper(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold);
 size_t merge_window_smem_bytes(int ld);
 void merge_window_preload();
 int launch_merge_one(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, uint64_t n, float threshold);

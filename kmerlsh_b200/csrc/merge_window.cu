@@ -161,8 +161,7 @@ struct PoolCtl {
   uint32_t finished;   // teams of this launch that ran out of buckets
   uint32_t helpers;    // cluster teams that stayed on as helpers after running out of buckets
   uint32_t big_active; // cluster teams whose current bucket is on its way to pooled windows (pool_min / 4 representatives)
-  uint32_t stop;       // set when the direct pipeline has finished: the helper kernel leaves
-  uint32_t pad[3];
+  uint32_t pad[4];
 };
 struct PoolPub {  // one per leader CTA
   uint4 af[kW * 8];      // the window's fp16 copy in A-fragment order: [(row tile * KS16 + k step) * 32 + lane]
@@ -2567,44 +2566,6 @@ __global__ void __launch_bounds__(Shape<TEAM>::kMT, Shape<TEAM>::kCtasPerSm) k_m
   }
 }
 
-// Helper kernel of the direct pipeline's screen pool: launched on the MAIN stream behind the main pipeline's
-// kernels, so it occupies SMs only once they have nothing else to do, and serves chunks of the cluster teams'
-// windows until the direct pipeline raises the stop word.
-// A helper CTA must never keep a kernel of the direct pipeline from becoming resident (that kernel is what ends
-// the helpers): it holds at most half of an SM's registers (256 threads x <= 128) and only the shared memory the
-// worker side needs (the cp.async ring, the parked pairs, two small arrays: 37 KB for rows of up to 32 floats,
-// 69 KB up to 64), and the launch has at most one helper CTA per two SMs — however they are placed, most SMs stay
-// entirely free.
-__host__ __device__ inline size_t helper_smem_bytes(int ld) {
-  return sizeof(uint32_t) * (8 + kW + kSurvCap + 1) + (size_t)(Shape<1>::kMT / 32) * kRing * 32 * (tc_width(ld) / 32) * 16 + 16;
-}
-template <int DR>
-__global__ void __launch_bounds__(Shape<1>::kMT, 2) k_pool_helper(MergeArgs A) {
-  extern __shared__ __align__(16) float smem_raw[];
-  Smem s;
-  {
-    uint32_t* u = reinterpret_cast<uint32_t*>(smem_raw);
-    s.ring = reinterpret_cast<uint4*>(u);
-    u += (size_t)(Shape<1>::kMT / 32) * kRing * 32 * (DR / 32) * 4;
-    s.surv = u; u += kSurvCap + 1;
-    s.w_f = u; u += kW;
-    s.ptask = u;
-    s.s_f = s.w_f;
-    s.ts = DR + 4;
-    s.hs = DR + 8;
-  }
-  for (;;) {
-    if (pool_help<Shape<1>::kMT, DR>(A, s, 0xFFFFFFFFu)) continue;
-    if (threadIdx.x == 0) s.ptask[5] = ld_acquire(&A.pool->stop);
-    __syncthreads();
-    const bool fin = s.ptask[5] != 0u;
-    __syncthreads();
-    if (fin) break;
-    __nanosleep(300);
-  }
-}
-__global__ void k_pool_stop(PoolCtl* pc) { st_release(&pc->stop, 1u); }
-
 template <int TEAM>
 const void* kernel_for(int ld) {
   if (ld <= 32) return (const void*)k_merge_window<TEAM, 32>;
@@ -2624,7 +2585,7 @@ size_t merge_window_smem_bytes(int ld) { return smem_bytes_for(ld, Shape<1>::kMT
 void merge_window_preload() {
   cudaFuncAttributes fa;
   const void* fns[] = {kernel_for<0>(32), kernel_for<0>(64), kernel_for<0>(128), kernel_for<1>(32), kernel_for<1>(64), kernel_for<1>(128),
-                       kernel_for<2>(32), kernel_for<2>(64), kernel_for<2>(128), (const void*)k_pool_helper<32>, (const void*)k_pool_helper<64>};
+                       kernel_for<2>(32), kernel_for<2>(64), kernel_for<2>(128)};
   for (const void* f : fns)
     if (cudaFuncGetAttributes(&fa, f) != cudaSuccess) (void)cudaGetLastError();
 }
@@ -2855,7 +2816,7 @@ int launch_merge_pool(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, floa
 
 static bool cluster_pool_on(const klsh_ctx* ctx) { return ctx->cpool && ctx->ld <= 64; }
 
-// Called once per pass BEFORE the fork: the stop word must be down before the direct pipeline starts.
+// Called once per pass BEFORE the fork: allocates the pool's control block, board and per-team blocks.
 int launch_pool_reset(klsh_ctx* ctx) {
   if (!cluster_pool_on(ctx)) return KLSH_OK;
   const uint32_t teams_max = (uint32_t)ctx->sm_count * 2u;
@@ -2865,32 +2826,6 @@ int launch_pool_reset(klsh_ctx* ctx) {
     KTRY(dev_reserve(ctx, ctx->pool_pub_b, sizeof(PoolPub) * (size_t)teams_max));
     KCUDA(ctx, cudaMemsetAsync(ctx->pool_pub_b.p, 0, ctx->pool_pub_b.bytes, ctx->stream));
   }
-  KCUDA(ctx, cudaMemsetAsync(&ctx->pool_ctl_b.as<PoolCtl>()->stop, 0, sizeof(uint32_t), ctx->stream));
-  return KLSH_OK;
-}
-
-// Called after the main pipeline's kernels are enqueued (the direct pipeline is already enqueued on stream2).
-int launch_pool_helper(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, float threshold) {
-  if (!cluster_pool_on(ctx) || ctx->cpool_helper_grid == 0) return KLSH_OK;
-  const int ld = ctx->ld;
-  MergeArgs A = base_args(ctx, s, rows_sorted, threshold);
-  A.dbg = nullptr;
-  A.pool = ctx->pool_ctl_b.as<PoolCtl>();
-  A.pool_board = reinterpret_cast<uint32_t*>(ctx->pool_ctl_b.as<PoolCtl>() + 1);
-  A.pool_pub = ctx->pool_pub_b.as<PoolPub>();
-  A.pool_n = (uint32_t)ctx->sm_count * 2u;
-  const size_t smem = helper_smem_bytes(ld);
-  const void* fn = ld <= 32 ? (const void*)k_pool_helper<32> : (const void*)k_pool_helper<64>;
-  KCUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(std::min<uint32_t>(ctx->cpool_helper_grid, (uint32_t)ctx->sm_count / 2u));
-  cfg.blockDim = dim3(Shape<1>::kMT);
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = ctx->stream;
-  void* args[] = {&A};
-  cudaError_t e = cudaLaunchKernelExC(&cfg, fn, args);
-  ctx->launches++;
-  if (e != cudaSuccess) return klsh_fail(ctx, KLSH_ERR_CUDA, "pool helper launch failed: %s", cudaGetErrorString(e));
   return KLSH_OK;
 }
 
@@ -2919,16 +2854,9 @@ int launch_merge_direct(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
   const int per_sm = std::max(1, ctx->cluster_ctas_per_sm);
   const int csize1 = ((uint64_t)n_direct_host * (uint64_t)ctx->cluster2_size <= (uint64_t)ctx->sm_count * per_sm) ? ctx->cluster2_size : ctx->cluster_size;
   const bool cpool = cluster_pool_on(ctx);
-  auto stop_helpers = [&]() -> int {
-    if (!cpool) return KLSH_OK;
-    k_pool_stop<<<1, 1, 0, st>>>(ctx->pool_ctl_b.as<PoolCtl>());
-    ctx->launches++;
-    KCUDA(ctx, cudaGetLastError());
-    return KLSH_OK;
-  };
   if (cpool) {
-    // screen pool of the cluster teams: their windows' screens are open to the helper kernel that follows the
-    // main pipeline on the other stream (and to teams of this launch told to stay on, none by default)
+    // screen pool of the cluster teams (opt-in): their windows' screens are split into chunks that the cluster's own
+    // CTAs claim, and that teams of this launch told to stay on after running out of buckets may claim too
     A.pool = ctx->pool_ctl_b.as<PoolCtl>();
     A.pool_board = reinterpret_cast<uint32_t*>(ctx->pool_ctl_b.as<PoolCtl>() + 1);
     A.pool_pub = ctx->pool_pub_b.as<PoolPub>();
@@ -2936,7 +2864,7 @@ int launch_merge_direct(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
     A.pool_helpers = ctx->cpool_helper_ctas / (uint32_t)csize1;
   }
   KTRY(launch_stage(ctx, st, ctx->team_ctl_b, 1, csize1, A, n_direct_host));
-  if (bucket_max_host <= ctx->cluster_max) return stop_helpers();
+  if (bucket_max_host <= ctx->cluster_max) return KLSH_OK;
 
   A.list_a = s.escb2.as<uint32_t>();
   A.n_a = &dc->nb_esc2;
@@ -2946,14 +2874,13 @@ int launch_merge_direct(klsh_ctx* ctx, PassScratch& s, uint32_t* rows_sorted, fl
   A.max_reps = ctx->cluster2_max;
   if (cpool) {
     A.pool_helpers = ctx->cpool_helper_ctas / (uint32_t)ctx->cluster2_size;
-    // with helpers the large clusters carry any bucket: no grid stage (a cooperative launch could not become
-    // resident beside the helper kernel)
+    // with the pool the large clusters carry any bucket: no grid stage
     A.esc_list = nullptr;
     A.esc_count = nullptr;
     A.max_reps = 0xFFFFFFFFu;
   }
   KTRY(launch_stage(ctx, st, ctx->team_ctl_b, 1, ctx->cluster2_size, A, 0));
-  if (cpool || bucket_max_host <= ctx->cluster2_max) return stop_helpers();
+  if (cpool || bucket_max_host <= ctx->cluster2_max) return KLSH_OK;
 
   A.pool = nullptr;
   A.list_a = s.escb3.as<uint32_t>();

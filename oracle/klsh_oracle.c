@@ -755,3 +755,203 @@ int klo_mode_c(const char* count_bin, const char* count_log, int D, float min_si
   free(vk);
   return rc;
 }
+
+
+/* ------------------------------------------------------------------------------------------
+ * Mode E statistics.
+ * Reference: AB::WRS (function/funcAB.cc:73-109) calls alglib::studentttest2 on the two halves of a
+ * centroid (values widened to double) and files the cluster's ids under group B when
+ * lefttail <= pvalue_thresh, else under group A when righttail <= pvalue_thresh; the caller
+ * (app/kmerLSH.cc:541-585) then walks kmer_set.hex and keeps the k-mers whose id is in either set.
+ *
+ * ALGLIB 3.15.0 is vendored third-party code (utils/alglib-3.15.0, Cephes-derived).  The test
+ * statistic below restates statistics.cpp:12502-12616 operation by operation and is bit-identical to
+ * it; studenttdistribution's finite series for t >= -2 restates specialfunctions.cpp:9559-9631.  For
+ * t < -2 ALGLIB evaluates 0.5*incompletebeta(k/2, 1/2, k/(k+t*t)) with Cephes' incbet (power series /
+ * two continued fractions / gamma function, specialfunctions.cpp:6975-7088, :7584-7900); that code is
+ * NOT restated: the same regularised incomplete beta function is evaluated here with the modified
+ * Lentz continued fraction.  Parity of this part is therefore to a tolerance (relative 1e-9 on the tail
+ * probabilities, pinned against ALGLIB itself through oracle/_ref/libklsh_ref.so and the fixtures in
+ * tests/golden/ttest.npz), not bit for bit.
+ * ---------------------------------------------------------------------------------------- */
+static double klo_betacf(double a, double b, double x) {
+  const double tiny = 1e-300;
+  double qab = a + b, qap = a + 1.0, qam = a - 1.0;
+  double c = 1.0, d = 1.0 - qab * x / qap;
+  if (fabs(d) < tiny) d = tiny;
+  d = 1.0 / d;
+  double h = d;
+  for (int m = 1; m <= 2000; ++m) {
+    double m2 = 2.0 * m;
+    double aa = m * (b - m) * x / ((qam + m2) * (a + m2));
+    d = 1.0 + aa * d;
+    if (fabs(d) < tiny) d = tiny;
+    c = 1.0 + aa / c;
+    if (fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    h *= d * c;
+    aa = -(a + m) * (qab + m) * x / ((a + m2) * (qap + m2));
+    d = 1.0 + aa * d;
+    if (fabs(d) < tiny) d = tiny;
+    c = 1.0 + aa / c;
+    if (fabs(c) < tiny) c = tiny;
+    d = 1.0 / d;
+    double del = d * c;
+    h *= del;
+    if (fabs(del - 1.0) < 2e-16) break;
+  }
+  return h;
+}
+
+/* regularised incomplete beta I_x(a, b), 0 <= x <= 1 */
+static double klo_incbeta(double a, double b, double x) {
+  if (x <= 0.0) return 0.0;
+  if (x >= 1.0) return 1.0;
+  double lbt = lgamma(a + b) - lgamma(a) - lgamma(b) + a * log(x) + b * log1p(-x);
+  double bt = exp(lbt);
+  if (x < (a + 1.0) / (a + b + 2.0)) return bt * klo_betacf(a, b, x) / a;
+  return 1.0 - bt * klo_betacf(b, a, 1.0 - x) / b;
+}
+
+/* specialfunctions.cpp:9559-9631 */
+static double klo_student_t_cdf(int k, double t) {
+  if (t == 0.0) return 0.5;
+  if (t < -2.0) {
+    double rk = (double)k;
+    double z = rk / (rk + t * t);
+    return 0.5 * klo_incbeta(0.5 * rk, 0.5, z);
+  }
+  double x = t < 0.0 ? -t : t;
+  double rk = (double)k;
+  double z = 1.0 + x * x / rk;
+  double p, f, tz;
+  int j;
+  if (k % 2 != 0) {
+    double xsqk = x / sqrt(rk);
+    p = atan(xsqk);
+    if (k > 1) {
+      f = 1.0;
+      tz = 1.0;
+      j = 3;
+      while (j <= k - 2 && tz / f > 5E-16) { /* ae_machineepsilon */
+        tz = tz * ((j - 1) / (z * j));
+        f = f + tz;
+        j = j + 2;
+      }
+      p = p + f * xsqk / z;
+    }
+    p = p * 2.0 / 3.14159265358979323846; /* ae_pi */
+  } else {
+    f = 1.0;
+    tz = 1.0;
+    j = 2;
+    while (j <= k - 2 && tz / f > 5E-16) {
+      tz = tz * ((j - 1) / (z * j));
+      f = f + tz;
+      j = j + 2;
+    }
+    p = f * x / sqrt(z * rk);
+  }
+  if (t < 0.0) p = -p;
+  return 0.5 + 0.5 * p;
+}
+
+/* statistics.cpp:12502-12616 */
+void klo_ttest2(const double* x, int n, const double* y, int m, double* bothtails, double* lefttail,
+                double* righttail) {
+  if (n <= 0 || m <= 0) {
+    *bothtails = 1.0;
+    *lefttail = 1.0;
+    *righttail = 1.0;
+    return;
+  }
+  double xmean = 0.0, x0 = x[0];
+  int samex = 1;
+  for (int i = 0; i < n; ++i) {
+    xmean = xmean + x[i];
+    samex = samex && (x[i] == x0);
+  }
+  xmean = samex ? x0 : xmean / n;
+  double ymean = 0.0, y0 = y[0];
+  int samey = 1;
+  for (int i = 0; i < m; ++i) {
+    ymean = ymean + y[i];
+    samey = samey && (y[i] == y0);
+  }
+  ymean = samey ? y0 : ymean / m;
+  double s = 0.0;
+  if (n + m > 2) {
+    for (int i = 0; i < n; ++i) s = s + (x[i] - xmean) * (x[i] - xmean);
+    for (int i = 0; i < m; ++i) s = s + (y[i] - ymean) * (y[i] - ymean);
+    s = sqrt(s * ((double)1 / (double)n + (double)1 / (double)m) / (n + m - 2));
+  }
+  if (s == 0.0) {
+    *bothtails = xmean == ymean ? 1.0 : 0.0;
+    *lefttail = xmean >= ymean ? 1.0 : 0.0;
+    *righttail = xmean <= ymean ? 1.0 : 0.0;
+    return;
+  }
+  double stat = (xmean - ymean) / s;
+  double p = klo_student_t_cdf(n + m - 2, stat);
+  *bothtails = 2 * (p < 1 - p ? p : 1 - p); /* ae_minreal */
+  *lefttail = p;
+  *righttail = 1 - p;
+}
+
+/* function/funcAB.cc:73-109, one call per row as in app/kmerLSH.cc:543-545 */
+void klo_wrs_rows(const float* values, const uint64_t* id_offsets, uint64_t n, int D, int num_sample1,
+                  int num_sample2, float pvalue_thresh, int size_thresh, uint8_t* group, double* lefttail,
+                  double* righttail) {
+  int n1 = num_sample1 > 0 ? num_sample1 : 0, n2 = num_sample2 > 0 ? num_sample2 : 0;
+  double* a = (double*)malloc(sizeof(double) * (size_t)(n1 + 1));
+  double* b = (double*)malloc(sizeof(double) * (size_t)(n2 + 1));
+  for (uint64_t r = 0; r < n; ++r) {
+    group[r] = 0;
+    if (lefttail) lefttail[r] = -1.0;
+    if (righttail) righttail[r] = -1.0;
+    uint64_t members = id_offsets[r + 1] - id_offsets[r];
+    /* `ids.size() > size_thresh`: size_t against int, the int is converted to size_t (:87) */
+    if (!(members > (uint64_t)(int64_t)size_thresh)) continue;
+    const float* v = values + r * (uint64_t)D;
+    for (int i = 0; i < n1; ++i) a[i] = (double)v[i];
+    for (int j = 0; j < n2; ++j) b[j] = (double)v[n1 + j];
+    double both, left, right;
+    klo_ttest2(a, num_sample1, b, num_sample2, &both, &left, &right);
+    if (lefttail) lefttail[r] = left;
+    if (righttail) righttail[r] = right;
+    if (left <= pvalue_thresh)
+      group[r] = 2;
+    else if (right <= pvalue_thresh)
+      group[r] = 1;
+  }
+  free(a);
+  free(b);
+}
+
+/* app/kmerLSH.cc:543-545 (the id sets) with the precedence of :571-576 */
+void klo_differential_ids(const uint8_t* group, const uint64_t* id_offsets, const uint64_t* ids, uint64_t n,
+                          uint64_t n_kmers, uint8_t* id_label) {
+  memset(id_label, 0, n_kmers);
+  for (int pass = 2; pass >= 1; --pass) /* set 1 wins when an id sits in both */
+    for (uint64_t r = 0; r < n; ++r)
+      if (group[r] == pass)
+        for (uint64_t k = id_offsets[r]; k < id_offsets[r + 1]; ++k)
+          if (ids[k] < n_kmers) id_label[ids[k]] = (uint8_t)pass;
+}
+
+/* app/kmerLSH.cc:565-579 */
+void klo_select_kmers(const uint8_t* records, uint64_t n_kmers, int record_bytes, const uint8_t* id_label,
+                      uint8_t* out_a, uint64_t* n_a, uint8_t* out_b, uint64_t* n_b) {
+  uint64_t ca = 0, cb = 0;
+  for (uint64_t i = 0; i < n_kmers; ++i) {
+    if (id_label[i] == 1) {
+      memcpy(out_a + ca * (uint64_t)record_bytes, records + i * (uint64_t)record_bytes, (size_t)record_bytes);
+      ++ca;
+    } else if (id_label[i] == 2) {
+      memcpy(out_b + cb * (uint64_t)record_bytes, records + i * (uint64_t)record_bytes, (size_t)record_bytes);
+      ++cb;
+    }
+  }
+  *n_a = ca;
+  *n_b = cb;
+}

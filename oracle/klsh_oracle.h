@@ -69,6 +69,25 @@ int klo_mode_c(const char* count_bin, const char* count_log, int D, float min_si
                const char* tmp_dir, const char* out_path, uint64_t batch_thresh,
                int64_t phase2_bucket_threshold, uint64_t seed, klo_iter_stats* phase2_stats /* may be NULL */);
 
+/* ---- mode E statistics (function/funcAB.cc:73-109, app/kmerLSH.cc:541-585) ---- */
+/* alglib::studentttest2 (utils/alglib-3.15.0/src/statistics.cpp:12502-12616) on x[n], y[m]. */
+void klo_ttest2(const double* x, int n, const double* y, int m, double* bothtails, double* lefttail,
+                double* righttail);
+/* AB::WRS for every row of a row set: group[r] = 2 if lefttail <= pvalue_thresh (the ids go to the group-B
+ * set, funcAB.cc:100-101), 1 if righttail <= pvalue_thresh (group-A set, :102-103), else 0; rows with
+ * |ids| <= size_thresh are not tested (0, tails reported as -1).  lefttail/righttail may be NULL. */
+void klo_wrs_rows(const float* values, const uint64_t* id_offsets, uint64_t n, int D, int num_sample1,
+                  int num_sample2, float pvalue_thresh, int size_thresh, uint8_t* group, double* lefttail,
+                  double* righttail);
+/* The two id sets of app/kmerLSH.cc:543-545 as one label per k-mer id < n_kmers (1: in g_kmer_id1,
+ * 2: only in g_kmer_id2, 0: neither — the precedence of the join at :571-576). */
+void klo_differential_ids(const uint8_t* group, const uint64_t* id_offsets, const uint64_t* ids, uint64_t n,
+                          uint64_t n_kmers, uint8_t* id_label);
+/* The join over kmer_set.hex (app/kmerLSH.cc:565-579): records of `record_bytes` bytes, record i belongs
+ * to k-mer id i; out_a / out_b receive the records labelled 1 / 2 in id order; returns the two counts. */
+void klo_select_kmers(const uint8_t* records, uint64_t n_kmers, int record_bytes, const uint8_t* id_label,
+                      uint8_t* out_a, uint64_t* n_a, uint8_t* out_b, uint64_t* n_b);
+
 #ifdef __cplusplus
 }
 #endif

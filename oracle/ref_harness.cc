@@ -17,6 +17,8 @@
 //   IOMat::convertHTMat         io/ioMatrix.cc:353-408
 //   IOMat::SaveResult/SaveBinary io/ioMatrix.cc:265-294, :322-351
 //   IOMat::ReadClusterAll       io/ioMatrix.cc:48-119
+//   AB::WRS                     function/funcAB.cc:73-109   (mode E statistics)
+//   alglib::studentttest2       utils/alglib-3.15.0/src/statistics.cpp:2277
 //
 // Determinism: load with OMP_THREAD_LIMIT=1 in the environment and pass threads=1
 // (SURVEY.md D7, D9).
@@ -29,6 +31,9 @@
 #include <vector>
 
 #include "function/cluster.h"
+#include "function/funcAB.h"
+#include "utils/alglib-3.15.0/src/statistics.h"
+#include <unordered_set>
 
 namespace {
 
@@ -148,6 +153,35 @@ void ref_result_copy(float* values, uint64_t* id_offsets, uint64_t* ids, int D) 
 void ref_save(const char* bin_path, int delfile, int ignore_small) {
   IOMat::SaveResult(&g_rows, std::string(bin_path) + ".clust", delfile != 0, ignore_small, false);
   IOMat::SaveBinary(&g_rows, bin_path, delfile != 0, ignore_small, false);
+}
+
+// alglib::studentttest2 as AB::WRS calls it (function/funcAB.cc:95-97)
+void ref_studentttest2(const double* x, int n, const double* y, int m, double* both, double* left, double* right) {
+  alglib::real_1d_array ax, ay;
+  ax.setcontent(n, x);
+  ay.setcontent(m, y);
+  alglib::studentttest2(ax, n, ay, m, *both, *left, *right);
+}
+
+// The loop of app/kmerLSH.cc:543-545 over a row set with the reference's own AB::WRS; the two id sets come
+// back as one label per k-mer id (1: g_kmer_id1, 2: g_kmer_id2 only) and, per row, which set its ids went to.
+void ref_wrs(const float* values, const uint64_t* id_offsets, const uint64_t* ids, uint64_t n, int D, int num_sample1,
+             int num_sample2, float pvalue_thresh, int size_thresh, uint64_t n_kmers, uint8_t* row_group,
+             uint8_t* id_label) {
+  std::vector<Abundance*> rows;
+  build_rows(&rows, values, id_offsets, ids, n, D);
+  std::unordered_set<uint64_t> g1, g2;
+  for (uint64_t r = 0; r < n; ++r) {
+    const size_t b1 = g1.size(), b2 = g2.size();
+    AB::WRS(&g1, &g2, rows[r], num_sample1, num_sample2, pvalue_thresh, size_thresh);
+    row_group[r] = g1.size() != b1 ? 1 : (g2.size() != b2 ? 2 : 0);
+  }
+  std::memset(id_label, 0, n_kmers);
+  for (uint64_t i = 0; i < n_kmers; ++i) {  // precedence of app/kmerLSH.cc:571-576
+    if (g1.find(i) != g1.end()) id_label[i] = 1;
+    else if (g2.find(i) != g2.end()) id_label[i] = 2;
+  }
+  for (size_t r = 0; r < rows.size(); ++r) delete rows[r];
 }
 
 }  // extern "C"

@@ -95,6 +95,12 @@ class Oracle:
         L.klo_save.argtypes = [C.c_void_p, C.c_char_p, C.c_int, i64]
         L.klo_read_cluster.restype = C.c_void_p
         L.klo_read_cluster.argtypes = [C.c_char_p, C.c_int, u64, u64]
+        f64p = C.POINTER(C.c_double)
+        u8p = C.POINTER(C.c_uint8)
+        L.klo_ttest2.argtypes = [f64p, C.c_int, f64p, C.c_int, f64p, f64p, f64p]
+        L.klo_wrs_rows.argtypes = [f32p, u64p, u64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, u8p, f64p, f64p]
+        L.klo_differential_ids.argtypes = [u8p, u64p, u64p, u64, u64, u8p]
+        L.klo_select_kmers.argtypes = [u8p, u64, C.c_int, u8p, u8p, u64p, u8p, u64p]
         L.klo_mode_c.restype = C.c_int
         L.klo_mode_c.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_float, C.c_int, C.c_char_p, C.c_char_p,
                                  u64, i64, u64, C.POINTER(IterStats)]
@@ -143,6 +149,47 @@ class Oracle:
 
     def threshold_after(self, min_similarity, iterations, steps):
         return np.float32(self.L.klo_threshold_after(min_similarity, iterations, steps))
+
+    # ---- mode E statistics
+    def ttest2(self, x, y):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        out = np.zeros(3, dtype=np.float64)
+        f64p = C.POINTER(C.c_double)
+        self.L.klo_ttest2(_p(x, f64p), x.shape[0], _p(y, f64p), y.shape[0], _p(out[0:], f64p), _p(out[1:], f64p), _p(out[2:], f64p))
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def wrs_rows(self, values, id_offsets, n1, n2, pvalue_thresh, size_thresh):
+        values = np.ascontiguousarray(values, dtype=np.float32)
+        offs = np.ascontiguousarray(id_offsets, dtype=np.uint64)
+        n, d = values.shape
+        group = np.zeros(n, dtype=np.uint8)
+        left = np.empty(n, dtype=np.float64)
+        right = np.empty(n, dtype=np.float64)
+        f64p = C.POINTER(C.c_double)
+        self.L.klo_wrs_rows(_p(values, f32p), _p(offs, u64p), n, d, n1, n2, pvalue_thresh, size_thresh,
+                            _p(group, C.POINTER(C.c_uint8)), _p(left, f64p), _p(right, f64p))
+        return group, left, right
+
+    def differential_ids(self, group, id_offsets, ids, n_kmers):
+        group = np.ascontiguousarray(group, dtype=np.uint8)
+        offs = np.ascontiguousarray(id_offsets, dtype=np.uint64)
+        ids = np.ascontiguousarray(ids, dtype=np.uint64)
+        label = np.zeros(max(n_kmers, 1), dtype=np.uint8)
+        u8p = C.POINTER(C.c_uint8)
+        self.L.klo_differential_ids(_p(group, u8p), _p(offs, u64p), _p(ids, u64p), group.shape[0], n_kmers, _p(label, u8p))
+        return label[:n_kmers]
+
+    def select_kmers(self, records, id_label):
+        records = np.ascontiguousarray(records, dtype=np.uint8)
+        n, rb = records.shape
+        id_label = np.ascontiguousarray(id_label, dtype=np.uint8)
+        a = np.empty((max(n, 1), rb), dtype=np.uint8)
+        b = np.empty((max(n, 1), rb), dtype=np.uint8)
+        na, nb = u64(0), u64(0)
+        u8p = C.POINTER(C.c_uint8)
+        self.L.klo_select_kmers(_p(records, u8p), n, rb, _p(id_label, u8p), _p(a, u8p), C.byref(na), _p(b, u8p), C.byref(nb))
+        return a[: na.value].copy(), b[: nb.value].copy()
 
     # ---- row sets
     def rows(self, values, id_offsets=None, ids=None):
@@ -270,6 +317,28 @@ class RefLib:
         L.ref_result_ids.restype = u64
         L.ref_result_copy.argtypes = [f32p, u64p, u64p, C.c_int]
         L.ref_save.argtypes = [C.c_char_p, C.c_int, C.c_int]
+        f64p = C.POINTER(C.c_double)
+        u8p = C.POINTER(C.c_uint8)
+        if hasattr(L, "ref_wrs"):
+            L.ref_studentttest2.argtypes = [f64p, C.c_int, f64p, C.c_int, f64p, f64p, f64p]
+            L.ref_wrs.argtypes = [f32p, u64p, u64p, u64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, u64, u8p, u8p]
+
+    def ttest2(self, x, y):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        y = np.ascontiguousarray(y, dtype=np.float64)
+        out = np.zeros(3, dtype=np.float64)
+        f64p = C.POINTER(C.c_double)
+        self.L.ref_studentttest2(_p(x, f64p), x.shape[0], _p(y, f64p), y.shape[0], _p(out[0:], f64p), _p(out[1:], f64p), _p(out[2:], f64p))
+        return float(out[0]), float(out[1]), float(out[2])
+
+    def wrs(self, values, id_offsets, ids, n1, n2, pvalue_thresh, size_thresh, n_kmers):
+        v, o, i = self._in(values, id_offsets, ids)
+        group = np.zeros(v.shape[0], dtype=np.uint8)
+        label = np.zeros(max(n_kmers, 1), dtype=np.uint8)
+        u8p = C.POINTER(C.c_uint8)
+        self.L.ref_wrs(_p(v, f32p), _p(o, u64p), _p(i, u64p), v.shape[0], v.shape[1], n1, n2, pvalue_thresh, size_thresh,
+                       n_kmers, _p(group, u8p), _p(label, u8p))
+        return group, label[:n_kmers]
 
     def reseed(self, seed):
         self.L.ref_reseed(seed)

@@ -227,15 +227,14 @@ def test_merge_team_variants(oracle, monkeypatch, cta_max, cluster_max, cluster2
     """The windowed merge with the escalation thresholds (representatives per team) forced low, so
     that small test buckets travel CTA -> cluster -> large cluster -> cooperative grid, against the oracle.
     Variants with an odd cta_max also switch the speculative resolver to its warp-parallel scan.  In the direct
-    pipeline the cluster teams' screen pool starts at 48 representatives for direct_min 40 and 100 (helper kernel,
-    claims, stale board entries), is off for direct_min 300 (so that pipeline's cooperative-grid stage runs too)."""
+    pipeline the cluster teams' opt-in screen pool is on from 48 representatives for direct_min 40 and 100 (chunk
+    claims, stale board entries), off (the default) for direct_min 300, so that pipeline's cooperative-grid stage runs too."""
     from kmerlsh_b200 import Context
 
     monkeypatch.setenv("KLSH_PAR_SCAN", "1" if cta_max % 2 else "0")
     if direct_min in (40, 100):
+        monkeypatch.setenv("KLSH_CPOOL", "1")
         monkeypatch.setenv("KLSH_CPOOL_MIN", "48")
-    if direct_min == 300:
-        monkeypatch.setenv("KLSH_CPOOL", "0")
     monkeypatch.setenv("KLSH_DIRECT_MIN", str(direct_min))
     monkeypatch.setenv("KLSH_CTA_MAX", str(cta_max))
     monkeypatch.setenv("KLSH_CLUSTER_MAX", str(cluster_max))
@@ -428,16 +427,16 @@ def test_stash_rows_equals_file_round_trip(gpu, oracle, tmp_path):
 
 
 @pytest.mark.parametrize("env", [{"KLSH_NO_SPEC": "1"}, {"KLSH_PAR_SCAN": "1"}, {"KLSH_SCAN": "0"}, {"KLSH_SCAN": "2"}, {},
-                                 {"KLSH_CPOOL": "0"},
-                                 {"KLSH_CPOOL_MIN": "64", "KLSH_DIRECT_MIN": "2000", "KLSH_CTA_MAX": "300"},
-                                 {"KLSH_CPOOL_MIN": "64", "KLSH_CPOOL_GRID": "0", "KLSH_CPOOL_HELPERS": "64", "KLSH_DIRECT_MIN": "2000"},
+                                 {"KLSH_DIRECT_MIN": "2000"},
+                                 {"KLSH_CPOOL": "1", "KLSH_CPOOL_MIN": "64", "KLSH_DIRECT_MIN": "2000", "KLSH_CTA_MAX": "300"},
+                                 {"KLSH_CPOOL": "1", "KLSH_CPOOL_MIN": "64", "KLSH_CPOOL_HELPERS": "64", "KLSH_DIRECT_MIN": "2000"},
                                  {"KLSH_POOL": "1", "KLSH_POOL_MIN": "64"}])
 def test_window_resolution_modes(oracle, monkeypatch, env):
     """However a window is resolved and whoever screens it, the clusters are the oracle's bit for bit: the
     sequential loop only; the speculative resolver with each of its scans (scalar replay, closed-form order,
-    lean replay; default: per team kind); the direct pipeline's cluster teams without the screen pool, with
-    the pool from 64 representatives on (helper kernel behind the main pipeline; or idle teams staying on as
-    helpers); single-CTA teams with the pool for every bucket."""
+    lean replay; default: per team kind); the direct pipeline's cluster teams from 2000 rows on without the screen
+    pool (the default) and with the opt-in pool from 64 representatives on (chunks claimed by the cluster's own CTAs;
+    or also by idle teams staying on as helpers); single-CTA teams with the pool for every bucket."""
     from kmerlsh_b200 import Context
 
     for k, v in env.items():
