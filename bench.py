@@ -329,6 +329,24 @@ def main():
     sampler.join(timeout=2)
     h2d_bytes = counts.nbytes + vk.nbytes
 
+    # ---- the first consumer of the result: mode E's statistics step on the clusters the
+    # last pass left on the device — AB::WRS per cluster and one label per k-mer id (app/kmerLSH.cc:541-585).
+    # Reported beside the headline, not in it.
+    stats_block = None
+    if world == 1:
+        e_ms = []
+        for k in range(3):
+            t0 = time.perf_counter()
+            label, tst = ctx.differential_ids(sa, sb, 0.01, 5, n)
+            e_ms.append((time.perf_counter() - t0) * 1e3)
+        stats_block = {
+            "what": "klsh_differential_ids on the final clusters: two-sample t-test (ALGLIB studentttest2 semantics) per cluster with more "
+                    "than 5 members, p <= 0.01, and a group label for each of the %d k-mer ids, D2H of the labels included" % n,
+            "ms": min(e_ms[1:]), "clusters": int(tst.rows), "tested": int(tst.tested), "clusters_a": int(tst.rows_a),
+            "clusters_b": int(tst.rows_b), "ids_a": int(tst.ids_a), "ids_b": int(tst.ids_b), "margin": int(tst.margin),
+            "d2h_bytes": int(label.nbytes),
+        }
+
     # ---- the communication-free decomposition (N > 1): phase 1 is one independent Cluster(I=1) per batch in the
     # reference (app/kmerLSH.cc:311-345), so every GPU clusters ITS OWN batch of this shape concurrently; the
     # survivors are then all-gathered in batch order over NVLink (klsh_mg_gather_rows) — the working set the
@@ -484,6 +502,7 @@ def main():
         "final_clusters": int(all_stats[-1][-1].rows_out),
         "phase1_ms_per_step": float(np.mean([st[0].ms_total for st in all_stats])) if world == 1 else None,
         "phase1_batch_per_gpu": p1_block,
+        "mode_e_statistics": stats_block,
     }
     print(json.dumps(out))
     if world > 1:
