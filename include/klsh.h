@@ -159,6 +159,18 @@ int klsh_differential_ids(klsh_ctx* ctx, int num_sample1, int num_sample2, float
 int klsh_select_kmers(klsh_ctx* ctx, const uint8_t* records, uint64_t n_kmers, int record_bytes, const uint8_t* id_label,
                       uint8_t* out_a, uint64_t* n_a, uint8_t* out_b, uint64_t* n_b);
 
+/* ---- read extraction votes ------------------------------------------------
+ * = IOFQ::CheckRead (io/ioFastQ.cc:5-75), the test IOFQ::ReadExtract (:77-158) applies to every read of a FASTQ part.
+ * klsh_kmer_set_load makes records[n_kmers][8] (Kmer::MAX_K/4 bytes each, the layout of kmer_set.hex and of
+ * klsh_select_kmers' output) the context's set of differential k-mers (g_kmer1 or g_kmer2, app/kmerLSH.cc:583-584).
+ * klsh_check_reads tests n_reads reads given as one character array and n_reads+1 offsets into it:
+ * record[r] = 1 iff the read has at least k+10 characters, does not start with a NUL character, and
+ * float(#k-mers of the read whose canonical form is in the set) / float(len-k+1) > kmer_vote (float arithmetic as the
+ * reference's; characters other than A, C, G, T count as A, kmer/Kmer.cc:139-144).  votes (optional) = the counts. */
+int klsh_kmer_set_load(klsh_ctx* ctx, const uint8_t* records, uint64_t n_kmers, int record_bytes /* 8 */);
+int klsh_check_reads(klsh_ctx* ctx, int k, const char* seq, const uint64_t* seq_offsets /* [n_reads+1] */, uint64_t n_reads,
+                     float kmer_vote, uint8_t* record /* [n_reads] */, uint32_t* votes /* [n_reads] or NULL */);
+
 /* ---- device-resident state control (benchmarks; multi-batch phase 1) --------------------------- */
 /* Remember / restore the current row set on the device (no host traffic). */
 int klsh_snapshot(klsh_ctx* ctx);

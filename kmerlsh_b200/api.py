@@ -87,6 +87,8 @@ SYMBOLS = [
     ("klsh_ttest", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, u8p, f64p, f64p, C.POINTER(TtestStats)]),
     ("klsh_differential_ids", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, u64, u8p, C.POINTER(TtestStats)]),
     ("klsh_select_kmers", C.c_int, [C.c_void_p, u8p, u64, C.c_int, u8p, u8p, u64p, u8p, u64p]),
+    ("klsh_kmer_set_load", C.c_int, [C.c_void_p, u8p, u64, C.c_int]),
+    ("klsh_check_reads", C.c_int, [C.c_void_p, C.c_int, C.c_char_p, u64p, u64, C.c_float, u8p, C.POINTER(C.c_uint32)]),
     ("klsh_stash_rows", C.c_int, [C.c_void_p]),
     ("klsh_stash_count", C.c_int, [C.c_void_p, u64p]),
     ("klsh_unstash_rows", C.c_int, [C.c_void_p]),
@@ -326,6 +328,23 @@ class Context:
         self._ck(self.lib.klsh_select_kmers(self.h, _p(records, u8p), n, rb, _p(id_label, u8p), _p(a, u8p), C.byref(na),
                                             _p(b, u8p), C.byref(nb)), "klsh_select_kmers")
         return a[: na.value].copy(), b[: nb.value].copy()
+
+    # ---- read extraction votes (reference io/ioFastQ.cc:5-75)
+    def kmer_set_load(self, records):
+        records = np.ascontiguousarray(records, dtype=np.uint8)
+        if records.ndim != 2:
+            raise KlshError("kmer_set_load: records must be [n][record_bytes]")
+        self._ck(self.lib.klsh_kmer_set_load(self.h, _p(records, u8p), records.shape[0], records.shape[1]), "klsh_kmer_set_load")
+
+    def check_reads(self, k: int, seq: bytes, offsets, kmer_vote: float):
+        """IOFQ::CheckRead over reads seq[offsets[r]:offsets[r+1]]: (record flags, votes)."""
+        offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = offs.shape[0] - 1
+        rec = np.zeros(max(n, 1), dtype=np.uint8)
+        votes = np.zeros(max(n, 1), dtype=np.uint32)
+        self._ck(self.lib.klsh_check_reads(self.h, k, seq, _p(offs, u64p), n, kmer_vote, _p(rec, u8p),
+                                           votes.ctypes.data_as(C.POINTER(C.c_uint32))), "klsh_check_reads")
+        return rec[:n], votes[:n]
 
     # ---- survivors of several batches, resident on the device
     def stash_rows(self):

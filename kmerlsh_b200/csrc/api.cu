@@ -187,6 +187,7 @@ void klsh_destroy(klsh_ctx* ctx) {
   dev_free(ctx->st_group); dev_free(ctx->st_left); dev_free(ctx->st_right); dev_free(ctx->st_counts); dev_free(ctx->st_label);
   dev_free(ctx->st_ids); dev_free(ctx->st_slot_row); dev_free(ctx->st_rec); dev_free(ctx->st_lab); dev_free(ctx->st_out_a);
   dev_free(ctx->st_out_b); dev_free(ctx->st_blk);
+  dev_free(ctx->rd_table); dev_free(ctx->rd_seq); dev_free(ctx->rd_offs); dev_free(ctx->rd_rec); dev_free(ctx->rd_votes);
   dev_free(ctx->dbg);
   dev_free(ctx->mg_counts); dev_free(ctx->mg_mod_rows); dev_free(ctx->mg_next_slot); dev_free(ctx->mg_next_val);
   dev_free(ctx->mg_splits); dev_free(ctx->mg_surv);

@@ -138,6 +138,8 @@ struct klsh_ctx {
   HostBuf h_cnt, h_head;               // export staging (pinned host)
   DevBuf st_group, st_left, st_right, st_counts, st_label, st_ids, st_slot_row;  // mode E statistics (stats.cu)
   DevBuf st_rec, st_lab, st_out_a, st_out_b, st_blk;
+  DevBuf rd_table, rd_seq, rd_offs, rd_rec, rd_votes;  // read extraction votes (reads.cu): k-mer hash set, staged reads
+  uint64_t rd_cap = 0, rd_n = 0;
   DevBuf eps_counter; // rows whose key needed the exact re-evaluation of at least one plane (cumulative)
   MgComm* comm = nullptr;  // NCCL communicator + exchange buffers (klsh_mg_init)
   MgLog mg;           // multi-GPU update logs (null pointers unless a sharded pass is running)

@@ -955,3 +955,89 @@ void klo_select_kmers(const uint8_t* records, uint64_t n_kmers, int record_bytes
   *n_a = ca;
   *n_b = cb;
 }
+
+
+/* ------------------------------------------------------------------------------------------
+ * Read extraction votes.
+ * Reference: IOFQ::CheckRead (io/ioFastQ.cc:5-75) slides a Kmer over every read of at least k+10 bases
+ * (Kmer(const char*) kmer/Kmer.cc:131-150, forwardBase :213-230), takes the canonical form
+ * `rep = (km < tw) ? km : tw` with tw = km.twin() (:160-185) and operator< = memcmp over the MAX_K/4 = 8
+ * bytes (:98-100), counts the reps found in the unordered_set g_kmer, and marks the read when
+ * kmer_count / (len - k + 1) > kmer_vote in float.  Byte layout as the reference: base i sits in byte i/4 at
+ * bit 2*(i%4); characters other than A, C, G, T leave the bits at 0 (= A) in both set_kmer and forwardBase.
+ * ---------------------------------------------------------------------------------------- */
+enum { KLO_KB = 8 }; /* Kmer::MAX_K / 4 with MAX_KMER_SIZE 32 (kmer/Kmer.h:4-5, :68) */
+
+static unsigned klo_base_code(char ch) {
+  switch (ch) {
+    case 'C': return 1u;
+    case 'G': return 2u;
+    case 'T': return 3u;
+    default: return 0u; /* 'A' and everything else */
+  }
+}
+
+void klo_kmer_from_string(const char* s, int k, uint8_t* out) { /* kmer/Kmer.cc:131-150 */
+  memset(out, 0, KLO_KB);
+  for (int i = 0; i < k; ++i) out[i / 4] |= (uint8_t)(klo_base_code(s[i]) << (2 * (i % 4)));
+}
+
+static void klo_kmer_forward(uint8_t* km, int k, char b) { /* kmer/Kmer.cc:213-230 */
+  const int k_bytes = (k + 3) / 4;
+  const unsigned k_modmask = (1u << (2 * ((k % 4) ? k % 4 : 4))) - 1u;
+  for (int i = 0; i < k_bytes - 1; ++i) { /* shiftRight(2), :330-341 */
+    km[i] >>= 2;
+    km[i] |= (uint8_t)(km[i + 1] << 6);
+  }
+  km[k_bytes - 1] >>= 2;
+  km[k_bytes - 1] &= (uint8_t)k_modmask;
+  km[k_bytes - 1] |= (uint8_t)(klo_base_code(b) << (2 * ((k + 3) % 4)));
+}
+
+static void klo_kmer_twin(const uint8_t* km, int k, uint8_t* tw) {
+  /* kmer/Kmer.cc:160-185 computes, by complementing, shifting and swapping bytes, the reverse complement in the
+   * same layout: base i of the twin is 3 - base (k-1-i); bytes from k_bytes on are copied (zero). */
+  const int k_bytes = (k + 3) / 4;
+  memcpy(tw, km, KLO_KB);
+  memset(tw, 0, (size_t)k_bytes);
+  for (int i = 0; i < k; ++i) {
+    const int j = k - 1 - i;
+    const unsigned b = 3u - ((km[j / 4] >> (2 * (j % 4))) & 3u);
+    tw[i / 4] |= (uint8_t)(b << (2 * (i % 4)));
+  }
+}
+
+void klo_kmer_rep(const uint8_t* km, int k, uint8_t* out) {
+  uint8_t tw[KLO_KB];
+  klo_kmer_twin(km, k, tw);
+  memcpy(out, memcmp(km, tw, KLO_KB) < 0 ? km : tw, KLO_KB);
+}
+
+static int klo_rec_cmp(const void* a, const void* b) { return memcmp(a, b, KLO_KB); }
+
+void klo_check_reads(const uint8_t* kmers, uint64_t n_kmers, int k, const char* seq, const uint64_t* seq_offsets,
+                     uint64_t n_reads, float kmer_vote, uint8_t* record, uint32_t* votes) {
+  uint8_t* set = (uint8_t*)malloc((size_t)(n_kmers ? n_kmers : 1) * KLO_KB);
+  memcpy(set, kmers, (size_t)n_kmers * KLO_KB);
+  qsort(set, (size_t)n_kmers, KLO_KB, klo_rec_cmp); /* membership only: the reference's set is unordered */
+  for (uint64_t r = 0; r < n_reads; ++r) {
+    const char* s = seq + seq_offsets[r];
+    const uint64_t len = seq_offsets[r + 1] - seq_offsets[r];
+    record[r] = 0;
+    if (votes) votes[r] = 0;
+    if (len == 0 || *s == '\0') continue;      /* "abnormal read entry skipped", io/ioFastQ.cc:21-25 */
+    if (len < (uint64_t)k + 10) continue;      /* :26 */
+    uint8_t km[KLO_KB], rep[KLO_KB];
+    klo_kmer_from_string(s, k, km);
+    float kmer_count = 0;
+    for (uint64_t j = 0; j <= len - (uint64_t)k; ++j) {
+      if (j > 0) klo_kmer_forward(km, k, s[j + (uint64_t)k - 1]);
+      klo_kmer_rep(km, k, rep);
+      if (n_kmers && bsearch(rep, set, (size_t)n_kmers, KLO_KB, klo_rec_cmp)) kmer_count++;
+    }
+    const float tmp_ratio = kmer_count / (float)(len - (uint64_t)k + 1); /* float / size_t, :57 */
+    if (tmp_ratio > kmer_vote) record[r] = 1;
+    if (votes) votes[r] = (uint32_t)kmer_count;
+  }
+  free(set);
+}

@@ -88,6 +88,19 @@ void klo_differential_ids(const uint8_t* group, const uint64_t* id_offsets, cons
 void klo_select_kmers(const uint8_t* records, uint64_t n_kmers, int record_bytes, const uint8_t* id_label,
                       uint8_t* out_a, uint64_t* n_a, uint8_t* out_b, uint64_t* n_b);
 
+/* ---- read extraction votes (io/ioFastQ.cc:5-75, kmer/Kmer.cc) ---- */
+/* Kmer(const char*) (kmer/Kmer.cc:131-150): the first k characters packed 2 bits per base, base i in byte i/4 at
+ * bit 2*(i%4), A=0 C=1 G=2 T=3, any other character 0; out is one 8-byte record (Kmer::MAX_K/4, zero padded). */
+void klo_kmer_from_string(const char* s, int k, uint8_t* out /* [8] */);
+/* Kmer::twin() (kmer/Kmer.cc:160-185) followed by the `rep = (km < tw) ? km : tw` of the callers (memcmp order). */
+void klo_kmer_rep(const uint8_t* km /* [8] */, int k, uint8_t* out /* [8] */);
+/* IOFQ::CheckRead (io/ioFastQ.cc:5-75) over reads given as one character array and n_reads+1 offsets:
+ * record[r] = 1 iff the read has at least k+10 characters, does not start with a NUL, and
+ * float(k-mers whose canonical form is in the set) / float(len-k+1) > kmer_vote.  kmers: n_kmers 8-byte records
+ * (any order, the set g_kmer).  votes (optional): the count per read (0 for skipped reads). */
+void klo_check_reads(const uint8_t* kmers, uint64_t n_kmers, int k, const char* seq, const uint64_t* seq_offsets,
+                     uint64_t n_reads, float kmer_vote, uint8_t* record, uint32_t* votes);
+
 #ifdef __cplusplus
 }
 #endif

@@ -19,6 +19,8 @@
 //   IOMat::ReadClusterAll       io/ioMatrix.cc:48-119
 //   AB::WRS                     function/funcAB.cc:73-109   (mode E statistics)
 //   alglib::studentttest2       utils/alglib-3.15.0/src/statistics.cpp:2277
+//   IOFQ::CheckRead             io/ioFastQ.cc:5-75          (read extraction votes)
+//   Kmer(const char*), twin(), operator<, writeBytes   kmer/Kmer.cc
 //
 // Determinism: load with OMP_THREAD_LIMIT=1 in the environment and pass threads=1
 // (SURVEY.md D7, D9).
@@ -34,6 +36,8 @@
 #include "function/funcAB.h"
 #include "utils/alglib-3.15.0/src/statistics.h"
 #include <unordered_set>
+#include <cstdio>
+#include "io/ioFastQ.h"
 
 namespace {
 
@@ -182,6 +186,56 @@ void ref_wrs(const float* values, const uint64_t* id_offsets, const uint64_t* id
     else if (g2.find(i) != g2.end()) id_label[i] = 2;
   }
   for (size_t r = 0; r < rows.size(); ++r) delete rows[r];
+}
+
+// Kmer::set_k may be called once per process (kmer/Kmer.cc:343-351): the first k wins, another k is refused.
+int ref_set_k(int k) {
+  if (Kmer::k == 0) Kmer::set_k((unsigned)k);
+  return (int)Kmer::k == k ? 0 : -1;
+}
+
+static void kmer_bytes(const Kmer& km, uint8_t* out) {  // the 8 bytes writeBytes emits (kmer/Kmer.cc:309-313)
+  char* buf = nullptr;
+  size_t len = 0;
+  FILE* f = open_memstream(&buf, &len);
+  km.writeBytes(f);
+  fclose(f);
+  std::memcpy(out, buf, Kmer::MAX_K / 4);
+  free(buf);
+}
+
+// rep = (km < tw) ? km : tw of the first k characters of s, as the record kmer_set.hex holds
+int ref_kmer_rep(const char* s, int k, uint8_t* km_out, uint8_t* rep_out) {
+  if (ref_set_k(k) != 0) return -1;
+  Kmer km(s);
+  Kmer tw = km.twin();
+  Kmer rep = (km < tw) ? km : tw;
+  kmer_bytes(km, km_out);
+  kmer_bytes(rep, rep_out);
+  return 0;
+}
+
+// IOFQ::CheckRead with one thread (tid 0 of 1) on reads given as one character array + offsets
+int ref_check_reads(const uint8_t* kmers, uint64_t n_kmers, int k, const char* seq, const uint64_t* offs, uint64_t n_reads,
+                    float kmer_vote, uint8_t* record) {
+  if (ref_set_k(k) != 0) return -1;
+  uset_t set;
+  for (uint64_t i = 0; i < n_kmers; ++i) set.insert(Kmer(const_cast<uint8_t*>(kmers + i * (Kmer::MAX_K / 4))));
+  std::vector<ReadEntry> reads(n_reads);
+  for (uint64_t r = 0; r < n_reads; ++r) {
+    const uint64_t len = offs[r + 1] - offs[r];
+    if (len >= sizeof(reads[r].s)) return -2;
+    std::memcpy(reads[r].s, seq + offs[r], len);
+    reads[r].s[len] = '\0';
+    reads[r].len = len;
+    std::snprintf(reads[r].name, sizeof(reads[r].name), "r%llu", (unsigned long long)r);
+    reads[r].name_len = std::strlen(reads[r].name);
+    reads[r].qual[0] = '\0';
+  }
+  std::vector<int> rec(n_reads, 0);
+  Utility::IOFQ::CheckRead(&set, reads, rec, 1, 0, kmer_vote);
+  for (uint64_t r = 0; r < n_reads; ++r) record[r] = (uint8_t)rec[r];
+  return 0;
 }
 
 }  // extern "C"

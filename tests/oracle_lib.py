@@ -101,6 +101,9 @@ class Oracle:
         L.klo_wrs_rows.argtypes = [f32p, u64p, u64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, u8p, f64p, f64p]
         L.klo_differential_ids.argtypes = [u8p, u64p, u64p, u64, u64, u8p]
         L.klo_select_kmers.argtypes = [u8p, u64, C.c_int, u8p, u8p, u64p, u8p, u64p]
+        L.klo_kmer_from_string.argtypes = [C.c_char_p, C.c_int, u8p]
+        L.klo_kmer_rep.argtypes = [u8p, C.c_int, u8p]
+        L.klo_check_reads.argtypes = [u8p, u64, C.c_int, C.c_char_p, u64p, u64, C.c_float, u8p, u32p]
         L.klo_mode_c.restype = C.c_int
         L.klo_mode_c.argtypes = [C.c_char_p, C.c_char_p, C.c_int, C.c_float, C.c_int, C.c_char_p, C.c_char_p,
                                  u64, i64, u64, C.POINTER(IterStats)]
@@ -190,6 +193,26 @@ class Oracle:
         u8p = C.POINTER(C.c_uint8)
         self.L.klo_select_kmers(_p(records, u8p), n, rb, _p(id_label, u8p), _p(a, u8p), C.byref(na), _p(b, u8p), C.byref(nb))
         return a[: na.value].copy(), b[: nb.value].copy()
+
+    # ---- read extraction votes
+    def kmer_rep(self, s: bytes, k: int):
+        """(Kmer(s) bytes, canonical rep bytes), 8 bytes each."""
+        km = np.zeros(8, dtype=np.uint8)
+        rep = np.zeros(8, dtype=np.uint8)
+        u8p = C.POINTER(C.c_uint8)
+        self.L.klo_kmer_from_string(s, k, _p(km, u8p))
+        self.L.klo_kmer_rep(_p(km, u8p), k, _p(rep, u8p))
+        return km, rep
+
+    def check_reads(self, kmers, k, seq: bytes, offsets, kmer_vote):
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint8).reshape(-1, 8)
+        offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = offs.shape[0] - 1
+        rec = np.zeros(max(n, 1), dtype=np.uint8)
+        votes = np.zeros(max(n, 1), dtype=np.uint32)
+        self.L.klo_check_reads(_p(kmers, C.POINTER(C.c_uint8)), kmers.shape[0], k, seq, _p(offs, u64p), n, kmer_vote,
+                               _p(rec, C.POINTER(C.c_uint8)), _p(votes, u32p))
+        return rec[:n], votes[:n]
 
     # ---- row sets
     def rows(self, values, id_offsets=None, ids=None):
@@ -322,6 +345,27 @@ class RefLib:
         if hasattr(L, "ref_wrs"):
             L.ref_studentttest2.argtypes = [f64p, C.c_int, f64p, C.c_int, f64p, f64p, f64p]
             L.ref_wrs.argtypes = [f32p, u64p, u64p, u64, C.c_int, C.c_int, C.c_int, C.c_float, C.c_int, u64, u8p, u8p]
+
+    def kmer_rep(self, s: bytes, k: int):
+        """Kmer(s) and rep = min(km, twin) as 8-byte records; k is fixed by the first call in the process."""
+        self.L.ref_kmer_rep.argtypes = [C.c_char_p, C.c_int, C.POINTER(C.c_uint8), C.POINTER(C.c_uint8)]
+        km = np.zeros(8, dtype=np.uint8)
+        rep = np.zeros(8, dtype=np.uint8)
+        if self.L.ref_kmer_rep(s, k, _p(km, C.POINTER(C.c_uint8)), _p(rep, C.POINTER(C.c_uint8))) != 0:
+            raise RuntimeError("Kmer::k is already set to another value in this process")
+        return km, rep
+
+    def check_reads(self, kmers, k, seq: bytes, offsets, kmer_vote):
+        self.L.ref_check_reads.argtypes = [C.POINTER(C.c_uint8), u64, C.c_int, C.c_char_p, u64p, u64, C.c_float, C.POINTER(C.c_uint8)]
+        kmers = np.ascontiguousarray(kmers, dtype=np.uint8).reshape(-1, 8)
+        offs = np.ascontiguousarray(offsets, dtype=np.uint64)
+        n = offs.shape[0] - 1
+        rec = np.zeros(max(n, 1), dtype=np.uint8)
+        rc = self.L.ref_check_reads(_p(kmers, C.POINTER(C.c_uint8)), kmers.shape[0], k, seq, _p(offs, u64p), n, kmer_vote,
+                                    _p(rec, C.POINTER(C.c_uint8)))
+        if rc != 0:
+            raise RuntimeError("ref_check_reads rc=%d" % rc)
+        return rec[:n]
 
     def ttest2(self, x, y):
         x = np.ascontiguousarray(x, dtype=np.float64)
