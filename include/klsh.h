@@ -128,6 +128,11 @@ int klsh_get_rows(klsh_ctx* ctx, float* values, uint64_t* id_offsets, uint64_t* 
 /* = IOMat::SaveResult(rows, path+".clust", delfile, ignore_small) + IOMat::SaveBinary(rows, path,
  * delfile, ignore_small) (io/ioMatrix.cc:265-294, :322-351). */
 int klsh_save(klsh_ctx* ctx, const char* bin_path, int delfile, int64_t ignore_small);
+/* Member-list file format used by klsh_save and klsh_load_cluster_file from now on: 0 = the reference's text
+ * <F>.clust (default), 1 = binary <F>.clust.bin — per cluster a uint64 count followed by that many uint64 ids, host
+ * endianness, same cluster order as <F>.  No reference counterpart (opt-in): it spares the
+ * decimal formatting and parsing of the spill files' 10^8 ids per batch.  The centroid file <F> is the same either way. */
+int klsh_set_id_format(klsh_ctx* ctx, int format);
 
 /* ---- mode E statistics on the clusters -------------------------------------
  * = the loop of app/kmerLSH.cc:541-545 over the clustering result: AB::WRS (function/funcAB.cc:73-109) per

@@ -84,6 +84,7 @@ SYMBOLS = [
     ("klsh_row_count", C.c_int, [C.c_void_p, u64p, u64p]),
     ("klsh_get_rows", C.c_int, [C.c_void_p, f32p, u64p, u64p]),
     ("klsh_save", C.c_int, [C.c_void_p, C.c_char_p, C.c_int, i64]),
+    ("klsh_set_id_format", C.c_int, [C.c_void_p, C.c_int]),
     ("klsh_ttest", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, u8p, f64p, f64p, C.POINTER(TtestStats)]),
     ("klsh_differential_ids", C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_int, u64, u8p, C.POINTER(TtestStats)]),
     ("klsh_select_kmers", C.c_int, [C.c_void_p, u8p, u64, C.c_int, u8p, u8p, u64p, u8p, u64p]),
@@ -293,6 +294,10 @@ class Context:
 
     def save(self, path: str, delfile: bool = True, ignore_small: int = 0):
         self._ck(self.lib.klsh_save(self.h, path.encode(), int(delfile), ignore_small), "klsh_save")
+
+    def set_id_format(self, fmt: int):
+        """0: text <F>.clust (the reference's), 1: binary <F>.clust.bin — for save() and load_cluster_file()."""
+        self._ck(self.lib.klsh_set_id_format(self.h, fmt), "klsh_set_id_format")
 
     # ---- mode E statistics (reference app/kmerLSH.cc:541-585, function/funcAB.cc:73-109)
     def ttest(self, num_sample1: int, num_sample2: int, pvalue_thresh: float, size_thresh: int, tails: bool = True):

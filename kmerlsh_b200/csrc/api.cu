@@ -356,7 +356,7 @@ extern "C" int klsh_load_cluster_file(klsh_ctx* ctx, const char* bin_path, int D
   if (!ctx || !bin_path || D <= 0) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_load_cluster_file: bad argument");
   std::vector<float> values;
   std::vector<uint64_t> offs, ids;
-  int rc = io_read_cluster(bin_path, D, start_line, num_lines, values, offs, ids);
+  int rc = io_read_cluster(bin_path, D, start_line, num_lines, values, offs, ids, ctx->id_format);
   if (rc != KLSH_OK) return klsh_fail(ctx, rc, "cannot read %s(.clust)", bin_path);
   return klsh_set_rows(ctx, values.data(), offs.data(), ids.data(), offs.size() - 1, D);
 }
@@ -864,6 +864,12 @@ extern "C" int klsh_get_rows(klsh_ctx* ctx, float* values, uint64_t* id_offsets,
   return export_rows(ctx, values, id_offsets, ids);
 }
 
+extern "C" int klsh_set_id_format(klsh_ctx* ctx, int format) {
+  if (!ctx || (format != 0 && format != 1)) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_set_id_format: format must be 0 (text) or 1 (binary)");
+  ctx->id_format = format;
+  return KLSH_OK;
+}
+
 extern "C" int klsh_save(klsh_ctx* ctx, const char* bin_path, int delfile, int64_t ignore_small) {
   if (!ctx || !bin_path) return klsh_fail(ctx, KLSH_ERR_ARG, "klsh_save: bad argument");
   KCUDA(ctx, cudaSetDevice(ctx->device));
@@ -874,7 +880,7 @@ extern "C" int klsh_save(klsh_ctx* ctx, const char* bin_path, int delfile, int64
   std::vector<float> v(n * (uint64_t)ctx->D + 1);
   std::vector<uint64_t> idv(n_ids + 1);
   KTRY(export_rows(ctx, v.data(), offs.data(), idv.data()));
-  int rc = io_save(bin_path, delfile, ignore_small, v.data(), ctx->D, offs.data(), idv.data(), n);
+  int rc = io_save(bin_path, delfile, ignore_small, v.data(), ctx->D, offs.data(), idv.data(), n, ctx->id_format);
   if (rc != KLSH_OK) return klsh_fail(ctx, rc, "cannot write %s(.clust)", bin_path);
   return KLSH_OK;
 }

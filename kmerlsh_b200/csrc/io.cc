@@ -8,6 +8,11 @@
 // first; both are opened in append mode (the reference appends batch after batch into tmp/0.bin).
 // Reading back: row k of <F> <-> line k of <F>.clust, first token = member count
 // (IOMat::ReadCluster / ReadClusterAll, io/ioMatrix.cc:121-196, :48-119).
+//
+// Opt-in binary member lists (klsh_set_id_format(ctx, 1); no reference counterpart):
+//   <F>.clust.bin : per cluster uint64 count, then count uint64 ids, host endianness, same order as <F>.
+// Formatting and parsing decimal text is what the spill of 10^8 ids per batch costs; the binary file is read and
+// written with plain fread/fwrite.
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -16,11 +21,31 @@
 #include "klsh_internal.cuh"
 
 int io_save(const char* bin_path, int delfile, int64_t ignore_small, const float* values, int D,
-            const uint64_t* id_offsets, const uint64_t* ids, uint64_t n) {
-  std::string clust = std::string(bin_path) + ".clust";
+            const uint64_t* id_offsets, const uint64_t* ids, uint64_t n, int id_format) {
+  std::string clust = std::string(bin_path) + (id_format == 1 ? ".clust.bin" : ".clust");
   if (delfile) {
     std::remove(clust.c_str());
     std::remove(bin_path);
+  }
+  if (id_format == 1) {
+    FILE* fi = std::fopen(clust.c_str(), "ab");
+    FILE* fv = std::fopen(bin_path, "ab");
+    if (!fi || !fv) {
+      if (fi) std::fclose(fi);
+      if (fv) std::fclose(fv);
+      return KLSH_ERR_IO;
+    }
+    for (uint64_t r = 0; r < n; ++r) {
+      const uint64_t b = id_offsets[r], e = id_offsets[r + 1], cnt = e - b;
+      if ((int64_t)cnt <= ignore_small) continue;
+      std::fwrite(&cnt, sizeof cnt, 1, fi);
+      std::fwrite(ids + b, sizeof(uint64_t), (size_t)cnt, fi);
+      std::fwrite(values + r * (uint64_t)D, sizeof(float), (size_t)D, fv);
+    }
+    const int bad = std::ferror(fi) | std::ferror(fv);
+    std::fclose(fi);
+    std::fclose(fv);
+    return bad ? KLSH_ERR_IO : KLSH_OK;
   }
   FILE* ft = std::fopen(clust.c_str(), "a");
   FILE* fb = std::fopen(bin_path, "ab");
@@ -53,7 +78,7 @@ int io_save(const char* bin_path, int delfile, int64_t ignore_small, const float
 }
 
 int io_read_cluster(const char* bin_path, int D, uint64_t start_line, uint64_t num_lines,
-                    std::vector<float>& values, std::vector<uint64_t>& id_offsets, std::vector<uint64_t>& ids) {
+                    std::vector<float>& values, std::vector<uint64_t>& id_offsets, std::vector<uint64_t>& ids, int id_format) {
   FILE* fb = std::fopen(bin_path, "rb");
   if (!fb) return KLSH_ERR_IO;
   std::fseek(fb, 0, SEEK_END);
@@ -70,11 +95,31 @@ int io_read_cluster(const char* bin_path, int D, uint64_t start_line, uint64_t n
   std::fclose(fb);
   if (got != num_lines) return KLSH_ERR_IO;
 
+  id_offsets.assign(1, 0);
+  ids.clear();
+  if (id_format == 1) {
+    const std::string cb = std::string(bin_path) + ".clust.bin";
+    FILE* fi = std::fopen(cb.c_str(), "rb");
+    if (!fi) return KLSH_ERR_IO;
+    uint64_t rec = 0, loc = 0, cnt = 0;
+    bool ok = true;
+    while (loc < num_lines && std::fread(&cnt, sizeof cnt, 1, fi) == 1) {
+      if (rec++ < start_line) {
+        if (std::fseek(fi, (long)(cnt * sizeof(uint64_t)), SEEK_CUR) != 0) { ok = false; break; }
+        continue;
+      }
+      const size_t at = ids.size();
+      ids.resize(at + cnt);
+      if (cnt && std::fread(ids.data() + at, sizeof(uint64_t), (size_t)cnt, fi) != cnt) { ok = false; break; }
+      id_offsets.push_back(ids.size());
+      ++loc;
+    }
+    std::fclose(fi);
+    return (ok && loc == num_lines) ? KLSH_OK : KLSH_ERR_IO;
+  }
   std::string clust = std::string(bin_path) + ".clust";
   FILE* ft = std::fopen(clust.c_str(), "r");
   if (!ft) return KLSH_ERR_IO;
-  id_offsets.assign(1, 0);
-  ids.clear();
   char* line = nullptr;
   size_t cap = 0;
   uint64_t lineno = 0, loc = 0;

@@ -113,6 +113,7 @@ struct klsh_ctx {
   bool stash_implicit = true;
   int stash_D = 0;
   std::vector<uint64_t> stash_ids;  // explicit member ids of the stash (when not implicit)
+  int id_format = 0;  // klsh_set_id_format: 0 text <F>.clust (the reference's), 1 binary <F>.clust.bin
   bool has_snap = false;
   uint64_t snap_born = 0, snap_slots = 0;
   // id payload of member slots: explicit (ids.size()==n_slots) or implicit id = id_base + slot
@@ -210,9 +211,9 @@ void planes_seek(PlaneSource* p, uint64_t seed, uint64_t drawn);
 
 // ---- io.cc -------------------------------------------------------------------------------------
 int io_save(const char* bin_path, int delfile, int64_t ignore_small, const float* values, int D,
-            const uint64_t* id_offsets, const uint64_t* ids, uint64_t n);
+            const uint64_t* id_offsets, const uint64_t* ids, uint64_t n, int id_format = 0);
 int io_read_cluster(const char* bin_path, int D, uint64_t start_line, uint64_t num_lines,
-                    std::vector<float>& values, std::vector<uint64_t>& id_offsets, std::vector<uint64_t>& ids);
+                    std::vector<float>& values, std::vector<uint64_t>& id_offsets, std::vector<uint64_t>& ids, int id_format = 0);
 
 // ---- kernels.cu (launch wrappers; all enqueue on ctx->stream) ---------------------------------
 int launch_transform(klsh_ctx* ctx, const uint16_t* d_counts, const float* d_vk, uint64_t batch,

@@ -11,6 +11,7 @@
 // iterations instead of being re-read from the spill files (the rows, their order and their member
 // lists are the same either way, so the results are too — SURVEY.md section 8f item 3); the spill
 // files are still written for compatibility.  --reload-tmp forces the reference's file round trip,
+// --binary-tmp-ids writes the spill files' member lists as <n>.bin.clust.bin (uint64 count + ids) instead of text.
 // --no-tmp-files skips writing the spill when it is not needed.  --resident does the same for an input of
 // SEVERAL batches on one GPU: every batch's survivors are appended to a device-resident stash.
 // --gpus=N runs the batches on N GPUs (see below), --stats-json=FILE writes one record per LSH iteration.
@@ -51,6 +52,7 @@ struct Params {
   int gpus = 1;
   uint64_t batch = 100000000ull;
   bool reload_tmp = false, no_tmp_files = false, resident = false;
+  bool binary_tmp_ids = false;  // --binary-tmp-ids: member lists of the spill files as <n>.bin.clust.bin (klsh_set_id_format)
   std::string stats_json;
 };
 
@@ -186,6 +188,7 @@ int main(int argc, char** argv) {
                                          {"gpus", required_argument, 0, 1005},
                                          {"stats-json", required_argument, 0, 1006},
                                          {"resident", no_argument, 0, 1007},
+                                         {"binary-tmp-ids", no_argument, 0, 1008},
                                          {0, 0, 0, 0}};
   for (;;) {
     int idx = 0;
@@ -210,6 +213,7 @@ int main(int argc, char** argv) {
       case 1005: p.gpus = atoi(optarg); break;
       case 1006: p.stats_json = optarg; break;
       case 1007: p.resident = true; break;
+      case 1008: p.binary_tmp_ids = true; break;
       default: break;  // -H -X -C -K -S -P -V: accepted, meaningless for mode C
     }
   }
@@ -288,6 +292,7 @@ int main(int argc, char** argv) {
     }
     klsh_set_plane_source(w.ctx, plane_tramp, &w);
     klsh_set_draws_done_callback(w.ctx, done_tramp, &w);
+    if (p.binary_tmp_ids) klsh_set_id_format(w.ctx, 1);  // spill files only; the result below is written as text
   }
   if (p.gpus > 1)
     std::cout << "kmerLSH_b200: " << p.gpus << " workers on " << physical << " GPU(s); phase-1 batches round-robin, one hyperplane stream"
@@ -429,7 +434,7 @@ int main(int argc, char** argv) {
     }
     if (std::remove(read_tmp.c_str()) != 0) perror("The temporary file deletion failed");
     else std::cout << read_tmp << "file are removed" << std::endl;
-    const std::string rc = read_tmp + ".clust";
+    const std::string rc = read_tmp + (p.binary_tmp_ids ? ".clust.bin" : ".clust");
     if (std::remove(rc.c_str()) != 0) perror("The temporary file deletion failed");
     else std::cout << rc << "file are removed" << std::endl;
   }
@@ -482,6 +487,7 @@ int main(int argc, char** argv) {
 
   // ---- reference app/kmerLSH.cc:498-499 ---------------------------------------------------------
   if (p.verbose) std::cout << "Saving cluster results starts: " << std::endl;
+  klsh_set_id_format(ctx, 0);  // <F>.clust is always the reference's text format
   if (klsh_save(ctx, p.clust_file_name.c_str(), 1, 5) != KLSH_OK) {
     std::cerr << "klsh_save failed: " << klsh_last_error(ctx) << std::endl;
     return 1;

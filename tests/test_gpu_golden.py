@@ -154,14 +154,15 @@ def test_reference_program_with_cluster_shim(tag, tmp_path):
     assert md5(out + ".clust") == m["clust_md5"]
 
 
-@pytest.mark.parametrize("extra", [[], ["--resident"], ["--resident", "--no-tmp-files"]])
+@pytest.mark.parametrize("extra", [[], ["--resident"], ["--resident", "--no-tmp-files"], ["--binary-tmp-ids"]])
 def test_mode_c_cli_two_batches(oracle, tmp_path, extra):
     """--batch smaller than the input: independent phase-1 batches appended to tmp/0.bin, the
     re-batch loop (similarity -= 0.001, 5 iterations per batch) while survivors exceed the batch
     size, then the -I iterations — byte-identical to the oracle's mode C with the same batch size
     (the reference hard-codes 100 M rows per batch, app/kmerLSH.cc:285).  With --resident the survivors
     of every batch are appended to a device-resident stash (klsh_stash_rows) instead of being re-read from
-    the spill files; with --no-tmp-files the spill is only written if a re-batch round needs it."""
+    the spill files; with --no-tmp-files the spill is only written if a re-batch round needs it; with
+    --binary-tmp-ids the spill files' member lists are binary (<n>.bin.clust.bin) and the result is the same text."""
     work = str(tmp_path)
     synth.write_mode_c_inputs(work, 30000, 3, 3, 99)
     out = os.path.join(work, "oracle_result.txt")
@@ -173,6 +174,44 @@ def test_mode_c_cli_two_batches(oracle, tmp_path, extra):
     res = os.path.join(work, "clustering_result.txt")
     assert md5(res) == md5(out)
     assert md5(res + ".clust") == md5(out + ".clust")
+    if "--binary-tmp-ids" in extra:
+        spills = os.listdir(os.path.join(work, "tmp"))
+        assert any(f.endswith(".clust.bin") for f in spills) and not any(f.endswith(".clust") for f in spills), spills
+
+
+def test_binary_member_lists_round_trip(oracle, gpu, tmp_path):
+    """klsh_set_id_format(1): <F>.clust.bin holds per cluster a uint64 count and the ids; saving (with append and
+    with ignore_small) and reading back (whole file and a window of lines) give the rows the text format gives."""
+    from helpers import assert_rows_equal, synth_rows
+
+    _, _, values, _ = synth_rows(oracle, 5000, 4, 4, 12)
+    gpu.set_id_format(0)
+    gpu.set_rows(values)
+    gpu.set_seed(3)
+    gpu.cluster(0.85, 4, 100000)
+    want = gpu.get_rows()
+    t, b = str(tmp_path / "t.bin"), str(tmp_path / "b.bin")
+    gpu.save(t, True, 0)
+    gpu.save(t, False, 2)            # append: clusters of more than 2 members once more
+    try:
+        gpu.set_id_format(1)
+        gpu.save(b, True, 0)
+        gpu.save(b, False, 2)
+        assert md5(t) == md5(b)      # the centroid file does not depend on the id format
+        assert not os.path.exists(b + ".clust")
+        raw = np.fromfile(b + ".clust.bin", dtype=np.uint64)
+        assert raw[0] == want[1][1] - want[1][0] and np.array_equal(raw[1:1 + int(raw[0])], want[2][: int(raw[0])])
+        gpu.load_cluster_file(b, 8)
+        got_b = gpu.get_rows()
+        gpu.load_cluster_file(b, 8, 7, 40)
+        win_b = gpu.get_rows()
+    finally:
+        gpu.set_id_format(0)
+    gpu.load_cluster_file(t, 8)
+    assert_rows_equal(got_b, gpu.get_rows(), "binary member lists, whole file")
+    gpu.load_cluster_file(t, 8, 7, 40)
+    assert_rows_equal(win_b, gpu.get_rows(), "binary member lists, lines 7..46")
+    assert len(got_b[1]) - 1 > len(want[1]) - 1
 
 
 def test_mode_c_cli_resident_batches_without_rebatch(oracle, tmp_path):
