@@ -11,6 +11,7 @@
 
 #include "exact_math.cuh"
 #include "klsh_internal.cuh"
+#include "sign_umma.cuh"
 
 namespace {
 
@@ -141,18 +142,19 @@ __global__ void k_fill_i32(int32_t* p, uint64_t n, int32_t v) {
 // Signing (reference LSH::random_projection, hash/lshash.cc:44-59):
 //   bit_h = (sum_h >= 0), sum_h = fl(fl(... fl(0 + fl(w_h0*x_0)) ...) + fl(w_h,D-1 * x_D-1))
 //   key = ((bit_0*2 + bit_1)*2 + ...) — plane 0 is the most significant bit.
-// D <= 64: k_sign_tc (tensor cores, below).  D > 64: k_sign_tc_wide (the same product walked in 64-column
-// chunks).  Both decide every bit with the reference's exact mul-then-add chain whenever the fast sum is
-// inside its error margin, and count those rows.
+// D <= 64: sign_umma::k_sign_umma (tcgen05.mma with the row operand and the sums in tensor memory, sign_umma.cuh).
+// D > 64: k_sign_tc_wide below (mma.sync, the same product walked in 64-column chunks).  Both decide every bit with
+// the reference's exact mul-then-add chain whenever the fast sum is inside its error margin, and count those rows.
 // ================================================================================================
 constexpr int kSignWarps = 4;
 
-// Tensor-core signing (rows of at most 64 floats).  ncu on the FMA kernel this replaced, at C2 scale: issue
+// Tensor-core signing.  ncu on the FMA kernel this replaced, at C2 scale: issue
 // slots 59 % busy at 44 % occupancy, 2.7 k warp instructions per 32 rows, 1.08 TB/s — contraction
 // bound, H*D fused multiply-adds per row against 4*D bytes (profiles/).  The projection is a
 // [rows x D] x [D x H] product, so it goes to the tensor cores as 3xTF32: every operand is split
 // into hi = tf32(v) and lo = tf32(v - hi) and the sum hi*hi + hi*lo + lo*hi is accumulated in fp32
-// (mma.sync.m16n8k8).  Error budget in units of 2^-24 * sum|w_i x_i| (<= 2^-24 * |w| * |x|):
+// (tcgen05.mma kind::tf32 / mma.sync.m16n8k8, K = 8 per instruction either way).  Error budget in units of
+// 2^-24 * sum|w_i x_i| (<= 2^-24 * |w| * |x|):
 //   28   the dropped lo*lo products and the split residues: rows are split by truncation (residue < 2^-20 |x|),
 //        planes by rounding (2^-22 |w|): (2^-21 + 2^-20 + 2^-22) per term;
 //   10   per mma for the tensor core's truncating fp32 accumulation (alignment of the 8 products to the
@@ -164,9 +166,7 @@ constexpr int kSignWarps = 4;
 // So   eps = (D + 34 + 30*ceil(D/8)) * 2^-24 * |x|   (D = 32: 186 * 2^-24 = 1.1e-5) on the sum with the unit plane
 // guarantees that a sum outside it has the sign of the reference's mul-then-add chain; a sum inside it
 // is re-evaluated with the reference's exact arithmetic (and the row counted), so every key bit is
-// the reference's.  A warp owns 32 rows: cp.async gathers them into a double-buffered shared tile
-// (the next tile is in flight while this one is multiplied), planes sit in shared memory already
-// split and in B-fragment order (one 16-byte load per k-step and 8 planes).
+// the reference's.
 __device__ __forceinline__ uint32_t tf32_rna(float x) {
   uint32_t r;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
@@ -188,211 +188,6 @@ __device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], 
 __device__ __forceinline__ void sign_cp_async16(void* smem_dst, const void* gsrc) {
   const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
-}
-
-template <int KS8>  // 8-wide k steps: 4 for rows of up to 32 floats, 8 for up to 64
-__global__ void __launch_bounds__(kSignWarps * 32)
-k_sign_tc(const float* __restrict__ vals, int D, int ld, const uint32_t* __restrict__ rows, uint64_t n,
-          const float* __restrict__ planes, int H, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ rows_out,
-          unsigned long long* eps_rows, uint32_t key_or) {
-  constexpr int KW = KS8 * 8;     // padded row width
-  constexpr int TS = KW + 4;      // tile row stride: fragment loads and per-row float4 walks are conflict-free
-  extern __shared__ __align__(16) float smem[];
-  float* pinv = smem;                                        // 1 / |w_h| per plane [32] (0: the plane is always decided exactly)
-  uint4* bfrag = reinterpret_cast<uint4*>(pinv + 32);        // [KS8][4][32] {hi b0, hi b1, lo b0, lo b1} of the UNIT planes
-  float* tiles = reinterpret_cast<float*>(bfrag + KS8 * 4 * 32);  // [kSignWarps][2][32][TS]
-  for (int i = threadIdx.x; i < kSignWarps * 2 * 32 * TS; i += blockDim.x) tiles[i] = 0.f;  // padding columns stay zero
-  for (int h = threadIdx.x; h < 32; h += blockDim.x) {
-    float m = 0.f;
-    if (h < H)
-      for (int i = 0; i < D; ++i) {
-        const float w = __ldg(planes + h * ld + i);
-        m = __fmaf_rn(w, w, m);
-      }
-    const float nrm = sqrtf(m);
-    pinv[h] = (nrm > 1e-30f && nrm < 1e30f) ? 1.f / nrm : 0.f;  // also false for NaN
-  }
-  __syncthreads();
-  // The fast path multiplies with the planes scaled to unit length (a positive factor per plane: the sign of the
-  // sum is the same), so that ONE margin per row, c * |x|, covers all planes.  Planes past H in the last tile of
-  // eight repeat plane 0: their sums can never be the only ones inside the margin, and their bits are masked out.
-  for (int i = threadIdx.x; i < KS8 * 4 * 32; i += blockDim.x) {
-    const int l = i & 31, nt = (i >> 5) & 3, ks = i >> 7;
-    int h = nt * 8 + (l >> 2);
-    if (h >= H) h = 0;
-    const int k0 = ks * 8 + (l & 3);
-    const float inv = H > 0 ? pinv[h] : 0.f;
-    float w0 = (H > 0 && k0 < ld) ? __ldg(planes + h * ld + k0) : 0.f;
-    float w1 = (H > 0 && k0 + 4 < ld) ? __ldg(planes + h * ld + k0 + 4) : 0.f;
-    w0 = inv != 0.f ? w0 * inv : 0.f;
-    w1 = inv != 0.f ? w1 * inv : 0.f;
-    const uint32_t h0 = tf32_rna(w0), h1 = tf32_rna(w1);
-    bfrag[i] = make_uint4(h0, h1, tf32_rna(w0 - __uint_as_float(h0)), tf32_rna(w1 - __uint_as_float(h1)));
-  }
-  __syncthreads();
-  const uint32_t lane = lane_id(), warp = threadIdx.x >> 5, g = lane >> 2, tg = lane & 3;
-  float* wt = tiles + (size_t)warp * 2 * 32 * TS;
-  const uint64_t nwarps_total = (uint64_t)gridDim.x * kSignWarps;
-  const int vec_per_row = ld >> 2;
-  const int rr_lane = (int)lane / vec_per_row, cc_lane = (int)lane - rr_lane * vec_per_row;
-  const int rr_step = 32 / vec_per_row, cc_step = 32 - rr_step * vec_per_row;
-  uint32_t my_eps = 0;
-  const float kc = ((float)D + 34.f + 30.f * (float)((D + 7) / 8)) * 5.9604645e-8f;
-  // which of this lane's 8 planes (nt*8 + 2*tg + e) exist
-  uint32_t vmask = 0u;
-#pragma unroll
-  for (int q = 0; q < 8; ++q) {
-    const int h = (q >> 1) * 8 + 2 * (int)tg + (q & 1);
-    if (h < H) vmask |= 1u << q;
-  }
-  // gather the 32 rows of the tile starting at t0 into buffer b; returns this lane's row index
-  auto issue = [&](uint64_t t0, int b) -> uint32_t {
-    uint32_t r = 0u;
-    if (t0 < n) {
-      const uint64_t t = t0 + lane;
-      r = (t < n) ? (rows ? rows[t] : (uint32_t)t) : 0u;
-      const int nrow = (int)min((uint64_t)32, n - t0);
-      const int total = nrow * vec_per_row;
-      float* tile = wt + (size_t)b * 32 * TS;
-      int rr = rr_lane, cc = cc_lane;  // (row, 16-byte chunk) of element v = v0 + lane, advanced without dividing
-      for (int v0 = 0; v0 < total; v0 += 32) {
-        const uint32_t ri = __shfl_sync(0xffffffffu, r, min(rr, 31));
-        if (v0 + (int)lane < total) sign_cp_async16(tile + rr * TS + cc * 4, vals + (uint64_t)ri * ld + cc * 4);
-        rr += rr_step;
-        cc += cc_step;
-        if (cc >= vec_per_row) {
-          cc -= vec_per_row;
-          ++rr;
-        }
-      }
-    }
-    asm volatile("cp.async.commit_group;" ::: "memory");
-    return r;
-  };
-  uint64_t t0 = ((uint64_t)blockIdx.x * kSignWarps + warp) * 32;
-  int buf = 0;
-  uint32_t r_cur = issue(t0, 0);
-  for (; t0 < n; t0 += nwarps_total * 32, buf ^= 1) {
-    const uint32_t r_next = issue(t0 + nwarps_total * 32, buf ^ 1);
-    asm volatile("cp.async.wait_group 1;" ::: "memory");
-    __syncwarp();
-    const float* tile = wt + (size_t)buf * 32 * TS;
-    // |x| of this lane's own row
-    float xx = 0.f;
-    {
-      const float4* x4 = reinterpret_cast<const float4*>(tile + lane * TS);
-#pragma unroll
-      for (int q = 0; q < KS8 * 2; ++q) {
-        const float4 x = x4[q];
-        xx = __fmaf_rn(x.x, x.x, xx);
-        xx = __fmaf_rn(x.y, x.y, xx);
-        xx = __fmaf_rn(x.z, x.z, xx);
-        xx = __fmaf_rn(x.w, x.w, xx);
-      }
-    }
-    const float xn = sqrtf(xx);
-    float c[2][4][4];
-#pragma unroll
-    for (int m = 0; m < 2; ++m)
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-#pragma unroll
-        for (int e = 0; e < 4; ++e) c[m][nt][e] = 0.f;
-#pragma unroll
-    for (int ks = 0; ks < KS8; ++ks) {
-      uint32_t ahi[2][4], alo[2][4];
-#pragma unroll
-      for (int m = 0; m < 2; ++m) {
-        const float* p0 = tile + (m * 16 + g) * TS + ks * 8 + tg;
-        const float a0 = p0[0], a1 = p0[8 * TS], a2 = p0[4], a3 = p0[8 * TS + 4];
-        tf32_split(a0, ahi[m][0], alo[m][0]);
-        tf32_split(a1, ahi[m][1], alo[m][1]);
-        tf32_split(a2, ahi[m][2], alo[m][2]);
-        tf32_split(a3, ahi[m][3], alo[m][3]);
-      }
-#pragma unroll
-      for (int nt = 0; nt < 4; ++nt)
-        if (nt * 8 < H) {  // warp-uniform
-          const uint4 b = bfrag[(ks * 4 + nt) * 32 + lane];
-#pragma unroll
-          for (int m = 0; m < 2; ++m) {
-            mma_tf32(c[m][nt], alo[m], b.x, b.y);
-            mma_tf32(c[m][nt], ahi[m], b.z, b.w);
-            mma_tf32(c[m][nt], ahi[m], b.x, b.y);
-          }
-        }
-    }
-    // c[m][nt][2*half + e]: row m*16 + half*8 + g, plane nt*8 + 2*tg + e.  Sign bits of the lane's 4 rows x 8
-    // planes; the smallest |sum| of a row against the row's margin decides whether anything needs a second look.
-    uint32_t part[4];
-    uint32_t slow = 0u;
-#pragma unroll
-    for (int m = 0; m < 2; ++m)
-#pragma unroll
-      for (int half = 0; half < 2; ++half) {
-        const int row = m * 16 + half * 8 + (int)g;
-        const float thr = kc * __shfl_sync(0xffffffffu, xn, row);
-        uint32_t bits = 0u;
-        float mn = 3.4e38f;
-#pragma unroll
-        for (int q = 0; q < 8; ++q) {
-          const float sum = c[m][q >> 1][2 * half + (q & 1)];
-          bits |= (sum >= 0.f ? 1u : 0u) << q;
-          if ((q >> 1) * 8 < H) mn = fminf(mn, fabsf(sum));  // warp-uniform: tiles of eight planes past H were not multiplied
-        }
-        if (!(mn > thr && thr <= 3.0e38f)) {  // rare; also taken for NaN or infinite |x|
-          uint32_t flag = 0u;
-#pragma unroll
-          for (int q = 0; q < 8; ++q) {
-            const float a = fabsf(c[m][q >> 1][2 * half + (q & 1)]);
-            flag |= ((a > thr && a <= 3.0e38f) ? 0u : 1u) << q;
-          }
-          flag &= vmask;
-          while (flag) {  // reference arithmetic: sum = fl(sum + fl(w_i * x_i)), i ascending (hash/lshash.cc:44-51)
-            const int q = __ffs(flag) - 1;
-            flag &= flag - 1;
-            const float* w = planes + ((q >> 1) * 8 + 2 * (int)tg + (q & 1)) * ld;
-            const float* x = tile + row * TS;
-            float sum = 0.f;
-            for (int j = 0; j < D; ++j) sum = __fadd_rn(sum, __fmul_rn(__ldg(w + j), x[j]));
-            bits = (bits & ~(1u << q)) | ((sum >= 0.f ? 1u : 0u) << q);
-            slow |= 1u << (m * 2 + half);
-          }
-        }
-        bits &= vmask;
-        // bit q = (nt, e) -> plane h = nt*8 + 2*tg + e -> key bit H-1-h (plane 0 is the most significant)
-        uint32_t byplane = 0u;
-#pragma unroll
-        for (int nt = 0; nt < 4; ++nt) byplane |= ((bits >> (2 * nt)) & 3u) << (nt * 8);
-        byplane <<= 2 * tg;  // bit h set <=> plane h non-negative
-        part[m * 2 + half] = H ? (__brev(byplane) >> (32 - H)) : 0u;
-      }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      part[q] |= __shfl_xor_sync(0xffffffffu, part[q], 1);
-      part[q] |= __shfl_xor_sync(0xffffffffu, part[q], 2);
-    }
-    slow |= __shfl_xor_sync(0xffffffffu, slow, 1);
-    slow |= __shfl_xor_sync(0xffffffffu, slow, 2);
-    {
-      // lane (g, tg) writes row slot tg of its group: rows g, g+8, g+16, g+24
-      const uint32_t key = tg == 0 ? part[0] : (tg == 1 ? part[1] : (tg == 2 ? part[2] : part[3]));
-      const uint64_t t = t0 + tg * 8 + g;
-      if (t < n) {
-        keys_out[t] = key | key_or;
-        my_eps += (slow >> tg) & 1u;
-      }
-      const uint64_t tl = t0 + lane;
-      if (tl < n) rows_out[tl] = r_cur;
-    }
-    r_cur = r_next;
-    __syncwarp();
-  }
-  asm volatile("cp.async.wait_all;" ::: "memory");
-  if (eps_rows) {
-    const uint32_t tot = __reduce_add_sync(0xffffffffu, my_eps);
-    if (lane == 0 && tot) atomicAdd(eps_rows, (unsigned long long)tot);
-  }
 }
 
 // Rows wider than 64 floats: the same 3xTF32 product, walked in chunks of 64 columns.  The accumulators
@@ -1306,17 +1101,17 @@ int launch_sign(klsh_ctx* ctx, const float* vals, int D, int ld, const uint32_t*
                 const float* d_planes, int H, uint32_t* keys_out, uint32_t* rows_out, uint32_t key_or) {
   if (!n) return KLSH_OK;
   KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long) * 4));
-  if (ld <= 64) {
-    const int ks8 = ld <= 32 ? 4 : 8, kw = ks8 * 8;
-    const size_t smem = sizeof(float) * 32 + 16 * (size_t)ks8 * 4 * 32 + sizeof(float) * (size_t)kSignWarps * 2 * 32 * (kw + 4);
-    auto fn = ld <= 32 ? k_sign_tc<4> : k_sign_tc<8>;
+  if (ld <= 64) {  // tcgen05 + tensor memory (sign_umma.cuh); H <= 32 by the ABI
+    if (H > 32) return klsh_fail(ctx, KLSH_ERR_ARG, "more than 32 hyperplanes (%d)", H);
+    auto fn = ld <= 32 ? sign_umma::k_sign_umma<32> : sign_umma::k_sign_umma<64>;
+    const size_t smem = ld <= 32 ? sign_umma::smem_bytes<32>() : sign_umma::smem_bytes<64>();
     KCUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    int per_sm = 1;
-    KCUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kSignWarps * 32, smem));
-    const uint64_t want = (n + kSignWarps * 32 - 1) / (kSignWarps * 32);
-    const uint32_t grid = (uint32_t)std::min<uint64_t>(want, (uint64_t)ctx->sm_count * std::max(per_sm, 1));
-    fn<<<grid, kSignWarps * 32, smem, ctx->stream>>>(vals, D, ld, rows, n, d_planes, H, keys_out, rows_out,
-                                                     ctx->eps_counter.as<unsigned long long>(), key_or);
+    // CTAs per SM by shared memory, registers and tensor-memory columns (the occupancy API reports 1 for this kernel)
+    const int per_sm = ld <= 32 ? sign_umma::ctas_per_sm<32>() : sign_umma::ctas_per_sm<64>();
+    const uint64_t ntiles = (n + 127) / 128;
+    const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * per_sm);
+    fn<<<grid, sign_umma::kThreads, smem, ctx->stream>>>(vals, D, ld, rows, n, d_planes, H, keys_out, rows_out,
+                                                         ctx->eps_counter.as<unsigned long long>(), key_or, nullptr);
     KLAUNCH(ctx);
     return KLSH_OK;
   }
