@@ -146,7 +146,6 @@ __global__ void k_fill_i32(int32_t* p, uint64_t n, int32_t v) {
 // D > 64: k_sign_tc_wide below (mma.sync, the same product walked in 64-column chunks).  Both decide every bit with
 // the reference's exact mul-then-add chain whenever the fast sum is inside its error margin, and count those rows.
 // ================================================================================================
-constexpr int kSignWarps = 4;
 
 // Tensor-core signing.  ncu on the FMA kernel this replaced, at C2 scale: issue
 // slots 59 % busy at 44 % occupancy, 2.7 k warp instructions per 32 rows, 1.08 TB/s — contraction
@@ -1103,11 +1102,11 @@ int launch_sign(klsh_ctx* ctx, const float* vals, int D, int ld, const uint32_t*
   KTRY(dev_reserve(ctx, ctx->eps_counter, sizeof(unsigned long long) * 4));
   if (ld <= 64) {  // tcgen05 + tensor memory (sign_umma.cuh); H <= 32 by the ABI
     if (H > 32) return klsh_fail(ctx, KLSH_ERR_ARG, "more than 32 hyperplanes (%d)", H);
-    auto fn = ld <= 32 ? sign_umma::k_sign_umma<32> : sign_umma::k_sign_umma<64>;
+    auto fn = ld <= 32 ? sign_umma::k_sign_umma<32, sign_umma::kPipe> : sign_umma::k_sign_umma<64, sign_umma::kPipe>;
     const size_t smem = ld <= 32 ? sign_umma::smem_bytes<32>() : sign_umma::smem_bytes<64>();
     KCUDA(ctx, cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     // CTAs per SM by shared memory, registers and tensor-memory columns (the occupancy API reports 1 for this kernel)
-    const int per_sm = ld <= 32 ? sign_umma::ctas_per_sm<32>() : sign_umma::ctas_per_sm<64>();
+    const int per_sm = ld <= 32 ? sign_umma::ctas_per_sm<32, sign_umma::kPipe>() : sign_umma::ctas_per_sm<64, sign_umma::kPipe>();
     const uint64_t ntiles = (n + 127) / 128;
     const uint32_t grid = (uint32_t)std::min<uint64_t>(ntiles, (uint64_t)ctx->sm_count * per_sm);
     fn<<<grid, sign_umma::kThreads, smem, ctx->stream>>>(vals, D, ld, rows, n, d_planes, H, keys_out, rows_out,

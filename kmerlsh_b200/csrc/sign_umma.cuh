@@ -28,6 +28,7 @@ namespace sign_umma {
 
 constexpr int kThreads = 128;  // = rows per tile = tensor-memory lanes
 constexpr int kStages = 2;
+constexpr bool kPipe = true;   // which variant the library launches (see PIPE below)
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -74,10 +75,11 @@ template <int KW>
 constexpr size_t smem_bytes() {
   return (size_t)2 * KW * 32 * 4 + (size_t)kStages * 128 * KW * 4 + 128;
 }
-template <int KW>
-constexpr int tmem_cols() { return 2 * KW + 32; }
-template <int KW>
-constexpr int ctas_per_sm() { return KW == 32 ? 5 : 2; }  // registers (92 / 196 per thread), shared and tensor memory
+// PIPE: two accumulator buffers, so the key packing of tile t-1 runs while the tensor core multiplies tile t.
+template <int KW, bool PIPE>
+constexpr int tmem_cols() { return 2 * KW + (PIPE ? 64 : 32); }
+template <int KW, bool PIPE>
+constexpr int ctas_per_sm() { return KW == 32 ? (PIPE ? 4 : 5) : 2; }  // registers, shared and tensor memory
 
 __device__ __forceinline__ void mma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t db, uint32_t accumulate) {
   asm volatile(
@@ -99,8 +101,8 @@ __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16
       : "memory");
 }
 
-template <int KW>
-__global__ void __launch_bounds__(kThreads, ctas_per_sm<KW>())
+template <int KW, bool PIPE>
+__global__ void __launch_bounds__(kThreads, ctas_per_sm<KW, PIPE>())
 k_sign_umma(const float* __restrict__ vals, int D, int ld, const uint32_t* __restrict__ rows, uint64_t n,
                const float* __restrict__ planes, int H, uint32_t* __restrict__ keys_out, uint32_t* __restrict__ rows_out,
                unsigned long long* eps_rows, uint32_t key_or, unsigned long long* prof) {
@@ -136,7 +138,7 @@ k_sign_umma(const float* __restrict__ vals, int D, int ld, const uint32_t* __res
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem[0])), "r"((uint32_t)(2 * KW)) : "memory");
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem[1])), "r"(32u) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&s_tmem[1])), "r"(PIPE ? 64u : 32u) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (tid == 0) {
@@ -198,23 +200,83 @@ k_sign_umma(const float* __restrict__ vals, int D, int ld, const uint32_t* __res
     return r;
   };
 
+  // this thread's 32 sums of one tile (accumulator columns at d_addr) -> key; r_e: the row's index, xn_e: its norm
+  auto epilogue = [&](uint64_t tile_e, uint32_t r_e, float xn_e, uint32_t d_addr) {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    uint32_t c[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7]), "=r"(c[8]), "=r"(c[9]),
+          "=r"(c[10]), "=r"(c[11]), "=r"(c[12]), "=r"(c[13]), "=r"(c[14]), "=r"(c[15]), "=r"(c[16]), "=r"(c[17]), "=r"(c[18]),
+          "=r"(c[19]), "=r"(c[20]), "=r"(c[21]), "=r"(c[22]), "=r"(c[23]), "=r"(c[24]), "=r"(c[25]), "=r"(c[26]), "=r"(c[27]),
+          "=r"(c[28]), "=r"(c[29]), "=r"(c[30]), "=r"(c[31])
+        : "r"(d_addr + lane_sel)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    // Sign bits: a sum outside the margin is finite and non-zero, so its sign bit IS the answer; every other sum
+    // (inside the margin, zero, NaN, or any sum of a row whose |x| is not finite) is flagged below and recomputed.
+    const float thr = kc * xn_e;
+    uint32_t neg = 0u;  // bit h: sign bit of plane h's sum
+    float mn = 3.4e38f;
+#pragma unroll
+    for (int h = 0; h < 32; ++h) {
+      neg |= (c[h] >> 31) << h;
+      if (h < H) mn = fminf(mn, fabsf(__uint_as_float(c[h])));
+    }
+    uint32_t pos = ~neg;
+    uint32_t slow = 0u;
+    if (!(mn > thr && thr <= 3.0e38f)) {  // rare; also taken for NaN or infinite |x|
+      uint32_t flag = 0u;
+#pragma unroll
+      for (int h = 0; h < 32; ++h) {
+        const float a = fabsf(__uint_as_float(c[h]));
+        flag |= ((a > thr && a <= 3.0e38f) ? 0u : 1u) << h;
+      }
+      flag &= hmask;
+      slow = flag ? 1u : 0u;
+      while (flag) {  // reference arithmetic: sum = fl(sum + fl(w_i * x_i)), i ascending (hash/lshash.cc:44-51)
+        const int h = __ffs(flag) - 1;
+        flag &= flag - 1;
+        const float* w = planes + h * ld;
+        const float* x = vals + (uint64_t)r_e * ld;
+        float sum = 0.f;
+        for (int j = 0; j < D; ++j) sum = __fadd_rn(sum, __fmul_rn(__ldg(w + j), __ldg(x + j)));
+        pos = (pos & ~(1u << h)) | ((sum >= 0.f ? 1u : 0u) << h);
+      }
+    }
+    const uint32_t key = H ? (__brev(pos & hmask) >> (32 - H)) : 0u;  // plane h -> key bit H-1-h
+    const uint64_t t = tile_e * 128 + tid;
+    if (t < n) {
+      keys_out[t] = key | key_or;
+      rows_out[t] = r_e;
+      my_eps += slow;
+    }
+  };
+
   uint64_t tile = blockIdx.x;
   uint32_t r_q[2];
   r_q[0] = issue(tile, 0);
   r_q[1] = issue(tile + gridDim.x, 1);
   uint32_t it = 0;
+  uint64_t tile_prev = 0;
+  uint32_t r_prev = 0u;
+  float xn_prev = 0.f;
   for (; tile < ntiles; tile += gridDim.x, ++it) {
     const int st = (int)(it & 1u);
     long long c0 = 0, c1 = 0, c2 = 0, c3 = 0, c4 = 0;
     if (prof) c0 = clock64();
     asm volatile("cp.async.wait_group 1;" ::: "memory");
     __syncwarp();
+    if (PIPE && it > 0) mbar_wait(bar, (it - 1u) & 1u);  // the products of the previous tile are done: A may be overwritten
     if (prof) c1 = clock64();
     // ---- this thread's row: norm, split, both halves into tensor-memory lane `tid` ----------------------
     const float* myrow = raw + ((size_t)st * 128 + tid) * KW;
     float xx = 0.f;
 #pragma unroll
-    for (int grp = 0; grp < KW / 16; ++grp) {  // 16 columns at a time keeps the live registers low (5 CTAs per SM)
+    for (int grp = 0; grp < KW / 16; ++grp) {  // 16 columns at a time keeps the live registers low
       uint32_t hi[16], lo[16];
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -237,75 +299,33 @@ k_sign_umma(const float* __restrict__ vals, int D, int ld, const uint32_t* __res
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (prof) c2 = clock64();
+    const uint32_t d_cur = tm_d + (PIPE ? (it & 1u) * 32u : 0u);
     if (tid == 0) {
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const uint32_t bh = smem_u32(b_hi), bl = smem_u32(b_lo);
 #pragma unroll
       for (int ks = 0; ks < KS; ++ks) {
         const uint64_t dbh = make_desc(bh + ks * 2 * 512, 512, 128), dbl = make_desc(bl + ks * 2 * 512, 512, 128);
-        mma_tf32_ts(tm_d, tm_a + (uint32_t)(KW + ks * 8), dbh, ks > 0 ? 1u : 0u);  // lo * hi
-        mma_tf32_ts(tm_d, tm_a + (uint32_t)(ks * 8), dbl, 1u);                      // hi * lo
-        mma_tf32_ts(tm_d, tm_a + (uint32_t)(ks * 8), dbh, 1u);                      // hi * hi
+        mma_tf32_ts(d_cur, tm_a + (uint32_t)(KW + ks * 8), dbh, ks > 0 ? 1u : 0u);  // lo * hi
+        mma_tf32_ts(d_cur, tm_a + (uint32_t)(ks * 8), dbl, 1u);                      // hi * lo
+        mma_tf32_ts(d_cur, tm_a + (uint32_t)(ks * 8), dbh, 1u);                      // hi * hi
       }
       asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
     }
-    mbar_wait(bar, it & 1u);
-    if (prof) c3 = clock64();
-    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    uint32_t c[32];
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-        : "=r"(c[0]), "=r"(c[1]), "=r"(c[2]), "=r"(c[3]), "=r"(c[4]), "=r"(c[5]), "=r"(c[6]), "=r"(c[7]), "=r"(c[8]), "=r"(c[9]),
-          "=r"(c[10]), "=r"(c[11]), "=r"(c[12]), "=r"(c[13]), "=r"(c[14]), "=r"(c[15]), "=r"(c[16]), "=r"(c[17]), "=r"(c[18]),
-          "=r"(c[19]), "=r"(c[20]), "=r"(c[21]), "=r"(c[22]), "=r"(c[23]), "=r"(c[24]), "=r"(c[25]), "=r"(c[26]), "=r"(c[27]),
-          "=r"(c[28]), "=r"(c[29]), "=r"(c[30]), "=r"(c[31])
-        : "r"(tm_d + lane_sel)
-        : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-    // Sign bits: a sum outside the margin is finite and non-zero, so its sign bit IS the answer; every other sum
-    // (inside the margin, zero, NaN, or any sum of a row whose |x| is not finite) is flagged below and recomputed.
-    const float thr = kc * xn;
-    uint32_t neg = 0u;  // bit h: sign bit of plane h's sum
-    float mn = 3.4e38f;
-#pragma unroll
-    for (int h = 0; h < 32; ++h) {
-      neg |= (c[h] >> 31) << h;
-      if (h < H) mn = fminf(mn, fabsf(__uint_as_float(c[h])));
-    }
-    uint32_t pos = ~neg;
-    uint32_t slow = 0u;
-    if (!(mn > thr && thr <= 3.0e38f)) {
-      uint32_t flag = 0u;
-#pragma unroll
-      for (int h = 0; h < 32; ++h) {
-        const float a = fabsf(__uint_as_float(c[h]));
-        flag |= ((a > thr && a <= 3.0e38f) ? 0u : 1u) << h;
-      }
-      flag &= hmask;
-      slow = flag ? 1u : 0u;
-      while (flag) {  // reference arithmetic: sum = fl(sum + fl(w_i * x_i)), i ascending (hash/lshash.cc:44-51)
-        const int h = __ffs(flag) - 1;
-        flag &= flag - 1;
-        const float* w = planes + h * ld;
-        const float* x = vals + (uint64_t)r_q[0] * ld;
-        float sum = 0.f;
-        for (int j = 0; j < D; ++j) sum = __fadd_rn(sum, __fmul_rn(__ldg(w + j), __ldg(x + j)));
-        pos = (pos & ~(1u << h)) | ((sum >= 0.f ? 1u : 0u) << h);
-      }
-    }
-    const uint32_t key = H ? (__brev(pos & hmask) >> (32 - H)) : 0u;
-    const uint64_t t = tile * 128 + tid;
-    if (t < n) {
-      keys_out[t] = key | key_or;
-      rows_out[t] = r_q[0];
-      my_eps += slow;
+    if (PIPE) {
+      if (prof) c3 = clock64();
+      if (it > 0) epilogue(tile_prev, r_prev, xn_prev, tm_d + ((it - 1u) & 1u) * 32u);  // while this tile is multiplied
+      tile_prev = tile;
+      r_prev = r_q[0];
+      xn_prev = xn;
+    } else {
+      mbar_wait(bar, it & 1u);
+      if (prof) c3 = clock64();
+      epilogue(tile, r_q[0], xn, d_cur);
     }
     r_q[0] = r_q[1];
     r_q[1] = r_new;
-    if (prof && tid == 0) {
+    if (prof && tid == 0) {  // cycles: waiting (gather, previous products), split + barrier, products, epilogue; tiles
       c4 = clock64();
       atomicAdd(prof + 0, (unsigned long long)(c1 - c0));
       atomicAdd(prof + 1, (unsigned long long)(c2 - c1));
@@ -313,6 +333,10 @@ k_sign_umma(const float* __restrict__ vals, int D, int ld, const uint32_t* __res
       atomicAdd(prof + 3, (unsigned long long)(c4 - c3));
       atomicAdd(prof + 4, 1ull);
     }
+  }
+  if (PIPE && it > 0) {
+    mbar_wait(bar, (it - 1u) & 1u);
+    epilogue(tile_prev, r_prev, xn_prev, tm_d + ((it - 1u) & 1u) * 32u);
   }
   asm volatile("cp.async.wait_all;" ::: "memory");
   if (eps_rows) {
@@ -323,7 +347,7 @@ k_sign_umma(const float* __restrict__ vals, int D, int ld, const uint32_t* __res
   __syncthreads();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_a), "r"((uint32_t)(2 * KW)) : "memory");
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_d), "r"(32u) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tm_d), "r"(PIPE ? 64u : 32u) : "memory");
   }
 }
 

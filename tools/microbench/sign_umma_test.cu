@@ -20,7 +20,7 @@
     }                                                                                      \
   } while (0)
 
-template <int KW>
+template <int KW, bool PIPE>
 int run(uint64_t n, int D, int H, bool indirect) {
   const int ld = (D + 3) & ~3;
   std::mt19937 g(1234 + D * 7 + H);
@@ -67,16 +67,16 @@ int run(uint64_t n, int D, int H, bool indirect) {
   CK(cudaMemset(d_eps, 0, 8));
   CK(cudaMemset(d_keys, 0xFF, n * 4));
   const bool ts = true;
-  auto fn = sign_umma::k_sign_umma<KW>;
+  auto fn = sign_umma::k_sign_umma<KW, PIPE>;
   const size_t smem = sign_umma::smem_bytes<KW>();
   CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int per_sm = 0, sms = 0;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, sign_umma::kThreads, smem));
   CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, 0));
   const uint64_t ntiles = (n + 127) / 128;
-  const int mult = getenv("SIGN_CTAS") ? atoi(getenv("SIGN_CTAS")) : sign_umma::ctas_per_sm<KW>();
+  const int mult = getenv("SIGN_CTAS") ? atoi(getenv("SIGN_CTAS")) : sign_umma::ctas_per_sm<KW, PIPE>();
   const unsigned grid = (unsigned)std::min<uint64_t>(ntiles, (uint64_t)sms * mult);
-  printf("%s KW=%d D=%d H=%d n=%llu indirect=%d smem=%zu ctas/sm=%d grid=%u\n", ts ? "TS" : "SS", KW, D, H, (unsigned long long)n, (int)indirect, smem, per_sm, grid);
+  printf("%s KW=%d D=%d H=%d n=%llu indirect=%d smem=%zu ctas/sm=%d grid=%u\n", PIPE ? "PIPE" : "PLAIN", KW, D, H, (unsigned long long)n, (int)indirect, smem, per_sm, grid);
   fn<<<grid, sign_umma::kThreads, smem>>>(d_vals, D, ld, indirect ? d_rows : nullptr, n, d_planes, H, d_keys, d_rout, d_eps, 0u, nullptr);
   CK(cudaGetLastError());
   CK(cudaDeviceSynchronize());
@@ -126,8 +126,9 @@ int main(int argc, char** argv) {
   const int D = argc > 2 ? atoi(argv[2]) : 32, H = argc > 3 ? atoi(argv[3]) : 25;
   const bool indirect = argc > 4 && atoi(argv[4]) != 0;
   const int ld = (D + 3) & ~3;
-  if (ld <= 32) return run<32>(n, D, H, indirect);
-  if (ld <= 64) return run<64>(n, D, H, indirect);
+  const bool pipe = getenv("SIGN_PIPE") && atoi(getenv("SIGN_PIPE"));
+  if (ld <= 32) return pipe ? run<32, true>(n, D, H, indirect) : run<32, false>(n, D, H, indirect);
+  if (ld <= 64) return pipe ? run<64, true>(n, D, H, indirect) : run<64, false>(n, D, H, indirect);
   printf("D too wide for this kernel\n");
   return 3;
 }
