@@ -460,7 +460,7 @@ def main():
         "algorithmic_bytes_per_step": merge_bytes / args.steps, "peak_source": peak_src,
         "share_of_step": (fam["merge"] / dev_total_ms if dev_total_ms else None) if world == 1 else None, "dominant_family": dom,
         "family_ms_per_step": {k: v / args.steps for k, v in fam.items()} if world == 1 else None,
-        "streaming": ({"kernel": "k_sign_tc (3xTF32 projection + key packing)", "achieved": sign_achieved, "unit": "GB/s",
+        "streaming": ({"kernel": "k_sign_umma (tcgen05.mma kind::tf32, 3xTF32 projection with rows and sums in tensor memory, + key packing; k_sign_tc_wide above 64 columns)", "achieved": sign_achieved, "unit": "GB/s",
                        "frac": sign_achieved / peak, "bytes_per_row": "4D+8"} if world == 1 else None),
         "job": {"achieved": job_achieved, "frac": job_achieved / (peak * world), "bytes_per_row_iter": "8D+32+s(4D+12)",
                 "peak_all_gpus": peak * world},
