@@ -64,7 +64,7 @@ def main():
         k[2] += m.get("dram__bytes_read.sum", 0.0)
         k[3] += m.get("dram__bytes_write.sum", 0.0)
     total_ms = sum(v[1] for v in kern.values())
-    lib = {k: v for k, v in kern.items() if k.startswith("k_")}
+    lib = {k: v for k, v in kern.items() if k.startswith("k_") or k.startswith("sign_umma::")}
     lib_ms = sum(v[1] for v in lib.values())
     fam = {}
     for fname, rx in FAMILIES:
