@@ -33,6 +33,7 @@
 #include <vector>
 
 #include "klsh.h"
+#include "modee.h"
 
 namespace {
 
@@ -52,6 +53,8 @@ struct Params {
   int gpus = 1;
   uint64_t batch = 100000000ull;
   bool reload_tmp = false, no_tmp_files = false, resident = false;
+  int kmer_size = 23, size_thresh = 500000;       // -K, -S, -P, -V: mode E (reference defaults, app/kmerLSH.cc:139-142)
+  float pval_thresh = 0.01f, kmer_vote = 0.5f;
   bool binary_tmp_ids = false;  // --binary-tmp-ids: member lists of the spill files as <n>.bin.clust.bin (klsh_set_id_format)
   std::string stats_json;
 };
@@ -158,6 +161,25 @@ bool cluster_call(Worker& w, const char* phase, uint64_t call, float sim, int it
 
 }  // namespace
 
+static int run_mode_c(Params p);
+
+static ModeEParams mode_e_params(const Params& p) {
+  ModeEParams e;
+  e.input1 = p.input1;
+  e.input2 = p.input2;
+  e.output1 = p.output1;
+  e.output2 = p.output2;
+  e.clust_file_name = p.clust_file_name;
+  e.k = p.kmer_size;
+  e.pval_thresh = p.pval_thresh;
+  e.size_thresh = p.size_thresh;
+  e.kmer_vote = p.kmer_vote;
+  e.threads_to_use = p.threads_to_use;
+  e.verbose = p.verbose;
+  e.device = p.device;
+  return e;
+}
+
 int main(int argc, char** argv) {
   Params p;
   int verbose_flag = 0, only_flag = 0;
@@ -205,6 +227,10 @@ int main(int argc, char** argv) {
       case 'D': if (optarg) p.tmp_dir = optarg; break;
       case 'F': if (optarg) p.clust_file_name = optarg; break;
       case 'M': if (optarg) p.mode = optarg; break;
+      case 'K': if (optarg) p.kmer_size = atoi(optarg); break;
+      case 'S': if (optarg) p.size_thresh = atoi(optarg); break;
+      case 'P': if (optarg) p.pval_thresh = (float)atof(optarg); break;
+      case 'V': if (optarg) p.kmer_vote = (float)atof(optarg); break;
       case 1000: p.have_seed = true; p.seed = strtoull(optarg, 0, 10); break;
       case 1001: p.device = atoi(optarg); break;
       case 1002: p.batch = strtoull(optarg, 0, 10); break;
@@ -214,15 +240,24 @@ int main(int argc, char** argv) {
       case 1006: p.stats_json = optarg; break;
       case 1007: p.resident = true; break;
       case 1008: p.binary_tmp_ids = true; break;
-      default: break;  // -H -X -C -K -S -P -V: accepted, meaningless for mode C
+      default: break;  // -H -X -C: accepted, meaningless for modes C and E
     }
   }
   p.verbose = verbose_flag != 0;
   p.only = only_flag != 0;
+  // reference app/kmerLSH.cc:236-271: -M E runs the extraction alone, -M C the clustering and — without --only — the
+  // extraction after it; modes K and B (KMC counting, bin-file construction) are the reference's own.
+  if (p.mode == "E") return run_mode_e(mode_e_params(p));
   if (p.mode != "C") {
-    std::cerr << "kmerLSH_b200 implements mode C only (-M C [--only]); modes K, B and E are the reference's." << std::endl;
+    std::cerr << "kmerLSH_b200 implements modes C and E (-M C [--only], -M E); modes K and B are the reference's." << std::endl;
     return 2;
   }
+  const int rc = run_mode_c(p);
+  if (rc != 0 || p.only) return rc;
+  return run_mode_e(mode_e_params(p));
+}
+
+static int run_mode_c(Params p) {
   if (p.batch < 1000) {
     std::cerr << "--batch must be at least 1000" << std::endl;
     return 2;

@@ -59,8 +59,9 @@ def test_product_does_not_reference_the_oracle():
 def test_cli_rejects_other_modes(tmp_path):
     exe = os.path.join(ROOT, "kmerlsh_b200", "kmerLSH_b200")
     assert os.path.exists(exe)
-    r = subprocess.run([exe, "-M", "E"], cwd=str(tmp_path), stderr=subprocess.PIPE, text=True)
-    assert r.returncode == 2 and "mode C only" in r.stderr
+    for mode in ("K", "B", ""):
+        r = subprocess.run([exe, "-M", mode] if mode else [exe], cwd=str(tmp_path), stderr=subprocess.PIPE, text=True)
+        assert r.returncode == 2 and "modes C and E" in r.stderr, mode
 
 
 def test_log_line_roundtrip():
