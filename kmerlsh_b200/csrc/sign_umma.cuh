@@ -219,14 +219,14 @@ k_sign_umma(const float* __restrict__ vals, int D, int ld, const uint32_t* __res
     // Sign bits: a sum outside the margin is finite and non-zero, so its sign bit IS the answer; every other sum
     // (inside the margin, zero, NaN, or any sum of a row whose |x| is not finite) is flagged below and recomputed.
     const float thr = kc * xn_e;
-    uint32_t neg = 0u;  // bit h: sign bit of plane h's sum
+    uint32_t sgn = 0u;  // after the loop: bit 31-h = sign bit of plane h's sum (one funnel shift per plane)
     float mn = 3.4e38f;
 #pragma unroll
     for (int h = 0; h < 32; ++h) {
-      neg |= (c[h] >> 31) << h;
+      sgn = __funnelshift_l(c[h], sgn, 1);  // (sgn << 1) | (c[h] >> 31)
       if (h < H) mn = fminf(mn, fabsf(__uint_as_float(c[h])));
     }
-    uint32_t pos = ~neg;
+    uint32_t pos = ~sgn;  // bit 31-h set <=> plane h non-negative: already in key order (plane 0 most significant)
     uint32_t slow = 0u;
     if (!(mn > thr && thr <= 3.0e38f)) {  // rare; also taken for NaN or infinite |x|
       uint32_t flag = 0u;
@@ -244,10 +244,11 @@ k_sign_umma(const float* __restrict__ vals, int D, int ld, const uint32_t* __res
         const float* x = vals + (uint64_t)r_e * ld;
         float sum = 0.f;
         for (int j = 0; j < D; ++j) sum = __fadd_rn(sum, __fmul_rn(__ldg(w + j), __ldg(x + j)));
-        pos = (pos & ~(1u << h)) | ((sum >= 0.f ? 1u : 0u) << h);
+        const uint32_t bit = 0x80000000u >> h;
+        pos = (pos & ~bit) | (sum >= 0.f ? bit : 0u);
       }
     }
-    const uint32_t key = H ? (__brev(pos & hmask) >> (32 - H)) : 0u;  // plane h -> key bit H-1-h
+    const uint32_t key = H ? (pos >> (32 - H)) : 0u;  // planes 0..H-1 -> key bits H-1..0; planes past H drop out
     const uint64_t t = tile_e * 128 + tid;
     if (t < n) {
       keys_out[t] = key | key_or;
