@@ -16,10 +16,11 @@
 //     and 512 bytes apart along K (LBO); the 128 x 32 sums land in 32 columns of tensor memory;
 //   * tcgen05.commit signals an mbarrier; every thread reads ITS row's 32 sums with one tcgen05.ld.32x32b.x32 and packs
 //     the key bits — no fragment shuffles, no per-lane transposition, no operand tiles in shared memory.
-// A CTA needs the planes (KW*256 bytes), the gather ring and 2*KW + 32 columns of tensor memory (two allocations: A hi
-// and lo, the sums), so five CTAs fit an SM at KW = 32 (two at KW = 64) and cover each other's gather / split /
-// products / epilogue latencies.  Per 32 rows this is about 600 warp instructions against 1250 for the mma.sync kernel.
-// Measured (tools/microbench/sign_umma_test.cu, profiles/): 8 M x 32 rows 3.08 TB/s algorithmic, 4 M x 64 2.68 TB/s.
+// A CTA needs the planes (KW*256 bytes), the gather ring and 2*KW + 64 columns of tensor memory (two allocations: A hi
+// and lo, two buffers of sums), so four CTAs fit an SM at KW = 32 (two at KW = 64) and cover each other's gather /
+// split / products / epilogue latencies.  Per 32 rows this is about 600 warp instructions against 1250 for the mma.sync kernel.
+// Measured (tools/microbench/sign_umma_test.cu, profiles/r02d_sign_umma_microbench.txt): 8 M x 32 rows 4.24 TB/s
+// algorithmic (65 % of the measured HBM copy peak), 4 M x 64 3.63 TB/s.
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
