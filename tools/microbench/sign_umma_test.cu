@@ -1,7 +1,7 @@
 // Stand-alone check and timing of k_sign_umma (kmerlsh_b200/csrc/sign_umma.cuh): keys against the reference's
 // mul-then-add chain computed on the host, then GB/s over repeated launches.
 //   nvcc -gencode arch=compute_100a,code=sm_100a -O3 -std=c++17 -fmad=false -lineinfo -o sign_umma_test sign_umma_test.cu
-//   ./sign_umma_test [rows] [D] [H] [indirect 0/1]
+//   [SIGN_PIPE=1] [SIGN_CTAS=n] ./sign_umma_test [rows] [D] [H] [indirect 0/1]
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -66,7 +66,6 @@ int run(uint64_t n, int D, int H, bool indirect) {
   CK(cudaMemcpy(d_rows, rows.data(), n * 4, cudaMemcpyHostToDevice));
   CK(cudaMemset(d_eps, 0, 8));
   CK(cudaMemset(d_keys, 0xFF, n * 4));
-  const bool ts = true;
   auto fn = sign_umma::k_sign_umma<KW, PIPE>;
   const size_t smem = sign_umma::smem_bytes<KW>();
   CK(cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
